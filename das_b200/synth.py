@@ -1,0 +1,175 @@
+"""Deterministic synthetic DAS head outputs (the decode path's inputs).
+
+Shapes and value distributions follow SURVEY.md section 8(d): one entry per pyramid
+level holding the raw predictor outputs the reference head produces right before its
+eval tail (``das_head.py:232-236``) plus the refinement feature map(s) each
+``RecursiveUpdateLayer`` projects from (``recursive_update.py:188`` output).
+
+Everything is generated with a seeded ``torch.Generator`` on the requested device
+(CPU for parity tests so the oracle sees the very same bits; CUDA for full-size
+benchmarks where 1.7 GB of features per batch would take too long on the host).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+@dataclass
+class HeadConfig:
+    """Keys mirror the reference head config (configs/_base_/models/das.py:24-51,
+    configs/das/exp_panoptic.py:31-44)."""
+    num_joints: int = 15
+    root_idx: int = 2
+    depth_factor: float = 20.0
+    z_norm: float = 50.0
+    strides: Sequence[int] = (8,)
+    num_heads: int = 4
+    feat_channels: int = 256
+    num_layers: int = 1
+    dim: int = 3
+
+    def as_dict(self):
+        return dict(num_joints=self.num_joints, root_idx=self.root_idx, depth_factor=self.depth_factor,
+                    z_norm=self.z_norm, strides=list(self.strides), num_heads=self.num_heads,
+                    feat_channels=self.feat_channels, num_layers=self.num_layers, dim=self.dim)
+
+
+PANOPTIC = HeadConfig(num_joints=15, root_idx=2, depth_factor=20.0, z_norm=50.0)
+MUPOTS17 = HeadConfig(num_joints=17, root_idx=14, depth_factor=1.0, z_norm=50.0, num_layers=3)
+
+
+def _gen(seed: int, device) -> torch.Generator:
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    return g
+
+
+def make_layers(cfg: HeadConfig, seed: int = 7, device="cpu") -> List[dict]:
+    """1x1 projection weights of every refinement layer, named after the reference
+    modules (recursive_update.py:171-180): so = sampling_offset [J*nh*2, C],
+    sc = sampling_conf [3J, C], uw = update_weight [3J, C], uv = update_offset_value [3J, C]."""
+    g = _gen(seed, device)
+    J, nh, C = cfg.num_joints, cfg.num_heads, cfg.feat_channels
+    bnd = 1.0 / math.sqrt(C)
+    layers = []
+    for _ in range(cfg.num_layers):
+        def w(o, std):
+            return torch.randn(o, C, generator=g, device=device) * std
+
+        def b(o):
+            return (torch.rand(o, generator=g, device=device) * 2 - 1) * bnd
+        layers.append(dict(so_w=w(J * nh * 2, 0.01), so_b=b(J * nh * 2),
+                           sc_w=w(3 * J, 0.02), sc_b=b(3 * J),
+                           uw_w=w(3 * J, 0.02), uw_b=b(3 * J),
+                           uv_w=w(3 * J, 0.02), uv_b=b(3 * J)))
+    return layers
+
+
+def _smooth(x: torch.Tensor, k: int = 9) -> torch.Tensor:
+    """k x k box filter, rescaled so the per-pixel std stays close to the input's."""
+    if k <= 1:
+        return x
+    return F.avg_pool2d(x, k, 1, k // 2, count_include_pad=False) * float(k)
+
+
+def make_level(cfg: HeadConfig, batch: int, h: int, w: int, stride: int, seed: int, device="cpu",
+               peaks: int = 16, smooth: int = 9, scales=(1.0, 1.0, 1.0, 1.0), channels_last: bool = True,
+               with_feats: bool = True) -> dict:
+    g = _gen(seed, device)
+    J, C = cfg.num_joints, cfg.feat_channels
+
+    def randn(*s):
+        return torch.randn(*s, generator=g, device=device)
+
+    def rand(*s):
+        return torch.rand(*s, generator=g, device=device)
+
+    cls = randn(batch, 1, h, w) - 6.0
+    if peaks > 0:
+        pos_y = torch.randint(0, h, (batch, peaks), generator=g, device=device)
+        pos_x = torch.randint(0, w, (batch, peaks), generator=g, device=device)
+        amp = rand(batch, peaks) * 6.0 - 1.0
+        flat = cls.view(batch, -1)
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                yy = (pos_y + dy).clamp(0, h - 1)
+                xx = (pos_x + dx).clamp(0, w - 1)
+                val = amp - 1.5 * float(dx * dx + dy * dy)
+                flat.scatter_reduce_(1, yy * w + xx, val, "amax", include_self=True)
+    ctr = randn(batch, 1, h, w) + 1.0
+
+    pose = torch.empty(batch, 3 + 6 * J, h, w, device=device)
+    pose[:, 0:2] = _smooth(randn(batch, 2, h, w) * 0.5, smooth)
+    pose[:, 2:3] = (0.05 + 0.45 * rand(batch, 1, h, w)) * cfg.depth_factor
+    if smooth > 1:
+        pose[:, 2:3] = F.avg_pool2d(pose[:, 2:3], smooth, 1, smooth // 2, count_include_pad=False)
+    uvd = _smooth(randn(batch, 3 * J, h, w), smooth)
+    uvd[:, 0::3] *= 4.0
+    uvd[:, 1::3] *= 4.0
+    pose[:, 3:3 + 3 * J] = uvd
+    pose[:, 3 + 3 * J:] = randn(batch, 3 * J, h, w)
+
+    lvl = dict(cls=cls, ctr=ctr, pose_raw=pose, stride=int(stride), scales=tuple(float(s) for s in scales),
+               feats=[])
+    if with_feats:
+        for _ in range(cfg.num_layers):
+            f = randn(batch, h, w, C).permute(0, 3, 1, 2)      # NHWC storage, NCHW logical view
+            if not channels_last:
+                f = f.contiguous()
+            lvl["feats"].append(f)
+    return lvl
+
+
+def make_levels(cfg: HeadConfig, batch: int, h: int, w: int, seed: int, device="cpu", **kw) -> List[dict]:
+    """One dict per stride in ``cfg.strides``; level l has size ceil(h / 2^l) x ceil(w / 2^l)."""
+    out = []
+    for l, s in enumerate(cfg.strides):
+        hl, wl = -(-h // (1 << l)), -(-w // (1 << l))
+        out.append(make_level(cfg, batch, hl, wl, s, seed + 101 * l, device, **kw))
+    return out
+
+
+def make_metas(batch: int, h: int, w: int, stride: int = 8, seed: int = 3, identity_rt: bool = False) -> List[dict]:
+    """img_metas entries with the keys the path reads: 'scale_factor' (np.float32[4], das_head.py:698),
+    'filename' (:684) and 'cam' {K,R,t} (formating.py:140)."""
+    rng = np.random.RandomState(seed)
+    metas = []
+    for b in range(batch):
+        sx, sy = 0.6 + 0.01 * rng.rand(), 0.6 + 0.01 * rng.rand()
+        fx, fy = 1400.0 + 50 * rng.rand(), 1410.0 + 50 * rng.rand()
+        K = np.array([[fx, 0.3 * rng.rand(), w * stride / sx / 2 + rng.rand()],
+                      [0.0, fy, h * stride / sy / 2 + rng.rand()],
+                      [0.0, 0.0, 1.0]])
+        if identity_rt:
+            R, t = np.eye(3), np.zeros((3, 1))
+        else:
+            a, bb, c = 0.3 * rng.rand(3)
+            Rx = np.array([[1, 0, 0], [0, math.cos(a), -math.sin(a)], [0, math.sin(a), math.cos(a)]])
+            Ry = np.array([[math.cos(bb), 0, math.sin(bb)], [0, 1, 0], [-math.sin(bb), 0, math.cos(bb)]])
+            Rz = np.array([[math.cos(c), -math.sin(c), 0], [math.sin(c), math.cos(c), 0], [0, 0, 1]])
+            R = Rz @ Ry @ Rx
+            t = np.array([[10.0 * rng.rand()], [-120.0 + 5 * rng.rand()], [300.0 + 20 * rng.rand()]])
+        metas.append(dict(scale_factor=np.array([sx, sy, sx, sy], dtype=np.float32),
+                          filename=f"synthetic_{b:05d}.jpg", cam=dict(K=K, R=R, t=t)))
+    return metas
+
+
+def levels_to(levels: List[dict], device) -> List[dict]:
+    out = []
+    for lv in levels:
+        d = dict(lv)
+        for k in ("cls", "ctr", "pose_raw"):
+            d[k] = lv[k].to(device)
+        d["feats"] = [f.to(device) for f in lv["feats"]]     # preserves the NHWC strides
+        out.append(d)
+    return out
+
+
+def layers_to(layers: List[dict], device) -> List[dict]:
+    return [{k: v.to(device) for k, v in l.items()} for l in layers]
