@@ -1,0 +1,114 @@
+"""ctypes binding of include/das_decode.h (the C-ABI drop-in boundary).
+
+There is deliberately no fallback: if the shared library is missing or the device is not
+available every entry point raises -- the product path never routes through the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+MAX_LEVELS = 5
+MAX_LAYERS = 4
+MAX_JOINTS = 32
+MAX_NMS_PRE = 2048
+CAM_DOUBLES = 18
+
+_f32p = C.POINTER(C.c_float)
+_i32p = C.POINTER(C.c_int32)
+_u32p = C.POINTER(C.c_uint32)
+_f64p = C.POINTER(C.c_double)
+
+
+class LevelDesc(C.Structure):
+    _fields_ = [("cls", C.c_void_p), ("ctr", C.c_void_p), ("pose", C.c_void_p),
+                ("feats", C.c_void_p * MAX_LAYERS),
+                ("H", C.c_int32), ("W", C.c_int32), ("stride", C.c_int32),
+                ("scale_offset", C.c_float), ("scale_depth", C.c_float),
+                ("scale_uv", C.c_float), ("scale_d", C.c_float)]
+
+
+class Levels(C.Structure):
+    _fields_ = [("n_levels", C.c_int32), ("batch", C.c_int32), ("lv", LevelDesc * MAX_LEVELS)]
+
+
+class DecodeCfg(C.Structure):
+    _fields_ = [("num_joints", C.c_int32), ("root_idx", C.c_int32), ("num_heads", C.c_int32),
+                ("feat_channels", C.c_int32), ("num_layers", C.c_int32),
+                ("depth_factor", C.c_float), ("z_norm", C.c_float),
+                ("nms_pre", C.c_int32), ("nms_post", C.c_int32),
+                ("nms_thr", C.c_float), ("score_thr", C.c_float),
+                ("peak_kernel", C.c_int32), ("refine", C.c_int32),
+                ("dataset_depth_factor", C.c_double)]
+
+
+class Buffers(C.Structure):
+    _fields_ = [("cand_score", C.c_void_p), ("cand_index", C.c_void_p),
+                ("cand_pose", C.c_void_p), ("cand_center", C.c_void_p),
+                ("out_count", C.c_void_p), ("out_score", C.c_void_p), ("out_slot", C.c_void_p),
+                ("out_pose", C.c_void_p), ("out_center", C.c_void_p),
+                ("out_cam", C.c_void_p), ("out_world", C.c_void_p)]
+
+
+# every symbol include/das_decode.h declares: (restype, argtypes)
+_VP = C.c_void_p
+SIGNATURES = {
+    "das_version": (C.c_char_p, []),
+    "das_last_error": (C.c_char_p, []),
+    "das_level_slots": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
+    "das_candidate_slots": (C.c_int32, [C.POINTER(Levels), C.c_int32]),
+    "das_output_slots": (C.c_int32, [C.c_int32, C.c_int32]),
+    "das_score_topk": (C.c_int, [_VP, C.POINTER(Levels), C.c_int32, C.c_int32, _VP, _VP, C.c_int32, _VP, _VP]),
+    "das_gather_refine_assemble": (C.c_int, [_VP, C.POINTER(Levels), C.POINTER(DecodeCfg), _VP, _VP, _VP, _VP, _VP,
+                                             C.c_int32, _VP, _VP, _VP, _VP]),
+    "das_refine_dense_layer": (C.c_int, [_VP, C.POINTER(Levels), C.c_int32, C.c_int32, C.POINTER(DecodeCfg), _VP, _VP,
+                                         _VP, _VP, _VP]),
+    "das_nms_backproject": (C.c_int, [C.POINTER(DecodeCfg), C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, Buffers, _VP]),
+    "das_pack_weights": (C.c_int, [C.POINTER(DecodeCfg)] + [_VP] * 10),
+    "das_packed_weight_floats": (C.c_int64, [C.POINTER(DecodeCfg)]),
+    "das_plan_create": (C.c_int, [C.POINTER(DecodeCfg), C.POINTER(Levels), C.POINTER(_VP)]),
+    "das_plan_destroy": (None, [_VP]),
+    "das_plan_set_weights": (C.c_int, [_VP, C.c_int32] + [_VP] * 9),
+    "das_plan_bind": (C.c_int, [_VP, C.POINTER(Levels), _VP]),
+    "das_plan_set_metas": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "das_plan_run": (C.c_int, [_VP, _VP, C.c_int32]),
+    "das_plan_buffers": (C.c_int, [_VP, C.POINTER(Buffers), _i32p, _i32p]),
+    "das_plan_kernel_launches": (C.c_int64, [_VP]),
+    "das_plan_run_host": (C.c_int, [_VP, C.POINTER(Levels), _VP, _VP, Buffers, _VP]),
+    "das_plan_h2d_bytes": (C.c_int64, [_VP]),
+    "das_plan_d2h_bytes": (C.c_int64, [_VP]),
+}
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libdas_decode.so")
+_lib = None
+
+
+class DasError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return LIB_PATH
+
+
+def load():
+    """Load libdas_decode.so (building it when absent and nvcc exists). Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        from . import build as _build
+        _build.build()
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header and library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = ""):
+    if status != 0:
+        msg = load().das_last_error().decode(errors="replace")
+        raise DasError(f"{what or 'das call'} failed with status {status}: {msg}")

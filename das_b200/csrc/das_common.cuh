@@ -1,0 +1,64 @@
+// Shared helpers for the DAS decode kernels (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "das_decode.h"
+
+namespace das {
+
+constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs
+
+void set_error(const char* fmt, ...);
+
+#define DAS_CUDA_CHECK(expr)                                                              \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            ::das::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return DAS_ERR_CUDA;                                                          \
+        }                                                                                 \
+    } while (0)
+
+#define DAS_REQUIRE(cond, code, ...)      \
+    do {                                  \
+        if (!(cond)) {                    \
+            ::das::set_error(__VA_ARGS__); \
+            return (code);                \
+        }                                 \
+    } while (0)
+
+__host__ __device__ __forceinline__ int level_slots(int hw, int nms_pre) {
+    // das_head.py:716-717: top-k only `if nms_pre > 0 and N > nms_pre`, else every cell passes through
+    return (nms_pre > 0 && hw > nms_pre) ? nms_pre : hw;
+}
+
+// Accurate (not __expf) so the score stays within ~2 ulp of a correctly rounded sigmoid; the CPU
+// reference's own sigmoid is only that accurate (hard parts).
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ int block_sum_1024(int v, int* red /* >= 33 ints smem */) {
+    v = __reduce_add_sync(0xffffffffu, v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    int t = (lane < nw) ? red[lane] : 0;
+    t = __reduce_add_sync(0xffffffffu, t);
+    return t;
+}
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// streaming 128-bit load that does not pollute L1 (score planes are read once per pass)
+__device__ __forceinline__ float4 ldg_f4_stream(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+}  // namespace das

@@ -1,0 +1,313 @@
+// Stage 5: score threshold, OKS-NMS, nms_post, output packing, depth de-normalisation and
+// back-projection to camera / world space.
+//
+// Reference semantics (file:line relative to the reference root):
+//   * concat / score_thr / areas / keep[:nms_post] ... das_head.py:751-794
+//   * oks_iou / oks_nms ............................... mmdet3d/core/post_processing/pose_nms.py:51-126
+//       float32 keypoints and areas, float64 exponent math, float32 OKS compared with `<= thr`;
+//       sigmas = COCO-17 table / 10 iff J == 17 else 0.08
+//   * depth de-normalisation .......................... mmdet3d/datasets/cmupanoptic_mono_dataset.py:391-401
+//   * pixel2world ...................................... mytools/vis_3d.py:16-26 (float64)
+// Ordering rule of this implementation: candidates are ranked by score, equal scores by the lower
+// candidate slot (the reference's `argsort()[::-1]` has no defined tie order).
+//
+// One CTA per image.  The reference does this on the host with 3 device->host copies per candidate
+// and an O(N^2) python loop; here the candidates never leave the GPU.
+#include "das_common.cuh"
+
+namespace das {
+
+constexpr int NM_THREADS = 1024;
+constexpr int NM_MAX_CAND = 8192;
+constexpr int NM_MATRIX_N = 64;   // up to this many candidates: all-pairs OKS + bitmask greedy
+
+struct NmsParams {
+    int B, CT, P, J, root, nms_post;
+    float nms_thr, score_thr;
+    double ddf;
+    const float* cand_score;
+    const float* cand_pose;
+    const float* cand_center;
+    const double* cam;
+    das_buffers out;
+};
+
+__device__ __forceinline__ double oks_var(int j, int J) {
+    // pose_nms.py:65-73: vars = (sigmas * 2) ** 2
+    const double tbl[17] = {.26, .25, .25, .35, .35, .79, .79, .72, .72, .62, .62, 1.07, 1.07, .87, .87, .89, .89};
+    const double s = (J == 17) ? tbl[j] / 10.0 : 0.08;
+    return (s * 2.0) * (s * 2.0);
+}
+
+// One joint's term exp(-e_j) of OKS(g, d); pose rows are [J,3] float32.
+__device__ __forceinline__ double oks_term(const float* __restrict__ pg, const float* __restrict__ pd,
+                                           float ag, float ad, int j, int J) {
+    const float dx = __fsub_rn(pd[3 * j], pg[3 * j]);
+    const float dy = __fsub_rn(pd[3 * j + 1], pg[3 * j + 1]);
+    const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    const float am = __fmul_rn(__fadd_rn(ag, ad), 0.5f);            // (a_g + a_d) / 2 in float32
+    const double e = static_cast<double>(d2) / oks_var(j, J) / (static_cast<double>(am) + 2.220446049250313e-16) / 2.0;
+    return exp(-e);
+}
+
+// group of G lanes (16 or 32) cooperates on one pair; every lane of the group returns the float32 OKS
+template <int G>
+__device__ __forceinline__ float oks_pair(const float* pg, const float* pd, float ag, float ad, int J, int gl) {
+    double t = (gl < J) ? oks_term(pg, pd, ag, ad, gl, J) : 0.0;
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return static_cast<float>(t / static_cast<double>(J));
+}
+
+__global__ void __launch_bounds__(NM_THREADS, 1)
+nms_backproject_kernel(const NmsParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: keys u64[n2] | area f32[CT] | order i32[CT] | flag u8[CT]
+    const int CT = p.CT;
+    int n2cap = 1;
+    while (n2cap < CT) n2cap <<= 1;
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+    float* area = reinterpret_cast<float*>(keys + n2cap);
+    int* order = reinterpret_cast<int*>(area + CT);
+    unsigned char* dead = reinterpret_cast<unsigned char*>(order + CT);
+    __shared__ int s_n, s_kept;
+    __shared__ unsigned long long s_mask[NM_MATRIX_N];
+    __shared__ int s_keep[NM_MATRIX_N];
+
+    const int b = blockIdx.x, tid = threadIdx.x, J = p.J;
+    const float* __restrict__ score = p.cand_score + static_cast<size_t>(b) * CT;
+    const float* __restrict__ pose = p.cand_pose + static_cast<size_t>(b) * CT * J * 3;
+    const float* __restrict__ center = p.cand_center + static_cast<size_t>(b) * CT * 3;
+    const int P = p.P;
+    int* kept_list = order;   // reused after ranking: kept_list[k] = candidate slot of output row k
+
+    if (tid == 0) { s_n = 0; s_kept = 0; }
+    __syncthreads();
+
+    // ---- validity (das_head.py:763-769) + stable compaction in slot order ---------------------------
+    // n is small against 1024 threads in every shipped config; a simple ordered scan keeps slot order.
+    for (int base = 0; base < CT; base += NM_THREADS) {
+        const int c = base + tid;
+        const bool ok = c < CT && (p.score_thr > 0.f ? (score[c] > p.score_thr) : true);
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        __shared__ int wcount[32];
+        const int lane = tid & 31, warp = tid >> 5;
+        if (lane == 0) wcount[warp] = __popc(bal);
+        __syncthreads();
+        int off = s_n;
+        for (int w = 0; w < warp; ++w) off += wcount[w];
+        if (ok) order[off + __popc(bal & ((1u << lane) - 1))] = c;
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int w = 0; w < 32; ++w) t += wcount[w];
+            s_n += t;
+        }
+        __syncthreads();
+    }
+    const int n = s_n;
+
+    int kept = 0;
+    if (p.nms_post > 0 && n > 0) {
+        // ---- rank by (score desc, slot asc); areas (das_head.py:773-775) ---------------------------
+        int n2 = 1;
+        while (n2 < n) n2 <<= 1;
+        for (int i = tid; i < n2; i += NM_THREADS) {
+            uint64_t k = 0;
+            if (i < n) {
+                const int c = order[i];
+                k = (static_cast<uint64_t>(__float_as_uint(score[c])) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(c));
+                const float* pc = pose + static_cast<size_t>(c) * J * 3;
+                float x0 = pc[0], x1 = pc[0], y0 = pc[1], y1 = pc[1];
+                for (int j = 1; j < J; ++j) {
+                    x0 = fminf(x0, pc[3 * j]); x1 = fmaxf(x1, pc[3 * j]);
+                    y0 = fminf(y0, pc[3 * j + 1]); y1 = fmaxf(y1, pc[3 * j + 1]);
+                }
+                area[c] = __fmul_rn(__fsub_rn(x1, x0), __fsub_rn(y1, y0));
+            }
+            keys[i] = k;
+        }
+        __syncthreads();
+        // bitonic sort, descending
+        for (int k = 2; k <= n2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (n2 >> 1); t += NM_THREADS) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int q = i | j;
+                    const bool desc = ((i & k) == 0);
+                    const uint64_t x = keys[i], y = keys[q];
+                    if ((x < y) == desc) { keys[i] = y; keys[q] = x; }
+                }
+                __syncthreads();
+            }
+        }
+        for (int i = tid; i < n; i += NM_THREADS) {
+            order[i] = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(keys[i] & 0xFFFFFFFFull));
+            dead[i] = 0;
+        }
+        __syncthreads();
+
+        const int limit = min(p.nms_post, n);
+        if (n <= NM_MATRIX_N) {
+            // ---- all pairs in parallel, then a 64-bit mask greedy pass by one thread ---------------
+            if (tid < n) s_mask[tid] = 0ull;
+            __syncthreads();
+            const int npairs = n * (n - 1) / 2;
+            if (J <= 16) {
+                const int grp = tid >> 4, gl = tid & 15;
+                for (int pr = grp; pr < ((npairs + 63) / 64) * 64; pr += NM_THREADS / 16) {
+                    // both half-warps must run the shuffles together -> loop bound is warp-uniform
+                    int i = 0, j = 1;
+                    const bool live = pr < npairs;
+                    if (live) {  // unrank pair index -> (i < j)
+                        int rem = pr;
+                        i = 0;
+                        while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
+                        j = i + 1 + rem;
+                    }
+                    const int ci = order[i], cj = order[live ? j : 1 % max(n, 1)];
+                    const float v = oks_pair<16>(pose + static_cast<size_t>(ci) * J * 3, pose + static_cast<size_t>(cj) * J * 3,
+                                                 area[ci], area[cj], J, gl);
+                    if (live && gl == 0 && v > p.nms_thr) atomicOr(&s_mask[i], 1ull << j);
+                }
+            } else {
+                const int grp = tid >> 5, gl = tid & 31;
+                for (int pr = grp; pr < npairs; pr += NM_THREADS / 32) {
+                    int rem = pr, i = 0;
+                    while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
+                    const int j = i + 1 + rem;
+                    const int ci = order[i], cj = order[j];
+                    const float v = oks_pair<32>(pose + static_cast<size_t>(ci) * J * 3, pose + static_cast<size_t>(cj) * J * 3,
+                                                 area[ci], area[cj], J, gl);
+                    if (gl == 0 && v > p.nms_thr) atomicOr(&s_mask[i], 1ull << j);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned long long alive = (n == 64) ? ~0ull : ((1ull << n) - 1ull);
+                int k = 0;
+                for (int i = 0; i < n && k < limit; ++i) {
+                    if ((alive >> i) & 1ull) {
+                        s_keep[k++] = order[i];
+                        alive &= ~s_mask[i];
+                    }
+                }
+                s_kept = k;
+            }
+            __syncthreads();
+            kept = s_kept;
+            __syncthreads();
+            if (tid < kept) kept_list[tid] = s_keep[tid];
+            __syncthreads();
+        } else {
+            // ---- iterative greedy: one pass over the survivors per pick --------------------------------
+            // kept slots are written over the front of `order` (k <= i always, and order[i] is read first)
+            const int grp = tid >> 5, gl = tid & 31;
+            for (int i = 0; i < n; ++i) {
+                if (dead[i]) continue;                 // block-uniform (shared flag, synced below)
+                const int ci = order[i];
+                __syncthreads();
+                if (tid == 0) kept_list[kept] = ci;
+                ++kept;
+                if (kept >= limit) break;
+                for (int j = i + 1 + grp; j < n; j += NM_THREADS / 32) {
+                    if (dead[j]) continue;             // warp-uniform
+                    const int cj = order[j];
+                    const float v = oks_pair<32>(pose + static_cast<size_t>(ci) * J * 3, pose + static_cast<size_t>(cj) * J * 3,
+                                                 area[ci], area[cj], J, gl);
+                    if (gl == 0 && v > p.nms_thr) dead[j] = 1;
+                }
+                __syncthreads();
+            }
+            __syncthreads();
+        }
+    } else {
+        // nms_post <= 0 (or nothing valid): survivors stay in slot order (das_head.py:770-772)
+        kept = n;
+        // order[] already holds the slots in ascending order == kept_list
+    }
+
+    // ---- outputs -----------------------------------------------------------------------------------
+    const das_buffers& o = p.out;
+    if (tid == 0) o.out_count[b] = kept;
+    const double* __restrict__ cam = p.cam + static_cast<size_t>(b) * DAS_CAM_DOUBLES;
+    const double K00 = cam[0], K01 = cam[1], K02 = cam[2], K10 = cam[3], K11 = cam[4], K12 = cam[5];
+    const double* R = cam + 6;
+    const double* T = cam + 15;
+    const double detK = K00 * K11 - K01 * K10;
+    const double nd = sqrt(K00 * K11);
+    // inverse of R (adjugate / determinant)
+    const double c00 = R[4] * R[8] - R[5] * R[7], c01 = R[2] * R[7] - R[1] * R[8], c02 = R[1] * R[5] - R[2] * R[4];
+    const double c10 = R[5] * R[6] - R[3] * R[8], c11 = R[0] * R[8] - R[2] * R[6], c12 = R[2] * R[3] - R[0] * R[5];
+    const double c20 = R[3] * R[7] - R[4] * R[6], c21 = R[1] * R[6] - R[0] * R[7], c22 = R[0] * R[4] - R[1] * R[3];
+    const double detR = R[0] * c00 + R[1] * c10 + R[2] * c20;
+
+    for (int k = tid; k < P; k += NM_THREADS) {
+        const bool live = k < kept;
+        const int c = live ? kept_list[k] : 0;
+        o.out_score[static_cast<size_t>(b) * P + k] = live ? score[c] : 0.f;
+        o.out_slot[static_cast<size_t>(b) * P + k] = live ? c : -1;
+        for (int d = 0; d < 3; ++d) o.out_center[(static_cast<size_t>(b) * P + k) * 3 + d] = live ? center[c * 3 + d] : 0.f;
+    }
+    for (int e = tid; e < P * J; e += NM_THREADS) {
+        const int k = e / J, j = e - k * J;
+        const size_t ob = ((static_cast<size_t>(b) * P + k) * J + j) * 3;
+        if (k < kept) {
+            const int c = kept_list[k];
+            const float* pc = pose + static_cast<size_t>(c) * J * 3;
+            const float fx = pc[3 * j], fy = pc[3 * j + 1], fz = pc[3 * j + 2];
+            o.out_pose[ob] = fx; o.out_pose[ob + 1] = fy; o.out_pose[ob + 2] = fz;
+            const double zr = static_cast<double>(pc[3 * p.root + 2]);
+            double Z = zr * nd + (static_cast<double>(fz) - zr);
+            Z *= p.ddf;
+            const double X0 = static_cast<double>(fx) - K02, X1 = static_cast<double>(fy) - K12;
+            const double a = (K11 * X0 - K01 * X1) / detK;
+            const double bb = (-K10 * X0 + K00 * X1) / detK;
+            const double cx = a * Z, cy = bb * Z, cz = Z;
+            o.out_cam[ob] = cx; o.out_cam[ob + 1] = cy; o.out_cam[ob + 2] = cz;
+            const double dx = cx - T[0], dy = cy - T[1], dz = cz - T[2];
+            o.out_world[ob] = (c00 * dx + c01 * dy + c02 * dz) / detR;
+            o.out_world[ob + 1] = (c10 * dx + c11 * dy + c12 * dz) / detR;
+            o.out_world[ob + 2] = (c20 * dx + c21 * dy + c22 * dz) / detR;
+        } else {
+            for (int d = 0; d < 3; ++d) { o.out_pose[ob + d] = 0.f; o.out_cam[ob + d] = 0.0; o.out_world[ob + d] = 0.0; }
+        }
+    }
+}
+
+}  // namespace das
+
+extern "C" int32_t das_output_slots(int32_t cand_slots, int32_t nms_post) {
+    return (nms_post > 0 && nms_post < cand_slots) ? nms_post : cand_slots;
+}
+
+extern "C" int das_nms_backproject(const das_decode_cfg* cfg, int32_t batch, int32_t cand_slots,
+                                   const float* cand_score, const float* cand_pose, const float* cand_center,
+                                   const double* cam, das_buffers out, void* stream) {
+    using namespace das;
+    DAS_REQUIRE(cfg && cand_score && cand_pose && cand_center && cam, DAS_ERR_ARG, "das_nms_backproject: null pointer");
+    DAS_REQUIRE(out.out_count && out.out_score && out.out_slot && out.out_pose && out.out_center && out.out_cam && out.out_world,
+                DAS_ERR_ARG, "das_nms_backproject: null output pointer");
+    DAS_REQUIRE(batch >= 1 && cand_slots >= 1, DAS_ERR_ARG, "batch=%d cand_slots=%d", batch, cand_slots);
+    DAS_REQUIRE(cand_slots <= NM_MAX_CAND, DAS_ERR_CAPACITY, "cand_slots=%d exceeds capacity %d", cand_slots, NM_MAX_CAND);
+    DAS_REQUIRE(cfg->num_joints >= 1 && cfg->num_joints <= DAS_MAX_JOINTS, DAS_ERR_CAPACITY, "num_joints=%d", cfg->num_joints);
+    NmsParams p{};
+    p.B = batch; p.CT = cand_slots; p.P = das_output_slots(cand_slots, cfg->nms_post);
+    p.J = cfg->num_joints; p.root = cfg->root_idx; p.nms_post = cfg->nms_post;
+    p.nms_thr = cfg->nms_thr; p.score_thr = cfg->score_thr;
+    p.ddf = cfg->dataset_depth_factor == 0.0 ? 1.0 : cfg->dataset_depth_factor;
+    p.cand_score = cand_score; p.cand_pose = cand_pose; p.cand_center = cand_center; p.cam = cam;
+    p.out = out;
+    int n2 = 1;
+    while (n2 < cand_slots) n2 <<= 1;
+    const size_t smem = static_cast<size_t>(n2) * 8 + static_cast<size_t>(cand_slots) * (4 + 4 + 1) + 16;
+    static bool attr_done = false;
+    if (!attr_done) {
+        DAS_CUDA_CHECK(cudaFuncSetAttribute(nms_backproject_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            NM_MAX_CAND * 8 + NM_MAX_CAND * 9 + 16));
+        attr_done = true;
+    }
+    nms_backproject_kernel<<<batch, NM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    DAS_CUDA_CHECK(cudaGetLastError());
+    return DAS_OK;
+}

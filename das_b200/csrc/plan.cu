@@ -1,0 +1,387 @@
+// Plan API: the whole DASHead.get_poses call (reference das_head.py:653-688) as one CUDA-graph
+// replay -- score scan + top-k, (dense layers 1..L-1,) sparse last-layer refinement + assembly,
+// OKS-NMS + back-projection -- plus the host-buffer entry used for end-to-end measurements.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "das_common.cuh"
+
+namespace das {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+}  // namespace das
+
+struct das_plan {
+    das_decode_cfg cfg{};
+    das_levels shape{};        // H, W, stride, batch (pointers unused)
+    das_levels bound{};        // last bound inputs (device pointers)
+    das_levels* d_levels = nullptr;
+    int B = 0, CT = 0, P = 0, hw_sum = 0;
+    das_buffers buf{};
+    uint32_t* scratch = nullptr;
+    int32_t* work_counter = nullptr;
+    float* d_scale_xy = nullptr;
+    double* d_cam = nullptr;
+    float* wpack[DAS_MAX_LAYERS] = {};
+    // dense layers (num_layers > 1): ping-pong NHWC [B,H,W,3J] maps per level + projection scratch
+    float* uvd_map[2][DAS_MAX_LEVELS] = {};
+    float* proj = nullptr;
+    const float** d_prev_ptrs = nullptr;
+    // host-entry staging
+    das_levels staging{};
+    bool staging_ready = false;
+    int64_t h2d_bytes = 0, d2h_bytes = 0;
+    // graph
+    cudaGraphExec_t exec = nullptr;
+    cudaStream_t cap_stream = nullptr;   // capture happens here (the caller's stream may be the legacy default stream)
+    int64_t launches = 0;
+    int launches_per_run = 0;
+};
+
+extern "C" const char* das_version(void) { return "das-b200 0.1 (sm_100a)"; }
+extern "C" const char* das_last_error(void) { return das::g_err; }
+
+extern "C" int32_t das_level_slots(int32_t H, int32_t W, int32_t nms_pre) { return das::level_slots(H * W, nms_pre); }
+
+extern "C" int32_t das_candidate_slots(const das_levels* lv, int32_t nms_pre) {
+    if (!lv) return 0;
+    int t = 0;
+    for (int l = 0; l < lv->n_levels; ++l) t += das::level_slots(lv->lv[l].H * lv->lv[l].W, nms_pre);
+    return t;
+}
+
+template <typename T>
+static int dev_alloc(T** p, size_t n) {
+    DAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T)));
+    return DAS_OK;
+}
+
+#define DAS_TRY(expr)                 \
+    do {                              \
+        int _s = (expr);              \
+        if (_s != DAS_OK) return _s;  \
+    } while (0)
+
+extern "C" int das_plan_create(const das_decode_cfg* cfg, const das_levels* shape, das_plan** out) {
+    using namespace das;
+    DAS_REQUIRE(cfg && shape && out, DAS_ERR_ARG, "das_plan_create: null pointer");
+    DAS_REQUIRE(shape->n_levels >= 1 && shape->n_levels <= DAS_MAX_LEVELS, DAS_ERR_ARG, "n_levels=%d", shape->n_levels);
+    DAS_REQUIRE(shape->batch >= 1, DAS_ERR_ARG, "batch=%d", shape->batch);
+    DAS_REQUIRE(cfg->num_joints >= 1 && cfg->num_joints <= DAS_MAX_JOINTS, DAS_ERR_CAPACITY, "num_joints=%d (max %d)",
+                cfg->num_joints, DAS_MAX_JOINTS);
+    DAS_REQUIRE(cfg->root_idx >= 0 && cfg->root_idx < cfg->num_joints, DAS_ERR_ARG, "root_idx=%d", cfg->root_idx);
+    DAS_REQUIRE(cfg->nms_pre <= DAS_MAX_NMS_PRE, DAS_ERR_CAPACITY, "nms_pre=%d (max %d)", cfg->nms_pre, DAS_MAX_NMS_PRE);
+    if (cfg->refine) {
+        DAS_REQUIRE(cfg->num_layers >= 1 && cfg->num_layers <= DAS_MAX_LAYERS, DAS_ERR_CAPACITY, "num_layers=%d", cfg->num_layers);
+        DAS_REQUIRE(cfg->num_heads == 4, DAS_ERR_UNSUPPORTED, "num_heads=%d: only 4 is built", cfg->num_heads);
+        DAS_REQUIRE(cfg->feat_channels == 128 || cfg->feat_channels == 256 || cfg->feat_channels == 512, DAS_ERR_UNSUPPORTED,
+                    "feat_channels=%d: only 128/256/512 are built", cfg->feat_channels);
+    }
+    das_plan* p = new (std::nothrow) das_plan();
+    DAS_REQUIRE(p, DAS_ERR_ARG, "out of host memory");
+    p->cfg = *cfg;
+    p->shape = *shape;
+    p->bound = *shape;
+    p->B = shape->batch;
+    for (int l = 0; l < shape->n_levels; ++l) {
+        DAS_REQUIRE(shape->lv[l].H > 0 && shape->lv[l].W > 0 && shape->lv[l].stride > 0, DAS_ERR_ARG, "level %d: bad shape", l);
+        p->hw_sum += shape->lv[l].H * shape->lv[l].W;
+    }
+    p->CT = das_candidate_slots(shape, cfg->nms_pre);
+    p->P = das_output_slots(p->CT, cfg->nms_post);
+    if (p->CT > 8192) {
+        set_error("candidate slots per image = %d exceed capacity 8192 (lower nms_pre)", p->CT);
+        delete p;
+        return DAS_ERR_CAPACITY;
+    }
+    const size_t B = p->B, CT = p->CT, P = p->P, J = cfg->num_joints;
+    int s = DAS_OK;
+    auto A = [&](int r) { if (s == DAS_OK) s = r; };
+    A(dev_alloc(&p->d_levels, 1));
+    A(dev_alloc(&p->buf.cand_score, B * CT));
+    A(dev_alloc(&p->buf.cand_index, B * CT));
+    A(dev_alloc(&p->buf.cand_pose, B * CT * J * 3));
+    A(dev_alloc(&p->buf.cand_center, B * CT * 3));
+    A(dev_alloc(&p->buf.out_count, B));
+    A(dev_alloc(&p->buf.out_score, B * P));
+    A(dev_alloc(&p->buf.out_slot, B * P));
+    A(dev_alloc(&p->buf.out_pose, B * P * J * 3));
+    A(dev_alloc(&p->buf.out_center, B * P * 3));
+    A(dev_alloc(&p->buf.out_cam, B * P * J * 3));
+    A(dev_alloc(&p->buf.out_world, B * P * J * 3));
+    A(dev_alloc(&p->scratch, B * static_cast<size_t>(p->hw_sum)));
+    A(dev_alloc(&p->work_counter, 4));
+    A(dev_alloc(&p->d_scale_xy, B * 2));
+    A(dev_alloc(&p->d_cam, B * DAS_CAM_DOUBLES));
+    if (cfg->refine) {
+        for (int k = 0; k < cfg->num_layers; ++k) A(dev_alloc(&p->wpack[k], static_cast<size_t>(das_packed_weight_floats(cfg))));
+        if (cfg->num_layers > 1) {
+            size_t max_hw = 0;
+            for (int l = 0; l < shape->n_levels; ++l) {
+                const size_t hw = static_cast<size_t>(shape->lv[l].H) * shape->lv[l].W;
+                max_hw = std::max(max_hw, hw);
+                A(dev_alloc(&p->uvd_map[0][l], B * hw * 3 * J));
+                if (cfg->num_layers > 2) A(dev_alloc(&p->uvd_map[1][l], B * hw * 3 * J));
+            }
+            A(dev_alloc(&p->proj, B * max_hw * (2 * cfg->num_heads + 6) * J));
+            A(dev_alloc(&p->d_prev_ptrs, DAS_MAX_LEVELS));
+        }
+    }
+    if (s != DAS_OK) { das_plan_destroy(p); return s; }
+    // identity metas until das_plan_set_metas is called
+    {
+        float* sxy = new float[B * 2];
+        double* cam = new double[B * DAS_CAM_DOUBLES];
+        for (size_t b = 0; b < B; ++b) {
+            sxy[2 * b] = sxy[2 * b + 1] = 1.f;
+            const double ident[DAS_CAM_DOUBLES] = {1, 0, 0, 0, 1, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+            std::memcpy(cam + b * DAS_CAM_DOUBLES, ident, sizeof(ident));
+        }
+        cudaError_t e1 = cudaMemcpy(p->d_scale_xy, sxy, B * 2 * sizeof(float), cudaMemcpyHostToDevice);
+        cudaError_t e2 = cudaMemcpy(p->d_cam, cam, B * DAS_CAM_DOUBLES * sizeof(double), cudaMemcpyHostToDevice);
+        delete[] sxy;
+        delete[] cam;
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {
+            set_error("das_plan_create: meta upload failed");
+            das_plan_destroy(p);
+            return DAS_ERR_CUDA;
+        }
+    }
+    p->h2d_bytes = 0;
+    for (int l = 0; l < shape->n_levels; ++l) {
+        const int64_t hw = static_cast<int64_t>(shape->lv[l].H) * shape->lv[l].W;
+        p->h2d_bytes += static_cast<int64_t>(B) * hw * 4 * (2 + 3 + 6 * J);
+        if (cfg->refine) p->h2d_bytes += static_cast<int64_t>(B) * hw * 4 * cfg->feat_channels * cfg->num_layers;
+    }
+    p->h2d_bytes += static_cast<int64_t>(B) * (2 * 4 + DAS_CAM_DOUBLES * 8);
+    p->d2h_bytes = static_cast<int64_t>(B) * 4 + static_cast<int64_t>(B) * P * (4 + 4 + 12 + J * 3 * (4 + 8 + 8));
+    *out = p;
+    return DAS_OK;
+}
+
+extern "C" void das_plan_destroy(das_plan* p) {
+    if (!p) return;
+    if (p->exec) cudaGraphExecDestroy(p->exec);
+    if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
+    void* ptrs[] = {p->d_levels, p->buf.cand_score, p->buf.cand_index, p->buf.cand_pose, p->buf.cand_center,
+                    p->buf.out_count, p->buf.out_score, p->buf.out_slot, p->buf.out_pose, p->buf.out_center,
+                    p->buf.out_cam, p->buf.out_world, p->scratch, p->work_counter, p->d_scale_xy, p->d_cam,
+                    p->proj, p->d_prev_ptrs};
+    for (void* q : ptrs) if (q) cudaFree(q);
+    for (int k = 0; k < DAS_MAX_LAYERS; ++k) if (p->wpack[k]) cudaFree(p->wpack[k]);
+    for (int i = 0; i < 2; ++i)
+        for (int l = 0; l < DAS_MAX_LEVELS; ++l) if (p->uvd_map[i][l]) cudaFree(p->uvd_map[i][l]);
+    if (p->staging_ready) {
+        for (int l = 0; l < p->shape.n_levels; ++l) {
+            cudaFree(const_cast<float*>(p->staging.lv[l].cls));
+            cudaFree(const_cast<float*>(p->staging.lv[l].ctr));
+            cudaFree(const_cast<float*>(p->staging.lv[l].pose));
+            for (int k = 0; k < DAS_MAX_LAYERS; ++k)
+                if (p->staging.lv[l].feats[k]) cudaFree(const_cast<float*>(p->staging.lv[l].feats[k]));
+        }
+    }
+    delete p;
+}
+
+extern "C" int das_plan_set_weights(das_plan* p, int32_t layer, const float* so_w, const float* so_b,
+                                    const float* sc_w, const float* sc_b, const float* uw_w, const float* uw_b,
+                                    const float* uv_w, const float* uv_b, void* stream) {
+    using namespace das;
+    DAS_REQUIRE(p, DAS_ERR_ARG, "null plan");
+    DAS_REQUIRE(p->cfg.refine, DAS_ERR_ARG, "plan was created with refine=0");
+    DAS_REQUIRE(layer >= 0 && layer < p->cfg.num_layers, DAS_ERR_ARG, "layer=%d of %d", layer, p->cfg.num_layers);
+    return das_pack_weights(&p->cfg, so_w, so_b, sc_w, sc_b, uw_w, uw_b, uv_w, uv_b, p->wpack[layer], stream);
+}
+
+extern "C" int das_plan_bind(das_plan* p, const das_levels* levels, void* stream) {
+    using namespace das;
+    DAS_REQUIRE(p && levels, DAS_ERR_ARG, "das_plan_bind: null pointer");
+    DAS_REQUIRE(levels->n_levels == p->shape.n_levels && levels->batch == p->shape.batch, DAS_ERR_ARG,
+                "bind: n_levels/batch (%d/%d) differ from the plan (%d/%d)", levels->n_levels, levels->batch,
+                p->shape.n_levels, p->shape.batch);
+    for (int l = 0; l < levels->n_levels; ++l) {
+        const das_level_desc& d = levels->lv[l];
+        DAS_REQUIRE(d.H == p->shape.lv[l].H && d.W == p->shape.lv[l].W && d.stride == p->shape.lv[l].stride, DAS_ERR_ARG,
+                    "bind: level %d shape differs from the plan", l);
+        DAS_REQUIRE(d.cls && d.ctr && d.pose, DAS_ERR_ARG, "bind: level %d has a null map", l);
+        if (p->cfg.refine)
+            for (int k = 0; k < p->cfg.num_layers; ++k) {
+                DAS_REQUIRE(d.feats[k], DAS_ERR_ARG, "bind: level %d layer %d feature map is null", l, k);
+                DAS_REQUIRE((reinterpret_cast<uintptr_t>(d.feats[k]) & 15) == 0, DAS_ERR_ARG, "feature maps must be 16-byte aligned");
+            }
+    }
+    p->bound = *levels;
+    // pageable host -> device copy of 0.5 KB: stream-ordered, returns after staging
+    DAS_CUDA_CHECK(cudaMemcpyAsync(p->d_levels, &p->bound, sizeof(das_levels), cudaMemcpyHostToDevice,
+                                   static_cast<cudaStream_t>(stream)));
+    return DAS_OK;
+}
+
+extern "C" int das_plan_set_metas(das_plan* p, const float* scale_xy, const double* cam, void* stream) {
+    using namespace das;
+    DAS_REQUIRE(p, DAS_ERR_ARG, "null plan");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (scale_xy) DAS_CUDA_CHECK(cudaMemcpyAsync(p->d_scale_xy, scale_xy, sizeof(float) * 2 * p->B, cudaMemcpyHostToDevice, st));
+    if (cam) DAS_CUDA_CHECK(cudaMemcpyAsync(p->d_cam, cam, sizeof(double) * DAS_CAM_DOUBLES * p->B, cudaMemcpyHostToDevice, st));
+    return DAS_OK;
+}
+
+static int enqueue(das_plan* p, cudaStream_t st, int* n_launch) {
+    const das_decode_cfg& c = p->cfg;
+    int n = 0;
+    DAS_TRY(das_score_topk(p->d_levels, &p->bound, c.nms_pre, c.peak_kernel, p->buf.cand_score, p->buf.cand_index,
+                           p->CT, p->scratch, st));
+    ++n;
+    const float* const* prev = nullptr;
+    if (c.refine && c.num_layers > 1) {
+        const float* host_prev[DAS_MAX_LEVELS] = {};
+        for (int l = 0; l < p->bound.n_levels; ++l) {
+            const float* in = nullptr;
+            for (int k = 0; k < c.num_layers - 1; ++k) {
+                float* outm = p->uvd_map[k & 1][l];
+                DAS_TRY(das_refine_dense_layer(p->d_levels, &p->bound, l, k, &c, p->wpack[k], in, outm, p->proj, st));
+                n += 2;
+                in = outm;
+            }
+            host_prev[l] = in;
+        }
+        // constant per plan; uploaded eagerly once (not part of the graph)
+        static_cast<void>(host_prev);
+        prev = p->d_prev_ptrs;
+    }
+    DAS_TRY(das_gather_refine_assemble(p->d_levels, &p->bound, &c, c.refine ? p->wpack[c.num_layers - 1] : nullptr, prev,
+                                       p->d_scale_xy, p->buf.cand_score, p->buf.cand_index, p->CT, p->buf.cand_pose,
+                                       p->buf.cand_center, p->work_counter, st));
+    ++n;
+    DAS_TRY(das_nms_backproject(&c, p->B, p->CT, p->buf.cand_score, p->buf.cand_pose, p->buf.cand_center, p->d_cam,
+                                p->buf, st));
+    ++n;
+    *n_launch = n;
+    return DAS_OK;
+}
+
+extern "C" int das_plan_run(das_plan* p, void* stream, int32_t use_graph) {
+    using namespace das;
+    DAS_REQUIRE(p, DAS_ERR_ARG, "null plan");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (p->cfg.refine && p->cfg.num_layers > 1 && p->launches == 0 && !p->exec) {
+        const float* host_prev[DAS_MAX_LEVELS] = {};
+        for (int l = 0; l < p->bound.n_levels; ++l) host_prev[l] = p->uvd_map[(p->cfg.num_layers - 2) & 1][l];
+        DAS_CUDA_CHECK(cudaMemcpyAsync(p->d_prev_ptrs, host_prev, sizeof(host_prev), cudaMemcpyHostToDevice, st));
+        DAS_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    if (!use_graph) {
+        int n = 0;
+        DAS_TRY(enqueue(p, st, &n));
+        p->launches_per_run = n;
+        p->launches += n;
+        return DAS_OK;
+    }
+    if (!p->exec) {
+        // eager warm-up first: lazy module loading and cudaFuncSetAttribute must not happen inside a capture
+        int n = 0;
+        DAS_TRY(enqueue(p, st, &n));
+        p->launches_per_run = n;
+        p->launches += n;
+        DAS_CUDA_CHECK(cudaStreamSynchronize(st));
+        cudaGraph_t g = nullptr;
+        if (!p->cap_stream) DAS_CUDA_CHECK(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
+        DAS_CUDA_CHECK(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
+        int s = enqueue(p, p->cap_stream, &n);
+        cudaError_t e = cudaStreamEndCapture(p->cap_stream, &g);
+        if (s != DAS_OK) { if (g) cudaGraphDestroy(g); return s; }
+        DAS_CUDA_CHECK(e);
+        e = cudaGraphInstantiate(&p->exec, g, 0);
+        cudaGraphDestroy(g);
+        DAS_CUDA_CHECK(e);
+    }
+    DAS_CUDA_CHECK(cudaGraphLaunch(p->exec, st));
+    p->launches += p->launches_per_run;
+    return DAS_OK;
+}
+
+extern "C" int das_plan_buffers(const das_plan* p, das_buffers* out, int32_t* cand_slots, int32_t* out_slots) {
+    using namespace das;
+    DAS_REQUIRE(p && out, DAS_ERR_ARG, "das_plan_buffers: null pointer");
+    *out = p->buf;
+    if (cand_slots) *cand_slots = p->CT;
+    if (out_slots) *out_slots = p->P;
+    return DAS_OK;
+}
+
+extern "C" int64_t das_plan_kernel_launches(const das_plan* p) { return p ? p->launches : 0; }
+extern "C" int64_t das_plan_h2d_bytes(const das_plan* p) { return p ? p->h2d_bytes : 0; }
+extern "C" int64_t das_plan_d2h_bytes(const das_plan* p) { return p ? p->d2h_bytes : 0; }
+
+extern "C" int das_plan_run_host(das_plan* p, const das_levels* levels, const float* scale_xy, const double* cam,
+                                 das_buffers host_out, void* stream) {
+    using namespace das;
+    DAS_REQUIRE(p && levels, DAS_ERR_ARG, "das_plan_run_host: null pointer");
+    DAS_REQUIRE(levels->n_levels == p->shape.n_levels && levels->batch == p->shape.batch, DAS_ERR_ARG,
+                "run_host: n_levels/batch differ from the plan");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t B = p->B, J = p->cfg.num_joints, C = p->cfg.feat_channels;
+    const int L = p->cfg.refine ? p->cfg.num_layers : 0;
+    if (!p->staging_ready) {
+        p->staging = p->shape;
+        for (int l = 0; l < p->shape.n_levels; ++l) {
+            const size_t hw = static_cast<size_t>(p->shape.lv[l].H) * p->shape.lv[l].W;
+            float *a = nullptr, *b = nullptr, *c = nullptr;
+            DAS_TRY(dev_alloc(&a, B * hw));
+            DAS_TRY(dev_alloc(&b, B * hw));
+            DAS_TRY(dev_alloc(&c, B * hw * (3 + 6 * J)));
+            p->staging.lv[l].cls = a; p->staging.lv[l].ctr = b; p->staging.lv[l].pose = c;
+            for (int k = 0; k < DAS_MAX_LAYERS; ++k) p->staging.lv[l].feats[k] = nullptr;
+            for (int k = 0; k < L; ++k) {
+                float* f = nullptr;
+                DAS_TRY(dev_alloc(&f, B * hw * C));
+                p->staging.lv[l].feats[k] = f;
+            }
+        }
+        p->staging_ready = true;
+    }
+    for (int l = 0; l < p->shape.n_levels; ++l) {
+        const das_level_desc& h = levels->lv[l];
+        das_level_desc& d = p->staging.lv[l];
+        DAS_REQUIRE(h.H == d.H && h.W == d.W && h.stride == d.stride, DAS_ERR_ARG, "run_host: level %d shape differs", l);
+        DAS_REQUIRE(h.cls && h.ctr && h.pose, DAS_ERR_ARG, "run_host: level %d has a null map", l);
+        const size_t hw = static_cast<size_t>(h.H) * h.W;
+        d.scale_offset = h.scale_offset; d.scale_depth = h.scale_depth; d.scale_uv = h.scale_uv; d.scale_d = h.scale_d;
+        DAS_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(d.cls), h.cls, B * hw * 4, cudaMemcpyHostToDevice, st));
+        DAS_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(d.ctr), h.ctr, B * hw * 4, cudaMemcpyHostToDevice, st));
+        DAS_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(d.pose), h.pose, B * hw * (3 + 6 * J) * 4, cudaMemcpyHostToDevice, st));
+        for (int k = 0; k < L; ++k) {
+            DAS_REQUIRE(h.feats[k], DAS_ERR_ARG, "run_host: level %d layer %d feature map is null", l, k);
+            DAS_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(d.feats[k]), h.feats[k], B * hw * C * 4, cudaMemcpyHostToDevice, st));
+        }
+    }
+    DAS_TRY(das_plan_bind(p, &p->staging, st));
+    DAS_TRY(das_plan_set_metas(p, scale_xy, cam, st));
+    DAS_TRY(das_plan_run(p, st, 1));
+    const size_t P = p->P;
+    auto D2H = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+        return dst ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st) : cudaSuccess;
+    };
+    DAS_CUDA_CHECK(D2H(host_out.out_count, p->buf.out_count, B * 4));
+    DAS_CUDA_CHECK(D2H(host_out.out_score, p->buf.out_score, B * P * 4));
+    DAS_CUDA_CHECK(D2H(host_out.out_slot, p->buf.out_slot, B * P * 4));
+    DAS_CUDA_CHECK(D2H(host_out.out_pose, p->buf.out_pose, B * P * J * 3 * 4));
+    DAS_CUDA_CHECK(D2H(host_out.out_center, p->buf.out_center, B * P * 3 * 4));
+    DAS_CUDA_CHECK(D2H(host_out.out_cam, p->buf.out_cam, B * P * J * 3 * 8));
+    DAS_CUDA_CHECK(D2H(host_out.out_world, p->buf.out_world, B * P * J * 3 * 8));
+    DAS_CUDA_CHECK(D2H(host_out.cand_score, p->buf.cand_score, B * p->CT * 4));
+    DAS_CUDA_CHECK(D2H(host_out.cand_index, p->buf.cand_index, B * p->CT * 4));
+    DAS_CUDA_CHECK(cudaStreamSynchronize(st));
+    return DAS_OK;
+}

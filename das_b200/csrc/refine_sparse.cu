@@ -1,0 +1,482 @@
+// Stage 3+4: gather at the selected centres, sparse evaluation of the LAST RecursiveUpdateLayer,
+// head eval tail and joint assembly.
+//
+// Reference semantics (file:line relative to the reference root):
+//   * gated blend + 1x1 projections ...... recursive_update.py:186-197
+//   * progressive sampling ................ recursive_update.py:34-82, 9-31 (F.grid_sample bilinear,
+//                                           padding_mode='zeros', align_corners=False)
+//   * eval tail ........................... das_head.py:252-262
+//   * gather + joint assembly ............. das_head.py:720-749
+// The reference runs the refinement densely over every cell and gathers K cells afterwards; scores
+// do not depend on it, so this kernel refines only the selected cells (divergence B).
+// For one (centre p, joint j) that needs 37 feature rows of the NHWC map: p itself, the 4 bilinear
+// corners of the current joint estimate t = p + O_j(p).xy, and the 4 corners of each of the 2*nh
+// sampling heads.  Every row is projected with that joint's 17 1x1-conv rows (8 sampling offsets,
+// 3 gate, 3 value, 3 confidence).
+//
+// Mapping: one warp per (centre, joint) work item, handed out by an atomic counter.  A lane owns
+// C/32 channels of every row (two coalesced 128-bit loads per 1 KB row at C=256); dot products are
+// finished with a transposing butterfly so 8 rows cost 9 shuffles per output instead of 40.
+#include "das_common.cuh"
+
+namespace das {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int RS_WARPS = 8;  // warps per CTA
+
+struct RefineParams {
+    const das_levels* lv;
+    const float* wpack;            // [J][NOUT][C] then [J][NOUT] biases
+    const float* const* prev_uvd;  // nullptr or device array [n_levels] of NHWC [B,H,W,3J]
+    const float* scale_xy;         // [B,2]
+    const float* cand_score;
+    const int32_t* cand_index;
+    float* cand_pose;
+    float* cand_center;
+    int* work_counter;
+    int CT, J, root, nms_pre, layer;
+    float depth_factor, z_norm, score_thr;
+    int n_items;
+};
+
+template <int CPL>
+struct Row {
+    float4 v[CPL / 4];
+};
+
+template <int CPL>
+__device__ __forceinline__ Row<CPL> load_row(const float* __restrict__ base, int lane, bool ok) {
+    Row<CPL> r;
+#pragma unroll
+    for (int q = 0; q < CPL / 4; ++q) {
+        r.v[q] = ok ? __ldg(reinterpret_cast<const float4*>(base + q * 128 + 4 * lane)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return r;
+}
+
+template <int CPL>
+__device__ __forceinline__ float dot_row(const Row<CPL>& f, const Row<CPL>& w) {
+    float a = 0.f;
+#pragma unroll
+    for (int q = 0; q < CPL / 4; ++q) {
+        a = fmaf(f.v[q].x, w.v[q].x, a);
+        a = fmaf(f.v[q].y, w.v[q].y, a);
+        a = fmaf(f.v[q].z, w.v[q].z, a);
+        a = fmaf(f.v[q].w, w.v[q].w, a);
+    }
+    return a;
+}
+
+__device__ __forceinline__ float warp_allsum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// Sum a[r] over the 32 lanes for 8 rows at once; lane L returns the total of row (L >> 2) & 7.
+__device__ __forceinline__ float reduce8_transposed(const float (&a)[8], int lane) {
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+    float b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = h16 ? a[i] : a[i + 4];
+        const float keep = h16 ? a[i + 4] : a[i];
+        b[i] = keep + __shfl_xor_sync(FULL, send, 16);
+    }
+    float c[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = h8 ? b[i] : b[i + 2];
+        const float keep = h8 ? b[i + 2] : b[i];
+        c[i] = keep + __shfl_xor_sync(FULL, send, 8);
+    }
+    const float send = h4 ? c[0] : c[1];
+    const float keep = h4 ? c[1] : c[0];
+    float d = keep + __shfl_xor_sync(FULL, send, 4);
+    d += __shfl_xor_sync(FULL, d, 2);
+    d += __shfl_xor_sync(FULL, d, 1);
+    return d;
+}
+
+// Index-space sample coordinate of `cell + 0.5 + off` after the reference's normalise ->
+// grid_sample un-normalise chain (recursive_update.py:52-54, ATen align_corners=False).
+__device__ __forceinline__ float sample_coord(int cell, float off, float size) {
+    const float loc = __fdiv_rn(__fadd_rn(static_cast<float>(cell) + 0.5f, off), size);
+    const float g = __fadd_rn(__fmul_rn(2.0f, loc), -1.0f);
+    return __fadd_rn(__fmul_rn(__fadd_rn(g, 1.0f), size * 0.5f), -0.5f);
+}
+
+struct Corner {
+    int x0, y0;        // north-west corner (clamped to a safe int range)
+    float w, n;        // distance to the west / north side
+};
+
+__device__ __forceinline__ Corner make_corner(float ix, float iy, int W, int H) {
+    Corner c;
+    const float fx = floorf(ix), fy = floorf(iy);
+    c.w = ix - fx;
+    c.n = iy - fy;
+    // clamp before the int conversion; anything outside [-1, size] has no in-bounds corner anyway
+    c.x0 = static_cast<int>(fminf(fmaxf(fx, -2.0f), static_cast<float>(W) + 1.0f));
+    c.y0 = static_cast<int>(fminf(fmaxf(fy, -2.0f), static_cast<float>(H) + 1.0f));
+    if (!(ix == ix) || !(iy == iy)) { c.x0 = -2; c.y0 = -2; c.w = 0.f; c.n = 0.f; }  // NaN -> nothing sampled
+    return c;
+}
+
+__device__ __forceinline__ bool corner_ok(const Corner& c, int k, int W, int H) {
+    const int x = c.x0 + (k & 1), y = c.y0 + (k >> 1);
+    return x >= 0 && x < W && y >= 0 && y < H;
+}
+__device__ __forceinline__ int corner_pix(const Corner& c, int k, int W) { return (c.y0 + (k >> 1)) * W + c.x0 + (k & 1); }
+__device__ __forceinline__ float corner_wgt(const Corner& c, int k) {
+    // ATen: nw = s*e, ne = s*w, sw = n*e, se = n*w with e = 1-w, s = 1-n
+    const float wx = (k & 1) ? c.w : (1.0f - c.w);
+    const float wy = (k >> 1) ? c.n : (1.0f - c.n);
+    return wy * wx;
+}
+
+template <int CPL, int NH>
+__global__ void __launch_bounds__(RS_WARPS * 32)
+refine_sparse_kernel(const RefineParams p) {
+    constexpr int C = CPL * 32;
+    constexpr int NOUT = 2 * NH + 9;
+    constexpr int O_GATE = 2 * NH, O_VAL = 2 * NH + 3, O_CONF = 2 * NH + 6;
+    const int lane = threadIdx.x & 31;
+    const das_levels* __restrict__ lvp = p.lv;
+    const int nl = lvp->n_levels;
+    const int J = p.J;
+
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(p.work_counter, 1);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= p.n_items) break;
+        const int j = item % J;
+        const int cs = item / J;          // b * CT + slot
+        const int b = cs / p.CT, slot = cs - b * p.CT;
+        const float score = __ldg(p.cand_score + cs);
+        if (p.score_thr > 0.f && !(score > p.score_thr)) continue;   // dropped by das_head.py:763-769 later
+
+        int l = 0, s0 = 0;
+        for (; l < nl - 1; ++l) {
+            const int ns = level_slots(lvp->lv[l].H * lvp->lv[l].W, p.nms_pre);
+            if (slot < s0 + ns) break;
+            s0 += ns;
+        }
+        const das_level_desc& d = lvp->lv[l];
+        const int H = d.H, W = d.W, HW = H * W;
+        const int idx = __ldg(p.cand_index + cs);
+        const int y = idx / W, x = idx - y * W;
+        const float* __restrict__ F = d.feats[p.layer] + static_cast<size_t>(b) * HW * C;
+        const float* __restrict__ pose = d.pose + static_cast<size_t>(b) * (3 + 6 * J) * HW;
+        const float* __restrict__ prev = p.prev_uvd ? p.prev_uvd[l] : nullptr;
+        if (prev) prev += static_cast<size_t>(b) * HW * 3 * J;
+        const float* __restrict__ Wj = p.wpack + static_cast<size_t>(j) * NOUT * C;
+        const float* __restrict__ Bj = p.wpack + static_cast<size_t>(J) * NOUT * C + j * NOUT;
+        const float fW = static_cast<float>(W), fH = static_cast<float>(H);
+
+        // previous-layer offset of joint j, dim k at cell `pix` (das_head.py:243-249 for layer 0)
+        auto prev_at = [&](int pix, int k) -> float {
+            if (prev) return __ldg(prev + static_cast<size_t>(pix) * 3 * J + 3 * j + k);
+            if (k == 2 && j == p.root) return 0.0f;
+            const float raw = __ldg(pose + static_cast<size_t>(3 + 3 * j + k) * HW + pix);
+            return raw * (k < 2 ? d.scale_uv : d.scale_d);
+        };
+
+        // ---- phase 1: cell p -> S_j(p) (2*NH), gate, value -> blended offset O_j(p) ---------------
+        float S[2 * NH];
+        float O[3];
+        {
+            const Row<CPL> f = load_row<CPL>(F + static_cast<size_t>(idx) * C, lane, true);
+            float acc[2 * NH + 6];
+#pragma unroll
+            for (int o = 0; o < 2 * NH + 6; ++o) {
+                const Row<CPL> w = load_row<CPL>(Wj + o * C, lane, true);
+                acc[o] = warp_allsum(dot_row<CPL>(f, w));
+            }
+#pragma unroll
+            for (int o = 0; o < 2 * NH; ++o) S[o] = acc[o] + __ldg(Bj + o);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float g = sigmoid_acc(acc[O_GATE + k] + __ldg(Bj + O_GATE + k));
+                const float n = acc[O_VAL + k] + __ldg(Bj + O_VAL + k);
+                O[k] = __fadd_rn(__fmul_rn(1.0f - g, prev_at(idx, k)), __fmul_rn(g, n));
+            }
+        }
+
+        // ---- phase 2: sampling offsets bilinearly read at t = p + O.xy ("from target" heads) -----
+        float hx[2 * NH], hy[2 * NH];   // per-head sampling offset (x, y)
+        {
+            const Corner ct = make_corner(sample_coord(x, O[0], fW), sample_coord(y, O[1], fH), W, H);
+            Row<CPL> fi;
+#pragma unroll
+            for (int q = 0; q < CPL / 4; ++q) fi.v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            float wsum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool ok = corner_ok(ct, k, W, H);
+                const float wk = ok ? corner_wgt(ct, k) : 0.f;
+                const Row<CPL> f = load_row<CPL>(F + static_cast<size_t>(ok ? corner_pix(ct, k, W) : 0) * C, lane, ok);
+                wsum += wk;
+#pragma unroll
+                for (int q = 0; q < CPL / 4; ++q) {
+                    fi.v[q].x = fmaf(wk, f.v[q].x, fi.v[q].x);
+                    fi.v[q].y = fmaf(wk, f.v[q].y, fi.v[q].y);
+                    fi.v[q].z = fmaf(wk, f.v[q].z, fi.v[q].z);
+                    fi.v[q].w = fmaf(wk, f.v[q].w, fi.v[q].w);
+                }
+            }
+            // the projection is linear, so Bil(W f + b) = W Bil(f) + b * (in-bounds weight sum)
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                const Row<CPL> wx = load_row<CPL>(Wj + (2 * h) * C, lane, true);
+                const Row<CPL> wy = load_row<CPL>(Wj + (2 * h + 1) * C, lane, true);
+                const float sx = warp_allsum(dot_row<CPL>(fi, wx)) + wsum * __ldg(Bj + 2 * h);
+                const float sy = warp_allsum(dot_row<CPL>(fi, wy)) + wsum * __ldg(Bj + 2 * h + 1);
+                hx[h] = sx + O[0];           // recursive_update.py:59
+                hy[h] = sy + O[1];
+                hx[NH + h] = S[2 * h];       // "from source" heads, recursive_update.py:62
+                hy[NH + h] = S[2 * h + 1];
+            }
+        }
+
+        // ---- phase 3: 2*NH heads x 4 corners; blended offset + confidence at every corner --------
+        const int r = (lane >> 2) & 7;      // row of the 8-row batch this lane post-processes
+        const int hh = r >> 2, ck = r & 3;  // head within the batch, corner
+        const int dim = lane & 3;           // u, v, d (lane 3 of each quad idles)
+        float hv[NH], hc[NH];
+#pragma unroll
+        for (int bt = 0; bt < NH; ++bt) {
+            const int h0 = 2 * bt, h1 = 2 * bt + 1;
+            const Corner c0 = make_corner(sample_coord(x, hx[h0], fW), sample_coord(y, hy[h0], fH), W, H);
+            const Corner c1 = make_corner(sample_coord(x, hx[h1], fW), sample_coord(y, hy[h1], fH), W, H);
+            Row<CPL> f[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool ok0 = corner_ok(c0, k, W, H), ok1 = corner_ok(c1, k, W, H);
+                f[k] = load_row<CPL>(F + static_cast<size_t>(ok0 ? corner_pix(c0, k, W) : 0) * C, lane, ok0);
+                f[4 + k] = load_row<CPL>(F + static_cast<size_t>(ok1 ? corner_pix(c1, k, W) : 0) * C, lane, ok1);
+            }
+            float res[9];
+#pragma unroll
+            for (int o = 0; o < 9; ++o) {
+                const Row<CPL> w = load_row<CPL>(Wj + (O_GATE + o) * C, lane, true);
+                float acc[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = dot_row<CPL>(f[k], w);
+                res[o] = reduce8_transposed(acc, lane);
+            }
+            // this lane: row r = (head hh, corner ck), dimension `dim`
+            const Corner& cm = hh ? c1 : c0;
+            const bool ok = corner_ok(cm, ck, W, H) && dim < 3;
+            float val = 0.f, cf = 0.f;
+            if (ok) {
+                const int pix = corner_pix(cm, ck, W);
+                const float rg = dim == 0 ? res[0] : (dim == 1 ? res[1] : res[2]);
+                const float rn = dim == 0 ? res[3] : (dim == 1 ? res[4] : res[5]);
+                const float rc = dim == 0 ? res[6] : (dim == 1 ? res[7] : res[8]);
+                const float g = sigmoid_acc(rg + __ldg(Bj + O_GATE + dim));
+                const float n = rn + __ldg(Bj + O_VAL + dim);
+                const float o = __fadd_rn(__fmul_rn(1.0f - g, prev_at(pix, dim)), __fmul_rn(g, n));
+                const float wk = corner_wgt(cm, ck);
+                val = o * wk;
+                cf = (rc + __ldg(Bj + O_CONF + dim)) * wk;
+            }
+            // bilinear sum over the 4 corners (lane bits 2,3)
+            val += __shfl_xor_sync(FULL, val, 4);
+            cf += __shfl_xor_sync(FULL, cf, 4);
+            val += __shfl_xor_sync(FULL, val, 8);
+            cf += __shfl_xor_sync(FULL, cf, 8);
+            const float sh = hh ? (dim == 0 ? hx[h1] : hy[h1]) : (dim == 0 ? hx[h0] : hy[h0]);
+            hv[bt] = val + (dim < 2 ? sh : 0.f);   // + diff, recursive_update.py:72-75, 28
+            hc[bt] = cf;
+        }
+        // softmax over the 2*NH heads (own NH + the partner half-warp's NH), recursive_update.py:29-31
+        float m = hc[0];
+#pragma unroll
+        for (int i = 1; i < NH; ++i) m = fmaxf(m, hc[i]);
+        m = fmaxf(m, __shfl_xor_sync(FULL, m, 16));
+        float e[NH], se = 0.f;
+#pragma unroll
+        for (int i = 0; i < NH; ++i) { e[i] = expf(hc[i] - m); se += e[i]; }
+        se += __shfl_xor_sync(FULL, se, 16);
+        float out = 0.f;
+#pragma unroll
+        for (int i = 0; i < NH; ++i) out += hv[i] * (e[i] / se);
+        out += __shfl_xor_sync(FULL, out, 16);
+
+        // ---- eval tail + assembly (das_head.py:254-262, 725-743) ----------------------------------
+        if (lane < 3) {
+            const float sx = __ldg(p.scale_xy + 2 * b), sy = __ldg(p.scale_xy + 2 * b + 1);
+            const float qf = sqrtf(sx * sy);
+            const float st = static_cast<float>(d.stride);
+            const float half = static_cast<float>(d.stride / 2);
+            float z = __ldg(pose + 2 * static_cast<size_t>(HW) + idx) * d.scale_depth;
+            z = __fdiv_rn(z, p.depth_factor);
+            const float zq = __fmul_rn(z, qf);
+            float v;
+            if (lane == 0) v = __fdiv_rn(__fadd_rn(__fmul_rn(out, st), static_cast<float>(x) * st + half), sx);
+            else if (lane == 1) v = __fdiv_rn(__fadd_rn(__fmul_rn(out, st), static_cast<float>(y) * st + half), sy);
+            else v = __fadd_rn((j == p.root) ? 0.0f : __fmul_rn(out, p.z_norm), zq);
+            p.cand_pose[(static_cast<size_t>(cs) * J + j) * 3 + lane] = v;
+            if (j == 0) {
+                float c;
+                if (lane == 2) c = zq;
+                else {
+                    const float off = __ldg(pose + static_cast<size_t>(lane) * HW + idx) * d.scale_offset;
+                    const float P = static_cast<float>(lane == 0 ? x : y) * st + half;
+                    c = __fdiv_rn(__fsub_rn(P, off), lane == 0 ? sx : sy);
+                }
+                p.cand_center[static_cast<size_t>(cs) * 3 + lane] = c;
+            }
+        }
+    }
+}
+
+// refine = 0: the pose maps are already final (reference get_poses contract): plain gather + assembly.
+__global__ void gather_assemble_kernel(const RefineParams p, int batch) {
+    const int J = p.J;
+    const int per = 3 * J + 3;
+    const long long total = static_cast<long long>(batch) * p.CT * per;
+    const das_levels* __restrict__ lvp = p.lv;
+    for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+         t += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int e = static_cast<int>(t % per);
+        const int cs = static_cast<int>(t / per);
+        const int b = cs / p.CT, slot = cs - b * p.CT;
+        int l = 0, s0 = 0;
+        for (; l < lvp->n_levels - 1; ++l) {
+            const int ns = level_slots(lvp->lv[l].H * lvp->lv[l].W, p.nms_pre);
+            if (slot < s0 + ns) break;
+            s0 += ns;
+        }
+        const das_level_desc& d = lvp->lv[l];
+        const int W = d.W, HW = d.H * d.W;
+        const int idx = __ldg(p.cand_index + cs);
+        const int y = idx / W, x = idx - y * W;
+        const float* __restrict__ pose = d.pose + static_cast<size_t>(b) * (3 + 6 * J) * HW;
+        const float sx = __ldg(p.scale_xy + 2 * b), sy = __ldg(p.scale_xy + 2 * b + 1);
+        const float qf = sqrtf(sx * sy);
+        const float st = static_cast<float>(d.stride), half = static_cast<float>(d.stride / 2);
+        const float zq = __fmul_rn(__ldg(pose + 2 * static_cast<size_t>(HW) + idx), qf);
+        if (e < 3 * J) {
+            const int k = e % 3;
+            const float raw = __ldg(pose + static_cast<size_t>(3 + e) * HW + idx);
+            float v;
+            if (k == 0) v = __fdiv_rn(__fadd_rn(raw, static_cast<float>(x) * st + half), sx);
+            else if (k == 1) v = __fdiv_rn(__fadd_rn(raw, static_cast<float>(y) * st + half), sy);
+            else v = __fadd_rn(raw, zq);
+            p.cand_pose[static_cast<size_t>(cs) * 3 * J + e] = v;
+        } else {
+            const int k = e - 3 * J;
+            float c;
+            if (k == 2) c = zq;
+            else {
+                const float off = __ldg(pose + static_cast<size_t>(k) * HW + idx);
+                const float P = static_cast<float>(k == 0 ? x : y) * st + half;
+                c = __fdiv_rn(__fsub_rn(P, off), k == 0 ? sx : sy);
+            }
+            p.cand_center[static_cast<size_t>(cs) * 3 + k] = c;
+        }
+    }
+}
+
+// nn.Conv2d layouts -> joint-major rows {so(2nh), uw(3), uv(3), sc(3)} x C, then biases
+__global__ void pack_weights_kernel(const float* so_w, const float* so_b, const float* sc_w, const float* sc_b,
+                                    const float* uw_w, const float* uw_b, const float* uv_w, const float* uv_b,
+                                    float* dst, int J, int nh, int C) {
+    const int NOUT = 2 * nh + 9;
+    const long long nW = static_cast<long long>(J) * NOUT * C;
+    const long long total = nW + static_cast<long long>(J) * NOUT;
+    for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+         t += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const bool is_b = t >= nW;
+        const long long u = is_b ? t - nW : t / C;
+        const int c = is_b ? 0 : static_cast<int>(t % C);
+        const int j = static_cast<int>(u / NOUT), o = static_cast<int>(u % NOUT);
+        const float *w, *bb;
+        int row;
+        if (o < 2 * nh) { w = so_w; bb = so_b; row = j * 2 * nh + o; }
+        else if (o < 2 * nh + 3) { w = uw_w; bb = uw_b; row = j * 3 + (o - 2 * nh); }
+        else if (o < 2 * nh + 6) { w = uv_w; bb = uv_b; row = j * 3 + (o - 2 * nh - 3); }
+        else { w = sc_w; bb = sc_b; row = j * 3 + (o - 2 * nh - 6); }
+        dst[t] = is_b ? bb[row] : w[static_cast<long long>(row) * C + c];
+    }
+}
+
+}  // namespace das
+
+extern "C" int64_t das_packed_weight_floats(const das_decode_cfg* cfg) {
+    if (!cfg) return 0;
+    return static_cast<int64_t>(cfg->num_joints) * (2 * cfg->num_heads + 9) * (cfg->feat_channels + 1);
+}
+
+extern "C" int das_pack_weights(const das_decode_cfg* cfg, const float* so_w, const float* so_b,
+                                const float* sc_w, const float* sc_b, const float* uw_w, const float* uw_b,
+                                const float* uv_w, const float* uv_b, float* dst, void* stream) {
+    using namespace das;
+    DAS_REQUIRE(cfg && so_w && so_b && sc_w && sc_b && uw_w && uw_b && uv_w && uv_b && dst, DAS_ERR_ARG,
+                "das_pack_weights: null pointer");
+    pack_weights_kernel<<<kSMs, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        so_w, so_b, sc_w, sc_b, uw_w, uw_b, uv_w, uv_b, dst, cfg->num_joints, cfg->num_heads, cfg->feat_channels);
+    DAS_CUDA_CHECK(cudaGetLastError());
+    return DAS_OK;
+}
+
+extern "C" int das_gather_refine_assemble(const das_levels* d_levels, const das_levels* h_levels,
+                                          const das_decode_cfg* cfg, const float* weights,
+                                          const float* const* prev_uvd, const float* scale_xy,
+                                          const float* cand_score, const int32_t* cand_index,
+                                          int32_t cand_slots, float* cand_pose, float* cand_center,
+                                          int32_t* work_counter, void* stream) {
+    using namespace das;
+    DAS_REQUIRE(d_levels && h_levels && cfg && scale_xy && cand_score && cand_index && cand_pose && cand_center,
+                DAS_ERR_ARG, "das_gather_refine_assemble: null pointer");
+    DAS_REQUIRE(cfg->num_joints >= 1 && cfg->num_joints <= DAS_MAX_JOINTS, DAS_ERR_CAPACITY, "num_joints=%d", cfg->num_joints);
+    DAS_REQUIRE(cfg->root_idx >= 0 && cfg->root_idx < cfg->num_joints, DAS_ERR_ARG, "root_idx=%d", cfg->root_idx);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    RefineParams p{};
+    p.lv = d_levels;
+    p.wpack = weights;
+    p.prev_uvd = prev_uvd;
+    p.scale_xy = scale_xy;
+    p.cand_score = cand_score;
+    p.cand_index = cand_index;
+    p.cand_pose = cand_pose;
+    p.cand_center = cand_center;
+    p.work_counter = work_counter;
+    p.CT = cand_slots;
+    p.J = cfg->num_joints;
+    p.root = cfg->root_idx;
+    p.nms_pre = cfg->nms_pre;
+    p.layer = cfg->num_layers - 1;
+    p.depth_factor = cfg->depth_factor;
+    p.z_norm = cfg->z_norm;
+    p.score_thr = cfg->score_thr;
+    const long long items = static_cast<long long>(h_levels->batch) * cand_slots * cfg->num_joints;
+    DAS_REQUIRE(items < (1ll << 31), DAS_ERR_CAPACITY, "too many work items");
+    p.n_items = static_cast<int>(items);
+    if (!cfg->refine) {
+        const long long total = static_cast<long long>(h_levels->batch) * cand_slots * (3 * cfg->num_joints + 3);
+        const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 4 * kSMs));
+        gather_assemble_kernel<<<grid, 256, 0, st>>>(p, h_levels->batch);
+        DAS_CUDA_CHECK(cudaGetLastError());
+        return DAS_OK;
+    }
+    DAS_REQUIRE(weights && work_counter, DAS_ERR_ARG, "refine=1 needs packed weights and a work counter");
+    DAS_REQUIRE(cfg->num_layers >= 1 && cfg->num_layers <= DAS_MAX_LAYERS, DAS_ERR_CAPACITY, "num_layers=%d", cfg->num_layers);
+    DAS_REQUIRE(cfg->num_heads == 4, DAS_ERR_UNSUPPORTED, "num_heads=%d: only 4 is built", cfg->num_heads);
+    DAS_CUDA_CHECK(cudaMemsetAsync(work_counter, 0, sizeof(int32_t), st));
+    const int threads = RS_WARPS * 32;
+    int grid = kSMs * 2;
+    switch (cfg->feat_channels) {
+        case 128: refine_sparse_kernel<4, 4><<<grid, threads, 0, st>>>(p); break;
+        case 256: refine_sparse_kernel<8, 4><<<grid, threads, 0, st>>>(p); break;
+        case 512: refine_sparse_kernel<16, 4><<<grid, threads, 0, st>>>(p); break;
+        default:
+            set_error("feat_channels=%d: only 128/256/512 are built", cfg->feat_channels);
+            return DAS_ERR_UNSUPPORTED;
+    }
+    DAS_CUDA_CHECK(cudaGetLastError());
+    return DAS_OK;
+}

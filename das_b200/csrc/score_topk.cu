@@ -1,0 +1,253 @@
+// Stage 1+2: fused centre-score scan and exact per-level top-k.
+//
+// Replaces DASHead._get_poses_single's per-level head (reference das_head.py:708-723): two sigmoids,
+// their product, `topk(nms_pre)` -- plus the optional north-star 3x3 max-pool peak mask (SURVEY.md
+// 8.0, divergence A).  One CTA per (image, level); the score plane is read with 128-bit coalesced
+// loads, the peak mask is evaluated from shared-memory row strips, and selection is exact with ties
+// broken towards the lower cell index (composite 64-bit keys: score bits << 32 | ~index).
+//
+// Selection strategy (K = nms_pre is small against H*W):
+//   A  every thread scans its cells, writes the 32-bit rank keys to an L2-resident scratch plane and
+//      keeps its own maximum;
+//   B  tau = K-th largest of the 1024 per-thread maxima (31-step bitwise search with
+//      __syncthreads_count) -- a lower bound of the true K-th score that only a handful of cells beat;
+//   C  cells with key >= tau are compacted into a shared-memory list, which is bitonic-sorted and the
+//      first K entries emitted.
+//   F  fallback (K > 128, or the list overflows): exact bitwise radix search over the scratch keys.
+#include "das_common.cuh"
+
+namespace das {
+
+constexpr int TK_THREADS = 1024;
+constexpr int TK_LIST_CAP = 4096;   // >= 2 * DAS_MAX_NMS_PRE
+constexpr int TK_FAST_K = 128;
+constexpr int TK_TILE_FLOATS = 16384;  // peak-mode row strip (64 KB)
+
+__device__ __forceinline__ uint64_t compose(uint32_t key, uint32_t idx) {
+    return (static_cast<uint64_t>(key) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - idx);
+}
+
+// in-place descending bitonic sort of n2 (power of two) u64 keys in shared memory
+__device__ void bitonic_desc(uint64_t* a, int n2) {
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int p = i | j;
+                const bool desc = ((i & k) == 0);
+                const uint64_t x = a[i], y = a[p];
+                if ((x < y) == desc) { a[i] = y; a[p] = x; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TK_THREADS, 1)
+score_topk_kernel(const das_levels* __restrict__ lvp, int nms_pre, int peak,
+                  float* __restrict__ cand_score, int32_t* __restrict__ cand_index, int cand_slots,
+                  uint32_t* __restrict__ scratch, int scratch_per_image) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* list = reinterpret_cast<uint64_t*>(smem_raw);                       // TK_LIST_CAP
+    float* tile = reinterpret_cast<float*>(smem_raw + TK_LIST_CAP * sizeof(uint64_t));  // peak mode only
+    __shared__ int red[33];
+    __shared__ int list_n;
+
+    const int nl = lvp->n_levels;
+    const int b = blockIdx.x / nl, l = blockIdx.x - b * nl;
+    const int H = lvp->lv[l].H, W = lvp->lv[l].W;
+    const int HW = H * W;
+    int slot0 = 0, sc0 = 0;
+    for (int i = 0; i < l; ++i) {
+        const int hw = lvp->lv[i].H * lvp->lv[i].W;
+        slot0 += level_slots(hw, nms_pre);
+        sc0 += hw;
+    }
+    const int K = level_slots(HW, nms_pre);
+    const float* __restrict__ cls = lvp->lv[l].cls + static_cast<size_t>(b) * HW;
+    const float* __restrict__ ctr = lvp->lv[l].ctr + static_cast<size_t>(b) * HW;
+    float* oscore = cand_score + static_cast<size_t>(b) * cand_slots + slot0;
+    int32_t* oidx = cand_index + static_cast<size_t>(b) * cand_slots + slot0;
+    const int tid = threadIdx.x;
+
+    if (K == HW) {  // pass-through: raster order, no ranking (das_head.py:717 false branch)
+        for (int i = tid; i < HW; i += TK_THREADS) {
+            oscore[i] = sigmoid_acc(cls[i]) * sigmoid_acc(ctr[i]);
+            oidx[i] = i;
+        }
+        return;
+    }
+    uint32_t* __restrict__ keys = scratch + static_cast<size_t>(b) * scratch_per_image + sc0;
+
+    // ---- A: rank keys -> scratch, per-thread maximum ---------------------------------------------
+    uint64_t best = 0;
+    if (!peak) {
+        const bool vec = ((HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(cls) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(ctr) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(keys) & 15) == 0);
+        if (vec) {
+            const int n4 = HW >> 2;
+            for (int q = tid; q < n4; q += TK_THREADS) {
+                const float4 a = ldg_f4_stream(cls + 4 * q);
+                const float4 c = ldg_f4_stream(ctr + 4 * q);
+                uint4 k;
+                k.x = __float_as_uint(sigmoid_acc(a.x) * sigmoid_acc(c.x));
+                k.y = __float_as_uint(sigmoid_acc(a.y) * sigmoid_acc(c.y));
+                k.z = __float_as_uint(sigmoid_acc(a.z) * sigmoid_acc(c.z));
+                k.w = __float_as_uint(sigmoid_acc(a.w) * sigmoid_acc(c.w));
+                reinterpret_cast<uint4*>(keys)[q] = k;
+                const uint32_t i0 = 4u * q;
+                uint64_t m = compose(k.x, i0);
+                uint64_t t1 = compose(k.y, i0 + 1); m = t1 > m ? t1 : m;
+                t1 = compose(k.z, i0 + 2); m = t1 > m ? t1 : m;
+                t1 = compose(k.w, i0 + 3); m = t1 > m ? t1 : m;
+                best = m > best ? m : best;
+            }
+        } else {
+            for (int i = tid; i < HW; i += TK_THREADS) {
+                const uint32_t k = __float_as_uint(sigmoid_acc(__ldg(cls + i)) * sigmoid_acc(__ldg(ctr + i)));
+                keys[i] = k;
+                const uint64_t c = compose(k, i);
+                best = c > best ? c : best;
+            }
+        }
+    } else {
+        // 3x3 peak mask from shared-memory row strips: rows [r0-1, r0+R] staged, rows [r0, r0+R) ranked
+        const int R = max(1, min(H, TK_TILE_FLOATS / W - 2));
+        for (int r0 = 0; r0 < H; r0 += R) {
+            const int rows = min(R, H - r0);
+            const int n_stage = (rows + 2) * W;
+            for (int e = tid; e < n_stage; e += TK_THREADS) {
+                const int ry = e / W, x = e - ry * W;
+                const int y = r0 - 1 + ry;
+                float s = 0.0f;  // scores are >= 0, so 0 stands in for "outside the map" (max-pool pads -inf)
+                if (y >= 0 && y < H) s = sigmoid_acc(__ldg(cls + y * W + x)) * sigmoid_acc(__ldg(ctr + y * W + x));
+                tile[e] = s;
+            }
+            __syncthreads();
+            for (int e = tid; e < rows * W; e += TK_THREADS) {
+                const int ry = e / W, x = e - ry * W;
+                const float* c = tile + (ry + 1) * W + x;
+                const float s = c[0];
+                float m = fmaxf(c[-W], c[W]);
+                if (x > 0) m = fmaxf(m, fmaxf(c[-1], fmaxf(c[-W - 1], c[W - 1])));
+                if (x < W - 1) m = fmaxf(m, fmaxf(c[1], fmaxf(c[-W + 1], c[W + 1])));
+                const uint32_t k = (s >= m) ? __float_as_uint(s) : 0u;
+                const int i = (r0 + ry) * W + x;
+                keys[i] = k;
+                const uint64_t cc = compose(k, i);
+                best = cc > best ? cc : best;
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) list_n = 0;
+    __syncthreads();  // also makes this block's scratch writes visible to the whole block
+
+    bool need_fallback = (K > TK_FAST_K);
+    if (!need_fallback) {
+        // ---- B: tau = K-th largest per-thread maximum (score bits only) ---------------------------
+        const uint32_t mykey = static_cast<uint32_t>(best >> 32);
+        uint32_t tau = 0;
+        for (int bit = 30; bit >= 0; --bit) {
+            const uint32_t trial = tau | (1u << bit);
+            if (__syncthreads_count(mykey >= trial) >= K) tau = trial;
+        }
+        // ---- C: compaction of cells with key >= tau ------------------------------------------------
+        for (int i = tid; i < HW; i += TK_THREADS) {
+            const uint32_t k = keys[i];
+            if (k >= tau) {
+                const int pos = atomicAdd(&list_n, 1);
+                if (pos < TK_LIST_CAP) list[pos] = compose(k, i);
+            }
+        }
+        __syncthreads();
+        if (list_n > TK_LIST_CAP || list_n < K) need_fallback = true;  // block-uniform
+    }
+
+    if (need_fallback) {
+        // ---- F: exact bitwise search over all keys -------------------------------------------------
+        __syncthreads();
+        if (tid == 0) list_n = 0;
+        uint32_t T = 0;
+        for (int bit = 30; bit >= 0; --bit) {
+            const uint32_t trial = T | (1u << bit);
+            int c = 0;
+            for (int i = tid; i < HW; i += TK_THREADS) c += (keys[i] >= trial);
+            if (block_sum_1024(c, red) >= K) T = trial;
+        }
+        int cg = 0;
+        for (int i = tid; i < HW; i += TK_THREADS) cg += (keys[i] > T);
+        cg = block_sum_1024(cg, red);
+        const int r = K - cg;  // how many cells with key == T are taken, lowest indices first (r >= 1)
+        // smallest I with count(key == T && idx <= I) >= r  <=>  largest prefix P with count(idx < P) < r
+        uint32_t P = 0;
+        for (int bit = 30; bit >= 0; --bit) {
+            const uint32_t trial = P | (1u << bit);
+            int c = 0;
+            for (int i = tid; i < HW; i += TK_THREADS) c += (keys[i] == T && static_cast<uint32_t>(i) < trial);
+            if (block_sum_1024(c, red) < r) P = trial;
+        }
+        __syncthreads();
+        for (int i = tid; i < HW; i += TK_THREADS) {
+            const uint32_t k = keys[i];
+            if (k > T || (k == T && static_cast<uint32_t>(i) <= P)) {
+                const int pos = atomicAdd(&list_n, 1);
+                if (pos < TK_LIST_CAP) list[pos] = compose(k, i);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- D: sort the short list, emit the first K -------------------------------------------------
+    const int n = min(list_n, TK_LIST_CAP);
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    for (int i = n + tid; i < n2; i += TK_THREADS) list[i] = 0;
+    __syncthreads();
+    bitonic_desc(list, n2);
+    for (int rnk = tid; rnk < K; rnk += TK_THREADS) {
+        const uint64_t c = list[rnk];
+        const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(c & 0xFFFFFFFFull);
+        float s = __uint_as_float(static_cast<uint32_t>(c >> 32));
+        if (peak) s = sigmoid_acc(__ldg(cls + idx)) * sigmoid_acc(__ldg(ctr + idx));  // masked cells rank as 0
+        oscore[rnk] = s;
+        oidx[rnk] = static_cast<int32_t>(idx);
+    }
+}
+
+}  // namespace das
+
+extern "C" int das_score_topk(const das_levels* d_levels, const das_levels* h_levels, int32_t nms_pre,
+                              int32_t peak_kernel, float* cand_score, int32_t* cand_index,
+                              int32_t cand_slots, uint32_t* scratch, void* stream) {
+    using namespace das;
+    DAS_REQUIRE(d_levels && h_levels && cand_score && cand_index && scratch, DAS_ERR_ARG, "das_score_topk: null pointer");
+    DAS_REQUIRE(h_levels->n_levels >= 1 && h_levels->n_levels <= DAS_MAX_LEVELS && h_levels->batch >= 1, DAS_ERR_ARG,
+                "das_score_topk: n_levels=%d batch=%d out of range", h_levels->n_levels, h_levels->batch);
+    DAS_REQUIRE(nms_pre <= DAS_MAX_NMS_PRE, DAS_ERR_CAPACITY, "nms_pre=%d exceeds capacity %d", nms_pre, DAS_MAX_NMS_PRE);
+    DAS_REQUIRE(peak_kernel == 0 || peak_kernel == 1 || peak_kernel == 3, DAS_ERR_UNSUPPORTED,
+                "peak_kernel=%d: only 0/1 (off) and 3 are built", peak_kernel);
+    const int peak = (peak_kernel == 3);
+    int total = 0, per_image = 0;
+    for (int l = 0; l < h_levels->n_levels; ++l) {
+        const int hw = h_levels->lv[l].H * h_levels->lv[l].W;
+        DAS_REQUIRE(hw > 0, DAS_ERR_ARG, "level %d has empty map", l);
+        DAS_REQUIRE(!peak || (h_levels->lv[l].W + 0) * 3 <= TK_TILE_FLOATS, DAS_ERR_CAPACITY, "map too wide for the peak tile");
+        total += level_slots(hw, nms_pre);
+        per_image += hw;
+    }
+    DAS_REQUIRE(total == cand_slots, DAS_ERR_ARG, "cand_slots=%d but levels give %d", cand_slots, total);
+    const size_t smem = TK_LIST_CAP * sizeof(uint64_t) + (peak ? TK_TILE_FLOATS * sizeof(float) : 0);
+    static bool attr_done = false;
+    if (!attr_done) {
+        DAS_CUDA_CHECK(cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(TK_LIST_CAP * sizeof(uint64_t) + TK_TILE_FLOATS * sizeof(float))));
+        attr_done = true;
+    }
+    const int grid = h_levels->batch * h_levels->n_levels;
+    score_topk_kernel<<<grid, TK_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+        d_levels, nms_pre, peak, cand_score, cand_index, cand_slots, scratch, per_image);
+    DAS_CUDA_CHECK(cudaGetLastError());
+    return DAS_OK;
+}

@@ -1,0 +1,361 @@
+"""Host-side mirror of the reference dense-head decode interface, backed by the CUDA C-ABI.
+
+``DASHeadB200`` keeps the reference plugin contract of ``DASHead`` for the inference decode
+(reference: mmdet3d/models/pose_heads/das_head.py:653-688 ``get_poses``; config keys from
+configs/_base_/models/das.py:24-51 and configs/das/exp_panoptic.py:31-53):
+
+* same constructor keys for the path (``num_joints, strides, depth_factor, z_norm, root_idx,
+  recursive_update{num_heads, feat_channels, num_layers, dim}``, ``test_cfg{nms_pre, nms_post,
+  nms_thr, score_thr, nms_type}``); unrelated keys (losses, conv towers) are accepted and ignored;
+* ``get_poses(cls_scores, pose_preds, centernesses, img_metas, cfg=None, rescale=None)`` returns
+  one dict per image with ``poses [N,J,3]``, ``vis [N,J]``, ``centers [N,3]``, ``image_paths`` and
+  ``scores`` (python list), plus ``poses_cam`` / ``poses_world`` (float64) -- the evaluator-side
+  back-projection (cmupanoptic_mono_dataset.py:391-402) moved onto the device;
+* the same python ``assert`` error behaviour on list-length / shape mismatch (das_head.py:660,701,711).
+
+When ``get_poses`` additionally receives the refinement feature maps (``refine_feats``), the pose
+maps are taken as RAW predictor outputs and the progressive refinement + eval tail
+(das_head.py:237-262) run sparsely at the selected centres on the GPU (SURVEY.md 8.0 divergence B).
+
+No CPU path exists here: everything raises if the CUDA library or device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Buffers, DecodeCfg, Levels
+
+
+class _DevArray:
+    """Expose plan-owned device memory to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = dict(shape=tuple(int(s) for s in shape), typestr=typestr,
+                                             data=(int(ptr), False), version=2, strides=None)
+
+
+def _as_tensor(ptr, shape, typestr, device):
+    if int(np.prod(shape)) == 0:
+        dt = {"<f4": torch.float32, "<i4": torch.int32, "<f8": torch.float64}[typestr]
+        return torch.empty(tuple(shape), dtype=dt, device=device)
+    return torch.as_tensor(_DevArray(ptr, shape, typestr), device=device)
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_f32(t: torch.Tensor, what: str):
+    if t.dtype != torch.float32:
+        raise TypeError(f"{what}: expected float32, got {t.dtype} (fp16 I/O is SURVEY 8(f) rank 3)")
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: the decode path only runs on CUDA tensors")
+
+
+class DecodePlan:
+    """One (batch, level shapes, config) instance of the C ``das_plan``."""
+
+    def __init__(self, *, num_joints, root_idx, depth_factor, z_norm, strides, level_sizes, batch,
+                 test_cfg, num_heads=4, feat_channels=256, num_layers=1, refine=True, peak_kernel=0,
+                 dataset_depth_factor=1.0, device="cuda"):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("das_b200 needs a CUDA device; there is no CPU path")
+        self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        nms_type = test_cfg.get("nms_type", "hard")
+        if nms_type != "hard":
+            raise NotImplementedError("nms_type != 'hard' (soft_oks_nms) is SURVEY 8(f) rank 3, not built yet")
+        nms_post = test_cfg.get("nms_post", -1)
+        self.cfg = DecodeCfg(num_joints=num_joints, root_idx=root_idx, num_heads=num_heads,
+                             feat_channels=feat_channels, num_layers=num_layers,
+                             depth_factor=float(depth_factor), z_norm=float(z_norm),
+                             nms_pre=int(test_cfg.get("nms_pre", -1)),
+                             # das_head.py:770,785: absent/<=0 skips NMS; when present the cap re-reads it
+                             nms_post=int(nms_post),
+                             nms_thr=float(test_cfg.get("nms_thr", 0.9)),
+                             score_thr=float(test_cfg.get("score_thr", 0.0)),
+                             peak_kernel=int(peak_kernel), refine=int(bool(refine)),
+                             dataset_depth_factor=float(dataset_depth_factor))
+        self.batch = int(batch)
+        self.strides = [int(s) for s in strides]
+        self.level_sizes = [(int(h), int(w)) for h, w in level_sizes]
+        assert len(self.strides) == len(self.level_sizes)
+        shape = Levels()
+        shape.n_levels = len(self.strides)
+        shape.batch = self.batch
+        for l, ((h, w), s) in enumerate(zip(self.level_sizes, self.strides)):
+            shape.lv[l].H, shape.lv[l].W, shape.lv[l].stride = h, w, s
+            shape.lv[l].scale_offset = shape.lv[l].scale_depth = shape.lv[l].scale_uv = shape.lv[l].scale_d = 1.0
+        self._shape = shape
+        self._plan = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.das_plan_create(C.byref(self.cfg), C.byref(shape), C.byref(self._plan)), "das_plan_create")
+            bufs = Buffers()
+            ct, p = C.c_int32(), C.c_int32()
+            _lib.check(self.lib.das_plan_buffers(self._plan, C.byref(bufs), C.byref(ct), C.byref(p)), "das_plan_buffers")
+        self.cand_slots, self.out_slots = ct.value, p.value
+        B, CT, P, J = self.batch, ct.value, p.value, num_joints
+        dev = self.device
+        self.t = dict(
+            cand_score=_as_tensor(bufs.cand_score, (B, CT), "<f4", dev),
+            cand_index=_as_tensor(bufs.cand_index, (B, CT), "<i4", dev),
+            cand_pose=_as_tensor(bufs.cand_pose, (B, CT, J, 3), "<f4", dev),
+            cand_center=_as_tensor(bufs.cand_center, (B, CT, 3), "<f4", dev),
+            out_count=_as_tensor(bufs.out_count, (B,), "<i4", dev),
+            out_score=_as_tensor(bufs.out_score, (B, P), "<f4", dev),
+            out_slot=_as_tensor(bufs.out_slot, (B, P), "<i4", dev),
+            out_pose=_as_tensor(bufs.out_pose, (B, P, J, 3), "<f4", dev),
+            out_center=_as_tensor(bufs.out_center, (B, P, 3), "<f4", dev),
+            out_cam=_as_tensor(bufs.out_cam, (B, P, J, 3), "<f8", dev),
+            out_world=_as_tensor(bufs.out_world, (B, P, J, 3), "<f8", dev),
+        )
+        self._keep = []          # tensors whose storage the plan currently points at
+
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None) and self._plan.value:
+                self.lib.das_plan_destroy(self._plan)
+                self._plan = C.c_void_p()
+        except Exception:
+            pass
+
+    # ---- inputs ------------------------------------------------------------------------------
+    def set_weights(self, layers: Sequence[Dict[str, torch.Tensor]]):
+        """layers[k]: dict(so_w, so_b, sc_w, sc_b, uw_w, uw_b, uv_w, uv_b) = the nn.Conv2d parameters of
+        recursive_update_branch.layer_k.next_level_offset.{sampling_offset, sampling_conf, update_weight,
+        update_offset_value} (weights [O,C] or [O,C,1,1])."""
+        assert len(layers) == self.cfg.num_layers, (len(layers), self.cfg.num_layers)
+        J, nh, Cc = self.cfg.num_joints, self.cfg.num_heads, self.cfg.feat_channels
+        want = dict(so=J * nh * 2, sc=3 * J, uw=3 * J, uv=3 * J)
+        with torch.cuda.device(self.device):
+            for k, lw in enumerate(layers):
+                args = []
+                hold = []
+                for name in ("so", "sc", "uw", "uv"):
+                    w = lw[name + "_w"].detach().to(self.device, torch.float32).reshape(want[name], Cc).contiguous()
+                    b = lw[name + "_b"].detach().to(self.device, torch.float32).reshape(want[name]).contiguous()
+                    hold += [w, b]
+                    args += [C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr())]
+                _lib.check(self.lib.das_plan_set_weights(self._plan, k, *args, _stream_ptr(self.device)), "das_plan_set_weights")
+                torch.cuda.current_stream(self.device).synchronize()   # `hold` may be freed afterwards
+
+    def _levels_struct(self, levels: Sequence[dict], host: bool = False) -> Levels:
+        lv = Levels()
+        lv.n_levels = len(levels)
+        lv.batch = self.batch
+        J = self.cfg.num_joints
+        keep = []
+        assert len(levels) == len(self.level_sizes), "number of levels differs from the plan"
+        for l, d in enumerate(levels):
+            h, w = self.level_sizes[l]
+            cls, ctr, pose = d["cls"], d["ctr"], d["pose"]
+            assert tuple(cls.shape) == (self.batch, 1, h, w), (tuple(cls.shape), (self.batch, 1, h, w))
+            assert tuple(ctr.shape) == (self.batch, 1, h, w)
+            assert tuple(pose.shape) == (self.batch, 3 + 6 * J, h, w), tuple(pose.shape)
+            for name, t in (("cls", cls), ("ctr", ctr), ("pose", pose)):
+                if not host:
+                    _check_f32(t, name)
+            cls, ctr, pose = cls.contiguous(), ctr.contiguous(), pose.contiguous()
+            keep += [cls, ctr, pose]
+            lv.lv[l].cls, lv.lv[l].ctr, lv.lv[l].pose = cls.data_ptr(), ctr.data_ptr(), pose.data_ptr()
+            lv.lv[l].H, lv.lv[l].W, lv.lv[l].stride = h, w, self.strides[l]
+            sc = d.get("scales", (1.0, 1.0, 1.0, 1.0))
+            lv.lv[l].scale_offset, lv.lv[l].scale_depth, lv.lv[l].scale_uv, lv.lv[l].scale_d = [float(s) for s in sc]
+            if self.cfg.refine:
+                feats = d["feats"]
+                assert len(feats) == self.cfg.num_layers, "one refinement feature map per layer is required"
+                for k, f in enumerate(feats):
+                    assert tuple(f.shape) == (self.batch, self.cfg.feat_channels, h, w), tuple(f.shape)
+                    if not host:
+                        _check_f32(f, "feats")
+                    # the kernels read NHWC; channels_last tensors are used in place, NCHW ones converted once
+                    f = f.contiguous(memory_format=torch.channels_last)
+                    keep.append(f)
+                    lv.lv[l].feats[k] = f.data_ptr()
+        self._keep_tmp = keep
+        return lv
+
+    def bind(self, levels: Sequence[dict]):
+        lv = self._levels_struct(levels)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.das_plan_bind(self._plan, C.byref(lv), _stream_ptr(self.device)), "das_plan_bind")
+        self._keep = self._keep_tmp
+
+    @staticmethod
+    def pack_metas(img_metas: Sequence[dict]):
+        B = len(img_metas)
+        sxy = np.ones((B, 2), dtype=np.float32)
+        cam = np.zeros((B, _lib.CAM_DOUBLES), dtype=np.float64)
+        for b, m in enumerate(img_metas):
+            sxy[b] = np.asarray(m["scale_factor"], dtype=np.float32)[:2]
+            c = m.get("cam")
+            if c is None:
+                K, R, t = np.eye(3), np.eye(3), np.zeros(3)
+            else:
+                K = np.asarray(c["K"], dtype=np.float64)
+                R = np.asarray(c.get("R", np.eye(3)), dtype=np.float64)
+                t = np.asarray(c.get("t", np.zeros(3)), dtype=np.float64).reshape(3)
+            cam[b, 0:3] = K[0, :3]
+            cam[b, 3:6] = K[1, :3]
+            cam[b, 6:15] = R.reshape(9)
+            cam[b, 15:18] = t
+        return sxy, cam
+
+    def set_metas(self, img_metas: Sequence[dict]):
+        assert len(img_metas) == self.batch
+        sxy, cam = self.pack_metas(img_metas)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.das_plan_set_metas(self._plan, C.c_void_p(sxy.ctypes.data), C.c_void_p(cam.ctypes.data),
+                                                   _stream_ptr(self.device)), "das_plan_set_metas")
+
+    # ---- run -----------------------------------------------------------------------------------
+    def run(self, use_graph: bool = True):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.das_plan_run(self._plan, _stream_ptr(self.device), int(use_graph)), "das_plan_run")
+
+    def run_host(self, levels: Sequence[dict], img_metas: Sequence[dict], host_out: Dict[str, torch.Tensor]):
+        """End-to-end entry with HOST tensors (pinned for full PCIe speed): H2D of every input,
+        decode, D2H of the packed outputs into ``host_out`` (see alloc_host_out), stream sync."""
+        lv = self._levels_struct(levels, host=True)
+        sxy, cam = self.pack_metas(img_metas)
+        ob = Buffers()
+        for k in ("out_count", "out_score", "out_slot", "out_pose", "out_center", "out_cam", "out_world"):
+            if k in host_out:
+                setattr(ob, k, host_out[k].data_ptr())
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.das_plan_run_host(self._plan, C.byref(lv), C.c_void_p(sxy.ctypes.data),
+                                                  C.c_void_p(cam.ctypes.data), ob, _stream_ptr(self.device)),
+                       "das_plan_run_host")
+
+    def alloc_host_out(self, pinned: bool = True) -> Dict[str, torch.Tensor]:
+        return {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=pinned)
+                for k, v in self.t.items() if k.startswith("out_")}
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.das_plan_kernel_launches(self._plan))
+
+    @property
+    def h2d_bytes(self) -> int:
+        return int(self.lib.das_plan_h2d_bytes(self._plan))
+
+    @property
+    def d2h_bytes(self) -> int:
+        return int(self.lib.das_plan_d2h_bytes(self._plan))
+
+    # ---- results ------------------------------------------------------------------------------
+    def results(self, img_metas: Sequence[dict], src: Optional[Dict[str, torch.Tensor]] = None) -> List[dict]:
+        """Build the reference's list-of-dicts (das_head.py:680-687) with ONE small device->host copy
+        (counts + scores); pose tensors stay on the device like the reference's."""
+        t = src or self.t
+        counts = t["out_count"].cpu().tolist() if t["out_count"].is_cuda else t["out_count"].tolist()
+        scores = t["out_score"].cpu() if t["out_score"].is_cuda else t["out_score"]
+        res = []
+        for b, m in enumerate(img_metas):
+            n = int(counts[b])
+            poses = t["out_pose"][b, :n].clone()
+            res.append(dict(poses=poses, vis=torch.ones(poses.shape[:2], dtype=poses.dtype, device=poses.device),
+                            centers=t["out_center"][b, :n].clone(),
+                            image_paths=[m.get("filename", "")],
+                            scores=scores[b, :n].tolist(),
+                            poses_cam=t["out_cam"][b, :n].clone(), poses_world=t["out_world"][b, :n].clone(),
+                            slots=t["out_slot"][b, :n].clone()))
+        return res
+
+
+class DASHeadB200:
+    """Drop-in for the inference decode of the reference ``DASHead`` (das_head.py:30-63, 653-796)."""
+
+    def __init__(self, num_classes=1, in_channels=256, *, num_joints=15, strides=(8, 16, 32, 64, 128),
+                 depth_factor=1, z_norm=1, root_idx=None, recursive_update=None, test_cfg=None,
+                 train_cfg=None, peak_kernel=0, device="cuda", **unused):
+        assert num_classes == 1, "the DAS head has one class (configs/_base_/models/das.py:26)"
+        ru = dict(num_heads=4, feat_channels=256, num_layers=1, dim=3)
+        ru.update(recursive_update or {})
+        assert ru["dim"] == 3, "dim=3 is the only shipped value (configs/_base_/models/das.py:49)"
+        self.num_classes = num_classes
+        self.cls_out_channels = 1
+        self.in_channels = in_channels
+        self.num_joints = int(num_joints)
+        self.strides = list(strides)
+        self.depth_factor = depth_factor
+        self.z_norm = z_norm
+        self.root_idx = int(root_idx)
+        self.recursive_update = ru
+        self.test_cfg = dict(test_cfg or {})
+        self.train_cfg = train_cfg
+        self.peak_kernel = peak_kernel
+        self.device = device
+        self.group_reg_dims = [2, 1, 3 * self.num_joints, 3 * self.num_joints]
+        self.training = False
+        self._plans: Dict[tuple, DecodePlan] = {}
+        self._layers = None
+        self.scales = [(1.0, 1.0, 1.0, 1.0) for _ in self.strides]
+
+    # refinement 1x1 weights (state_dict names in SURVEY.md section 5, checkpoint row)
+    def load_refine_weights(self, layers: Sequence[Dict[str, torch.Tensor]]):
+        self._layers = list(layers)
+        for p in self._plans.values():
+            if p.cfg.refine:
+                p.set_weights(self._layers)
+
+    def _plan(self, batch, sizes, cfg, refine) -> DecodePlan:
+        key = (batch, tuple(sizes), tuple(sorted(cfg.items())), bool(refine))
+        p = self._plans.get(key)
+        if p is None:
+            p = DecodePlan(num_joints=self.num_joints, root_idx=self.root_idx, depth_factor=self.depth_factor,
+                           z_norm=self.z_norm, strides=self.strides[:len(sizes)], level_sizes=sizes, batch=batch,
+                           test_cfg=cfg, num_heads=self.recursive_update["num_heads"],
+                           feat_channels=self.recursive_update["feat_channels"],
+                           num_layers=self.recursive_update["num_layers"], refine=refine,
+                           peak_kernel=self.peak_kernel, device=self.device)
+            if refine:
+                assert self._layers is not None, "call load_refine_weights() before a refining decode"
+                p.set_weights(self._layers)
+            self._plans[key] = p
+        return p
+
+    def get_poses(self, cls_scores, pose_preds, centernesses, *rest, cfg=None, rescale=None):
+        """Reference call: get_poses(cls_scores, pose_preds, centernesses, img_metas, cfg=None, rescale=None)
+        with pose_preds already refined + eval-tailed (das_head.py:264-267 outputs).
+        Extended call: get_poses(cls_scores, raw_pose_preds, centernesses, refine_feats, img_metas, ...)
+        where refine_feats[level] is the list of per-layer feature maps; refinement then runs on the GPU."""
+        if len(rest) == 1:
+            refine_feats, img_metas = None, rest[0]
+        elif len(rest) == 2 and isinstance(rest[1], (list, tuple)) and (len(rest[1]) == 0 or isinstance(rest[1][0], dict)):
+            refine_feats, img_metas = rest
+        elif len(rest) >= 2:                      # positional cfg / rescale like the reference allows
+            refine_feats, img_metas = None, rest[0]
+            cfg = rest[1] if cfg is None else cfg
+        else:
+            raise TypeError("get_poses() missing img_metas")
+        assert len(cls_scores) == len(pose_preds) == len(centernesses)
+        cfg = self.test_cfg if cfg is None else dict(cfg)
+        num_levels = len(cls_scores)
+        batch = len(img_metas)
+        sizes = [tuple(int(s) for s in c.shape[-2:]) for c in cls_scores]
+        refine = refine_feats is not None
+        plan = self._plan(batch, sizes, cfg, refine)
+        levels = []
+        for l in range(num_levels):
+            assert cls_scores[l].shape[-2:] == pose_preds[l].shape[-2:]
+            d = dict(cls=cls_scores[l].detach(), ctr=centernesses[l].detach(), pose=pose_preds[l].detach(),
+                     scales=self.scales[l])
+            if refine:
+                d["feats"] = [f.detach() for f in refine_feats[l]]
+            levels.append(d)
+        plan.bind(levels)
+        plan.set_metas(img_metas)
+        plan.run()
+        return plan.results(img_metas)
+
+    def simple_test_decode(self, outs, img_metas, rescale=False):
+        """What DAS.simple_test does after the head forward (detectors/das.py:74-79)."""
+        return self.get_poses(*outs, img_metas, rescale=rescale)

@@ -1,0 +1,182 @@
+/*
+ * das_decode.h -- C ABI of the B200-native DAS dense-head inference decode.
+ *
+ * The reference (wangzt-halo/das, an mmdetection3d fork) has NO native interface for this path:
+ * it is eager PyTorch + NumPy.  The entry points below are what a binding for the
+ * path replaces, one reference function (file:line, relative to the reference root) per launcher:
+ *
+ *   das_score_topk ............ DASHead._get_poses_single, das_head.py:708-723
+ *                               (two sigmoids, score product, per-level topk(nms_pre))
+ *   das_gather_refine_assemble  das_head.py:720-749 (gather + joint assembly), das_head.py:237-262
+ *                               (eval tail) and the LAST RecursiveUpdateLayer evaluated sparsely at
+ *                               the selected centres (recursive_update.py:186-197, 9-82)
+ *   das_refine_dense_layer .... one full-map RecursiveUpdateLayer, recursive_update.py:220-235
+ *                               (only needed for layers 1..L-1 when num_layers > 1)
+ *   das_nms_backproject ....... das_head.py:751-794 (score_thr, areas, OKS-NMS, nms_post),
+ *                               pose_nms.py:51-126, cmupanoptic_mono_dataset.py:391-401 (depth
+ *                               de-normalisation) and mytools/vis_3d.py:16-26 (pixel2world)
+ *   das_plan_* ................ DASHead.get_poses, das_head.py:653-688 (the whole call)
+ *
+ * Conventions: every function returns DAS_OK (0) or a negative das_status; launchers take raw
+ * DEVICE pointers plus explicit sizes and a cudaStream_t (passed as void*), never allocate, never
+ * synchronise, and are CUDA-graph capturable.  Only das_plan_create / das_plan_destroy allocate.
+ * All tensors are fp32 unless stated; "NCHW" = [B, C, H, W] contiguous, "NHWC" = [B, H, W, C].
+ */
+#ifndef DAS_DECODE_H_
+#define DAS_DECODE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAS_MAX_LEVELS 5      /* reference pyramids have 4 (exp_panoptic.py:35) or 5 (_base_/models/das.py:30) */
+#define DAS_MAX_LAYERS 4      /* recursive_update.num_layers: 1 (Panoptic), 2 (MuPoTS), 3 (BASELINE config 3) */
+#define DAS_MAX_JOINTS 32
+#define DAS_MAX_NMS_PRE 2048  /* per-level top-k capacity (reference configs use 1000) */
+#define DAS_CAM_DOUBLES 18    /* K[0,:3], K[1,:3], R row-major 3x3, t[3] */
+
+typedef enum das_status {
+    DAS_OK = 0,
+    DAS_ERR_ARG = -1,          /* bad argument (null pointer, size out of range) */
+    DAS_ERR_CUDA = -2,         /* a CUDA runtime call failed; see das_last_error() */
+    DAS_ERR_CAPACITY = -3,     /* nms_pre / candidate count / joints beyond compiled capacity */
+    DAS_ERR_UNSUPPORTED = -4   /* feature not built (e.g. channel count other than 128/256/512) */
+} das_status;
+
+/* One pyramid level.  All pointers are device pointers owned by the caller. */
+typedef struct das_level_desc {
+    const float* cls;                    /* [B,1,H,W] centre-heat-map logits (cls_score)          */
+    const float* ctr;                    /* [B,1,H,W] centerness logits                           */
+    const float* pose;                   /* [B,3+6J,H,W] NCHW. refine=1: RAW predictor output     */
+                                         /*                    refine=0: final pose_pred (ref. API) */
+    const float* feats[DAS_MAX_LAYERS];  /* refine=1: per refinement layer, NHWC [B,H,W,C]        */
+    int32_t H, W, stride;
+    float scale_offset, scale_depth, scale_uv, scale_d;   /* mmcv Scale params, das_head.py:171-173 */
+} das_level_desc;
+
+typedef struct das_levels {
+    int32_t n_levels;
+    int32_t batch;
+    das_level_desc lv[DAS_MAX_LEVELS];
+} das_levels;
+
+/* Head + test_cfg keys of the path (configs/_base_/models/das.py:24-51, exp_panoptic.py:31-53). */
+typedef struct das_decode_cfg {
+    int32_t num_joints;      /* J */
+    int32_t root_idx;
+    int32_t num_heads;       /* recursive_update.num_heads (4) */
+    int32_t feat_channels;   /* recursive_update.feat_channels (256) */
+    int32_t num_layers;      /* recursive_update.num_layers */
+    float depth_factor;
+    float z_norm;
+    int32_t nms_pre;         /* <=0: keep every cell (das_head.py:716-717) */
+    int32_t nms_post;        /* <=0: skip OKS-NMS (das_head.py:770-772) */
+    float nms_thr;
+    float score_thr;         /* <=0: no threshold (das_head.py:763-764) */
+    int32_t peak_kernel;     /* 0/1: reference behaviour; 3: north-star 3x3 max-pool peak mask */
+    int32_t refine;          /* 1: pose maps are raw, run refinement + eval tail; 0: maps are final */
+    double dataset_depth_factor; /* cmupanoptic_mono_dataset.py:399 (dataset-side factor, 1.0) */
+} das_decode_cfg;
+
+/* Device buffers of one decode.  CT = candidate slots per image (das_candidate_slots()),
+ * P = das_output_slots(). Slot order is level-major, rank order inside a level. */
+typedef struct das_buffers {
+    /* stage 1-2 */
+    float*   cand_score;   /* [B,CT]  sigmoid(cls)*sigmoid(ctr) of the selected cell              */
+    int32_t* cand_index;   /* [B,CT]  flat cell index y*W+x inside its level                      */
+    /* stage 3-4 */
+    float*   cand_pose;    /* [B,CT,J,3] joints: x,y original-image px, z = d + z_root*sqrt(sx*sy) */
+    float*   cand_center;  /* [B,CT,3]                                                            */
+    /* stage 5 outputs */
+    int32_t* out_count;    /* [B]                                                                 */
+    float*   out_score;    /* [B,P]                                                               */
+    int32_t* out_slot;     /* [B,P]   candidate slot each output row came from                    */
+    float*   out_pose;     /* [B,P,J,3]                                                           */
+    float*   out_center;   /* [B,P,3]                                                             */
+    double*  out_cam;      /* [B,P,J,3] camera space (vis_3d.py x2)                               */
+    double*  out_world;    /* [B,P,J,3] world space  (vis_3d.py x3)                               */
+} das_buffers;
+
+const char* das_version(void);
+const char* das_last_error(void);
+
+/* slot bookkeeping (host-side pure functions) */
+int32_t das_level_slots(int32_t H, int32_t W, int32_t nms_pre);          /* min(HW, nms_pre) rule */
+int32_t das_candidate_slots(const das_levels* lv, int32_t nms_pre);      /* CT = sum over levels  */
+int32_t das_output_slots(int32_t cand_slots, int32_t nms_post);          /* P                     */
+
+/* ---- stage launchers (device pointers, stream, no allocation, no sync) ------------------------ */
+
+/* Stage 1+2: fused sigmoid*sigmoid (+ optional 3x3 peak mask) and exact per-level top-k, ties to
+ * the lower cell index.  d_levels: device copy of das_levels.  scratch: >= B*sum(HW) uint32. */
+int das_score_topk(const das_levels* d_levels, const das_levels* h_levels, int32_t nms_pre,
+                   int32_t peak_kernel, float* cand_score, int32_t* cand_index, int32_t cand_slots,
+                   uint32_t* scratch, void* stream);
+
+/* Stage 3+4(+eval tail): gather at the selected cells, sparse last-layer refinement, assembly.
+ * weights: das_pack_weights() layout of the LAST layer; prev_uvd: NULL (use scaled raw uvd of
+ * lv.pose) or [n_levels] device pointers to NHWC [B,H,W,3J] maps produced by dense layers.
+ * scale_xy: [B,2] device (img_metas['scale_factor'][:2]). */
+int das_gather_refine_assemble(const das_levels* d_levels, const das_levels* h_levels,
+                               const das_decode_cfg* cfg, const float* weights,
+                               const float* const* prev_uvd, const float* scale_xy,
+                               const float* cand_score, const int32_t* cand_index, int32_t cand_slots,
+                               float* cand_pose, float* cand_center, int32_t* work_counter,
+                               void* stream);
+
+/* One dense refinement layer over a whole level (layers 1..L-1 when num_layers > 1).
+ * uvd_in NULL -> scaled raw uvd from lv.pose.  uvd_out NHWC [B,H,W,3J]. proj: scratch
+ * [B,H,W,14J] fp32. */
+int das_refine_dense_layer(const das_levels* d_levels, const das_levels* h_levels, int32_t level,
+                           int32_t layer, const das_decode_cfg* cfg, const float* weights,
+                           const float* uvd_in, float* uvd_out, float* proj, void* stream);
+
+/* Stage 5: score_thr, OKS-NMS, nms_post, output packing, depth de-norm + back-projection.
+ * cam: [B,DAS_CAM_DOUBLES] device doubles. */
+int das_nms_backproject(const das_decode_cfg* cfg, int32_t batch, int32_t cand_slots,
+                        const float* cand_score, const float* cand_pose, const float* cand_center,
+                        const double* cam, das_buffers out, void* stream);
+
+/* Repack the four 1x1 convolutions of one RecursiveUpdateLayer (nn.Conv2d weight [O,C] + bias [O],
+ * recursive_update.py:171-180) into the joint-major layout the kernels read:
+ * dst[j][17][C] rows = {sampling_offset 2*nh, update_weight 3, update_offset_value 3, sampling_conf 3}
+ * followed by dst_bias[j][17].  All pointers device; dst holds J*(2nh+9)*(C+1) floats. */
+int das_pack_weights(const das_decode_cfg* cfg, const float* so_w, const float* so_b,
+                     const float* sc_w, const float* sc_b, const float* uw_w, const float* uw_b,
+                     const float* uv_w, const float* uv_b, float* dst, void* stream);
+int64_t das_packed_weight_floats(const das_decode_cfg* cfg);
+
+/* ---- plan: the whole get_poses call, CUDA-graph captured --------------------------------------- */
+typedef struct das_plan das_plan;
+
+int das_plan_create(const das_decode_cfg* cfg, const das_levels* shape /* H,W,stride,batch only */,
+                    das_plan** out);
+void das_plan_destroy(das_plan* plan);
+/* device weights of layer `layer` (nn.Conv2d layouts); repacked on `stream`. */
+int das_plan_set_weights(das_plan* plan, int32_t layer, const float* so_w, const float* so_b,
+                         const float* sc_w, const float* sc_b, const float* uw_w, const float* uw_b,
+                         const float* uv_w, const float* uv_b, void* stream);
+/* bind device inputs (pointers + per-level Scale values); cheap, no graph rebuild. */
+int das_plan_bind(das_plan* plan, const das_levels* levels, void* stream);
+/* per-image metas from HOST memory: scale_xy [B,2] fp32, cam [B,18] fp64. */
+int das_plan_set_metas(das_plan* plan, const float* scale_xy, const double* cam, void* stream);
+/* enqueue one decode on `stream` (first call captures the graph). use_graph=0 launches eagerly. */
+int das_plan_run(das_plan* plan, void* stream, int32_t use_graph);
+int das_plan_buffers(const das_plan* plan, das_buffers* out, int32_t* cand_slots, int32_t* out_slots);
+int64_t das_plan_kernel_launches(const das_plan* plan);   /* kernels enqueued by das_plan_run so far */
+
+/* Host-buffer entry (the end-to-end call): copies every input from HOST memory (pinned for full
+ * speed) to plan-owned device staging, runs the decode and copies the packed results back to the
+ * host arrays of `host_out` (same layout as das_buffers, any pointer may be NULL), then
+ * synchronises `stream`. `levels` holds HOST pointers here. */
+int das_plan_run_host(das_plan* plan, const das_levels* levels, const float* scale_xy,
+                      const double* cam, das_buffers host_out, void* stream);
+int64_t das_plan_h2d_bytes(const das_plan* plan);
+int64_t das_plan_d2h_bytes(const das_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAS_DECODE_H_ */
