@@ -72,6 +72,8 @@ SIGNATURES = {
     "das_plan_bind": (C.c_int, [_VP, C.POINTER(Levels), _VP]),
     "das_plan_set_metas": (C.c_int, [_VP, _VP, _VP, _VP]),
     "das_plan_run": (C.c_int, [_VP, _VP, C.c_int32]),
+    "das_plan_stage_ms": (C.c_int, [_VP, _f32p]),
+    "das_plan_output_block": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(C.c_int64)]),
     "das_plan_buffers": (C.c_int, [_VP, C.POINTER(Buffers), _i32p, _i32p]),
     "das_plan_kernel_launches": (C.c_int64, [_VP]),
     "das_plan_run_host": (C.c_int, [_VP, C.POINTER(Levels), _VP, _VP, Buffers, _VP]),

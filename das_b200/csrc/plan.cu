@@ -42,8 +42,12 @@ struct das_plan {
     das_levels staging{};
     bool staging_ready = false;
     int64_t h2d_bytes = 0, d2h_bytes = 0;
+    unsigned char* out_block = nullptr;   // all out_* buffers live in this one allocation (one D2H / one all-gather)
+    size_t out_block_bytes = 0;
     // graph
     cudaGraphExec_t exec = nullptr;
+    cudaGraphExec_t exec_prof = nullptr;   // same graph with event-record nodes between the stages
+    cudaEvent_t ev[DAS_NUM_STAGES + 1] = {};
     cudaStream_t cap_stream = nullptr;   // capture happens here (the caller's stream may be the legacy default stream)
     int64_t launches = 0;
     int launches_per_run = 0;
@@ -113,13 +117,29 @@ extern "C" int das_plan_create(const das_decode_cfg* cfg, const das_levels* shap
     A(dev_alloc(&p->buf.cand_index, B * CT));
     A(dev_alloc(&p->buf.cand_pose, B * CT * J * 3));
     A(dev_alloc(&p->buf.cand_center, B * CT * 3));
-    A(dev_alloc(&p->buf.out_count, B));
-    A(dev_alloc(&p->buf.out_score, B * P));
-    A(dev_alloc(&p->buf.out_slot, B * P));
-    A(dev_alloc(&p->buf.out_pose, B * P * J * 3));
-    A(dev_alloc(&p->buf.out_center, B * P * 3));
-    A(dev_alloc(&p->buf.out_cam, B * P * J * 3));
-    A(dev_alloc(&p->buf.out_world, B * P * J * 3));
+    {
+        // carve every output out of one block: [count | score | slot | pose | center | cam | world], 256 B aligned
+        auto up = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
+        const size_t o_count = 0;
+        const size_t o_score = up(o_count + B * 4);
+        const size_t o_slot = up(o_score + B * P * 4);
+        const size_t o_pose = up(o_slot + B * P * 4);
+        const size_t o_center = up(o_pose + B * P * J * 3 * 4);
+        const size_t o_cam = up(o_center + B * P * 3 * 4);
+        const size_t o_world = up(o_cam + B * P * J * 3 * 8);
+        p->out_block_bytes = up(o_world + B * P * J * 3 * 8);
+        A(dev_alloc(&p->out_block, p->out_block_bytes));
+        if (s == DAS_OK) {
+            unsigned char* q = p->out_block;
+            p->buf.out_count = reinterpret_cast<int32_t*>(q + o_count);
+            p->buf.out_score = reinterpret_cast<float*>(q + o_score);
+            p->buf.out_slot = reinterpret_cast<int32_t*>(q + o_slot);
+            p->buf.out_pose = reinterpret_cast<float*>(q + o_pose);
+            p->buf.out_center = reinterpret_cast<float*>(q + o_center);
+            p->buf.out_cam = reinterpret_cast<double*>(q + o_cam);
+            p->buf.out_world = reinterpret_cast<double*>(q + o_world);
+        }
+    }
     A(dev_alloc(&p->scratch, B * static_cast<size_t>(p->hw_sum)));
     A(dev_alloc(&p->work_counter, 4));
     A(dev_alloc(&p->d_scale_xy, B * 2));
@@ -174,9 +194,10 @@ extern "C" void das_plan_destroy(das_plan* p) {
     if (!p) return;
     if (p->exec) cudaGraphExecDestroy(p->exec);
     if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
+    if (p->exec_prof) cudaGraphExecDestroy(p->exec_prof);
+    for (cudaEvent_t e : p->ev) if (e) cudaEventDestroy(e);
     void* ptrs[] = {p->d_levels, p->buf.cand_score, p->buf.cand_index, p->buf.cand_pose, p->buf.cand_center,
-                    p->buf.out_count, p->buf.out_score, p->buf.out_slot, p->buf.out_pose, p->buf.out_center,
-                    p->buf.out_cam, p->buf.out_world, p->scratch, p->work_counter, p->d_scale_xy, p->d_cam,
+                    p->out_block, p->scratch, p->work_counter, p->d_scale_xy, p->d_cam,
                     p->proj, p->d_prev_ptrs};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (int k = 0; k < DAS_MAX_LAYERS; ++k) if (p->wpack[k]) cudaFree(p->wpack[k]);
@@ -237,15 +258,21 @@ extern "C" int das_plan_set_metas(das_plan* p, const float* scale_xy, const doub
     return DAS_OK;
 }
 
-static int enqueue(das_plan* p, cudaStream_t st, int* n_launch) {
+static int enqueue(das_plan* p, cudaStream_t st, int* n_launch, bool events) {
     const das_decode_cfg& c = p->cfg;
     int n = 0;
+    auto mark = [&](int i) -> int {
+        // external: becomes a real event-record node when captured, so cudaEventElapsedTime works after a replay
+        if (events) DAS_CUDA_CHECK(cudaEventRecordWithFlags(p->ev[i], st, cudaEventRecordExternal));
+        return DAS_OK;
+    };
+    DAS_TRY(mark(0));
     DAS_TRY(das_score_topk(p->d_levels, &p->bound, c.nms_pre, c.peak_kernel, p->buf.cand_score, p->buf.cand_index,
                            p->CT, p->scratch, st));
     ++n;
+    DAS_TRY(mark(1));
     const float* const* prev = nullptr;
     if (c.refine && c.num_layers > 1) {
-        const float* host_prev[DAS_MAX_LEVELS] = {};
         for (int l = 0; l < p->bound.n_levels; ++l) {
             const float* in = nullptr;
             for (int k = 0; k < c.num_layers - 1; ++k) {
@@ -254,60 +281,83 @@ static int enqueue(das_plan* p, cudaStream_t st, int* n_launch) {
                 n += 2;
                 in = outm;
             }
-            host_prev[l] = in;
         }
-        // constant per plan; uploaded eagerly once (not part of the graph)
-        static_cast<void>(host_prev);
-        prev = p->d_prev_ptrs;
+        prev = p->d_prev_ptrs;   // uploaded once in das_plan_run: uvd_map[(L-2)&1][level]
     }
+    DAS_TRY(mark(2));
     DAS_TRY(das_gather_refine_assemble(p->d_levels, &p->bound, &c, c.refine ? p->wpack[c.num_layers - 1] : nullptr, prev,
                                        p->d_scale_xy, p->buf.cand_score, p->buf.cand_index, p->CT, p->buf.cand_pose,
                                        p->buf.cand_center, p->work_counter, st));
     ++n;
+    DAS_TRY(mark(3));
     DAS_TRY(das_nms_backproject(&c, p->B, p->CT, p->buf.cand_score, p->buf.cand_pose, p->buf.cand_center, p->d_cam,
                                 p->buf, st));
     ++n;
+    DAS_TRY(mark(4));
     *n_launch = n;
     return DAS_OK;
 }
 
-extern "C" int das_plan_run(das_plan* p, void* stream, int32_t use_graph) {
+static int capture(das_plan* p, cudaGraphExec_t* exec, bool events) {
+    cudaGraph_t g = nullptr;
+    int n = 0;
+    if (!p->cap_stream) DAS_CUDA_CHECK(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
+    DAS_CUDA_CHECK(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int s = enqueue(p, p->cap_stream, &n, events);
+    cudaError_t e = cudaStreamEndCapture(p->cap_stream, &g);
+    if (s != DAS_OK) { if (g) cudaGraphDestroy(g); return s; }
+    DAS_CUDA_CHECK(e);
+    e = cudaGraphInstantiate(exec, g, 0);
+    cudaGraphDestroy(g);
+    DAS_CUDA_CHECK(e);
+    return DAS_OK;
+}
+
+// mode: 0 = eager launches, 1 = CUDA graph replay, 2 = graph replay with stage-boundary events
+extern "C" int das_plan_run(das_plan* p, void* stream, int32_t mode) {
     using namespace das;
     DAS_REQUIRE(p, DAS_ERR_ARG, "null plan");
+    DAS_REQUIRE(mode >= 0 && mode <= 2, DAS_ERR_ARG, "mode=%d", mode);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (p->cfg.refine && p->cfg.num_layers > 1 && p->launches == 0 && !p->exec) {
-        const float* host_prev[DAS_MAX_LEVELS] = {};
-        for (int l = 0; l < p->bound.n_levels; ++l) host_prev[l] = p->uvd_map[(p->cfg.num_layers - 2) & 1][l];
-        DAS_CUDA_CHECK(cudaMemcpyAsync(p->d_prev_ptrs, host_prev, sizeof(host_prev), cudaMemcpyHostToDevice, st));
-        DAS_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (p->launches == 0) {
+        if (p->cfg.refine && p->cfg.num_layers > 1) {
+            const float* host_prev[DAS_MAX_LEVELS] = {};
+            for (int l = 0; l < p->bound.n_levels; ++l) host_prev[l] = p->uvd_map[(p->cfg.num_layers - 2) & 1][l];
+            DAS_CUDA_CHECK(cudaMemcpy(p->d_prev_ptrs, host_prev, sizeof(host_prev), cudaMemcpyHostToDevice));
+        }
+        for (cudaEvent_t& e : p->ev) DAS_CUDA_CHECK(cudaEventCreate(&e));
     }
-    if (!use_graph) {
+    if (mode == 0 || p->launches == 0) {
+        // the very first run is always eager: module loading and cudaFuncSetAttribute must not land inside a capture
         int n = 0;
-        DAS_TRY(enqueue(p, st, &n));
+        DAS_TRY(enqueue(p, st, &n, false));
         p->launches_per_run = n;
         p->launches += n;
-        return DAS_OK;
-    }
-    if (!p->exec) {
-        // eager warm-up first: lazy module loading and cudaFuncSetAttribute must not happen inside a capture
-        int n = 0;
-        DAS_TRY(enqueue(p, st, &n));
-        p->launches_per_run = n;
-        p->launches += n;
+        if (mode == 0) return DAS_OK;
         DAS_CUDA_CHECK(cudaStreamSynchronize(st));
-        cudaGraph_t g = nullptr;
-        if (!p->cap_stream) DAS_CUDA_CHECK(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
-        DAS_CUDA_CHECK(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
-        int s = enqueue(p, p->cap_stream, &n);
-        cudaError_t e = cudaStreamEndCapture(p->cap_stream, &g);
-        if (s != DAS_OK) { if (g) cudaGraphDestroy(g); return s; }
-        DAS_CUDA_CHECK(e);
-        e = cudaGraphInstantiate(&p->exec, g, 0);
-        cudaGraphDestroy(g);
-        DAS_CUDA_CHECK(e);
     }
-    DAS_CUDA_CHECK(cudaGraphLaunch(p->exec, st));
+    cudaGraphExec_t* ex = (mode == 2) ? &p->exec_prof : &p->exec;
+    if (!*ex) DAS_TRY(capture(p, ex, mode == 2));
+    DAS_CUDA_CHECK(cudaGraphLaunch(*ex, st));
     p->launches += p->launches_per_run;
+    return DAS_OK;
+}
+
+// Milliseconds of each stage of the last mode-2 replay: {score_topk, dense layers, refine+assemble, nms+backproject}.
+// The caller must have synchronised the stream.
+extern "C" int das_plan_stage_ms(das_plan* p, float* ms) {
+    using namespace das;
+    DAS_REQUIRE(p && ms, DAS_ERR_ARG, "das_plan_stage_ms: null pointer");
+    DAS_REQUIRE(p->exec_prof, DAS_ERR_ARG, "das_plan_stage_ms: no mode-2 run yet");
+    for (int i = 0; i < DAS_NUM_STAGES; ++i) DAS_CUDA_CHECK(cudaEventElapsedTime(&ms[i], p->ev[i], p->ev[i + 1]));
+    return DAS_OK;
+}
+
+extern "C" int das_plan_output_block(const das_plan* p, void** ptr, int64_t* bytes) {
+    using namespace das;
+    DAS_REQUIRE(p && ptr && bytes, DAS_ERR_ARG, "das_plan_output_block: null pointer");
+    *ptr = p->out_block;
+    *bytes = static_cast<int64_t>(p->out_block_bytes);
     return DAS_OK;
 }
 

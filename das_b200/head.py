@@ -216,9 +216,25 @@ class DecodePlan:
                                                    _stream_ptr(self.device)), "das_plan_set_metas")
 
     # ---- run -----------------------------------------------------------------------------------
-    def run(self, use_graph: bool = True):
+    def run(self, use_graph: bool = True, stage_events: bool = False):
+        """Enqueue one decode on the current stream: eager launches, a CUDA-graph replay, or a replay
+        with event nodes at the stage boundaries (then stage_ms() after a synchronize)."""
+        mode = 2 if stage_events else int(bool(use_graph))
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.das_plan_run(self._plan, _stream_ptr(self.device), int(use_graph)), "das_plan_run")
+            _lib.check(self.lib.das_plan_run(self._plan, _stream_ptr(self.device), mode), "das_plan_run")
+
+    def stage_ms(self) -> List[float]:
+        """[score_topk, dense layers, refine+assemble, nms+backproject] of the last stage_events run."""
+        arr = (C.c_float * 4)()
+        _lib.check(self.lib.das_plan_stage_ms(self._plan, arr), "das_plan_stage_ms")
+        return [float(x) for x in arr]
+
+    def output_block(self) -> torch.Tensor:
+        """uint8 view of the single device block holding every out_* buffer (one NCCL all-gather
+        moves a rank's whole result)."""
+        ptr, n = C.c_void_p(), C.c_int64()
+        _lib.check(self.lib.das_plan_output_block(self._plan, C.byref(ptr), C.byref(n)), "das_plan_output_block")
+        return torch.as_tensor(_DevArray(ptr.value, (n.value,), "|u1"), device=self.device)
 
     def run_host(self, levels: Sequence[dict], img_metas: Sequence[dict], host_out: Dict[str, torch.Tensor]):
         """End-to-end entry with HOST tensors (pinned for full PCIe speed): H2D of every input,
@@ -237,6 +253,22 @@ class DecodePlan:
     def alloc_host_out(self, pinned: bool = True) -> Dict[str, torch.Tensor]:
         return {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=pinned)
                 for k, v in self.t.items() if k.startswith("out_")}
+
+    def views_of_block(self, block: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Typed views into a copy of an output block (this rank's, or one gathered from a peer rank);
+        layout = das_plan_create's: [count | score | slot | pose | center | cam | world], 256 B aligned."""
+        B, P, J = self.batch, self.out_slots, self.cfg.num_joints
+        up = lambda v: (v + 255) & ~255
+        spec = [("out_count", torch.int32, (B,)), ("out_score", torch.float32, (B, P)), ("out_slot", torch.int32, (B, P)),
+                ("out_pose", torch.float32, (B, P, J, 3)), ("out_center", torch.float32, (B, P, 3)),
+                ("out_cam", torch.float64, (B, P, J, 3)), ("out_world", torch.float64, (B, P, J, 3))]
+        out, off = {}, 0
+        for name, dt, shape in spec:
+            n = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+            out[name] = block[off:off + n].view(dt).view(shape)
+            off = up(off + n)
+        assert off == block.numel(), (off, block.numel())
+        return out
 
     @property
     def kernel_launches(self) -> int:

@@ -36,6 +36,7 @@ extern "C" {
 #define DAS_MAX_JOINTS 32
 #define DAS_MAX_NMS_PRE 2048  /* per-level top-k capacity (reference configs use 1000) */
 #define DAS_CAM_DOUBLES 18    /* K[0,:3], K[1,:3], R row-major 3x3, t[3] */
+#define DAS_NUM_STAGES 4      /* score_topk | dense layers | refine+assemble | nms+backproject */
 
 typedef enum das_status {
     DAS_OK = 0,
@@ -162,8 +163,13 @@ int das_plan_set_weights(das_plan* plan, int32_t layer, const float* so_w, const
 int das_plan_bind(das_plan* plan, const das_levels* levels, void* stream);
 /* per-image metas from HOST memory: scale_xy [B,2] fp32, cam [B,18] fp64. */
 int das_plan_set_metas(das_plan* plan, const float* scale_xy, const double* cam, void* stream);
-/* enqueue one decode on `stream` (first call captures the graph). use_graph=0 launches eagerly. */
-int das_plan_run(das_plan* plan, void* stream, int32_t use_graph);
+/* enqueue one decode on `stream`. mode 0: eager launches; 1: CUDA-graph replay (captured on first
+ * use); 2: graph replay with event-record nodes at the stage boundaries (for das_plan_stage_ms). */
+int das_plan_run(das_plan* plan, void* stream, int32_t mode);
+/* per-stage milliseconds of the last mode-2 replay (stream must be synchronised): ms[DAS_NUM_STAGES] */
+int das_plan_stage_ms(das_plan* plan, float* ms);
+/* all out_* buffers are carved from one device block (one D2H, or one NCCL all-gather across ranks) */
+int das_plan_output_block(const das_plan* plan, void** ptr, int64_t* bytes);
 int das_plan_buffers(const das_plan* plan, das_buffers* out, int32_t* cand_slots, int32_t* out_slots);
 int64_t das_plan_kernel_launches(const das_plan* plan);   /* kernels enqueued by das_plan_run so far */
 
