@@ -57,6 +57,34 @@ def _check_f32(t: torch.Tensor, what: str):
         raise RuntimeError(f"{what}: the decode path only runs on CUDA tensors")
 
 
+_BLOCK_SPEC = (("out_count", torch.int32, 0), ("out_score", torch.float32, 1), ("out_slot", torch.int32, 1),
+               ("out_pose", torch.float32, 2), ("out_center", torch.float32, 3), ("out_cam", torch.float64, 2),
+               ("out_world", torch.float64, 2))
+
+
+def block_layout(B: int, P: int, J: int):
+    """(name, dtype, shape, byte offset) of every out_* buffer inside the packed output block, and its size.
+    Mirrors das_plan_create: [count | score | slot | pose | center | cam | world], each 256-byte aligned."""
+    shapes = {0: (B,), 1: (B, P), 2: (B, P, J, 3), 3: (B, P, 3)}
+    out, off = [], 0
+    for name, dt, kind in _BLOCK_SPEC:
+        shape = shapes[kind]
+        n = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+        out.append((name, dt, shape, off))
+        off = (off + n + 255) & ~255
+    return out, off
+
+
+def block_views(block: torch.Tensor, B: int, P: int, J: int) -> Dict[str, torch.Tensor]:
+    lay, total = block_layout(B, P, J)
+    assert block.dtype == torch.uint8 and block.numel() == total, (block.dtype, block.numel(), total)
+    views = {}
+    for name, dt, shape, off in lay:
+        n = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+        views[name] = block[off:off + n].view(dt).view(shape)
+    return views
+
+
 class DecodePlan:
     """One (batch, level shapes, config) instance of the C ``das_plan``."""
 
@@ -255,20 +283,8 @@ class DecodePlan:
                 for k, v in self.t.items() if k.startswith("out_")}
 
     def views_of_block(self, block: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """Typed views into a copy of an output block (this rank's, or one gathered from a peer rank);
-        layout = das_plan_create's: [count | score | slot | pose | center | cam | world], 256 B aligned."""
-        B, P, J = self.batch, self.out_slots, self.cfg.num_joints
-        up = lambda v: (v + 255) & ~255
-        spec = [("out_count", torch.int32, (B,)), ("out_score", torch.float32, (B, P)), ("out_slot", torch.int32, (B, P)),
-                ("out_pose", torch.float32, (B, P, J, 3)), ("out_center", torch.float32, (B, P, 3)),
-                ("out_cam", torch.float64, (B, P, J, 3)), ("out_world", torch.float64, (B, P, J, 3))]
-        out, off = {}, 0
-        for name, dt, shape in spec:
-            n = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
-            out[name] = block[off:off + n].view(dt).view(shape)
-            off = up(off + n)
-        assert off == block.numel(), (off, block.numel())
-        return out
+        """Typed views into a copy of an output block (this rank's, or one gathered from a peer rank)."""
+        return block_views(block, self.batch, self.out_slots, self.cfg.num_joints)
 
     @property
     def kernel_launches(self) -> int:

@@ -80,7 +80,7 @@ def _smooth(x: torch.Tensor, k: int = 9) -> torch.Tensor:
 
 def make_level(cfg: HeadConfig, batch: int, h: int, w: int, stride: int, seed: int, device="cpu",
                peaks: int = 16, smooth: int = 9, scales=(1.0, 1.0, 1.0, 1.0), channels_last: bool = True,
-               with_feats: bool = True) -> dict:
+               with_feats: bool = True, coherent: int = 0) -> dict:
     g = _gen(seed, device)
     J, C = cfg.num_joints, cfg.feat_channels
 
@@ -112,6 +112,18 @@ def make_level(cfg: HeadConfig, batch: int, h: int, w: int, stride: int, seed: i
     uvd = _smooth(randn(batch, 3 * J, h, w), smooth)
     uvd[:, 0::3] *= 4.0
     uvd[:, 1::3] *= 4.0
+    if coherent > 0:
+        # person-like fields: every cell of a coherent x coherent block points at the same joints (u = target - x),
+        # so neighbouring candidates decode to near-identical poses and OKS-NMS has something to suppress
+        blk = coherent
+        ys = torch.arange(h, device=device, dtype=torch.float32).view(1, 1, h, 1)
+        xs = torch.arange(w, device=device, dtype=torch.float32).view(1, 1, 1, w)
+        bh, bw = -(-h // blk), -(-w // blk)
+        per_block = randn(batch, 3 * J, bh, bw)
+        per_block = per_block.repeat_interleave(blk, 2)[:, :, :h].repeat_interleave(blk, 3)[:, :, :, :w]
+        uvd = 0.02 * uvd + per_block
+        uvd[:, 0::3] = uvd[:, 0::3] * 4.0 + (torch.floor(xs / blk) * blk + blk / 2 - xs)
+        uvd[:, 1::3] = uvd[:, 1::3] * 4.0 + (torch.floor(ys / blk) * blk + blk / 2 - ys)
     pose[:, 3:3 + 3 * J] = uvd
     pose[:, 3 + 3 * J:] = randn(batch, 3 * J, h, w)
 

@@ -58,6 +58,12 @@ def cell_centres(h: int, w: int, dtype=torch.float32) -> torch.Tensor:
 # --------------------------------------------------------------------------
 # progressive refinement (dense, as the reference runs it)
 # --------------------------------------------------------------------------
+def _f32_unless_f64(t: torch.Tensor) -> torch.Tensor:
+    """The reference forces ``.float()`` before grid_sample (recursive_update.py:25,56).  Feeding float64
+    maps keeps float64 instead: that is the fp64 ARBITER mode the noise-floor tests use."""
+    return t if t.dtype == torch.float64 else t.float()
+
+
 def project_1x1(feat: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     """nn.Conv2d(C, O, 1) forward: weight [O, C], bias [O]."""
     return F.conv2d(feat, weight[:, :, None, None], bias)
@@ -92,7 +98,7 @@ def progressive_sample(uvd, samp_off, joint_conf, num_joints: int, num_heads: in
     # heads anchored at the current joint estimate ("from target")
     tgt = ((pts + to_target) / wh).permute(0, 2, 3, 1)
     so_map = samp_off.view(bj, num_heads * 2, h, w)
-    from_target = F.grid_sample(so_map.float(), 2 * tgt - 1, mode="bilinear",
+    from_target = F.grid_sample(_f32_unless_f64(so_map), 2 * tgt - 1, mode="bilinear",
                                 padding_mode="zeros", align_corners=False)
     from_target = from_target.view(bj, num_heads, 2, h, w) + to_target[:, None]
     # heads anchored at the source cell ("from source")
@@ -109,7 +115,7 @@ def progressive_sample(uvd, samp_off, joint_conf, num_joints: int, num_heads: in
     else:
         diff = heads
     stacked = torch.cat([off, conf], dim=1)
-    sampled = F.grid_sample(stacked.float(), 2 * loc - 1, mode="bilinear",
+    sampled = F.grid_sample(_f32_unless_f64(stacked), 2 * loc - 1, mode="bilinear",
                             padding_mode="zeros", align_corners=False)
     s_off, s_conf = torch.split(sampled, [dim, dim], dim=1)
     per_head = s_off + diff

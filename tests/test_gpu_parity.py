@@ -1,0 +1,321 @@
+"""GPU: the CUDA path, called through the C-ABI plan, against the CPU oracle on the same seeded inputs,
+against the golden vectors of the reference's own code, and through size-independent properties at
+the full BASELINE size.
+
+Bars: person order / selected cells bit-exact when every rank boundary has a
+margin >= 16 ulp (the CPU reference's own fp32 sigmoid is only accurate to ~2 ulp);
+scores within 8 ulp; 3D joint coordinates within 1e-4 relative to their magnitude (floor 1 unit).
+"""
+import dataclasses
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import util
+from das_b200 import synth
+from das_b200.head import DASHeadB200
+from oracle import das_oracle as O
+from oracle import make_golden as G
+
+pytestmark = pytest.mark.gpu
+
+P = synth.PANOPTIC
+TOL = 1e-4
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def compare(plan, got, ref, margin, strict_order=True):
+    ci = plan.t["cand_index"].cpu()
+    for b, (g, o) in enumerate(zip(got, ref)):
+        lv, idx = util.slot_to_level_index(plan, g["slots"].cpu(), ci[b])
+        ref_pairs = list(zip(o["level"].tolist(), o["index"].tolist()))
+        if margin >= 16 and strict_order:
+            assert list(zip(lv, idx)) == ref_pairs, f"image {b}: person order differs (margin {margin} ulp)"
+        else:
+            assert sorted(zip(lv, idx)) == sorted(ref_pairs) or margin < 16, f"image {b}: selected set differs"
+            if list(zip(lv, idx)) != ref_pairs:
+                continue
+        if not idx:
+            assert g["poses"].shape[0] == 0
+            continue
+        assert int(util.ulp_gap(torch.tensor(g["scores"]), o["scores"]).max()) <= 8
+        assert util.rel_err(g["poses"].cpu().numpy(), o["poses"].numpy()) < TOL
+        assert util.rel_err(g["centers"].cpu().numpy(), o["centers"].numpy()) < TOL
+        assert util.rel_err(g["poses_cam"].cpu().numpy(), o["poses_cam"]) < TOL
+        assert util.rel_err(g["poses_world"].cpu().numpy(), o["poses_world"]) < TOL
+        assert torch.all(g["vis"] == 1)
+
+
+CASES = [
+    # id, cfg, B, H, W, test_cfg, kwargs
+    ("small", P, 2, 24, 40, dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0), {}),
+    ("cfg1_128x208", P, 1, 128, 208, dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0), {}),
+    ("scales_thr", P, 2, 64, 96, dict(nms_pre=50, nms_post=20, nms_thr=0.9, score_thr=0.07),
+     dict(scales=(1.1, 0.9, 1.05, 0.95), peaks=24)),
+    ("pyramid4", dataclasses.replace(P, strides=(8, 16, 32, 64)), 2, 64, 96,
+     dict(nms_pre=100, nms_post=30, nms_thr=0.9, score_thr=0.05), dict(peaks=24)),
+    ("mupots17", dataclasses.replace(synth.MUPOTS17, num_layers=1), 2, 48, 64,
+     dict(nms_pre=20, nms_post=20, nms_thr=0.9, score_thr=0.0), {}),
+    ("coherent_nms", P, 2, 48, 64, dict(nms_pre=30, nms_post=30, nms_thr=0.9, score_thr=0.0), dict(coherent=8)),
+    ("reference_cfg", P, 1, 80, 144, dict(nms_pre=1000, nms_post=100, nms_thr=0.9, score_thr=0.07), dict(peaks=30)),
+    ("crowded_cfg4", P, 1, 256, 416, dict(nms_pre=64, nms_post=64, nms_thr=0.9, score_thr=0.0), dict(peaks=80)),
+    ("no_nms", P, 2, 24, 40, dict(nms_pre=12, nms_thr=0.9, score_thr=0.02), {}),
+    ("odd_size_unaligned", P, 3, 23, 37, dict(nms_pre=9, nms_post=9, nms_thr=0.9, score_thr=0.0), {}),
+]
+
+
+@pytest.mark.parametrize("case_id,cfg,B,H,W,tc,kw", CASES, ids=[c[0] for c in CASES])
+def test_full_path_matches_oracle(case_id, cfg, B, H, W, tc, kw):
+    case = util.make_case(cfg, B, H, W, seed=1234, **kw)
+    ref, _ = util.run_oracle(case, tc)
+    plan, got = util.run_gpu(case, tc, refine=True)
+    margin = util.rank_margin_ulps(case["levels"], tc.get("nms_pre", -1), tc.get("score_thr", 0.0))
+    compare(plan, got, ref, margin)
+
+
+@pytest.mark.parametrize("case_id,cfg,B,H,W,tc,kw", CASES[:5], ids=[c[0] for c in CASES[:5]])
+def test_reference_contract_decode_only(case_id, cfg, B, H, W, tc, kw):
+    """get_poses with already-refined pose maps (the reference signature): the decode arithmetic is the same
+    fp32 op sequence, so poses must be BIT-equal to the oracle's."""
+    case = util.make_case(cfg, B, H, W, seed=99, **kw)
+    ref, pose_preds = util.run_oracle(case, tc)
+    plan, got = util.run_gpu(case, tc, refine=False, pose_override=pose_preds)
+    margin = util.rank_margin_ulps(case["levels"], tc.get("nms_pre", -1), tc.get("score_thr", 0.0))
+    compare(plan, got, ref, margin)
+    if margin >= 16:
+        for g, o in zip(got, ref):
+            assert torch.equal(g["poses"].cpu(), o["poses"]) and torch.equal(g["centers"].cpu(), o["centers"])
+
+
+@pytest.mark.parametrize("name", sorted(G.CASES))
+def test_golden_vectors_of_the_reference(name):
+    if G.CASES[name][0].num_layers > 1:
+        pytest.skip("num_layers > 1 is covered by test_gpu_dense_layers.py")
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cfg, levels, layers, metas, tc = G.build_case(name)
+    np.testing.assert_allclose(G.checksum(levels), gold["checksum"], rtol=1e-9, atol=1e-6)
+    case = dict(cfg=cfg, levels=levels, layers=layers, metas=metas, batch=levels[0]["cls"].shape[0])
+    plan, got = util.run_gpu(case, tc, refine=True)
+    margin = util.rank_margin_ulps(levels, tc.get("nms_pre", -1), tc.get("score_thr", 0.0))
+    ci = plan.t["cand_index"].cpu()
+    for i, g in enumerate(got):
+        lv, idx = util.slot_to_level_index(plan, g["slots"].cpu(), ci[i])
+        if margin >= 16:
+            assert idx == gold[f"index_{i}"].tolist() and lv == gold[f"level_{i}"].tolist()
+        elif idx != gold[f"index_{i}"].tolist():
+            continue
+        assert util.rel_err(g["poses"].cpu().numpy(), gold[f"poses_{i}"]) < TOL
+        assert util.rel_err(g["poses_cam"].cpu().numpy(), gold[f"cam_{i}"]) < TOL
+        assert util.rel_err(g["poses_world"].cpu().numpy(), gold[f"world_{i}"]) < TOL
+
+
+def test_peak_mask_mode_matches_oracle_variant():
+    tc = dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)
+    for (h, w) in ((48, 64), (130, 210)):
+        case = util.make_case(P, 2, h, w, seed=5)
+        ref, _ = util.run_oracle(case, tc, peak_kernel=3)
+        plan, got = util.run_gpu(case, tc, refine=True, peak_kernel=3)
+        compare(plan, got, ref, margin=10 ** 6)
+        # a 3x3 bump contributes exactly one candidate under the peak mask
+        for g in got:
+            assert len(set(g["slots"].tolist())) == len(g["scores"])
+
+
+def test_ties_break_towards_lower_index():
+    """Constant logits: every score ties. Rule: lower cell index first (north_star), pinned by the stable oracle."""
+    tc = dict(nms_pre=7, nms_thr=0.9, score_thr=0.0)         # no nms_post: order = top-k order
+    case = util.make_case(P, 2, 16, 20, seed=3)
+    for lv in case["levels"]:
+        lv["cls"].fill_(0.25)
+        lv["ctr"].fill_(-0.5)
+        lv["cls"][0, 0, 5, 7] = 3.0                           # one clear winner, then ties
+    ref, _ = util.run_oracle(case, tc, stable=True)
+    plan, got = util.run_gpu(case, tc, refine=True)
+    ci = plan.t["cand_index"].cpu()
+    assert ci[0, :7].tolist() == [5 * 20 + 7, 0, 1, 2, 3, 4, 5]
+    assert ci[1, :7].tolist() == [0, 1, 2, 3, 4, 5, 6]
+    compare(plan, got, ref, margin=10 ** 6)
+
+
+def test_large_k_exact_select_with_many_ties():
+    """K > 128 takes the exact radix path; quantised logits create heavy ties at the K-th score."""
+    tc = dict(nms_pre=300, nms_thr=0.9, score_thr=0.0)
+    case = util.make_case(P, 2, 40, 50, seed=8)
+    for lv in case["levels"]:
+        lv["cls"].copy_(torch.round(lv["cls"] * 2) / 2)
+        lv["ctr"].fill_(0.0)
+    ref, _ = util.run_oracle(case, tc, stable=True)
+    plan, got = util.run_gpu(case, tc, refine=True)
+    ci = plan.t["cand_index"].cpu()
+    for b, o in enumerate(ref):
+        assert ci[b].tolist() == o["cand_index"].tolist()
+
+
+def test_nothing_survives_score_thr():
+    tc = dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.9999)
+    case = util.make_case(P, 2, 24, 40, seed=11)
+    plan, got = util.run_gpu(case, tc, refine=True)
+    for g in got:
+        assert g["poses"].shape == (0, 15, 3) and g["scores"] == [] and g["centers"].shape == (0, 3)
+
+
+def test_pass_through_level_keeps_raster_order():
+    """HW <= nms_pre: no top-k, every cell in raster order (das_head.py:717)."""
+    tc = dict(nms_pre=100, nms_thr=0.9, score_thr=0.0)
+    case = util.make_case(P, 1, 6, 9, seed=12)
+    ref, _ = util.run_oracle(case, tc)
+    plan, got = util.run_gpu(case, tc, refine=True)
+    assert plan.t["cand_index"].cpu()[0].tolist() == list(range(54))
+    compare(plan, got, ref, margin=10 ** 6)
+
+
+def test_targets_outside_the_map_sample_zero():
+    """Huge offsets push every sampling location out of the map: grid_sample's zero padding."""
+    tc = dict(nms_pre=8, nms_post=8, nms_thr=0.9, score_thr=0.0)
+    case = util.make_case(P, 2, 20, 28, seed=13)
+    J = P.num_joints
+    for lv in case["levels"]:
+        lv["pose_raw"][:, 3:3 + 3 * J:3] += 500.0
+        lv["pose_raw"][1, 4:3 + 3 * J:3] -= 37.25      # and some joints only partially outside
+    ref, _ = util.run_oracle(case, tc)
+    plan, got = util.run_gpu(case, tc, refine=True)
+    compare(plan, got, ref, margin=util.rank_margin_ulps(case["levels"], 8))
+
+
+def test_white_noise_fields_within_reference_noise_floor():
+    """Unsmoothed pose fields amplify fp32 coordinate round-off; the fp64 run of the same algorithm arbitrates:
+    the GPU must be as close to it as the fp32 reference is, within 3x + 1e-5."""
+    tc = dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)
+    case = util.make_case(P, 2, 32, 48, seed=21, smooth=1)
+    ref32, _ = util.run_oracle(case, tc)
+    case64 = dict(case)
+    case64["levels"] = [dict(lv, cls=lv["cls"], ctr=lv["ctr"], pose_raw=lv["pose_raw"].double(),
+                             feats=[f.double() for f in lv["feats"]]) for lv in case["levels"]]
+    case64["layers"] = [{k: v.double() for k, v in l.items()} for l in case["layers"]]
+    pp64 = [O.head_eval_tail(lv["pose_raw"], lv["feats"], case64["layers"], lv["scales"], num_joints=15, num_heads=4,
+                             root_idx=2, depth_factor=20.0, z_norm=50.0, stride=lv["stride"]) for lv in case64["levels"]]
+    ref64 = O.get_poses([lv["cls"] for lv in case["levels"]], [p.float() for p in pp64],
+                        [lv["ctr"] for lv in case["levels"]], case["metas"], tc, [8], 15)
+    plan, got = util.run_gpu(case, tc, refine=True)
+    for g, a, e in zip(got, ref32, ref64):
+        if a["index"].tolist() != e["index"].tolist():
+            continue
+        err_ref = util.rel_err(a["poses"].numpy(), e["poses"].numpy())
+        err_gpu = util.rel_err(g["poses"].cpu().numpy(), e["poses"].numpy())
+        assert err_gpu <= 3 * err_ref + 1e-5, (err_gpu, err_ref)
+
+
+def test_graph_replay_eager_and_repeat_are_identical():
+    tc = dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)
+    case = util.make_case(P, 4, 32, 48, seed=31)
+    plan, got = util.run_gpu(case, tc, refine=True, use_graph=False)
+    a = plan.output_block().clone()
+    for _ in range(3):
+        plan.run(use_graph=True)
+    torch.cuda.synchronize()
+    b = plan.output_block().clone()
+    plan.run(stage_events=True)
+    torch.cuda.synchronize()
+    c = plan.output_block().clone()
+    assert torch.equal(a, b) and torch.equal(a, c)
+    assert all(t >= 0 for t in plan.stage_ms())
+    assert plan.kernel_launches >= 3 * 5
+
+
+def test_host_entry_equals_device_entry():
+    tc = dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)
+    case = util.make_case(P, 3, 24, 40, seed=41, scales=(1.1, 0.9, 1.05, 0.95))
+    plan, got = util.run_gpu(case, tc, refine=True)
+    host_levels = [dict(cls=lv["cls"].pin_memory(), ctr=lv["ctr"].pin_memory(), pose=lv["pose_raw"].pin_memory(),
+                        feats=[f.permute(0, 2, 3, 1).contiguous().pin_memory().permute(0, 3, 1, 2) for f in lv["feats"]],
+                        scales=lv["scales"]) for lv in case["levels"]]
+    out = plan.alloc_host_out()
+    plan.run_host(host_levels, case["metas"], out)
+    res = plan.results(case["metas"], src=out)
+    for g, h in zip(got, res):
+        assert g["scores"] == h["scores"] and torch.equal(g["poses"].cpu(), h["poses"]) and torch.equal(g["poses_cam"].cpu(), h["poses_cam"])
+    assert plan.h2d_bytes > 3 * 24 * 40 * 256 * 4 and plan.d2h_bytes > 0
+
+
+def test_drop_in_head_api():
+    """DASHeadB200.get_poses with the reference signature and return structure (das_head.py:653-688)."""
+    tc = dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)
+    case = util.make_case(P, 2, 24, 40, seed=51)
+    ref, pose_preds = util.run_oracle(case, tc)
+    head = DASHeadB200(num_classes=1, in_channels=256, num_joints=15, strides=[8], depth_factor=20, z_norm=50, root_idx=2,
+                       recursive_update=dict(num_heads=4, feat_channels=256, num_layers=1, dim=3, num_joints=15), test_cfg=tc,
+                       loss_cls=dict(type="FocalLoss"), train_cfg=None)       # unrelated keys are accepted
+    dl = synth.levels_to(case["levels"], "cuda")
+    # (a) reference call: refined maps
+    res = head.get_poses([lv["cls"] for lv in dl], [p.cuda() for p in pose_preds], [lv["ctr"] for lv in dl], case["metas"],
+                         rescale=True)
+    assert isinstance(res, list) and len(res) == 2
+    for r, o, m in zip(res, ref, case["metas"]):
+        assert set(r) >= {"poses", "vis", "centers", "image_paths", "scores", "poses_cam"}
+        assert isinstance(r["scores"], list) and r["image_paths"] == [m["filename"]]
+        assert r["poses"].is_cuda and tuple(r["poses"].shape) == tuple(o["poses"].shape) and r["vis"].shape == r["poses"].shape[:2]
+        assert util.rel_err(r["poses"].cpu().numpy(), o["poses"].numpy()) < TOL
+    # (b) extended call: raw maps + refinement features
+    head.load_refine_weights(synth.layers_to(case["layers"], "cuda"))
+    res2 = head.get_poses([lv["cls"] for lv in dl], [lv["pose_raw"] for lv in dl], [lv["ctr"] for lv in dl],
+                          [lv["feats"] for lv in dl], case["metas"])
+    for r, o in zip(res2, ref):
+        assert util.rel_err(r["poses_cam"].cpu().numpy(), o["poses_cam"]) < TOL
+    # (c) the reference's assert on mismatched level lists
+    with pytest.raises(AssertionError):
+        head.get_poses([dl[0]["cls"]], [], [dl[0]["ctr"]], case["metas"])
+
+
+def test_full_size_properties_config2():
+    """BASELINE config #2 (B=64, 128x208, K=10) generated on the device; properties the domain offers."""
+    tc = dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)
+    B, H, W = 64, 128, 208
+    dev = torch.device("cuda")
+    levels = synth.make_levels(P, B, H, W, seed=1234, device=dev)
+    layers = synth.make_layers(P, seed=1235, device=dev)
+    metas = synth.make_metas(B, H, W)
+    case = dict(cfg=P, levels=levels, layers=layers, metas=metas, batch=B)
+    plan = util.make_plan(case, tc)
+    lv = levels[0]
+    plan.bind([dict(cls=lv["cls"], ctr=lv["ctr"], pose=lv["pose_raw"], feats=lv["feats"], scales=lv["scales"])])
+    plan.set_metas(metas)
+    plan.run()
+    torch.cuda.synchronize()
+    t = {k: v.clone() for k, v in plan.t.items()}
+    # selected cells are exactly torch.topk's on the same device scores (set equality; ordering by score)
+    score = (lv["cls"].sigmoid() * lv["ctr"].sigmoid()).flatten(1)
+    top_v, top_i = score.topk(10, dim=1)
+    assert torch.equal(torch.sort(t["cand_index"].long(), 1)[0], torch.sort(top_i, 1)[0])
+    assert torch.all(t["cand_score"][:, :-1] >= t["cand_score"][:, 1:])
+    assert int(util.ulp_gap(t["cand_score"].cpu(), top_v.cpu()).max()) <= 8
+    # counts, ordering and finiteness of the outputs
+    cnt = t["out_count"]
+    assert int(cnt.min()) >= 1 and int(cnt.max()) <= 10
+    for b in range(0, B, 7):
+        n = int(cnt[b])
+        s = t["out_score"][b, :n]
+        assert torch.all(s[:-1] >= s[1:])
+        assert torch.isfinite(t["out_pose"][b, :n]).all() and torch.isfinite(t["out_cam"][b, :n]).all()
+        assert torch.all(t["out_score"][b, n:] == 0)
+    # batch independence: image 5 decoded alone gives the same rows (images are independent, das_head.py:666)
+    one = dict(cfg=P, levels=[dict(lv, cls=lv["cls"][5:6], ctr=lv["ctr"][5:6], pose_raw=lv["pose_raw"][5:6],
+                                   feats=[f[5:6] for f in lv["feats"]])], layers=layers, metas=metas[5:6], batch=1)
+    p1 = util.make_plan(one, tc)
+    l1 = one["levels"][0]
+    p1.bind([dict(cls=l1["cls"], ctr=l1["ctr"], pose=l1["pose_raw"], feats=l1["feats"], scales=l1["scales"])])
+    p1.set_metas(metas[5:6])
+    p1.run()
+    torch.cuda.synchronize()
+    assert torch.equal(p1.t["out_pose"][0], t["out_pose"][5]) and torch.equal(p1.t["out_cam"][0], t["out_cam"][5])
+    # spot parity against the CPU oracle for two images of the full-size batch
+    sub = [dict(lv, cls=lv["cls"][b:b + 1].cpu(), ctr=lv["ctr"][b:b + 1].cpu(), pose_raw=lv["pose_raw"][b:b + 1].cpu(),
+                feats=[f[b:b + 1].cpu() for f in lv["feats"]]) for b in (0, 63)]
+    lay_cpu = synth.layers_to(layers, "cpu")
+    for b, s in zip((0, 63), sub):
+        ref, _ = O.decode_full([s], lay_cpu, metas[b:b + 1], P.as_dict(), tc)
+        n = int(cnt[b])
+        if t["cand_index"][b, t["out_slot"][b, :n].long()].tolist() == ref[0]["index"].tolist():
+            assert util.rel_err(t["out_cam"][b, :n].cpu().numpy(), ref[0]["poses_cam"]) < TOL

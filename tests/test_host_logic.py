@@ -1,0 +1,78 @@
+"""CPU: host-side logic of the drop-in head -- sharding, meta packing, output-block layout, and that
+the product path refuses to run without its CUDA library/device (no silent fallback)."""
+import numpy as np
+import pytest
+import torch
+
+from das_b200 import dist as ddist
+from das_b200 import head as H
+from das_b200 import synth
+
+
+def test_shard_bounds_partition_the_batch():
+    for total in (1, 7, 64, 128):
+        for world in (1, 2, 3, 4, 8):
+            spans = [ddist.shard_bounds(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_pack_metas_layout():
+    metas = synth.make_metas(3, 16, 24)
+    sxy, cam = H.DecodePlan.pack_metas(metas)
+    assert sxy.shape == (3, 2) and cam.shape == (3, 18) and sxy.dtype == np.float32 and cam.dtype == np.float64
+    for b, m in enumerate(metas):
+        assert np.array_equal(sxy[b], m["scale_factor"][:2])
+        assert np.array_equal(cam[b, :3], m["cam"]["K"][0]) and np.array_equal(cam[b, 3:6], m["cam"]["K"][1])
+        assert np.array_equal(cam[b, 6:15], m["cam"]["R"].reshape(9)) and np.array_equal(cam[b, 15:], m["cam"]["t"].reshape(3))
+    # MuPoTS-style 2x3 intrinsics and a missing 'cam' (identity) are accepted
+    sxy, cam = H.DecodePlan.pack_metas([dict(scale_factor=np.ones(4, np.float32), cam=dict(K=np.arange(6.).reshape(2, 3))),
+                                        dict(scale_factor=np.ones(4, np.float32))])
+    assert cam[0, :6].tolist() == [0, 1, 2, 3, 4, 5] and cam[1, 6:15].tolist() == np.eye(3).reshape(9).tolist()
+
+
+def test_block_layout_is_aligned_and_roundtrips():
+    B, P, J = 3, 10, 15
+    lay, total = H.block_layout(B, P, J)
+    assert total % 256 == 0 and all(off % 256 == 0 for *_, off in lay)
+    block = torch.zeros(total, dtype=torch.uint8)
+    v = H.block_views(block, B, P, J)
+    v["out_count"][:] = torch.tensor([1, 2, 3], dtype=torch.int32)
+    v["out_cam"][2, 9, 14, 2] = 7.5
+    w = H.block_views(block.clone(), B, P, J)
+    assert w["out_count"].tolist() == [1, 2, 3] and float(w["out_cam"][2, 9, 14, 2]) == 7.5
+    assert w["out_pose"].shape == (B, P, J, 3) and w["out_world"].dtype == torch.float64
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_product_path_fails_loudly_without_cuda():
+    head = H.DASHeadB200(num_joints=15, strides=(8,), depth_factor=20, z_norm=50, root_idx=2,
+                         test_cfg=dict(nms_pre=10, nms_post=10))
+    cls = torch.zeros(1, 1, 8, 8)
+    pose = torch.zeros(1, 93, 8, 8)
+    metas = synth.make_metas(1, 8, 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        head.get_poses([cls], [pose], [cls], metas)
+
+
+def test_head_rejects_unsupported_config_keys():
+    with pytest.raises(AssertionError):
+        H.DASHeadB200(num_classes=2, num_joints=15, root_idx=2)
+    head = H.DASHeadB200(num_joints=15, strides=(8,), root_idx=2, test_cfg=dict(nms_type="soft", nms_pre=10, nms_post=10))
+    if not torch.cuda.is_available():
+        with pytest.raises((NotImplementedError, RuntimeError)):
+            head.get_poses([torch.zeros(1, 1, 4, 4)], [torch.zeros(1, 93, 4, 4)], [torch.zeros(1, 1, 4, 4)],
+                           synth.make_metas(1, 4, 4))
+
+
+def test_product_package_never_imports_the_oracle():
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "das_b200")
+    for dp, _, fs in os.walk(root):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f"{f} imports the oracle"

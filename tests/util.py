@@ -11,8 +11,9 @@ from oracle import das_oracle as O
 
 
 def make_case(cfg: synth.HeadConfig, batch, h, w, seed=1234, peaks=16, scales=(1.0, 1.0, 1.0, 1.0), smooth=9,
-              identity_rt=False):
-    levels = synth.make_levels(cfg, batch, h, w, seed=seed, peaks=peaks, scales=scales, smooth=smooth)
+              identity_rt=False, coherent=0):
+    levels = synth.make_levels(cfg, batch, h, w, seed=seed, peaks=peaks, scales=scales, smooth=smooth,
+                               coherent=coherent)
     layers = synth.make_layers(cfg, seed=seed + 1)
     metas = synth.make_metas(batch, h, w, stride=cfg.strides[0], seed=seed + 2, identity_rt=identity_rt)
     return dict(cfg=cfg, levels=levels, layers=layers, metas=metas, batch=batch)
