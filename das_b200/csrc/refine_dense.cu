@@ -1,11 +1,199 @@
-// Dense RecursiveUpdateLayer over a whole level (layers 1..L-1 when num_layers > 1).
-// Reference: recursive_update.py:220-235 (layer), :186-197 (projections + gated blend), :34-82 (sampling).
-#include "das_common.cuh"
+// Dense RecursiveUpdateLayer over a whole level -- layers 1..L-1 when recursive_update.num_layers > 1
+// (the last layer is always evaluated sparsely by refine_sparse.cu).
+//
+// Reference: recursive_update.py:220-235 (layer), :186-197 (four 1x1 projections + gated blend),
+// :34-82 and :9-31 (progressive sampling).  The reference materialises a [B*J*2nh, 6, H, W] tensor with
+// repeat_interleave/cat and runs two full grid_samples over it; here the layer is two kernels:
+//   dense_project_kernel  F[B,HW,C] (NHWC) x W[17J,C] -> proj[B,HW,J,14] = {S(2nh), conf(3), blended O(3)}
+//   dense_sample_kernel   one thread per (cell, joint): 4 + 2nh*4 bilinear taps in proj -> uvd_out[B,HW,3J]
+// This first version of the projection is fp32 SIMT (warp per 8 cells, same building blocks as the sparse
+// kernel); it is the parity reference for the tcgen05 GEMM that replaces it.
+#include <algorithm>
+
+#include "refine_common.cuh"
+
+namespace das {
+
+constexpr int DP_WARPS = 8;
+
+struct DenseParams {
+    const das_levels* lv;
+    const float* wpack;
+    const float* uvd_in;   // nullptr -> scaled raw uvd from lv.pose (layer 0); else NHWC [B,HW,3J]
+    float* uvd_out;        // NHWC [B,HW,3J]
+    float* proj;           // [B,HW,J,PW]
+    int level, layer, J, root, B;
+};
+
+template <int CPL, int NH>
+__global__ void __launch_bounds__(DP_WARPS * 32)
+dense_project_kernel(const DenseParams p) {
+    constexpr int C = CPL * 32;
+    constexpr int NOUT = 2 * NH + 9, PW = 2 * NH + 6;
+    constexpr int O_GATE = 2 * NH, O_VAL = 2 * NH + 3, O_CONF = 2 * NH + 6;
+    const das_level_desc& d = p.lv->lv[p.level];
+    const int HW = d.H * d.W, J = p.J;
+    const long long total = static_cast<long long>(p.B) * HW;
+    const int lane = threadIdx.x & 31;
+    const int r = (lane >> 2) & 7, q = lane & 3;
+    const long long n_groups = (total + 7) / 8;
+    const float* __restrict__ F = d.feats[p.layer];
+    for (long long g = static_cast<long long>(blockIdx.x) * DP_WARPS + (threadIdx.x >> 5); g < n_groups;
+         g += static_cast<long long>(gridDim.x) * DP_WARPS) {
+        const long long base = g * 8;
+        Row<CPL> f[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const bool ok = base + k < total;
+            f[k] = load_row<CPL>(F + (ok ? base + k : 0) * C, lane, ok);
+        }
+        const long long cell = base + r;             // the cell this lane post-processes
+        const bool live = cell < total;
+        const int b = live ? static_cast<int>(cell / HW) : 0;
+        const int pix = live ? static_cast<int>(cell - static_cast<long long>(b) * HW) : 0;
+        for (int j = 0; j < J; ++j) {
+            const float* __restrict__ Wj = p.wpack + static_cast<size_t>(j) * NOUT * C;
+            const float* __restrict__ Bj = p.wpack + static_cast<size_t>(J) * NOUT * C + j * NOUT;
+            float res[NOUT];
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) {
+                const Row<CPL> w = load_row<CPL>(Wj + o * C, lane, true);
+                float acc[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = dot_row<CPL>(f[k], w);
+                res[o] = reduce8_transposed(acc, lane) + __ldg(Bj + o);
+            }
+            if (!live) continue;
+            float* out = p.proj + (static_cast<size_t>(cell) * J + j) * PW;
+            // the quad of lanes owning this cell shares the 14 stores: lane q writes S[2q], S[2q+1] and dim q
+#pragma unroll
+            for (int o = 0; o < 2 * NH; ++o)
+                if ((o >> 1) == q) out[o] = res[o];
+            if (q < 3) {
+                const float rg = q == 0 ? res[O_GATE] : (q == 1 ? res[O_GATE + 1] : res[O_GATE + 2]);
+                const float rn = q == 0 ? res[O_VAL] : (q == 1 ? res[O_VAL + 1] : res[O_VAL + 2]);
+                const float rc = q == 0 ? res[O_CONF] : (q == 1 ? res[O_CONF + 1] : res[O_CONF + 2]);
+                float prev;
+                if (p.uvd_in) prev = __ldg(p.uvd_in + static_cast<size_t>(cell) * 3 * J + 3 * j + q);
+                else if (q == 2 && j == p.root) prev = 0.f;
+                else prev = __ldg(d.pose + (static_cast<size_t>(b) * (3 + 6 * J) + 3 + 3 * j + q) * HW + pix) *
+                            (q < 2 ? d.scale_uv : d.scale_d);
+                const float gate = sigmoid_acc(rg);
+                out[2 * NH + q] = rc;                                                       // confidence logits
+                out[2 * NH + 3 + q] = __fadd_rn(__fmul_rn(1.0f - gate, prev), __fmul_rn(gate, rn));  // blended offset
+            }
+        }
+    }
+}
+
+template <int NH>
+__global__ void __launch_bounds__(256)
+dense_sample_kernel(const DenseParams p) {
+    constexpr int PW = 2 * NH + 6;
+    const das_level_desc& d = p.lv->lv[p.level];
+    const int H = d.H, W = d.W, HW = H * W, J = p.J;
+    const float fW = static_cast<float>(W), fH = static_cast<float>(H);
+    const long long total = static_cast<long long>(p.B) * HW * J;
+    for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+         t += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int j = static_cast<int>(t % J);
+        const long long cell = t / J;
+        const int b = static_cast<int>(cell / HW);
+        const int pix = static_cast<int>(cell - static_cast<long long>(b) * HW);
+        const int y = pix / W, x = pix - y * W;
+        const float* __restrict__ pj = p.proj + static_cast<size_t>(b) * HW * J * PW + static_cast<size_t>(j) * PW;
+        auto at = [&](int px) { return pj + static_cast<size_t>(px) * J * PW; };
+        const float* me = at(pix);
+        const float ox = me[2 * NH + 3], oy = me[2 * NH + 4];
+        float hx[2 * NH], hy[2 * NH];
+        {
+            const Corner ct = make_corner(sample_coord(x, ox, fW), sample_coord(y, oy, fH), W, H);
+            float s[2 * NH];
+#pragma unroll
+            for (int o = 0; o < 2 * NH; ++o) s[o] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!corner_ok(ct, k, W, H)) continue;
+                const float wk = corner_wgt(ct, k);
+                const float* c = at(corner_pix(ct, k, W));
+#pragma unroll
+                for (int o = 0; o < 2 * NH; ++o) s[o] = __fadd_rn(s[o], __fmul_rn(c[o], wk));
+            }
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                hx[h] = s[2 * h] + ox;
+                hy[h] = s[2 * h + 1] + oy;
+                hx[NH + h] = me[2 * h];
+                hy[NH + h] = me[2 * h + 1];
+            }
+        }
+        float hv[2 * NH][3], hc[2 * NH][3];
+#pragma unroll
+        for (int h = 0; h < 2 * NH; ++h) {
+            const Corner ch = make_corner(sample_coord(x, hx[h], fW), sample_coord(y, hy[h], fH), W, H);
+            float v[3] = {0.f, 0.f, 0.f}, cf[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!corner_ok(ch, k, W, H)) continue;
+                const float wk = corner_wgt(ch, k);
+                const float* c = at(corner_pix(ch, k, W)) + 2 * NH;
+#pragma unroll
+                for (int e = 0; e < 3; ++e) {
+                    cf[e] = __fadd_rn(cf[e], __fmul_rn(c[e], wk));
+                    v[e] = __fadd_rn(v[e], __fmul_rn(c[3 + e], wk));
+                }
+            }
+            hv[h][0] = v[0] + hx[h];
+            hv[h][1] = v[1] + hy[h];
+            hv[h][2] = v[2];
+            hc[h][0] = cf[0]; hc[h][1] = cf[1]; hc[h][2] = cf[2];
+        }
+        float* out = p.uvd_out + static_cast<size_t>(cell) * 3 * J + 3 * j;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            float m = hc[0][e];
+#pragma unroll
+            for (int h = 1; h < 2 * NH; ++h) m = fmaxf(m, hc[h][e]);
+            float ex[2 * NH], se = 0.f;
+#pragma unroll
+            for (int h = 0; h < 2 * NH; ++h) { ex[h] = expf(hc[h][e] - m); se += ex[h]; }
+            float o = 0.f;
+#pragma unroll
+            for (int h = 0; h < 2 * NH; ++h) o += hv[h][e] * (ex[h] / se);
+            out[e] = o;
+        }
+    }
+}
+
+}  // namespace das
 
 extern "C" int das_refine_dense_layer(const das_levels* d_levels, const das_levels* h_levels, int32_t level,
                                       int32_t layer, const das_decode_cfg* cfg, const float* weights,
                                       const float* uvd_in, float* uvd_out, float* proj, void* stream) {
-    (void)d_levels; (void)h_levels; (void)level; (void)layer; (void)cfg; (void)weights; (void)uvd_in; (void)uvd_out; (void)proj; (void)stream;
-    das::set_error("das_refine_dense_layer: not built yet (num_layers > 1)");
-    return DAS_ERR_UNSUPPORTED;
+    using namespace das;
+    DAS_REQUIRE(d_levels && h_levels && cfg && weights && uvd_out && proj, DAS_ERR_ARG, "das_refine_dense_layer: null pointer");
+    DAS_REQUIRE(level >= 0 && level < h_levels->n_levels, DAS_ERR_ARG, "level=%d", level);
+    DAS_REQUIRE(layer >= 0 && layer < cfg->num_layers, DAS_ERR_ARG, "layer=%d", layer);
+    DAS_REQUIRE(cfg->num_heads == 4, DAS_ERR_UNSUPPORTED, "num_heads=%d: only 4 is built", cfg->num_heads);
+    DAS_REQUIRE(cfg->num_joints >= 1 && cfg->num_joints <= DAS_MAX_JOINTS, DAS_ERR_CAPACITY, "num_joints=%d", cfg->num_joints);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DenseParams p{};
+    p.lv = d_levels; p.wpack = weights; p.uvd_in = uvd_in; p.uvd_out = uvd_out; p.proj = proj;
+    p.level = level; p.layer = layer; p.J = cfg->num_joints; p.root = cfg->root_idx; p.B = h_levels->batch;
+    const long long cells = static_cast<long long>(h_levels->batch) * h_levels->lv[level].H * h_levels->lv[level].W;
+    const int grid1 = static_cast<int>(std::min<long long>((cells / 8 + DP_WARPS) / DP_WARPS, 4LL * kSMs));
+    switch (cfg->feat_channels) {
+        case 128: dense_project_kernel<4, 4><<<grid1, DP_WARPS * 32, 0, st>>>(p); break;
+        case 256: dense_project_kernel<8, 4><<<grid1, DP_WARPS * 32, 0, st>>>(p); break;
+        case 512: dense_project_kernel<16, 4><<<grid1, DP_WARPS * 32, 0, st>>>(p); break;
+        default:
+            set_error("feat_channels=%d: only 128/256/512 are built", cfg->feat_channels);
+            return DAS_ERR_UNSUPPORTED;
+    }
+    DAS_CUDA_CHECK(cudaGetLastError());
+    const long long threads = cells * cfg->num_joints;
+    const int grid2 = static_cast<int>(std::min<long long>((threads + 255) / 256, 16LL * kSMs));
+    dense_sample_kernel<4><<<grid2, 256, 0, st>>>(p);
+    DAS_CUDA_CHECK(cudaGetLastError());
+    return DAS_OK;
 }

@@ -1,0 +1,48 @@
+"""GPU: recursive_update.num_layers > 1 -- dense layers 1..L-1 followed by the sparse last layer,
+against the oracle (which runs every layer densely like the reference) and the L=3 golden vectors."""
+import dataclasses
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import util
+from das_b200 import synth
+from oracle import make_golden as G
+from test_gpu_parity import compare, TOL, GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("layers,J,root", [(2, 15, 2), (3, 17, 14), (2, 21, 14)])
+def test_multi_layer_refinement_matches_oracle(layers, J, root):
+    cfg = synth.HeadConfig(num_joints=J, root_idx=root, depth_factor=1.0, z_norm=50.0, num_layers=layers)
+    tc = dict(nms_pre=20, nms_post=20, nms_thr=0.9, score_thr=0.0)
+    case = util.make_case(cfg, 2, 28, 36, seed=600 + layers, scales=(1.05, 0.95, 1.1, 0.9))
+    ref, _ = util.run_oracle(case, tc)
+    plan, got = util.run_gpu(case, tc, refine=True)
+    compare(plan, got, ref, util.rank_margin_ulps(case["levels"], 20))
+
+
+def test_multi_layer_pyramid():
+    cfg = synth.HeadConfig(num_joints=15, root_idx=2, depth_factor=20.0, z_norm=50.0, num_layers=2, strides=(8, 16, 32))
+    tc = dict(nms_pre=50, nms_post=30, nms_thr=0.9, score_thr=0.03)
+    case = util.make_case(cfg, 2, 32, 48, seed=700, peaks=20)
+    ref, _ = util.run_oracle(case, tc)
+    plan, got = util.run_gpu(case, tc, refine=True)
+    compare(plan, got, ref, util.rank_margin_ulps(case["levels"], 50, 0.03))
+
+
+def test_golden_mupots17_three_layers():
+    name = "mupots17_L3"
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cfg, levels, layers, metas, tc = G.build_case(name)
+    case = dict(cfg=cfg, levels=levels, layers=layers, metas=metas, batch=levels[0]["cls"].shape[0])
+    plan, got = util.run_gpu(case, tc, refine=True)
+    ci = plan.t["cand_index"].cpu()
+    for i, g in enumerate(got):
+        lv, idx = util.slot_to_level_index(plan, g["slots"].cpu(), ci[i])
+        assert idx == gold[f"index_{i}"].tolist()
+        assert util.rel_err(g["poses"].cpu().numpy(), gold[f"poses_{i}"]) < TOL
+        assert util.rel_err(g["poses_cam"].cpu().numpy(), gold[f"cam_{i}"]) < TOL
