@@ -22,17 +22,27 @@ __device__ __forceinline__ Row<CPL> load_row(const float* __restrict__ base, int
     return r;
 }
 
+// Packed fp32x2 FMA (sm_100a: one FFMA2 issue slot does two fp32 FMAs). d = a * b + c, lane-wise.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+
 template <int CPL>
 __device__ __forceinline__ float dot_row(const Row<CPL>& f, const Row<CPL>& w) {
-    float a = 0.f;
+    float2 a = make_float2(0.f, 0.f);
 #pragma unroll
     for (int q = 0; q < CPL / 4; ++q) {
-        a = fmaf(f.v[q].x, w.v[q].x, a);
-        a = fmaf(f.v[q].y, w.v[q].y, a);
-        a = fmaf(f.v[q].z, w.v[q].z, a);
-        a = fmaf(f.v[q].w, w.v[q].w, a);
+        a = ffma2(make_float2(f.v[q].x, f.v[q].y), make_float2(w.v[q].x, w.v[q].y), a);
+        a = ffma2(make_float2(f.v[q].z, f.v[q].w), make_float2(w.v[q].z, w.v[q].w), a);
     }
-    return a;
+    return a.x + a.y;
 }
 
 __device__ __forceinline__ float warp_allsum(float v) {
@@ -41,29 +51,31 @@ __device__ __forceinline__ float warp_allsum(float v) {
     return v;
 }
 
-// Sum a[r] over the 32 lanes for 8 rows at once; lane L returns the total of row (L >> 2) & 7.
-__device__ __forceinline__ float reduce8_transposed(const float (&a)[8], int lane) {
-    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+// Sum over the 32 lanes for 8 rows at once.  PRECONDITION: lane L accumulated row (k ^ r(L)) into a[k], with
+// r(L) = (L >> 2) & 7 (the callers load their rows in that lane-permuted order), which makes every exchange of
+// the transposing butterfly static -- no per-lane selects.  Lane L returns the total of row r(L).
+__device__ __forceinline__ float reduce8_permuted(const float (&a)[8]) {
     float b[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float send = h16 ? a[i] : a[i + 4];
-        const float keep = h16 ? a[i + 4] : a[i];
-        b[i] = keep + __shfl_xor_sync(FULL, send, 16);
-    }
+    for (int i = 0; i < 4; ++i) b[i] = a[i] + __shfl_xor_sync(FULL, a[i + 4], 16);
     float c[2];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float send = h8 ? b[i] : b[i + 2];
-        const float keep = h8 ? b[i + 2] : b[i];
-        c[i] = keep + __shfl_xor_sync(FULL, send, 8);
-    }
-    const float send = h4 ? c[0] : c[1];
-    const float keep = h4 ? c[1] : c[0];
-    float d = keep + __shfl_xor_sync(FULL, send, 4);
+    for (int i = 0; i < 2; ++i) c[i] = b[i] + __shfl_xor_sync(FULL, b[i + 2], 8);
+    float d = c[0] + __shfl_xor_sync(FULL, c[1], 4);
     d += __shfl_xor_sync(FULL, d, 2);
     d += __shfl_xor_sync(FULL, d, 1);
     return d;
+}
+
+// 4-row variant: lane L accumulated row (k ^ c(L)) into a[k], c(L) = (L >> 3) & 3; returns the total of row c(L).
+__device__ __forceinline__ float reduce4_permuted(const float (&a)[4]) {
+    const float b0 = a[0] + __shfl_xor_sync(FULL, a[2], 16);
+    const float b1 = a[1] + __shfl_xor_sync(FULL, a[3], 16);
+    float c = b0 + __shfl_xor_sync(FULL, b1, 8);
+    c += __shfl_xor_sync(FULL, c, 4);
+    c += __shfl_xor_sync(FULL, c, 2);
+    c += __shfl_xor_sync(FULL, c, 1);
+    return c;
 }
 
 // Index-space sample coordinate of `cell + 0.5 + off` after the reference's normalise ->

@@ -43,9 +43,10 @@ dense_project_kernel(const DenseParams p) {
         const long long base = g * 8;
         Row<CPL> f[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const bool ok = base + k < total;
-            f[k] = load_row<CPL>(F + (ok ? base + k : 0) * C, lane, ok);
+        for (int k = 0; k < 8; ++k) {          // lane-permuted: row (k ^ r) goes to f[k] (see reduce8_permuted)
+            const long long row = base + (k ^ r);
+            const bool ok = row < total;
+            f[k] = load_row<CPL>(F + (ok ? row : 0) * C, lane, ok);
         }
         const long long cell = base + r;             // the cell this lane post-processes
         const bool live = cell < total;
@@ -61,7 +62,7 @@ dense_project_kernel(const DenseParams p) {
                 float acc[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) acc[k] = dot_row<CPL>(f[k], w);
-                res[o] = reduce8_transposed(acc, lane) + __ldg(Bj + o);
+                res[o] = reduce8_permuted(acc) + __ldg(Bj + o);
             }
             if (!live) continue;
             float* out = p.proj + (static_cast<size_t>(cell) * J + j) * PW;

@@ -16,7 +16,8 @@
 //
 // Mapping: one warp per (centre, joint) work item, handed out by an atomic counter.  A lane owns
 // C/32 channels of every row (two coalesced 128-bit loads per 1 KB row at C=256); dot products are
-// finished with a transposing butterfly so 8 rows cost 9 shuffles per output instead of 40.
+// finished with a transposing butterfly so 8 rows cost 9 shuffles per output instead of 40; rows are loaded
+// in a lane-permuted order so that butterfly needs no selects, and FMAs are packed fma.rn.f32x2.
 #include <algorithm>
 
 #include "refine_common.cuh"
@@ -40,8 +41,8 @@ struct RefineParams {
     int n_items;
 };
 
-template <int CPL, int NH>
-__global__ void __launch_bounds__(RS_WARPS * 32)
+template <int CPL, int NH, int MINB>
+__global__ void __launch_bounds__(RS_WARPS * 32, MINB)
 refine_sparse_kernel(const RefineParams p) {
     constexpr int C = CPL * 32;
     constexpr int NOUT = 2 * NH + 9;
@@ -145,70 +146,60 @@ refine_sparse_kernel(const RefineParams p) {
             }
         }
 
-        // ---- phase 3: 2*NH heads x 4 corners; blended offset + confidence at every corner --------
-        const int r = (lane >> 2) & 7;      // row of the 8-row batch this lane post-processes
-        const int hh = r >> 2, ck = r & 3;  // head within the batch, corner
-        const int dim = lane & 3;           // u, v, d (lane 3 of each quad idles)
-        float hv[NH], hc[NH];
+        // ---- phase 3: 2*NH heads, one head (4 corner rows) per batch; blended offset + confidence per corner ----
+        const int ck = (lane >> 3) & 3;     // corner of the batch this lane post-processes (lanes 8ck..8ck+7)
+        const int dim = lane & 7;           // u, v, d for dim < 3; the other lanes of the group idle in the epilogue
+        float sm_m = -INFINITY, sm_e = 0.f, sm_v = 0.f;   // online softmax over the heads (recursive_update.py:29-31)
 #pragma unroll
-        for (int bt = 0; bt < NH; ++bt) {
-            const int h0 = 2 * bt, h1 = 2 * bt + 1;
-            const Corner c0 = make_corner(sample_coord(x, hx[h0], fW), sample_coord(y, hy[h0], fH), W, H);
-            const Corner c1 = make_corner(sample_coord(x, hx[h1], fW), sample_coord(y, hy[h1], fH), W, H);
-            Row<CPL> f[8];
+        for (int h = 0; h < 2 * NH; ++h) {
+            const Corner c = make_corner(sample_coord(x, hx[h], fW), sample_coord(y, hy[h], fH), W, H);
+            // this lane's own corner: issue the previous-offset gather now so it overlaps the row loads
+            const bool ok_me = corner_ok(c, ck, W, H) && dim < 3;
+            const int pix_me = ok_me ? corner_pix(c, ck, W) : 0;
+            const float prev_me = ok_me ? prev_at(pix_me, dim) : 0.f;
+            // lane-permuted batch: row (k ^ ck) goes to f[k] (see reduce4_permuted); a warp-wide load then reads
+            // one full 128 B line from each of the 4 corner cells
+            Row<CPL> f[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const bool ok0 = corner_ok(c0, k, W, H), ok1 = corner_ok(c1, k, W, H);
-                f[k] = load_row<CPL>(F + static_cast<size_t>(ok0 ? corner_pix(c0, k, W) : 0) * C, lane, ok0);
-                f[4 + k] = load_row<CPL>(F + static_cast<size_t>(ok1 ? corner_pix(c1, k, W) : 0) * C, lane, ok1);
+                const int kk = k ^ ck;
+                const bool ok = corner_ok(c, kk, W, H);
+                f[k] = load_row<CPL>(F + static_cast<size_t>(ok ? corner_pix(c, kk, W) : 0) * C, lane, ok);
             }
             float res[9];
 #pragma unroll
             for (int o = 0; o < 9; ++o) {
                 const Row<CPL> w = load_row<CPL>(Wj + (O_GATE + o) * C, lane, true);
-                float acc[8];
+                float acc[4];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] = dot_row<CPL>(f[k], w);
-                res[o] = reduce8_transposed(acc, lane);
+                for (int k = 0; k < 4; ++k) acc[k] = dot_row<CPL>(f[k], w);
+                res[o] = reduce4_permuted(acc);
             }
-            // this lane: row r = (head hh, corner ck), dimension `dim`
-            const Corner& cm = hh ? c1 : c0;
-            const bool ok = corner_ok(cm, ck, W, H) && dim < 3;
             float val = 0.f, cf = 0.f;
-            if (ok) {
-                const int pix = corner_pix(cm, ck, W);
+            if (ok_me) {
                 const float rg = dim == 0 ? res[0] : (dim == 1 ? res[1] : res[2]);
                 const float rn = dim == 0 ? res[3] : (dim == 1 ? res[4] : res[5]);
                 const float rc = dim == 0 ? res[6] : (dim == 1 ? res[7] : res[8]);
                 const float g = sigmoid_acc(rg + __ldg(Bj + O_GATE + dim));
                 const float n = rn + __ldg(Bj + O_VAL + dim);
-                const float o = __fadd_rn(__fmul_rn(1.0f - g, prev_at(pix, dim)), __fmul_rn(g, n));
-                const float wk = corner_wgt(cm, ck);
+                const float o = __fadd_rn(__fmul_rn(1.0f - g, prev_me), __fmul_rn(g, n));
+                const float wk = corner_wgt(c, ck);
                 val = o * wk;
                 cf = (rc + __ldg(Bj + O_CONF + dim)) * wk;
             }
-            // bilinear sum over the 4 corners (lane bits 2,3)
-            val += __shfl_xor_sync(FULL, val, 4);
-            cf += __shfl_xor_sync(FULL, cf, 4);
+            // bilinear sum over the 4 corners (lane bits 3,4)
             val += __shfl_xor_sync(FULL, val, 8);
             cf += __shfl_xor_sync(FULL, cf, 8);
-            const float sh = hh ? (dim == 0 ? hx[h1] : hy[h1]) : (dim == 0 ? hx[h0] : hy[h0]);
-            hv[bt] = val + (dim < 2 ? sh : 0.f);   // + diff, recursive_update.py:72-75, 28
-            hc[bt] = cf;
+            val += __shfl_xor_sync(FULL, val, 16);
+            cf += __shfl_xor_sync(FULL, cf, 16);
+            const float hv = val + (dim == 0 ? hx[h] : (dim == 1 ? hy[h] : 0.f));   // + diff, recursive_update.py:72-75, 28
+            const float m_new = fmaxf(sm_m, cf);
+            const float s_old = expf(sm_m - m_new), e_new = expf(cf - m_new);
+            sm_e = sm_e * s_old + e_new;
+            sm_v = sm_v * s_old + hv * e_new;
+            sm_m = m_new;
         }
-        // softmax over the 2*NH heads (own NH + the partner half-warp's NH), recursive_update.py:29-31
-        float m = hc[0];
-#pragma unroll
-        for (int i = 1; i < NH; ++i) m = fmaxf(m, hc[i]);
-        m = fmaxf(m, __shfl_xor_sync(FULL, m, 16));
-        float e[NH], se = 0.f;
-#pragma unroll
-        for (int i = 0; i < NH; ++i) { e[i] = expf(hc[i] - m); se += e[i]; }
-        se += __shfl_xor_sync(FULL, se, 16);
-        float out = 0.f;
-#pragma unroll
-        for (int i = 0; i < NH; ++i) out += hv[i] * (e[i] / se);
-        out += __shfl_xor_sync(FULL, out, 16);
+        const float out = sm_v / sm_e;
 
         // ---- eval tail + assembly (das_head.py:254-262, 725-743) ----------------------------------
         if (lane < 3) {
@@ -373,11 +364,10 @@ extern "C" int das_gather_refine_assemble(const das_levels* d_levels, const das_
     DAS_REQUIRE(cfg->num_heads == 4, DAS_ERR_UNSUPPORTED, "num_heads=%d: only 4 is built", cfg->num_heads);
     DAS_CUDA_CHECK(cudaMemsetAsync(work_counter, 0, sizeof(int32_t), st));
     const int threads = RS_WARPS * 32;
-    int grid = kSMs * 2;
     switch (cfg->feat_channels) {
-        case 128: refine_sparse_kernel<4, 4><<<grid, threads, 0, st>>>(p); break;
-        case 256: refine_sparse_kernel<8, 4><<<grid, threads, 0, st>>>(p); break;
-        case 512: refine_sparse_kernel<16, 4><<<grid, threads, 0, st>>>(p); break;
+        case 128: refine_sparse_kernel<4, 4, 3><<<kSMs * 3, threads, 0, st>>>(p); break;
+        case 256: refine_sparse_kernel<8, 4, 3><<<kSMs * 3, threads, 0, st>>>(p); break;
+        case 512: refine_sparse_kernel<16, 4, 2><<<kSMs * 2, threads, 0, st>>>(p); break;
         default:
             set_error("feat_channels=%d: only 128/256/512 are built", cfg->feat_channels);
             return DAS_ERR_UNSUPPORTED;

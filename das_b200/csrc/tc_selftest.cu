@@ -1,0 +1,106 @@
+// Self-test of the tcgen05 building blocks in tc_common.cuh: D[128,N] = A[128,K] * B[N,K]^T on the tensor
+// cores (kind::tf32, fp32 accumulation in TMEM), single TF32 pass or the 3xTF32 split
+// (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo) that the refinement projection uses to stay at fp32-level accuracy.
+#include "das_common.cuh"
+#include "tc_common.cuh"
+
+namespace das {
+
+template <int N>
+__global__ void __launch_bounds__(128, 1)
+tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int K, int split) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    // carve (1024-B aligned): A_hi 16 KB | A_lo 16 KB | B_hi N*128 | B_lo N*128
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~static_cast<uintptr_t>(1023));
+    unsigned char* sA = base;
+    unsigned char* sAl = base + 16384;
+    unsigned char* sB = base + 32768;
+    unsigned char* sBl = sB + ((N * 128 + 1023) & ~1023);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::mbar_fence_init(); }
+    if (warp == 0) tc::tmem_alloc(&tmem_base, 32);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = tmem_base;
+    constexpr uint32_t idesc = tc::instr_desc_tf32(128, N);
+    uint32_t phase = 0;
+
+    for (int kb = 0; kb < K / 32; ++kb) {
+        // gather one k-block: 128 rows x 8 chunks (A), N rows x 8 chunks (B); 8 consecutive threads = one 128-B row
+        for (int i = tid; i < 128 * 8; i += 128) {
+            const int row = i >> 3, ch = i & 7;
+            tc::cp_async16(tc::smem_u32(sA) + tc::swz128(row, ch), A + static_cast<size_t>(row) * K + kb * 32 + ch * 4, true);
+        }
+        for (int i = tid; i < N * 8; i += 128) {
+            const int row = i >> 3, ch = i & 7;
+            tc::cp_async16(tc::smem_u32(sB) + tc::swz128(row, ch), B + static_cast<size_t>(row) * K + kb * 32 + ch * 4, true);
+        }
+        tc::cp_async_commit();
+        tc::cp_async_wait<0>();
+        __syncthreads();
+        if (split) {   // lo = a - tf32(a); the position inside the tile does not matter for an elementwise pass
+            for (int i = tid; i < 128 * 32; i += 128) {
+                const float a = reinterpret_cast<const float*>(sA)[i];
+                reinterpret_cast<float*>(sAl)[i] = a - tc::tf32_hi(a);
+            }
+            for (int i = tid; i < N * 32; i += 128) {
+                const float b = reinterpret_cast<const float*>(sB)[i];
+                reinterpret_cast<float*>(sBl)[i] = b - tc::tf32_hi(b);
+            }
+        }
+        tc::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc::tc_fence_after();
+            for (int k = 0; k < 4; ++k) {
+                const uint64_t da = tc::smem_desc_sw128(tc::smem_u32(sA) + k * 32);
+                const uint64_t db = tc::smem_desc_sw128(tc::smem_u32(sB) + k * 32);
+                tc::umma_tf32(tmem_d, da, db, idesc, (kb | k) != 0);
+                if (split) {
+                    const uint64_t dal = tc::smem_desc_sw128(tc::smem_u32(sAl) + k * 32);
+                    const uint64_t dbl = tc::smem_desc_sw128(tc::smem_u32(sBl) + k * 32);
+                    tc::umma_tf32(tmem_d, dal, db, idesc, true);
+                    tc::umma_tf32(tmem_d, da, dbl, idesc, true);
+                }
+            }
+            tc::umma_commit(&bar);     // implies tcgen05.fence::before_thread_sync
+        }
+        tc::mbar_wait(&bar, phase);    // smem of this k-block may be overwritten once the MMAs have read it
+        phase ^= 1;
+        tc::tc_fence_after();
+    }
+    // epilogue: thread t <-> TMEM lane (row) t
+    float v[16];
+#pragma unroll
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        tc::tmem_ld16(tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) D[static_cast<size_t>(tid) * N + c0 + i] = v[i];
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, 32);
+}
+
+}  // namespace das
+
+extern "C" int das_tc_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t split, void* stream) {
+    using namespace das;
+    DAS_REQUIRE(A && B && D, DAS_ERR_ARG, "das_tc_selftest: null pointer");
+    DAS_REQUIRE((N == 16 || N == 32) && K >= 32 && K % 32 == 0, DAS_ERR_ARG, "das_tc_selftest: N=%d K=%d", N, K);
+    const size_t smem = 1024 + 32768 + 2 * 4096;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (N == 16) {
+        DAS_CUDA_CHECK(cudaFuncSetAttribute(tc_selftest_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        tc_selftest_kernel<16><<<1, 128, smem, st>>>(A, B, D, K, split);
+    } else {
+        DAS_CUDA_CHECK(cudaFuncSetAttribute(tc_selftest_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        tc_selftest_kernel<32><<<1, 128, smem, st>>>(A, B, D, K, split);
+    }
+    DAS_CUDA_CHECK(cudaGetLastError());
+    return DAS_OK;
+}

@@ -182,6 +182,11 @@ int das_plan_run_host(das_plan* plan, const das_levels* levels, const float* sca
 int64_t das_plan_h2d_bytes(const das_plan* plan);
 int64_t das_plan_d2h_bytes(const das_plan* plan);
 
+/* ---- diagnostics ------------------------------------------------------------------------------- */
+/* Self-test of the tcgen05/TMEM building blocks: D[128,N] = A[128,K] * B[N,K]^T (row-major fp32 device
+ * buffers; N in {16,32}, K a multiple of 32). split=0: one TF32 pass; split=1: 3xTF32 (fp32-level accuracy). */
+int das_tc_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t split, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
