@@ -212,7 +212,8 @@ def run_b200(args):
         plan = DecodePlan(num_joints=head.num_joints, root_idx=head.root_idx, depth_factor=head.depth_factor,
                           z_norm=head.z_norm, strides=head.strides, level_sizes=[(w["h"], w["w"])], batch=B,
                           test_cfg=TEST_CFG, num_heads=head.num_heads, feat_channels=head.feat_channels,
-                          num_layers=head.num_layers, refine=True, device=dev)
+                          num_layers=head.num_layers, refine=True, device=dev,
+                          refine_mode=(int(os.environ['DAS_REFINE_MODE']) if 'DAS_REFINE_MODE' in os.environ else None))
         plan.set_weights(layers)
         plan.bind([dict(cls=lv["cls"], ctr=lv["ctr"], pose=lv["pose_raw"], feats=lv["feats"], scales=lv["scales"])
                    for lv in levels])

@@ -61,6 +61,13 @@ SIGNATURES = {
     "das_score_topk": (C.c_int, [_VP, C.POINTER(Levels), C.c_int32, C.c_int32, _VP, _VP, C.c_int32, _VP, _VP]),
     "das_gather_refine_assemble": (C.c_int, [_VP, C.POINTER(Levels), C.POINTER(DecodeCfg), _VP, _VP, _VP, _VP, _VP,
                                              C.c_int32, _VP, _VP, _VP, _VP]),
+    "das_refine_heads": (C.c_int, [_VP, C.POINTER(Levels), C.POINTER(DecodeCfg), _VP, _VP, _VP, _VP, C.c_int32, _VP, _VP, _VP, _VP]),
+    "das_refine_tc": (C.c_int, [_VP, C.POINTER(Levels), C.POINTER(DecodeCfg), _VP, _VP, _VP, _VP, _VP, C.c_int32, _VP, _VP, _VP,
+                                _VP, _VP, C.c_int32, _VP]),
+    "das_pack_tc_panels": (C.c_int, [C.POINTER(DecodeCfg), _VP, _VP, _VP]),
+    "das_tc_set_debug_buffer": (C.c_int, [_VP]),
+    "das_tc_panel_bytes": (C.c_int64, [C.POINTER(DecodeCfg)]),
+    "das_plan_set_refine_mode": (C.c_int, [_VP, C.c_int32]),
     "das_refine_dense_layer": (C.c_int, [_VP, C.POINTER(Levels), C.c_int32, C.c_int32, C.POINTER(DecodeCfg), _VP, _VP,
                                          _VP, _VP, _VP]),
     "das_nms_backproject": (C.c_int, [C.POINTER(DecodeCfg), C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, Buffers, _VP]),
@@ -78,6 +85,7 @@ SIGNATURES = {
     "das_plan_kernel_launches": (C.c_int64, [_VP]),
     "das_plan_run_host": (C.c_int, [_VP, C.POINTER(Levels), _VP, _VP, Buffers, _VP]),
     "das_tc_selftest": (C.c_int, [_VP, _VP, _VP, C.c_int32, C.c_int32, C.c_int32, _VP]),
+    "das_tc_mma_bench": (C.c_int, [C.c_int32, C.c_int32, _VP, _VP]),
     "das_plan_h2d_bytes": (C.c_int64, [_VP]),
     "das_plan_d2h_bytes": (C.c_int64, [_VP]),
 }

@@ -34,6 +34,11 @@ struct das_plan {
     float* d_scale_xy = nullptr;
     double* d_cam = nullptr;
     float* wpack[DAS_MAX_LAYERS] = {};
+    // tensor-core refinement (C = 256, nh = 4)
+    int refine_mode = 0;              // 0 SIMT, 1 tcgen05 3xTF32, 2 tcgen05 single TF32
+    unsigned char* tc_panels = nullptr;
+    float* item_heads = nullptr;
+    int32_t* valid_list = nullptr;
     // dense layers (num_layers > 1): ping-pong NHWC [B,H,W,3J] maps per level + projection scratch
     float* uvd_map[2][DAS_MAX_LEVELS] = {};
     float* proj = nullptr;
@@ -146,6 +151,12 @@ extern "C" int das_plan_create(const das_decode_cfg* cfg, const das_levels* shap
     A(dev_alloc(&p->d_cam, B * DAS_CAM_DOUBLES));
     if (cfg->refine) {
         for (int k = 0; k < cfg->num_layers; ++k) A(dev_alloc(&p->wpack[k], static_cast<size_t>(das_packed_weight_floats(cfg))));
+        if (cfg->feat_channels == 256 && cfg->num_heads == 4) {
+            p->refine_mode = 1;
+            A(dev_alloc(&p->tc_panels, static_cast<size_t>(das_tc_panel_bytes(cfg))));
+            A(dev_alloc(&p->item_heads, B * CT * J * 16));
+            A(dev_alloc(&p->valid_list, B * CT));
+        }
         if (cfg->num_layers > 1) {
             size_t max_hw = 0;
             for (int l = 0; l < shape->n_levels; ++l) {
@@ -198,7 +209,7 @@ extern "C" void das_plan_destroy(das_plan* p) {
     for (cudaEvent_t e : p->ev) if (e) cudaEventDestroy(e);
     void* ptrs[] = {p->d_levels, p->buf.cand_score, p->buf.cand_index, p->buf.cand_pose, p->buf.cand_center,
                     p->out_block, p->scratch, p->work_counter, p->d_scale_xy, p->d_cam,
-                    p->proj, p->d_prev_ptrs};
+                    p->proj, p->d_prev_ptrs, p->tc_panels, p->item_heads, p->valid_list};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (int k = 0; k < DAS_MAX_LAYERS; ++k) if (p->wpack[k]) cudaFree(p->wpack[k]);
     for (int i = 0; i < 2; ++i)
@@ -222,7 +233,9 @@ extern "C" int das_plan_set_weights(das_plan* p, int32_t layer, const float* so_
     DAS_REQUIRE(p, DAS_ERR_ARG, "null plan");
     DAS_REQUIRE(p->cfg.refine, DAS_ERR_ARG, "plan was created with refine=0");
     DAS_REQUIRE(layer >= 0 && layer < p->cfg.num_layers, DAS_ERR_ARG, "layer=%d of %d", layer, p->cfg.num_layers);
-    return das_pack_weights(&p->cfg, so_w, so_b, sc_w, sc_b, uw_w, uw_b, uv_w, uv_b, p->wpack[layer], stream);
+    DAS_TRY(das_pack_weights(&p->cfg, so_w, so_b, sc_w, sc_b, uw_w, uw_b, uv_w, uv_b, p->wpack[layer], stream));
+    if (layer == p->cfg.num_layers - 1 && p->tc_panels) DAS_TRY(das_pack_tc_panels(&p->cfg, p->wpack[layer], p->tc_panels, stream));
+    return DAS_OK;
 }
 
 extern "C" int das_plan_bind(das_plan* p, const das_levels* levels, void* stream) {
@@ -285,10 +298,20 @@ static int enqueue(das_plan* p, cudaStream_t st, int* n_launch, bool events) {
         prev = p->d_prev_ptrs;   // uploaded once in das_plan_run: uvd_map[(L-2)&1][level]
     }
     DAS_TRY(mark(2));
-    DAS_TRY(das_gather_refine_assemble(p->d_levels, &p->bound, &c, c.refine ? p->wpack[c.num_layers - 1] : nullptr, prev,
-                                       p->d_scale_xy, p->buf.cand_score, p->buf.cand_index, p->CT, p->buf.cand_pose,
-                                       p->buf.cand_center, p->work_counter, st));
-    ++n;
+    if (c.refine && p->refine_mode != 0) {
+        const float* w = p->wpack[c.num_layers - 1];
+        DAS_TRY(das_refine_heads(p->d_levels, &p->bound, &c, w, prev, p->buf.cand_score, p->buf.cand_index, p->CT,
+                                 p->item_heads, p->valid_list, p->work_counter, st));
+        DAS_TRY(das_refine_tc(p->d_levels, &p->bound, &c, w, p->tc_panels, prev, p->d_scale_xy, p->buf.cand_index, p->CT,
+                              p->item_heads, p->valid_list, p->work_counter + 1, p->buf.cand_pose, p->buf.cand_center,
+                              p->refine_mode == 1 ? 1 : (p->refine_mode == 2 ? 0 : p->refine_mode - 2), st));
+        n += 2;
+    } else {
+        DAS_TRY(das_gather_refine_assemble(p->d_levels, &p->bound, &c, c.refine ? p->wpack[c.num_layers - 1] : nullptr, prev,
+                                           p->d_scale_xy, p->buf.cand_score, p->buf.cand_index, p->CT, p->buf.cand_pose,
+                                           p->buf.cand_center, p->work_counter, st));
+        ++n;
+    }
     DAS_TRY(mark(3));
     DAS_TRY(das_nms_backproject(&c, p->B, p->CT, p->buf.cand_score, p->buf.cand_pose, p->buf.cand_center, p->d_cam,
                                 p->buf, st));
@@ -358,6 +381,16 @@ extern "C" int das_plan_output_block(const das_plan* p, void** ptr, int64_t* byt
     DAS_REQUIRE(p && ptr && bytes, DAS_ERR_ARG, "das_plan_output_block: null pointer");
     *ptr = p->out_block;
     *bytes = static_cast<int64_t>(p->out_block_bytes);
+    return DAS_OK;
+}
+
+extern "C" int das_plan_set_refine_mode(das_plan* p, int32_t mode) {
+    using namespace das;
+    DAS_REQUIRE(p, DAS_ERR_ARG, "null plan");
+    DAS_REQUIRE(mode >= 0 && mode <= 40, DAS_ERR_ARG, "refine mode %d", mode);   // 3..9: timing experiments (split bits = mode - 2)
+    DAS_REQUIRE(p->launches == 0, DAS_ERR_ARG, "das_plan_set_refine_mode must be called before the first run");
+    DAS_REQUIRE(mode == 0 || p->tc_panels, DAS_ERR_UNSUPPORTED, "tensor-core refinement needs refine=1, feat_channels=256, num_heads=4");
+    p->refine_mode = mode;
     return DAS_OK;
 }
 

@@ -35,13 +35,15 @@ struct RefineParams {
     const int32_t* cand_index;
     float* cand_pose;
     float* cand_center;
-    int* work_counter;
+    int* work_counter;             // [0] work queue head, [1] number of valid candidates (heads-only mode)
+    float* item_heads;             // heads-only mode: [B*CT*J][16] = hx[8], hy[8]
+    int32_t* valid_list;           // heads-only mode: candidate slots (b*CT+slot) that pass score_thr
     int CT, J, root, nms_pre, layer;
     float depth_factor, z_norm, score_thr;
     int n_items;
 };
 
-template <int CPL, int NH, int MINB>
+template <int CPL, int NH, int MINB, bool HEADS_ONLY>
 __global__ void __launch_bounds__(RS_WARPS * 32, MINB)
 refine_sparse_kernel(const RefineParams p) {
     constexpr int C = CPL * 32;
@@ -144,6 +146,20 @@ refine_sparse_kernel(const RefineParams p) {
                 hx[NH + h] = S[2 * h];       // "from source" heads, recursive_update.py:62
                 hy[NH + h] = S[2 * h + 1];
             }
+        }
+
+        if constexpr (HEADS_ONLY) {
+            // phases 1-2 only: hand the 2*NH sampling offsets to the tensor-core kernel (refine_tc.cu)
+            if (lane == 0) {
+                float4* dst = reinterpret_cast<float4*>(p.item_heads + static_cast<size_t>(item) * 16);
+                static_assert(NH == 4, "item_heads layout is hx[8], hy[8]");
+                dst[0] = make_float4(hx[0], hx[1], hx[2], hx[3]);
+                dst[1] = make_float4(hx[4], hx[5], hx[6], hx[7]);
+                dst[2] = make_float4(hy[0], hy[1], hy[2], hy[3]);
+                dst[3] = make_float4(hy[4], hy[5], hy[6], hy[7]);
+                if (j == 0) p.valid_list[atomicAdd(p.work_counter + 1, 1)] = cs;
+            }
+            continue;
         }
 
         // ---- phase 3: 2*NH heads, one head (4 corner rows) per batch; blended offset + confidence per corner ----
@@ -365,13 +381,41 @@ extern "C" int das_gather_refine_assemble(const das_levels* d_levels, const das_
     DAS_CUDA_CHECK(cudaMemsetAsync(work_counter, 0, sizeof(int32_t), st));
     const int threads = RS_WARPS * 32;
     switch (cfg->feat_channels) {
-        case 128: refine_sparse_kernel<4, 4, 3><<<kSMs * 3, threads, 0, st>>>(p); break;
-        case 256: refine_sparse_kernel<8, 4, 3><<<kSMs * 3, threads, 0, st>>>(p); break;
-        case 512: refine_sparse_kernel<16, 4, 2><<<kSMs * 2, threads, 0, st>>>(p); break;
+        case 128: refine_sparse_kernel<4, 4, 3, false><<<kSMs * 3, threads, 0, st>>>(p); break;
+        case 256: refine_sparse_kernel<8, 4, 3, false><<<kSMs * 3, threads, 0, st>>>(p); break;
+        case 512: refine_sparse_kernel<16, 4, 2, false><<<kSMs * 2, threads, 0, st>>>(p); break;
         default:
             set_error("feat_channels=%d: only 128/256/512 are built", cfg->feat_channels);
             return DAS_ERR_UNSUPPORTED;
     }
+    DAS_CUDA_CHECK(cudaGetLastError());
+    return DAS_OK;
+}
+
+// Phases 1-2 of the sparse refinement only (feeds das_refine_tc): writes the 2*nh sampling offsets of every
+// (candidate, joint) item to item_heads[item][16] and the candidates passing score_thr to valid_list;
+// counters[0] is the work-queue head, counters[1] receives the number of valid candidates.
+extern "C" int das_refine_heads(const das_levels* d_levels, const das_levels* h_levels, const das_decode_cfg* cfg,
+                                const float* weights, const float* const* prev_uvd, const float* cand_score,
+                                const int32_t* cand_index, int32_t cand_slots, float* item_heads,
+                                int32_t* valid_list, int32_t* counters, void* stream) {
+    using namespace das;
+    DAS_REQUIRE(d_levels && h_levels && cfg && weights && cand_score && cand_index && item_heads && valid_list && counters,
+                DAS_ERR_ARG, "das_refine_heads: null pointer");
+    DAS_REQUIRE(cfg->feat_channels == 256 && cfg->num_heads == 4, DAS_ERR_UNSUPPORTED,
+                "das_refine_heads is built for feat_channels=256, num_heads=4");
+    DAS_REQUIRE(cfg->num_joints >= 1 && cfg->num_joints <= DAS_MAX_JOINTS, DAS_ERR_CAPACITY, "num_joints=%d", cfg->num_joints);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    RefineParams p{};
+    p.lv = d_levels; p.wpack = weights; p.prev_uvd = prev_uvd; p.cand_score = cand_score; p.cand_index = cand_index;
+    p.work_counter = counters; p.item_heads = item_heads; p.valid_list = valid_list;
+    p.CT = cand_slots; p.J = cfg->num_joints; p.root = cfg->root_idx; p.nms_pre = cfg->nms_pre; p.layer = cfg->num_layers - 1;
+    p.depth_factor = cfg->depth_factor; p.z_norm = cfg->z_norm; p.score_thr = cfg->score_thr;
+    const long long items = static_cast<long long>(h_levels->batch) * cand_slots * cfg->num_joints;
+    DAS_REQUIRE(items < (1ll << 31), DAS_ERR_CAPACITY, "too many work items");
+    p.n_items = static_cast<int>(items);
+    DAS_CUDA_CHECK(cudaMemsetAsync(counters, 0, 2 * sizeof(int32_t), st));
+    refine_sparse_kernel<8, 4, 3, true><<<kSMs * 3, RS_WARPS * 32, 0, st>>>(p);
     DAS_CUDA_CHECK(cudaGetLastError());
     return DAS_OK;
 }

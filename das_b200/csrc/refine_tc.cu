@@ -1,0 +1,480 @@
+// Stage 3+4 on the tensor cores: the sampling phase of the sparse last-layer refinement as a gathered
+// 3xTF32 GEMM (tcgen05.mma kind::tf32, accumulator in TMEM), for C = 256, num_heads = 4.
+//
+// Reference semantics: recursive_update.py:186-197 (gate / value / confidence 1x1 projections and the gated
+// blend), :34-82 + :9-31 (bilinear sampling with zero padding, softmax over the 2*nh heads), das_head.py:252-262
+// and :725-743 (eval tail + joint assembly).  refine_sparse.cu (phases 1-2, "heads only" mode) has already
+// produced, for every (centre, joint) item, the 2*nh sampling offsets; what is left is, per item, 32 feature
+// rows (8 heads x 4 bilinear corners) times that joint's 9 projection rows -- a real dense contraction once
+// items of the SAME joint are batched:
+//
+//   tile   = 4 items of one joint = 128 gathered feature rows  (A: 128 x 256, fp32 as tf32 hi/lo)
+//   B      = that joint's {gate 3, value 3, conf 3} rows, zero-padded to N = 16, pre-split into hi/lo and
+//            pre-swizzled on the host side of the kernel (das_pack_tc_panels)
+//   D      = A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T   (3xTF32: fp32-level accuracy, fp32 accumulation in TMEM)
+//
+// One CTA (16 warps) per SM walks a contiguous range of tiles.  Rows are gathered k-block by k-block
+// (32 channels = one 128-B swizzle span) with cp.async into a 7-stage ring, 3 k-blocks ahead and across tile
+// boundaries; every thread splits the chunks it copied itself (hi stays in place -- the tensor core drops the
+// low mantissa bits -- lo goes to a 4-deep side ring); a dedicated warp issues 8 MMAs per k-block and
+// commits them to the stage's mbarrier.  Epilogue: thread t owns TMEM lane t = row t (item, head, corner):
+// bias, sigmoid gate, blend with the previous offset, bilinear weight / zero padding, corner sum (2 shuffles),
+// softmax over the 8 heads (3 shuffles), eval tail, assembly.
+#include "refine_common.cuh"
+#include "tc_common.cuh"
+
+namespace das {
+
+constexpr int TC_EPI_WARPS = 4;                 // one epilogue group = 4 warps = the 128 TMEM lanes (row setup + epilogue)
+constexpr int TC_EPI_GROUPS = 2;                // group e handles tiles e, e+2, ... with TMEM buffer / pointer buffer e
+constexpr int TC_PRODUCER_WARPS = 12;           // gather + hi/lo split: warps 8.. whose id % 4 != 3
+constexpr int TC_FIRST_PRODUCER = TC_EPI_WARPS * TC_EPI_GROUPS;
+// Warp w is scheduled by SM sub-partition w % 4.  Sub-partition 3 hosts only the MMA issuer (warp 11), the two
+// mostly-sleeping quadrant-3 epilogue warps (3, 7) and idle filler warps, so the single-thread tcgen05.mma issue
+// stream does not compete with the producers for issue slots.
+constexpr int TC_MMA_WARP = 11;
+constexpr int TC_WARPS = 24;
+constexpr int TC_THREADS = 32 * TC_WARPS;
+constexpr int TC_NS = 7;                       // A_hi ring stages
+constexpr int TC_PD = 3;                       // prefetch distance in k-blocks
+constexpr int TC_NLO = 4;                      // A_lo buffers = how many k-blocks the producers may run ahead of the MMAs
+static_assert(TC_NS - TC_PD == TC_NLO, "ring reuse distance and A_lo depth must agree");
+constexpr int TC_N = 16;                       // MMA N: 9 projection rows + zero padding
+constexpr int TC_KB = 8;                       // k-blocks of 32 channels (C = 256)
+constexpr int TC_C = 256;
+constexpr int TC_NH = 4;
+constexpr int TC_A_BYTES = 128 * 128;          // one k-block of 128 rows
+constexpr int TC_B_BYTES = TC_KB * TC_N * 128; // hi or lo rows of one joint: 16 KB (a joint's panel = 2x that)
+constexpr int TC_BK_BYTES = 2 * TC_N * 128;    // panel bytes per k-block: 16 hi rows followed by 16 lo rows
+constexpr int TC_SMEM = 1024 + TC_NS * TC_A_BYTES + TC_NLO * TC_A_BYTES + 2 * TC_B_BYTES;
+constexpr int TC_NOUT = 2 * TC_NH + 9;
+constexpr int TC_OGATE = 2 * TC_NH;
+
+struct TcParams {
+    const das_levels* lv;
+    const float* wpack;              // biases live behind the [J][17][C] weights
+    const unsigned char* bpanel;     // [J][2][TC_B_BYTES] swizzled hi / lo panels
+    const float* const* prev_uvd;
+    const float* scale_xy;
+    const int32_t* cand_index;
+    const float* item_heads;         // [B*CT*J][16]: hx[8], hy[8]
+    const int32_t* valid_list;       // candidates that survive score_thr, any order
+    const int32_t* n_valid;
+    float* cand_pose;
+    float* cand_center;
+    int CT, J, root, nms_pre, layer, split;
+    float depth_factor, z_norm;
+    long long* dbg;                  // optional [gridDim.x][16] cycle counters (profiling builds of the host code)
+};
+
+struct RowState {                    // what thread t keeps about row t of a tile until its epilogue
+    const float* ptr;                // feature row, nullptr = outside the map / padding row
+    float wk, prev0, prev1, prev2, hxv, hyv;
+    int cs, idx, lvl;
+    bool item_ok;
+};
+
+__device__ __forceinline__ RowState setup_row(const TcParams& p, int tile, int n_groups, int n_valid, int tid) {
+    RowState r;
+    const int j = tile / n_groups, g = tile - j * n_groups;
+    const int li = tid >> 5, h = (tid >> 2) & 7, ck = tid & 3;
+    const int vi = g * 4 + li;
+    r.item_ok = vi < n_valid;
+    r.cs = r.item_ok ? __ldg(p.valid_list + vi) : 0;
+    r.ptr = nullptr; r.wk = 0.f; r.prev0 = r.prev1 = r.prev2 = 0.f; r.hxv = r.hyv = 0.f; r.idx = 0; r.lvl = 0;
+    if (!r.item_ok) return r;
+    const das_levels* __restrict__ lvp = p.lv;
+    const int b = r.cs / p.CT, slot = r.cs - b * p.CT;
+    int l = 0, s0 = 0;
+    for (; l < lvp->n_levels - 1; ++l) {
+        const int ns = level_slots(lvp->lv[l].H * lvp->lv[l].W, p.nms_pre);
+        if (slot < s0 + ns) break;
+        s0 += ns;
+    }
+    r.lvl = l;
+    const das_level_desc& d = lvp->lv[l];
+    const int H = d.H, W = d.W, HW = H * W, J = p.J;
+    r.idx = __ldg(p.cand_index + r.cs);
+    const int y = r.idx / W, x = r.idx - y * W;
+    const float* heads = p.item_heads + (static_cast<size_t>(r.cs) * J + j) * 16;
+    r.hxv = __ldg(heads + h);
+    r.hyv = __ldg(heads + 8 + h);
+    const Corner c = make_corner(sample_coord(x, r.hxv, static_cast<float>(W)), sample_coord(y, r.hyv, static_cast<float>(H)), W, H);
+    if (!corner_ok(c, ck, W, H)) return r;
+    const int pix = corner_pix(c, ck, W);
+    r.wk = corner_wgt(c, ck);
+    r.ptr = d.feats[p.layer] + (static_cast<size_t>(b) * HW + pix) * TC_C;
+    // the producers gather this row one to two tiles from now: pull its 8 lines into L2 already, so that a
+    // k-block's arrival is bounded by L2 latency instead of by its slowest DRAM miss
+#pragma unroll
+    for (int q = 0; q < TC_C * 4 / 128; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(r.ptr + q * 32));
+    const float* prev = p.prev_uvd ? p.prev_uvd[l] : nullptr;
+    if (prev) {
+        const float* q = prev + (static_cast<size_t>(b) * HW + pix) * 3 * J + 3 * j;
+        r.prev0 = __ldg(q); r.prev1 = __ldg(q + 1); r.prev2 = __ldg(q + 2);
+    } else {
+        const float* q = d.pose + (static_cast<size_t>(b) * (3 + 6 * J) + 3 + 3 * j) * HW + pix;
+        r.prev0 = __ldg(q) * d.scale_uv;
+        r.prev1 = __ldg(q + HW) * d.scale_uv;
+        r.prev2 = (j == p.root) ? 0.f : __ldg(q + 2 * static_cast<size_t>(HW)) * d.scale_d;
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+refine_tc_kernel(const TcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    unsigned char* sA = base;                                   // TC_NS stages of A_hi
+    unsigned char* sAl = sA + TC_NS * TC_A_BYTES;               // TC_NLO buffers of A_lo
+    unsigned char* sB = sAl + TC_NLO * TC_A_BYTES;              // per k-block: 16 hi rows then 16 lo rows
+    __shared__ uint64_t full[TC_NS], empty[TC_NS];              // producers -> MMA warp, MMA warp -> producers
+    __shared__ uint64_t acc_full[2], acc_free[2], rows_ready[2];// MMA -> epilogue, epilogue -> MMA, epilogue -> producers
+    __shared__ uint32_t tmem_base;
+    __shared__ const float* s_rowptr[2][128];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long kernel_t0 = clock64();
+    const int J = p.J;
+    const int n_valid = __ldg(p.n_valid);
+    const int n_groups = (n_valid + 3) >> 2;
+    const int n_tiles = J * n_groups;
+    const int t0 = static_cast<int>(static_cast<long long>(n_tiles) * blockIdx.x / gridDim.x);
+    const int t1 = static_cast<int>(static_cast<long long>(n_tiles) * (blockIdx.x + 1) / gridDim.x);
+    if (t0 >= t1) return;
+    const int my_tiles = t1 - t0;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_NS; ++s) { tc::mbar_init(&full[s], TC_PRODUCER_WARPS); tc::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&acc_full[s], 1); tc::mbar_init(&acc_free[s], TC_EPI_WARPS); tc::mbar_init(&rows_ready[s], TC_EPI_WARPS); }
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) tc::tmem_alloc(&tmem_base, 64);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = tmem_base;
+    const uint32_t sA_u = tc::smem_u32(sA), sAl_u = tc::smem_u32(sAl), sB_u = tc::smem_u32(sB);
+
+    if (warp == TC_MMA_WARP) {
+        // ===== MMA issuer warp =====================================================================================
+        constexpr uint32_t idesc32 = tc::instr_desc_tf32(128, 2 * TC_N);   // A_hi x [B_hi ; B_lo]  -> D[:, 0:32]
+        constexpr uint32_t idesc16 = tc::instr_desc_tf32(128, TC_N);       // A_lo x  B_hi          -> D[:, 0:16]
+        int g = 0;
+        long long dbg_a = 0, dbg_b = 0, dbg_c = 0;   // wait full | issue | wait acc_free
+        for (int i = 0; i < my_tiles; ++i) {
+            const uint32_t dcol = tmem_d + (i & 1) * 32;
+            { const long long c0 = clock64();
+              if (i >= 2) tc::mbar_wait(&acc_free[i & 1], ((i >> 1) - 1) & 1);   // epilogue of tile i-2 has drained this buffer
+              dbg_c += clock64() - c0; }
+            for (int kb = 0; kb < TC_KB; ++kb, ++g) {
+                const int st = g % TC_NS;
+                const long long c0 = clock64();
+                tc::mbar_wait(&full[st], (g / TC_NS) & 1);
+                tc::tc_fence_after();
+                const long long c1 = clock64();
+                dbg_a += c1 - c0;
+                if (!(p.split & 2)) {            // (bit 1: timing experiment without MMAs)
+                    const uint32_t a_hi = sA_u + st * TC_A_BYTES, a_lo = sAl_u + (g % TC_NLO) * TC_A_BYTES;
+                    const uint32_t b_pk = sB_u + kb * TC_BK_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t da = tc::smem_desc_sw128(a_hi + k * 32);
+                        const uint64_t db = tc::smem_desc_sw128(b_pk + k * 32);
+                        if (p.split & 1) {
+                            tc::umma_tf32_elect(dcol, da, db, idesc32, (kb | k) != 0);
+                            tc::umma_tf32_elect(dcol, tc::smem_desc_sw128(a_lo + k * 32), db, idesc16, true);
+                        } else {
+                            tc::umma_tf32_elect(dcol, da, db, idesc16, (kb | k) != 0);
+                        }
+                    }
+                }
+                tc::umma_commit_elect(&empty[st]);
+                if (kb == TC_KB - 1) tc::umma_commit_elect(&acc_full[i & 1]);
+                __syncwarp();
+                dbg_b += clock64() - c1;
+            }
+        }
+        if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 16 + 0] = dbg_a; p.dbg[blockIdx.x * 16 + 1] = dbg_b; p.dbg[blockIdx.x * 16 + 2] = dbg_c; }
+    } else if (warp >= TC_FIRST_PRODUCER && (warp & 3) == 3) {
+        // filler warps of sub-partition 3: nothing to do
+    } else if (warp >= TC_FIRST_PRODUCER) {
+        // ===== producer warps: gather feature rows (cp.async), split hi/lo, hand k-blocks to the MMA warp ===========
+        const int ptid = (((warp - TC_FIRST_PRODUCER) >> 2) * 3 + (warp & 3)) * 32 + lane;
+        constexpr int NPT = 32 * TC_PRODUCER_WARPS;
+        constexpr int NIT = (1024 + NPT - 1) / NPT;
+        const int total_kb = my_tiles * TC_KB;
+        auto wait_consumed = [&](int g) { tc::mbar_wait(&empty[g % TC_NS], (g / TC_NS) & 1); };
+        // this thread always handles the same (row, 16-B chunk) pairs: chunk c = ptid + NPT * it
+        uint32_t soff[NIT];
+        const float* rp[2][NIT];     // feature-row pointers (+ chunk offset) of the tile being gathered, per pointer buffer
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int c = ptid + NPT * it;
+            soff[it] = tc::swz128((c & 1023) >> 3, c & 7);
+            rp[0][it] = rp[1][it] = nullptr;
+        }
+        // stage k-block gi (tile gi / 8) into ring slot gi % NS
+        auto gather = [&](int gi) {
+            const int i = gi / TC_KB, kb = gi - i * TC_KB, st = gi % TC_NS;
+            if (kb == 0) {
+                tc::mbar_wait(&rows_ready[i & 1], (i >> 1) & 1);   // row pointers of tile i are in s_rowptr[i & 1]
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    const int c = ptid + NPT * it;
+                    const float* src = (c < 1024) ? s_rowptr[i & 1][c >> 3] : nullptr;
+                    if (i & 1) rp[1][it] = src ? src + (c & 7) * 4 : nullptr; else rp[0][it] = src ? src + (c & 7) * 4 : nullptr;
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int c = ptid + NPT * it;
+                if (c < 1024) {
+                    const float* src = (i & 1) ? rp[1][it] : rp[0][it];
+                    tc::cp_async16_ca(sA_u + st * TC_A_BYTES + soff[it], src ? src + kb * 32 : p.wpack, src != nullptr);
+                }
+            }
+        };
+        for (int gi = 0; gi < TC_PD && gi < total_kb; ++gi) { gather(gi); tc::cp_async_commit(); }
+        for (int gi = total_kb; gi < TC_PD; ++gi) tc::cp_async_commit();
+        int cur_j = -1;
+        long long d_wc = 0, d_g = 0, d_w = 0, d_s = 0, d_f = 0;   // wait consumed | gather (incl. rows_ready) | cp.async wait | split | fence+arrive
+        for (int g = 0; g < total_kb; ++g) {
+            const int i = g / TC_KB, kb = g - i * TC_KB, st = g % TC_NS;
+            const long long c0 = clock64();
+            // k-block g-NLO consumed => ring slot (g+PD)%NS and A_lo[g%NLO] are free again
+            if (g >= TC_NLO) wait_consumed(g - TC_NLO);
+            const long long c1 = clock64();
+            if (g + TC_PD < total_kb) gather(g + TC_PD);
+            tc::cp_async_commit();             // possibly empty: keeps the group count uniform
+            const long long c2 = clock64();
+            if (kb == 0) {
+                const int j = (t0 + i) / n_groups;
+                if (j != cur_j) {
+                    // new joint: its panels replace the old ones once every earlier MMA has finished reading them
+                    if (g > 0) wait_consumed(g - 1);
+                    const unsigned char* src = p.bpanel + static_cast<size_t>(j) * 2 * TC_B_BYTES;
+                    for (int c = ptid; c < 2 * TC_B_BYTES / 16; c += NPT) tc::cp_async16(sB_u + c * 16, src + c * 16, true);
+                    tc::cp_async_commit();
+                    tc::cp_async_wait<0>();
+                    cur_j = j;
+                }
+            }
+            tc::cp_async_wait<TC_PD>();        // this thread's chunks of k-block g have landed
+            const long long c3 = clock64();
+            if ((p.split & 1) && !(p.split & 4)) {
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    const int c = ptid + NPT * it;
+                    if (c < 1024) {
+                        const uint32_t off = soff[it];
+                        const float4 a = *reinterpret_cast<const float4*>(sA + st * TC_A_BYTES + off);
+                        float4 lo;
+                        lo.x = a.x - tc::tf32_hi(a.x); lo.y = a.y - tc::tf32_hi(a.y);
+                        lo.z = a.z - tc::tf32_hi(a.z); lo.w = a.w - tc::tf32_hi(a.w);
+                        *reinterpret_cast<float4*>(sAl + (g % TC_NLO) * TC_A_BYTES + off) = lo;
+                    }
+                }
+            }
+            const long long c4 = clock64();
+            if (!(p.split & 8)) tc::fence_proxy_async();     // bit 3: timing experiment only
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&full[st]);
+            const long long c5 = clock64();
+            d_wc += c1 - c0; d_g += c2 - c1; d_w += c3 - c2; d_s += c4 - c3; d_f += c5 - c4;
+        }
+        tc::cp_async_wait<0>();
+        if (p.dbg && ptid == 0) {
+            long long* o = p.dbg + blockIdx.x * 16;
+            o[3] = d_wc; o[4] = d_g; o[5] = d_w; o[6] = d_s; o[7] = d_f; o[8] = total_kb;
+        }
+    } else {
+        // ===== epilogue / row-setup warps: thread t <-> row t = (item warp, head lane>>2, corner lane&3) ===========
+        const int e = warp / TC_EPI_WARPS;          // epilogue group: tiles e, e+2, ...; buffers e
+        const int rt = tid - e * 32 * TC_EPI_WARPS; // row of the tile this thread owns (= TMEM lane)
+        const int qw = warp % TC_EPI_WARPS;         // TMEM lane quadrant this warp may read
+        RowState cur{};
+        if (e < my_tiles) {
+            cur = setup_row(p, t0 + e, n_groups, n_valid, rt);
+            s_rowptr[e][rt] = cur.ptr;
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&rows_ready[e]);
+        }
+#pragma unroll 1
+        for (int i = e; i < my_tiles; i += TC_EPI_GROUPS) {
+            const int tile = t0 + i;
+            const int j = tile / n_groups;
+            const float* Bj = p.wpack + static_cast<size_t>(J) * TC_NOUT * TC_C + j * TC_NOUT + TC_OGATE;
+            const long long e0 = clock64();
+            tc::mbar_wait(&acc_full[i & 1], (i >> 1) & 1);
+            tc::tc_fence_after();
+            const long long e1 = clock64();
+            float v[16], v2[16];
+            const uint32_t taddr = tmem_d + (static_cast<uint32_t>(qw * 32) << 16) + (i & 1) * 32;
+            tc::tmem_ld16(taddr, v);
+            if (p.split & 1) {
+                tc::tmem_ld16(taddr + TC_N, v2);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) v[k] += v2[k];
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&acc_free[i & 1]);
+            // next-but-one tile: its rows reuse this tile's pointer buffer (every gather of this tile was issued
+            // before its MMAs could complete); start the dependent loads now, they overlap the math below
+            const long long e2 = clock64();
+            RowState nx{};
+            if (i + 2 < my_tiles) {
+                nx = setup_row(p, tile + 2, n_groups, n_valid, rt);
+                s_rowptr[e][rt] = nx.ptr;
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&rows_ready[e]);
+            }
+            const long long e3 = clock64();
+            float val[3], cf[3];
+            {
+                const float pv[3] = {cur.prev0, cur.prev1, cur.prev2};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float gte = sigmoid_acc(v[k] + __ldg(Bj + k));
+                    const float n = v[3 + k] + __ldg(Bj + 3 + k);
+                    const float o = __fadd_rn(__fmul_rn(1.0f - gte, pv[k]), __fmul_rn(gte, n));
+                    const bool ok = cur.ptr != nullptr;
+                    val[k] = ok ? o * cur.wk : 0.f;
+                    cf[k] = ok ? (v[6 + k] + __ldg(Bj + 6 + k)) * cur.wk : 0.f;
+                }
+            }
+            float out[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                // bilinear sum over the 4 corners (lane bits 0,1)
+                val[k] += __shfl_xor_sync(FULL, val[k], 1);
+                cf[k] += __shfl_xor_sync(FULL, cf[k], 1);
+                val[k] += __shfl_xor_sync(FULL, val[k], 2);
+                cf[k] += __shfl_xor_sync(FULL, cf[k], 2);
+                const float hv = val[k] + (k == 0 ? cur.hxv : (k == 1 ? cur.hyv : 0.f));   // + diff
+                // softmax over the 8 heads (lane bits 2,3,4); every corner lane carries the same head value
+                float m = cf[k];
+                m = fmaxf(m, __shfl_xor_sync(FULL, m, 4));
+                m = fmaxf(m, __shfl_xor_sync(FULL, m, 8));
+                m = fmaxf(m, __shfl_xor_sync(FULL, m, 16));
+                const float e = expf(cf[k] - m);
+                float se = e;
+                se += __shfl_xor_sync(FULL, se, 4);
+                se += __shfl_xor_sync(FULL, se, 8);
+                se += __shfl_xor_sync(FULL, se, 16);
+                float o = hv * (e / se);
+                o += __shfl_xor_sync(FULL, o, 4);
+                o += __shfl_xor_sync(FULL, o, 8);
+                o += __shfl_xor_sync(FULL, o, 16);
+                out[k] = o;
+            }
+            if (cur.item_ok && lane < 3) {
+                // eval tail + assembly (das_head.py:254-262, 725-743)
+                const das_level_desc& d = p.lv->lv[cur.lvl];
+                const int W = d.W, HW = d.H * d.W;
+                const int b = cur.cs / p.CT;
+                const int y = cur.idx / W, x = cur.idx - y * W;
+                const float* pose = d.pose + static_cast<size_t>(b) * (3 + 6 * J) * HW;
+                const float sx = __ldg(p.scale_xy + 2 * b), sy = __ldg(p.scale_xy + 2 * b + 1);
+                const float qf = sqrtf(sx * sy);
+                const float stf = static_cast<float>(d.stride), half = static_cast<float>(d.stride / 2);
+                float z = __ldg(pose + 2 * static_cast<size_t>(HW) + cur.idx) * d.scale_depth;
+                z = __fdiv_rn(z, p.depth_factor);
+                const float zq = __fmul_rn(z, qf);
+                const float o = lane == 0 ? out[0] : (lane == 1 ? out[1] : out[2]);
+                float r;
+                if (lane == 0) r = __fdiv_rn(__fadd_rn(__fmul_rn(o, stf), static_cast<float>(x) * stf + half), sx);
+                else if (lane == 1) r = __fdiv_rn(__fadd_rn(__fmul_rn(o, stf), static_cast<float>(y) * stf + half), sy);
+                else r = __fadd_rn((j == p.root) ? 0.0f : __fmul_rn(o, p.z_norm), zq);
+                p.cand_pose[(static_cast<size_t>(cur.cs) * J + j) * 3 + lane] = r;
+                if (j == 0) {
+                    float c;
+                    if (lane == 2) c = zq;
+                    else {
+                        const float off = __ldg(pose + static_cast<size_t>(lane) * HW + cur.idx) * d.scale_offset;
+                        const float P = static_cast<float>(lane == 0 ? x : y) * stf + half;
+                        c = __fdiv_rn(__fsub_rn(P, off), lane == 0 ? sx : sy);
+                    }
+                    p.cand_center[static_cast<size_t>(cur.cs) * 3 + lane] = c;
+                }
+            }
+            cur = nx;
+            if (p.dbg && tid == 0) {
+                long long* o = p.dbg + blockIdx.x * 16;
+                o[9] += e1 - e0; o[10] += e2 - e1; o[11] += e3 - e2; o[12] += clock64() - e3;
+            }
+        }
+    }
+    if (p.dbg && tid == 0) p.dbg[blockIdx.x * 16 + 13] = clock64() - kernel_t0;
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, 64);
+}
+
+// [J][17][C] packed weights -> per joint [8 k-blocks][32 rows = 16 hi + 16 lo][128 B swizzled]
+__global__ void pack_tc_panels_kernel(const float* __restrict__ wpack, unsigned char* __restrict__ dst, int J) {
+    const int total = J * 2 * TC_KB * TC_N * 32;   // one thread per float
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int e = t & 31;                      // channel inside the k-block
+        const int row = (t >> 5) % TC_N;
+        const int kb = (t / (32 * TC_N)) % TC_KB;
+        const int part = (t / (32 * TC_N * TC_KB)) & 1;
+        const int j = t / (32 * TC_N * TC_KB * 2);
+        float w = 0.f;
+        if (row < 9) w = wpack[(static_cast<size_t>(j) * TC_NOUT + TC_OGATE + row) * TC_C + kb * 32 + e];
+        const float hi = tc::tf32_hi(w);
+        const float v = part == 0 ? hi : (w - hi);
+        const int prow = part * TC_N + row;          // 16 hi rows then 16 lo rows inside the k-block tile (N = 32 view)
+        const uint32_t off = static_cast<uint32_t>(prow) * 128u + ((static_cast<uint32_t>(e >> 2) ^ (prow & 7)) << 4) + (e & 3) * 4;
+        *reinterpret_cast<float*>(dst + static_cast<size_t>(j) * 2 * TC_B_BYTES + kb * TC_BK_BYTES + off) = v;
+    }
+}
+
+}  // namespace das
+
+static long long* g_tc_dbg = nullptr;
+// profiling aid: per-CTA cycle counters of the three warp roles ([148][16] int64 device buffer, or NULL to disable)
+extern "C" int das_tc_set_debug_buffer(long long* dev_buf) { g_tc_dbg = dev_buf; return DAS_OK; }
+
+extern "C" int64_t das_tc_panel_bytes(const das_decode_cfg* cfg) {
+    return cfg ? static_cast<int64_t>(cfg->num_joints) * 2 * das::TC_B_BYTES : 0;
+}
+
+extern "C" int das_pack_tc_panels(const das_decode_cfg* cfg, const float* packed_weights, void* panels, void* stream) {
+    using namespace das;
+    DAS_REQUIRE(cfg && packed_weights && panels, DAS_ERR_ARG, "das_pack_tc_panels: null pointer");
+    DAS_REQUIRE(cfg->feat_channels == TC_C && cfg->num_heads == TC_NH, DAS_ERR_UNSUPPORTED,
+                "tensor-core refinement is built for feat_channels=256, num_heads=4");
+    pack_tc_panels_kernel<<<kSMs, 256, 0, static_cast<cudaStream_t>(stream)>>>(packed_weights, static_cast<unsigned char*>(panels),
+                                                                              cfg->num_joints);
+    DAS_CUDA_CHECK(cudaGetLastError());
+    return DAS_OK;
+}
+
+extern "C" int das_refine_tc(const das_levels* d_levels, const das_levels* h_levels, const das_decode_cfg* cfg,
+                             const float* weights, const void* panels, const float* const* prev_uvd,
+                             const float* scale_xy, const int32_t* cand_index, int32_t cand_slots,
+                             const float* item_heads, const int32_t* valid_list, const int32_t* n_valid,
+                             float* cand_pose, float* cand_center, int32_t split, void* stream) {
+    using namespace das;
+    DAS_REQUIRE(d_levels && h_levels && cfg && weights && panels && scale_xy && cand_index && item_heads && valid_list &&
+                n_valid && cand_pose && cand_center, DAS_ERR_ARG, "das_refine_tc: null pointer");
+    DAS_REQUIRE(cfg->feat_channels == TC_C && cfg->num_heads == TC_NH, DAS_ERR_UNSUPPORTED,
+                "tensor-core refinement is built for feat_channels=256, num_heads=4");
+    TcParams p{};
+    p.lv = d_levels; p.wpack = weights; p.bpanel = static_cast<const unsigned char*>(panels); p.prev_uvd = prev_uvd;
+    p.scale_xy = scale_xy; p.cand_index = cand_index; p.item_heads = item_heads; p.valid_list = valid_list; p.n_valid = n_valid;
+    p.cand_pose = cand_pose; p.cand_center = cand_center;
+    p.CT = cand_slots; p.J = cfg->num_joints; p.root = cfg->root_idx; p.nms_pre = cfg->nms_pre; p.layer = cfg->num_layers - 1;
+    p.split = split; p.depth_factor = cfg->depth_factor; p.z_norm = cfg->z_norm;
+    p.dbg = g_tc_dbg;
+    static bool attr_done = false;
+    if (!attr_done) {
+        DAS_CUDA_CHECK(cudaFuncSetAttribute(refine_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+        attr_done = true;
+    }
+    refine_tc_kernel<<<kSMs, TC_THREADS, TC_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+    DAS_CUDA_CHECK(cudaGetLastError());
+    return DAS_OK;
+}

@@ -86,7 +86,67 @@ tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
     if (warp == 0) tc::tmem_dealloc(tmem_base, 32);
 }
 
+// Micro-benchmark: one thread issues `iters` back-to-back MMAs (M=128, N, K=8) on resident smem tiles and
+// waits for their completion; reports SM cycles for (a) issue only and (b) issue + completion.
+template <int N>
+__global__ void __launch_bounds__(128, 1) tc_mma_bench_kernel(int iters, long long* out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~static_cast<uintptr_t>(1023));
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<float*>(base)[i] = 1.0f;
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::mbar_fence_init(); }
+    if (warp == 0) tc::tmem_alloc(&tmem_base, 256);
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    if (tid == 0) {
+        constexpr uint32_t idesc = tc::instr_desc_tf32(128, N);
+        const uint32_t a = tc::smem_u32(base), b = tc::smem_u32(base + 16384);
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            const uint64_t da = tc::smem_desc_sw128(a + (i & 3) * 32);
+            const uint64_t db = tc::smem_desc_sw128(b + (i & 3) * 32);
+            tc::umma_tf32(tmem_base, da, db, idesc, i != 0);
+        }
+        const long long t1 = clock64();
+        tc::umma_commit(&bar);
+        tc::mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        out[0] = t1 - t0;
+        out[1] = t2 - t0;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, 256);
+}
+
 }  // namespace das
+
+extern "C" int das_tc_mma_bench(int32_t N, int32_t iters, long long* out_cycles, void* stream) {
+    using namespace das;
+    DAS_REQUIRE(out_cycles && iters > 0, DAS_ERR_ARG, "das_tc_mma_bench: bad argument");
+    const size_t smem = 1024 + 16384 + 32768;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define DAS_BENCH_CASE(NN)                                                                                              \
+    case NN:                                                                                                            \
+        DAS_CUDA_CHECK(cudaFuncSetAttribute(tc_mma_bench_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+        tc_mma_bench_kernel<NN><<<1, 128, smem, st>>>(iters, out_cycles);                                              \
+        break;
+    switch (N) {
+        DAS_BENCH_CASE(16)
+        DAS_BENCH_CASE(32)
+        DAS_BENCH_CASE(64)
+        DAS_BENCH_CASE(128)
+        DAS_BENCH_CASE(256)
+        default: set_error("das_tc_mma_bench: N=%d", N); return DAS_ERR_ARG;
+    }
+#undef DAS_BENCH_CASE
+    DAS_CUDA_CHECK(cudaGetLastError());
+    return DAS_OK;
+}
 
 extern "C" int das_tc_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t split, void* stream) {
     using namespace das;

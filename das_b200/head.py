@@ -90,7 +90,7 @@ class DecodePlan:
 
     def __init__(self, *, num_joints, root_idx, depth_factor, z_norm, strides, level_sizes, batch,
                  test_cfg, num_heads=4, feat_channels=256, num_layers=1, refine=True, peak_kernel=0,
-                 dataset_depth_factor=1.0, device="cuda"):
+                 dataset_depth_factor=1.0, device="cuda", refine_mode=None):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("das_b200 needs a CUDA device; there is no CPU path")
@@ -128,6 +128,8 @@ class DecodePlan:
             bufs = Buffers()
             ct, p = C.c_int32(), C.c_int32()
             _lib.check(self.lib.das_plan_buffers(self._plan, C.byref(bufs), C.byref(ct), C.byref(p)), "das_plan_buffers")
+            if refine_mode is not None:      # 0 fp32 SIMT, 1 tcgen05 3xTF32 (default when supported), 2 tcgen05 TF32
+                _lib.check(self.lib.das_plan_set_refine_mode(self._plan, int(refine_mode)), "das_plan_set_refine_mode")
         self.cand_slots, self.out_slots = ct.value, p.value
         B, CT, P, J = self.batch, ct.value, p.value, num_joints
         dev = self.device

@@ -127,6 +127,26 @@ int das_gather_refine_assemble(const das_levels* d_levels, const das_levels* h_l
                                float* cand_pose, float* cand_center, int32_t* work_counter,
                                void* stream);
 
+/* Tensor-core variant of stage 3+4 (feat_channels = 256, num_heads = 4), two launches:
+ *   das_refine_heads  phases 1-2 per (candidate, joint): sampling offsets -> item_heads [B*CT*J][16],
+ *                     surviving candidates -> valid_list, counters[1] = their number (counters: 2 int32)
+ *   das_refine_tc     the 32 sampled rows per item as a gathered tcgen05 GEMM (split=1: 3xTF32, fp32-level
+ *                     accuracy; split=0: one TF32 pass) + gate/blend/softmax epilogue, eval tail, assembly.
+ * panels: das_pack_tc_panels() image of the last layer's packed weights (das_tc_panel_bytes() bytes). */
+int das_refine_heads(const das_levels* d_levels, const das_levels* h_levels, const das_decode_cfg* cfg,
+                     const float* weights, const float* const* prev_uvd, const float* cand_score,
+                     const int32_t* cand_index, int32_t cand_slots, float* item_heads,
+                     int32_t* valid_list, int32_t* counters, void* stream);
+int das_refine_tc(const das_levels* d_levels, const das_levels* h_levels, const das_decode_cfg* cfg,
+                  const float* weights, const void* panels, const float* const* prev_uvd,
+                  const float* scale_xy, const int32_t* cand_index, int32_t cand_slots,
+                  const float* item_heads, const int32_t* valid_list, const int32_t* n_valid,
+                  float* cand_pose, float* cand_center, int32_t split, void* stream);
+int das_pack_tc_panels(const das_decode_cfg* cfg, const float* packed_weights, void* panels, void* stream);
+int64_t das_tc_panel_bytes(const das_decode_cfg* cfg);
+/* profiling aid: per-CTA cycle counters of das_refine_tc's warp roles ([148][16] int64 device buffer; NULL = off) */
+int das_tc_set_debug_buffer(long long* dev_buf);
+
 /* One dense refinement layer over a whole level (layers 1..L-1 when num_layers > 1).
  * uvd_in NULL -> scaled raw uvd from lv.pose.  uvd_out NHWC [B,H,W,3J]. proj: scratch
  * [B,H,W,14J] fp32. */
@@ -170,6 +190,9 @@ int das_plan_run(das_plan* plan, void* stream, int32_t mode);
 int das_plan_stage_ms(das_plan* plan, float* ms);
 /* all out_* buffers are carved from one device block (one D2H, or one NCCL all-gather across ranks) */
 int das_plan_output_block(const das_plan* plan, void** ptr, int64_t* bytes);
+/* refinement implementation: 0 = fp32 SIMT (any supported C), 1 = tensor cores 3xTF32 (default when
+ * feat_channels = 256 and num_heads = 4), 2 = tensor cores, single TF32 pass. Call before the first run. */
+int das_plan_set_refine_mode(das_plan* plan, int32_t mode);
 int das_plan_buffers(const das_plan* plan, das_buffers* out, int32_t* cand_slots, int32_t* out_slots);
 int64_t das_plan_kernel_launches(const das_plan* plan);   /* kernels enqueued by das_plan_run so far */
 
@@ -186,6 +209,8 @@ int64_t das_plan_d2h_bytes(const das_plan* plan);
 /* Self-test of the tcgen05/TMEM building blocks: D[128,N] = A[128,K] * B[N,K]^T (row-major fp32 device
  * buffers; N in {16,32}, K a multiple of 32). split=0: one TF32 pass; split=1: 3xTF32 (fp32-level accuracy). */
 int das_tc_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t split, void* stream);
+/* tcgen05.mma issue/throughput micro-benchmark: out_cycles[0] = issue only, [1] = issue + completion (device int64[2]) */
+int das_tc_mma_bench(int32_t N, int32_t iters, long long* out_cycles, void* stream);
 
 #ifdef __cplusplus
 }

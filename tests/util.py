@@ -53,21 +53,23 @@ def run_oracle(case, test_cfg, stable=False, peak_kernel=0):
                          stable=stable, peak_kernel=peak_kernel)
 
 
-def make_plan(case, test_cfg, refine=True, peak_kernel=0, device="cuda"):
+def make_plan(case, test_cfg, refine=True, peak_kernel=0, device="cuda", refine_mode=None):
     cfg = case["cfg"]
     sizes = [tuple(lv["cls"].shape[-2:]) for lv in case["levels"]]
     plan = DecodePlan(num_joints=cfg.num_joints, root_idx=cfg.root_idx, depth_factor=cfg.depth_factor,
                       z_norm=cfg.z_norm, strides=cfg.strides, level_sizes=sizes, batch=case["batch"],
                       test_cfg=test_cfg, num_heads=cfg.num_heads, feat_channels=cfg.feat_channels,
-                      num_layers=cfg.num_layers, refine=refine, peak_kernel=peak_kernel, device=device)
+                      num_layers=cfg.num_layers, refine=refine, peak_kernel=peak_kernel, device=device,
+                      refine_mode=refine_mode)
     if refine:
         plan.set_weights(synth.layers_to(case["layers"], device))
     return plan
 
 
-def run_gpu(case, test_cfg, refine=True, peak_kernel=0, pose_override=None, use_graph=True, device="cuda"):
+def run_gpu(case, test_cfg, refine=True, peak_kernel=0, pose_override=None, use_graph=True, device="cuda",
+            refine_mode=None):
     """Decode on the GPU through the C-ABI plan. pose_override: per-level final pose maps for refine=False."""
-    plan = make_plan(case, test_cfg, refine, peak_kernel, device)
+    plan = make_plan(case, test_cfg, refine, peak_kernel, device, refine_mode)
     dl = synth.levels_to(case["levels"], device)
     levels = []
     for l, lv in enumerate(dl):
