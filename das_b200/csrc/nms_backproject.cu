@@ -59,7 +59,8 @@ __device__ __forceinline__ float oks_pair(const float* pg, const float* pd, floa
     return static_cast<float>(t / static_cast<double>(J));
 }
 
-__global__ void __launch_bounds__(NM_THREADS, 1)
+template <int NT>
+__global__ void __launch_bounds__(NT, 1)
 nms_backproject_kernel(const NmsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: keys u64[n2] | area f32[CT] | order i32[CT] | flag u8[CT]
@@ -86,7 +87,7 @@ nms_backproject_kernel(const NmsParams p) {
 
     // ---- validity (das_head.py:763-769) + stable compaction in slot order ---------------------------
     // n is small against 1024 threads in every shipped config; a simple ordered scan keeps slot order.
-    for (int base = 0; base < CT; base += NM_THREADS) {
+    for (int base = 0; base < CT; base += NT) {
         const int c = base + tid;
         const bool ok = c < CT && (p.score_thr > 0.f ? (score[c] > p.score_thr) : true);
         const unsigned bal = __ballot_sync(0xffffffffu, ok);
@@ -100,7 +101,7 @@ nms_backproject_kernel(const NmsParams p) {
         __syncthreads();
         if (tid == 0) {
             int t = 0;
-            for (int w = 0; w < 32; ++w) t += wcount[w];
+            for (int w = 0; w < NT / 32; ++w) t += wcount[w];
             s_n += t;
         }
         __syncthreads();
@@ -112,7 +113,7 @@ nms_backproject_kernel(const NmsParams p) {
         // ---- rank by (score desc, slot asc); areas (das_head.py:773-775) ---------------------------
         int n2 = 1;
         while (n2 < n) n2 <<= 1;
-        for (int i = tid; i < n2; i += NM_THREADS) {
+        for (int i = tid; i < n2; i += NT) {
             uint64_t k = 0;
             if (i < n) {
                 const int c = order[i];
@@ -128,24 +129,37 @@ nms_backproject_kernel(const NmsParams p) {
             keys[i] = k;
         }
         __syncthreads();
-        // bitonic sort, descending
-        for (int k = 2; k <= n2; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int t = tid; t < (n2 >> 1); t += NM_THREADS) {
-                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                    const int q = i | j;
-                    const bool desc = ((i & k) == 0);
-                    const uint64_t x = keys[i], y = keys[q];
-                    if ((x < y) == desc) { keys[i] = y; keys[q] = x; }
-                }
-                __syncthreads();
+        if (n <= NT) {
+            // few candidates: rank by counting (keys are distinct) -- three barriers instead of a bitonic network
+            int rnk = 0, c = 0;
+            if (tid < n) {
+                const uint64_t k = keys[tid];
+                c = order[tid];
+                for (int j = 0; j < n; ++j) rnk += (keys[j] > k);
             }
+            __syncthreads();
+            if (tid < n) { order[rnk] = c; dead[tid] = 0; }
+            __syncthreads();
+        } else {
+            // bitonic sort, descending
+            for (int k = 2; k <= n2; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = tid; t < (n2 >> 1); t += NT) {
+                        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                        const int q = i | j;
+                        const bool desc = ((i & k) == 0);
+                        const uint64_t x = keys[i], y = keys[q];
+                        if ((x < y) == desc) { keys[i] = y; keys[q] = x; }
+                    }
+                    __syncthreads();
+                }
+            }
+            for (int i = tid; i < n; i += NT) {
+                order[i] = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(keys[i] & 0xFFFFFFFFull));
+                dead[i] = 0;
+            }
+            __syncthreads();
         }
-        for (int i = tid; i < n; i += NM_THREADS) {
-            order[i] = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(keys[i] & 0xFFFFFFFFull));
-            dead[i] = 0;
-        }
-        __syncthreads();
 
         const int limit = min(p.nms_post, n);
         if (n <= NM_MATRIX_N) {
@@ -155,7 +169,7 @@ nms_backproject_kernel(const NmsParams p) {
             const int npairs = n * (n - 1) / 2;
             if (J <= 16) {
                 const int grp = tid >> 4, gl = tid & 15;
-                for (int pr = grp; pr < ((npairs + 63) / 64) * 64; pr += NM_THREADS / 16) {
+                for (int pr = grp; pr < ((npairs + 63) / 64) * 64; pr += NT / 16) {
                     // both half-warps must run the shuffles together -> loop bound is warp-uniform
                     int i = 0, j = 1;
                     const bool live = pr < npairs;
@@ -172,7 +186,7 @@ nms_backproject_kernel(const NmsParams p) {
                 }
             } else {
                 const int grp = tid >> 5, gl = tid & 31;
-                for (int pr = grp; pr < npairs; pr += NM_THREADS / 32) {
+                for (int pr = grp; pr < npairs; pr += NT / 32) {
                     int rem = pr, i = 0;
                     while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
                     const int j = i + 1 + rem;
@@ -210,7 +224,7 @@ nms_backproject_kernel(const NmsParams p) {
                 if (tid == 0) kept_list[kept] = ci;
                 ++kept;
                 if (kept >= limit) break;
-                for (int j = i + 1 + grp; j < n; j += NM_THREADS / 32) {
+                for (int j = i + 1 + grp; j < n; j += NT / 32) {
                     if (dead[j]) continue;             // warp-uniform
                     const int cj = order[j];
                     const float v = oks_pair<32>(pose + static_cast<size_t>(ci) * J * 3, pose + static_cast<size_t>(cj) * J * 3,
@@ -242,14 +256,14 @@ nms_backproject_kernel(const NmsParams p) {
     const double c20 = R[3] * R[7] - R[4] * R[6], c21 = R[1] * R[6] - R[0] * R[7], c22 = R[0] * R[4] - R[1] * R[3];
     const double detR = R[0] * c00 + R[1] * c10 + R[2] * c20;
 
-    for (int k = tid; k < P; k += NM_THREADS) {
+    for (int k = tid; k < P; k += NT) {
         const bool live = k < kept;
         const int c = live ? kept_list[k] : 0;
         o.out_score[static_cast<size_t>(b) * P + k] = live ? score[c] : 0.f;
         o.out_slot[static_cast<size_t>(b) * P + k] = live ? c : -1;
         for (int d = 0; d < 3; ++d) o.out_center[(static_cast<size_t>(b) * P + k) * 3 + d] = live ? center[c * 3 + d] : 0.f;
     }
-    for (int e = tid; e < P * J; e += NM_THREADS) {
+    for (int e = tid; e < P * J; e += NT) {
         const int k = e / J, j = e - k * J;
         const size_t ob = ((static_cast<size_t>(b) * P + k) * J + j) * 3;
         if (k < kept) {
@@ -303,11 +317,13 @@ extern "C" int das_nms_backproject(const das_decode_cfg* cfg, int32_t batch, int
     const size_t smem = static_cast<size_t>(n2) * 8 + static_cast<size_t>(cand_slots) * (4 + 4 + 1) + 16;
     static bool attr_done = false;
     if (!attr_done) {
-        DAS_CUDA_CHECK(cudaFuncSetAttribute(nms_backproject_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        DAS_CUDA_CHECK(cudaFuncSetAttribute(nms_backproject_kernel<NM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             NM_MAX_CAND * 8 + NM_MAX_CAND * 9 + 16));
         attr_done = true;
     }
-    nms_backproject_kernel<<<batch, NM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    // few candidates (the usual case): 8 warps keep the ~20 block barriers of this latency-bound kernel cheap
+    if (cand_slots <= 128) nms_backproject_kernel<256><<<batch, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    else nms_backproject_kernel<NM_THREADS><<<batch, NM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
     DAS_CUDA_CHECK(cudaGetLastError());
     return DAS_OK;
 }

@@ -7,6 +7,9 @@
 // broken towards the lower cell index (composite 64-bit keys: score bits << 32 | ~index).
 //
 // Selection strategy (K = nms_pre is small against H*W):
+//   Q  (no peak mask, K <= 128) bounded fast path: score <= sigmoid(cls), so after a first sweep over the cls
+//      plane alone a logit threshold leaves a few dozen cells for which the exact score is computed;
+//   otherwise, or if Q's list overflows:
 //   A  every thread scans its cells, writes the 32-bit rank keys to an L2-resident scratch plane and
 //      keeps its own maximum;
 //   B  tau = K-th largest of the 1024 per-thread maxima (31-step bitwise search with
@@ -79,128 +82,239 @@ score_topk_kernel(const das_levels* __restrict__ lvp, int nms_pre, int peak,
     }
     uint32_t* __restrict__ keys = scratch + static_cast<size_t>(b) * scratch_per_image + sc0;
 
-    // ---- A: rank keys -> scratch, per-thread maximum ---------------------------------------------
-    uint64_t best = 0;
-    if (!peak) {
-        const bool vec = ((HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(cls) & 15) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(ctr) & 15) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(keys) & 15) == 0);
+    if (tid == 0) list_n = 0;
+    __syncthreads();
+    bool done = false;
+    if (!peak && K <= TK_FAST_K) {
+        // ---- Q: bounded fast path ---------------------------------------------------------------------------
+        // score = sigmoid(cls) * sigmoid(ctr) <= sigmoid(cls), so once a lower bound tau of the K-th best score is
+        // known, only cells with cls >= logit(tau) can matter: the exp/div work and the centerness reads shrink from
+        // every cell to a few dozen.  tau = K-th largest of the exact scores of each thread's best-cls cell (1024
+        // distinct cells => a valid lower bound).
+        const bool vec = ((HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(cls) & 15) == 0);
+        float bc = -INFINITY;
+        int bi = -1;
         if (vec) {
             const int n4 = HW >> 2;
             for (int q = tid; q < n4; q += TK_THREADS) {
-                const float4 a = ldg_f4_stream(cls + 4 * q);
-                const float4 c = ldg_f4_stream(ctr + 4 * q);
-                uint4 k;
-                k.x = __float_as_uint(sigmoid_acc(a.x) * sigmoid_acc(c.x));
-                k.y = __float_as_uint(sigmoid_acc(a.y) * sigmoid_acc(c.y));
-                k.z = __float_as_uint(sigmoid_acc(a.z) * sigmoid_acc(c.z));
-                k.w = __float_as_uint(sigmoid_acc(a.w) * sigmoid_acc(c.w));
-                reinterpret_cast<uint4*>(keys)[q] = k;
-                const uint32_t i0 = 4u * q;
-                uint64_t m = compose(k.x, i0);
-                uint64_t t1 = compose(k.y, i0 + 1); m = t1 > m ? t1 : m;
-                t1 = compose(k.z, i0 + 2); m = t1 > m ? t1 : m;
-                t1 = compose(k.w, i0 + 3); m = t1 > m ? t1 : m;
-                best = m > best ? m : best;
+                const float4 a = ldg_f4(cls + 4 * q);          // stays in L1 for the second sweep
+                if (a.x > bc) { bc = a.x; bi = 4 * q; }
+                if (a.y > bc) { bc = a.y; bi = 4 * q + 1; }
+                if (a.z > bc) { bc = a.z; bi = 4 * q + 2; }
+                if (a.w > bc) { bc = a.w; bi = 4 * q + 3; }
             }
         } else {
             for (int i = tid; i < HW; i += TK_THREADS) {
-                const uint32_t k = __float_as_uint(sigmoid_acc(__ldg(cls + i)) * sigmoid_acc(__ldg(ctr + i)));
-                keys[i] = k;
-                const uint64_t c = compose(k, i);
-                best = c > best ? c : best;
+                const float a = __ldg(cls + i);
+                if (a > bc) { bc = a; bi = i; }
             }
         }
-    } else {
-        // 3x3 peak mask from shared-memory row strips: rows [r0-1, r0+R] staged, rows [r0, r0+R) ranked
-        const int R = max(1, min(H, TK_TILE_FLOATS / W - 2));
-        for (int r0 = 0; r0 < H; r0 += R) {
-            const int rows = min(R, H - r0);
-            const int n_stage = (rows + 2) * W;
-            for (int e = tid; e < n_stage; e += TK_THREADS) {
-                const int ry = e / W, x = e - ry * W;
-                const int y = r0 - 1 + ry;
-                float s = 0.0f;  // scores are >= 0, so 0 stands in for "outside the map" (max-pool pads -inf)
-                if (y >= 0 && y < H) s = sigmoid_acc(__ldg(cls + y * W + x)) * sigmoid_acc(__ldg(ctr + y * W + x));
-                tile[e] = s;
-            }
-            __syncthreads();
-            for (int e = tid; e < rows * W; e += TK_THREADS) {
-                const int ry = e / W, x = e - ry * W;
-                const float* c = tile + (ry + 1) * W + x;
-                const float s = c[0];
-                float m = fmaxf(c[-W], c[W]);
-                if (x > 0) m = fmaxf(m, fmaxf(c[-1], fmaxf(c[-W - 1], c[W - 1])));
-                if (x < W - 1) m = fmaxf(m, fmaxf(c[1], fmaxf(c[-W + 1], c[W + 1])));
-                const uint32_t k = (s >= m) ? __float_as_uint(s) : 0u;
-                const int i = (r0 + ry) * W + x;
-                keys[i] = k;
-                const uint64_t cc = compose(k, i);
-                best = cc > best ? cc : best;
-            }
-            __syncthreads();
-        }
-    }
-    if (tid == 0) list_n = 0;
-    __syncthreads();  // also makes this block's scratch writes visible to the whole block
-
-    bool need_fallback = (K > TK_FAST_K);
-    if (!need_fallback) {
-        // ---- B: tau = K-th largest per-thread maximum (score bits only) ---------------------------
-        const uint32_t mykey = static_cast<uint32_t>(best >> 32);
         uint32_t tau = 0;
-        for (int bit = 30; bit >= 0; --bit) {
-            const uint32_t trial = tau | (1u << bit);
-            if (__syncthreads_count(mykey >= trial) >= K) tau = trial;
-        }
-        // ---- C: compaction of cells with key >= tau ------------------------------------------------
-        for (int i = tid; i < HW; i += TK_THREADS) {
-            const uint32_t k = keys[i];
-            if (k >= tau) {
-                const int pos = atomicAdd(&list_n, 1);
-                if (pos < TK_LIST_CAP) list[pos] = compose(k, i);
+        if (K <= 32) {
+            // tau = K-th largest of the 32 exact scores of each warp's best-cls cell: 32 distinct cells, so still a
+            // valid lower bound, and it needs one shuffle sort in warp 0 instead of 31 block-wide barriers.
+            const int lane = tid & 31, warp = tid >> 5;
+            float wb = bc;
+            int wi = bi;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, wb, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+                if (ob > wb || (ob == wb && oi >= 0 && (wi < 0 || oi < wi))) { wb = ob; wi = oi; }
+            }
+            if (lane == 0) red[warp] = (wi >= 0) ? static_cast<int>(__float_as_uint(sigmoid_acc(wb) * sigmoid_acc(__ldg(ctr + wi)))) : 0;
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t v = static_cast<uint32_t>(red[lane]);
+                // bitonic sort of 32 keys across the lanes, descending
+#pragma unroll
+                for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+                    for (int j = k >> 1; j > 0; j >>= 1) {
+                        const uint32_t o = __shfl_xor_sync(0xffffffffu, v, j);
+                        const bool up = ((lane & k) == 0) == ((lane & j) == 0);   // keep the larger one here?
+                        v = up ? max(v, o) : min(v, o);
+                    }
+                }
+                if (lane == K - 1) red[32] = static_cast<int>(v);
+            }
+            __syncthreads();
+            tau = static_cast<uint32_t>(red[32]);
+        } else {
+            uint32_t mykey = 0;
+            if (bi >= 0) mykey = __float_as_uint(sigmoid_acc(bc) * sigmoid_acc(__ldg(ctr + bi)));
+            for (int bit = 30; bit >= 0; --bit) {
+                const uint32_t trial = tau | (1u << bit);
+                if (__syncthreads_count(mykey >= trial) >= K) tau = trial;
             }
         }
-        __syncthreads();
-        if (list_n > TK_LIST_CAP || list_n < K) need_fallback = true;  // block-uniform
+        if (tau > 0) {
+            const float tf = fminf(__uint_as_float(tau), 0.999999f);
+            const float a_thr = fminf(logf(tf / (1.0f - tf)) - 0.01f, 13.0f);   // conservative logit(tau)
+            auto consider = [&](float a, int i) {
+                if (a >= a_thr) {
+                    const uint32_t k = __float_as_uint(sigmoid_acc(a) * sigmoid_acc(__ldg(ctr + i)));
+                    if (k >= tau) {
+                        const int pos = atomicAdd(&list_n, 1);
+                        if (pos < TK_LIST_CAP) list[pos] = compose(k, i);
+                    }
+                }
+            };
+            if (vec) {
+                const int n4 = HW >> 2;
+                for (int q = tid; q < n4; q += TK_THREADS) {
+                    const float4 a = ldg_f4(cls + 4 * q);
+                    consider(a.x, 4 * q); consider(a.y, 4 * q + 1); consider(a.z, 4 * q + 2); consider(a.w, 4 * q + 3);
+                }
+            } else {
+                for (int i = tid; i < HW; i += TK_THREADS) consider(__ldg(cls + i), i);
+            }
+            __syncthreads();
+            done = (list_n <= TK_LIST_CAP && list_n >= K);   // block-uniform
+        }
     }
-
-    if (need_fallback) {
-        // ---- F: exact bitwise search over all keys -------------------------------------------------
+    if (!done) {
         __syncthreads();
+        // ---- A: rank keys -> scratch, per-thread maximum ---------------------------------------------
+        uint64_t best = 0;
+        if (!peak) {
+            const bool vec = ((HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(cls) & 15) == 0) &&
+                             ((reinterpret_cast<uintptr_t>(ctr) & 15) == 0) &&
+                             ((reinterpret_cast<uintptr_t>(keys) & 15) == 0);
+            if (vec) {
+                const int n4 = HW >> 2;
+                for (int q = tid; q < n4; q += TK_THREADS) {
+                    const float4 a = ldg_f4_stream(cls + 4 * q);
+                    const float4 c = ldg_f4_stream(ctr + 4 * q);
+                    uint4 k;
+                    k.x = __float_as_uint(sigmoid_acc(a.x) * sigmoid_acc(c.x));
+                    k.y = __float_as_uint(sigmoid_acc(a.y) * sigmoid_acc(c.y));
+                    k.z = __float_as_uint(sigmoid_acc(a.z) * sigmoid_acc(c.z));
+                    k.w = __float_as_uint(sigmoid_acc(a.w) * sigmoid_acc(c.w));
+                    reinterpret_cast<uint4*>(keys)[q] = k;
+                    const uint32_t i0 = 4u * q;
+                    uint64_t m = compose(k.x, i0);
+                    uint64_t t1 = compose(k.y, i0 + 1); m = t1 > m ? t1 : m;
+                    t1 = compose(k.z, i0 + 2); m = t1 > m ? t1 : m;
+                    t1 = compose(k.w, i0 + 3); m = t1 > m ? t1 : m;
+                    best = m > best ? m : best;
+                }
+            } else {
+                for (int i = tid; i < HW; i += TK_THREADS) {
+                    const uint32_t k = __float_as_uint(sigmoid_acc(__ldg(cls + i)) * sigmoid_acc(__ldg(ctr + i)));
+                    keys[i] = k;
+                    const uint64_t c = compose(k, i);
+                    best = c > best ? c : best;
+                }
+            }
+        } else {
+            // 3x3 peak mask from shared-memory row strips: rows [r0-1, r0+R] staged, rows [r0, r0+R) ranked
+            const int R = max(1, min(H, TK_TILE_FLOATS / W - 2));
+            for (int r0 = 0; r0 < H; r0 += R) {
+                const int rows = min(R, H - r0);
+                const int n_stage = (rows + 2) * W;
+                for (int e = tid; e < n_stage; e += TK_THREADS) {
+                    const int ry = e / W, x = e - ry * W;
+                    const int y = r0 - 1 + ry;
+                    float s = 0.0f;  // scores are >= 0, so 0 stands in for "outside the map" (max-pool pads -inf)
+                    if (y >= 0 && y < H) s = sigmoid_acc(__ldg(cls + y * W + x)) * sigmoid_acc(__ldg(ctr + y * W + x));
+                    tile[e] = s;
+                }
+                __syncthreads();
+                for (int e = tid; e < rows * W; e += TK_THREADS) {
+                    const int ry = e / W, x = e - ry * W;
+                    const float* c = tile + (ry + 1) * W + x;
+                    const float s = c[0];
+                    float m = fmaxf(c[-W], c[W]);
+                    if (x > 0) m = fmaxf(m, fmaxf(c[-1], fmaxf(c[-W - 1], c[W - 1])));
+                    if (x < W - 1) m = fmaxf(m, fmaxf(c[1], fmaxf(c[-W + 1], c[W + 1])));
+                    const uint32_t k = (s >= m) ? __float_as_uint(s) : 0u;
+                    const int i = (r0 + ry) * W + x;
+                    keys[i] = k;
+                    const uint64_t cc = compose(k, i);
+                    best = cc > best ? cc : best;
+                }
+                __syncthreads();
+            }
+        }
         if (tid == 0) list_n = 0;
-        uint32_t T = 0;
-        for (int bit = 30; bit >= 0; --bit) {
-            const uint32_t trial = T | (1u << bit);
-            int c = 0;
-            for (int i = tid; i < HW; i += TK_THREADS) c += (keys[i] >= trial);
-            if (block_sum_1024(c, red) >= K) T = trial;
-        }
-        int cg = 0;
-        for (int i = tid; i < HW; i += TK_THREADS) cg += (keys[i] > T);
-        cg = block_sum_1024(cg, red);
-        const int r = K - cg;  // how many cells with key == T are taken, lowest indices first (r >= 1)
-        // smallest I with count(key == T && idx <= I) >= r  <=>  largest prefix P with count(idx < P) < r
-        uint32_t P = 0;
-        for (int bit = 30; bit >= 0; --bit) {
-            const uint32_t trial = P | (1u << bit);
-            int c = 0;
-            for (int i = tid; i < HW; i += TK_THREADS) c += (keys[i] == T && static_cast<uint32_t>(i) < trial);
-            if (block_sum_1024(c, red) < r) P = trial;
-        }
-        __syncthreads();
-        for (int i = tid; i < HW; i += TK_THREADS) {
-            const uint32_t k = keys[i];
-            if (k > T || (k == T && static_cast<uint32_t>(i) <= P)) {
-                const int pos = atomicAdd(&list_n, 1);
-                if (pos < TK_LIST_CAP) list[pos] = compose(k, i);
+        __syncthreads();  // also makes this block's scratch writes visible to the whole block
+
+        bool need_fallback = (K > TK_FAST_K);
+        if (!need_fallback) {
+            // ---- B: tau = K-th largest per-thread maximum (score bits only) ---------------------------
+            const uint32_t mykey = static_cast<uint32_t>(best >> 32);
+            uint32_t tau = 0;
+            for (int bit = 30; bit >= 0; --bit) {
+                const uint32_t trial = tau | (1u << bit);
+                if (__syncthreads_count(mykey >= trial) >= K) tau = trial;
             }
+            // ---- C: compaction of cells with key >= tau ------------------------------------------------
+            for (int i = tid; i < HW; i += TK_THREADS) {
+                const uint32_t k = keys[i];
+                if (k >= tau) {
+                    const int pos = atomicAdd(&list_n, 1);
+                    if (pos < TK_LIST_CAP) list[pos] = compose(k, i);
+                }
+            }
+            __syncthreads();
+            if (list_n > TK_LIST_CAP || list_n < K) need_fallback = true;  // block-uniform
         }
-        __syncthreads();
+
+        if (need_fallback) {
+            // ---- F: exact bitwise search over all keys -------------------------------------------------
+            __syncthreads();
+            if (tid == 0) list_n = 0;
+            uint32_t T = 0;
+            for (int bit = 30; bit >= 0; --bit) {
+                const uint32_t trial = T | (1u << bit);
+                int c = 0;
+                for (int i = tid; i < HW; i += TK_THREADS) c += (keys[i] >= trial);
+                if (block_sum_1024(c, red) >= K) T = trial;
+            }
+            int cg = 0;
+            for (int i = tid; i < HW; i += TK_THREADS) cg += (keys[i] > T);
+            cg = block_sum_1024(cg, red);
+            const int r = K - cg;  // how many cells with key == T are taken, lowest indices first (r >= 1)
+            // smallest I with count(key == T && idx <= I) >= r  <=>  largest prefix P with count(idx < P) < r
+            uint32_t P = 0;
+            for (int bit = 30; bit >= 0; --bit) {
+                const uint32_t trial = P | (1u << bit);
+                int c = 0;
+                for (int i = tid; i < HW; i += TK_THREADS) c += (keys[i] == T && static_cast<uint32_t>(i) < trial);
+                if (block_sum_1024(c, red) < r) P = trial;
+            }
+            __syncthreads();
+            for (int i = tid; i < HW; i += TK_THREADS) {
+                const uint32_t k = keys[i];
+                if (k > T || (k == T && static_cast<uint32_t>(i) <= P)) {
+                    const int pos = atomicAdd(&list_n, 1);
+                    if (pos < TK_LIST_CAP) list[pos] = compose(k, i);
+                }
+            }
+            __syncthreads();
+        }
+
     }
 
-    // ---- D: sort the short list, emit the first K -------------------------------------------------
+    // ---- D: order the short list, emit the first K -------------------------------------------------
     const int n = min(list_n, TK_LIST_CAP);
+    if (n <= 256) {
+        // rank by counting (keys are distinct): no sort, no further barriers
+        for (int i = tid; i < n; i += TK_THREADS) {
+            const uint64_t c = list[i];
+            int rnk = 0;
+            for (int j = 0; j < n; ++j) rnk += (list[j] > c);
+            if (rnk < K) {
+                const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(c & 0xFFFFFFFFull);
+                float sc = __uint_as_float(static_cast<uint32_t>(c >> 32));
+                if (peak) sc = sigmoid_acc(__ldg(cls + idx)) * sigmoid_acc(__ldg(ctr + idx));
+                oscore[rnk] = sc;
+                oidx[rnk] = static_cast<int32_t>(idx);
+            }
+        }
+        return;
+    }
     int n2 = 1;
     while (n2 < n) n2 <<= 1;
     for (int i = n + tid; i < n2; i += TK_THREADS) list[i] = 0;

@@ -319,3 +319,28 @@ def test_full_size_properties_config2():
         n = int(cnt[b])
         if t["cand_index"][b, t["out_slot"][b, :n].long()].tolist() == ref[0]["index"].tolist():
             assert util.rel_err(t["out_cam"][b, :n].cpu().numpy(), ref[0]["poses_cam"]) < TOL
+
+
+@pytest.mark.parametrize("mode,tol", [(1, TOL), (2, 5e-2)])
+def test_tensor_core_refinement_modes(mode, tol):
+    """tcgen05 path (das_refine_heads + das_refine_tc): 3xTF32 meets the fp32 bar, single-pass TF32 is looser."""
+    tc = dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)
+    for (B, H, W, seed, kw) in ((3, 40, 56, 71, {}), (2, 64, 96, 72, dict(scales=(1.1, 0.9, 1.05, 0.95)))):
+        case = util.make_case(P, B, H, W, seed=seed, **kw)
+        ref, _ = util.run_oracle(case, tc)
+        plan, got = util.run_gpu(case, tc, refine=True, refine_mode=mode)
+        plan0, got0 = util.run_gpu(case, tc, refine=True, refine_mode=0)
+        for g, g0, o in zip(got, got0, ref):
+            assert g["scores"] == g0["scores"]
+            if g["slots"].tolist() == g0["slots"].tolist():
+                assert util.rel_err(g["poses"].cpu().numpy(), o["poses"].numpy()) < tol
+                assert util.rel_err(g["poses_cam"].cpu().numpy(), o["poses_cam"]) < tol
+
+
+def test_tensor_core_refinement_with_threshold_and_pyramid():
+    cfg = dataclasses.replace(P, strides=(8, 16, 32))
+    tc = dict(nms_pre=60, nms_post=30, nms_thr=0.9, score_thr=0.05)
+    case = util.make_case(cfg, 2, 48, 64, seed=73, peaks=20)
+    ref, _ = util.run_oracle(case, tc)
+    plan, got = util.run_gpu(case, tc, refine=True, refine_mode=1)
+    compare(plan, got, ref, util.rank_margin_ulps(case["levels"], 60, 0.05))
