@@ -223,30 +223,56 @@ def run_b200(args):
     torch.cuda.synchronize()
 
     blocks = [p.output_block() for p in plans]
-    gathered = torch.empty((world, blocks[0].numel()), dtype=torch.uint8, device=dev) if world > 1 else None
+
+    # Independent batches are pipelined over `n_streams` CUDA streams (one per rotating input set / plan): the
+    # 64-CTA top-k and NMS kernels of one batch overlap the refinement of another.
+    n_streams = max(1, min(args.streams, n_sets))
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)] if n_streams > 1 else [torch.cuda.current_stream(dev)]
+    gathered_s = [torch.empty((world, blocks[0].numel()), dtype=torch.uint8, device=dev) for _ in range(n_sets)] if world > 1 else None
 
     def step(i):
-        p = plans[i % n_sets]
-        p.run(use_graph=True)
-        if world > 1:       # the final small pose lists: one all-gather of the packed output block
-            dist.all_gather_into_tensor(gathered.view(-1), blocks[i % n_sets])
+        k = i % n_sets
+        with torch.cuda.stream(streams[k % n_streams]):
+            plans[k].run(use_graph=True)
+            if world > 1:       # the final small pose lists: one all-gather of the packed output block
+                dist.all_gather_into_tensor(gathered_s[k].view(-1), blocks[k])
+
+    def fork():
+        if n_streams > 1:
+            cur = torch.cuda.current_stream(dev)
+            for st in streams:
+                st.wait_stream(cur)
+
+    def join():
+        if n_streams > 1:
+            cur = torch.cuda.current_stream(dev)
+            for st in streams:
+                cur.wait_stream(st)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    fork()
     for i in range(max(args.warmup, 3)):
         step(i)
+    join()
     barrier()
     launches0 = sum(p.kernel_launches for p in plans)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
+    if args.profile_region:
+        torch.cuda.profiler.start()
     e0.record()
+    fork()
     for i in range(args.steps):
         step(i)
+    join()
     e1.record()
     barrier()
+    if args.profile_region:
+        torch.cuda.profiler.stop()
     t_wall1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = sum(p.kernel_launches for p in plans) - launches0
@@ -329,6 +355,7 @@ def run_b200(args):
                        "algorithm": "sparse last-layer refinement at the selected centres (SURVEY 8.0 divergence B)",
                        "l2": f"{n_sets} distinct input sets of {plans[0].h2d_bytes / 1e9:.2f} GB rotated round-robin "
                              f"(each far larger than the 126 MB L2)",
+                       "streams": n_streams,
                        "parallelism": f"dp{world} batch-sharded, one NCCL all-gather of the packed pose lists per step"
                                       if world > 1 else "single GPU"},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
@@ -350,6 +377,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--input-sets", type=int, default=3)
+    ap.add_argument("--streams", type=int, default=3, help="independent batches in flight (<= input sets)")
+    ap.add_argument("--profile-region", action="store_true", help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
