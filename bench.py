@@ -358,7 +358,7 @@ def run_b200(args):
                        "streams": n_streams,
                        "parallelism": f"dp{world} batch-sharded, one NCCL all-gather of the packed pose lists per step"
                                       if world > 1 else "single GPU"},
-            "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
+            "clocks": clocks, "gpu_launches": int(launches) * world, "roofline": roofline,
         }
         if e2e is not None:
             out["e2e"] = e2e
