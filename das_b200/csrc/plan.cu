@@ -152,9 +152,9 @@ extern "C" int das_plan_create(const das_decode_cfg* cfg, const das_levels* shap
     if (cfg->refine) {
         for (int k = 0; k < cfg->num_layers; ++k) A(dev_alloc(&p->wpack[k], static_cast<size_t>(das_packed_weight_floats(cfg))));
         if (cfg->feat_channels == 256 && cfg->num_heads == 4) {
-            // the tensor-core variant is built and parity-tested but currently slower than the fp32 SIMT kernel
-            // (shared-memory bandwidth bound); opt in with das_plan_set_refine_mode(plan, 1 or 2)
-            p->refine_mode = 0;
+            // tensor-core refinement (tcgen05 3xTF32, A operand through TMEM) is the default where it is built;
+            // das_plan_set_refine_mode(plan, 0) selects the fp32 SIMT kernel
+            p->refine_mode = 1;
             A(dev_alloc(&p->tc_panels, static_cast<size_t>(das_tc_panel_bytes(cfg))));
             A(dev_alloc(&p->item_heads, B * CT * J * 16));
             A(dev_alloc(&p->valid_list, B * CT));

@@ -70,6 +70,7 @@ struct TcParams {
 struct RowState {                    // what thread t keeps about row t of a tile until its epilogue
     const float* ptr;                // feature row, nullptr = outside the map / padding row
     float wk, prev0, prev1, prev2, hxv, hyv;
+    float z, sx, sy;                 // eval-tail inputs of the item (root depth, image scale), fetched early
     int cs, idx, lvl;
     bool item_ok;
 };
@@ -82,6 +83,7 @@ __device__ __forceinline__ RowState setup_row(const TcParams& p, int tile, int n
     r.item_ok = vi < n_valid;
     r.cs = r.item_ok ? __ldg(p.valid_list + vi) : 0;
     r.ptr = nullptr; r.wk = 0.f; r.prev0 = r.prev1 = r.prev2 = 0.f; r.hxv = r.hyv = 0.f; r.idx = 0; r.lvl = 0;
+    r.z = 0.f; r.sx = r.sy = 1.f;
     if (!r.item_ok) return r;
     const das_levels* __restrict__ lvp = p.lv;
     const int b = r.cs / p.CT, slot = r.cs - b * p.CT;
@@ -96,6 +98,9 @@ __device__ __forceinline__ RowState setup_row(const TcParams& p, int tile, int n
     const int H = d.H, W = d.W, HW = H * W, J = p.J;
     r.idx = __ldg(p.cand_index + r.cs);
     const int y = r.idx / W, x = r.idx - y * W;
+    r.z = __ldg(d.pose + (static_cast<size_t>(b) * (3 + 6 * J) + 2) * HW + r.idx);
+    r.sx = __ldg(p.scale_xy + 2 * b);
+    r.sy = __ldg(p.scale_xy + 2 * b + 1);
     const float* heads = p.item_heads + (static_cast<size_t>(r.cs) * J + j) * 16;
     r.hxv = __ldg(heads + h);
     r.hyv = __ldg(heads + 8 + h);
@@ -120,6 +125,80 @@ __device__ __forceinline__ RowState setup_row(const TcParams& p, int tile, int n
     }
     return r;
 }
+
+// Row epilogue shared by both tensor-core kernels: v[0..8] = this row's {gate 3, value 3, conf 3} projections.
+// Lanes of a warp = the 32 rows of one item (head = lane >> 2, corner = lane & 3).
+__device__ __forceinline__ void tc_epilogue(const TcParams& p, const RowState& cur, const float (&v)[16], int j, int lane) {
+    const int J = p.J;
+    const float* Bj = p.wpack + static_cast<size_t>(J) * TC_NOUT * TC_C + j * TC_NOUT + TC_OGATE;
+    float val[3], cf[3];
+    {
+        const float pv[3] = {cur.prev0, cur.prev1, cur.prev2};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float gte = sigmoid_acc(v[k] + __ldg(Bj + k));
+            const float n = v[3 + k] + __ldg(Bj + 3 + k);
+            const float o = __fadd_rn(__fmul_rn(1.0f - gte, pv[k]), __fmul_rn(gte, n));
+            const bool ok = cur.ptr != nullptr;
+            val[k] = ok ? o * cur.wk : 0.f;
+            cf[k] = ok ? (v[6 + k] + __ldg(Bj + 6 + k)) * cur.wk : 0.f;
+        }
+    }
+    float out[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        // bilinear sum over the 4 corners (lane bits 0,1)
+        val[k] += __shfl_xor_sync(FULL, val[k], 1);
+        cf[k] += __shfl_xor_sync(FULL, cf[k], 1);
+        val[k] += __shfl_xor_sync(FULL, val[k], 2);
+        cf[k] += __shfl_xor_sync(FULL, cf[k], 2);
+        const float hv = val[k] + (k == 0 ? cur.hxv : (k == 1 ? cur.hyv : 0.f));   // + diff
+        // softmax over the 8 heads (lane bits 2,3,4); every corner lane carries the same head value
+        float m = cf[k];
+        m = fmaxf(m, __shfl_xor_sync(FULL, m, 4));
+        m = fmaxf(m, __shfl_xor_sync(FULL, m, 8));
+        m = fmaxf(m, __shfl_xor_sync(FULL, m, 16));
+        const float e = expf(cf[k] - m);
+        float se = e;
+        se += __shfl_xor_sync(FULL, se, 4);
+        se += __shfl_xor_sync(FULL, se, 8);
+        se += __shfl_xor_sync(FULL, se, 16);
+        float o = hv * (e / se);
+        o += __shfl_xor_sync(FULL, o, 4);
+        o += __shfl_xor_sync(FULL, o, 8);
+        o += __shfl_xor_sync(FULL, o, 16);
+        out[k] = o;
+    }
+    if (cur.item_ok && lane < 3) {
+        // eval tail + assembly (das_head.py:254-262, 725-743)
+        const das_level_desc& d = p.lv->lv[cur.lvl];
+        const int W = d.W, HW = d.H * d.W;
+        const int b = cur.cs / p.CT;
+        const int y = cur.idx / W, x = cur.idx - y * W;
+        const float* pose = d.pose + static_cast<size_t>(b) * (3 + 6 * J) * HW;
+        const float sx = cur.sx, sy = cur.sy;
+        const float qf = sqrtf(sx * sy);
+        const float stf = static_cast<float>(d.stride), half = static_cast<float>(d.stride / 2);
+        float z = cur.z * d.scale_depth;
+        z = __fdiv_rn(z, p.depth_factor);
+        const float zq = __fmul_rn(z, qf);
+        const float o = lane == 0 ? out[0] : (lane == 1 ? out[1] : out[2]);
+        float r;
+        if (lane == 0) r = __fdiv_rn(__fadd_rn(__fmul_rn(o, stf), static_cast<float>(x) * stf + half), sx);
+        else if (lane == 1) r = __fdiv_rn(__fadd_rn(__fmul_rn(o, stf), static_cast<float>(y) * stf + half), sy);
+        else r = __fadd_rn((j == p.root) ? 0.0f : __fmul_rn(o, p.z_norm), zq);
+        p.cand_pose[(static_cast<size_t>(cur.cs) * J + j) * 3 + lane] = r;
+        if (j == 0) {
+            float c;
+            if (lane == 2) c = zq;
+            else {
+                const float off = __ldg(pose + static_cast<size_t>(lane) * HW + cur.idx) * d.scale_offset;
+                const float P = static_cast<float>(lane == 0 ? x : y) * stf + half;
+                c = __fdiv_rn(__fsub_rn(P, off), lane == 0 ? sx : sy);
+            }
+            p.cand_center[static_cast<size_t>(cur.cs) * 3 + lane] = c;
+        }
+    }}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 refine_tc_kernel(const TcParams p) {
@@ -304,7 +383,6 @@ refine_tc_kernel(const TcParams p) {
         for (int i = e; i < my_tiles; i += TC_EPI_GROUPS) {
             const int tile = t0 + i;
             const int j = tile / n_groups;
-            const float* Bj = p.wpack + static_cast<size_t>(J) * TC_NOUT * TC_C + j * TC_NOUT + TC_OGATE;
             const long long e0 = clock64();
             tc::mbar_wait(&acc_full[i & 1], (i >> 1) & 1);
             tc::tc_fence_after();
@@ -331,74 +409,7 @@ refine_tc_kernel(const TcParams p) {
                 if (lane == 0) tc::mbar_arrive(&rows_ready[e]);
             }
             const long long e3 = clock64();
-            float val[3], cf[3];
-            {
-                const float pv[3] = {cur.prev0, cur.prev1, cur.prev2};
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const float gte = sigmoid_acc(v[k] + __ldg(Bj + k));
-                    const float n = v[3 + k] + __ldg(Bj + 3 + k);
-                    const float o = __fadd_rn(__fmul_rn(1.0f - gte, pv[k]), __fmul_rn(gte, n));
-                    const bool ok = cur.ptr != nullptr;
-                    val[k] = ok ? o * cur.wk : 0.f;
-                    cf[k] = ok ? (v[6 + k] + __ldg(Bj + 6 + k)) * cur.wk : 0.f;
-                }
-            }
-            float out[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                // bilinear sum over the 4 corners (lane bits 0,1)
-                val[k] += __shfl_xor_sync(FULL, val[k], 1);
-                cf[k] += __shfl_xor_sync(FULL, cf[k], 1);
-                val[k] += __shfl_xor_sync(FULL, val[k], 2);
-                cf[k] += __shfl_xor_sync(FULL, cf[k], 2);
-                const float hv = val[k] + (k == 0 ? cur.hxv : (k == 1 ? cur.hyv : 0.f));   // + diff
-                // softmax over the 8 heads (lane bits 2,3,4); every corner lane carries the same head value
-                float m = cf[k];
-                m = fmaxf(m, __shfl_xor_sync(FULL, m, 4));
-                m = fmaxf(m, __shfl_xor_sync(FULL, m, 8));
-                m = fmaxf(m, __shfl_xor_sync(FULL, m, 16));
-                const float e = expf(cf[k] - m);
-                float se = e;
-                se += __shfl_xor_sync(FULL, se, 4);
-                se += __shfl_xor_sync(FULL, se, 8);
-                se += __shfl_xor_sync(FULL, se, 16);
-                float o = hv * (e / se);
-                o += __shfl_xor_sync(FULL, o, 4);
-                o += __shfl_xor_sync(FULL, o, 8);
-                o += __shfl_xor_sync(FULL, o, 16);
-                out[k] = o;
-            }
-            if (cur.item_ok && lane < 3) {
-                // eval tail + assembly (das_head.py:254-262, 725-743)
-                const das_level_desc& d = p.lv->lv[cur.lvl];
-                const int W = d.W, HW = d.H * d.W;
-                const int b = cur.cs / p.CT;
-                const int y = cur.idx / W, x = cur.idx - y * W;
-                const float* pose = d.pose + static_cast<size_t>(b) * (3 + 6 * J) * HW;
-                const float sx = __ldg(p.scale_xy + 2 * b), sy = __ldg(p.scale_xy + 2 * b + 1);
-                const float qf = sqrtf(sx * sy);
-                const float stf = static_cast<float>(d.stride), half = static_cast<float>(d.stride / 2);
-                float z = __ldg(pose + 2 * static_cast<size_t>(HW) + cur.idx) * d.scale_depth;
-                z = __fdiv_rn(z, p.depth_factor);
-                const float zq = __fmul_rn(z, qf);
-                const float o = lane == 0 ? out[0] : (lane == 1 ? out[1] : out[2]);
-                float r;
-                if (lane == 0) r = __fdiv_rn(__fadd_rn(__fmul_rn(o, stf), static_cast<float>(x) * stf + half), sx);
-                else if (lane == 1) r = __fdiv_rn(__fadd_rn(__fmul_rn(o, stf), static_cast<float>(y) * stf + half), sy);
-                else r = __fadd_rn((j == p.root) ? 0.0f : __fmul_rn(o, p.z_norm), zq);
-                p.cand_pose[(static_cast<size_t>(cur.cs) * J + j) * 3 + lane] = r;
-                if (j == 0) {
-                    float c;
-                    if (lane == 2) c = zq;
-                    else {
-                        const float off = __ldg(pose + static_cast<size_t>(lane) * HW + cur.idx) * d.scale_offset;
-                        const float P = static_cast<float>(lane == 0 ? x : y) * stf + half;
-                        c = __fdiv_rn(__fsub_rn(P, off), lane == 0 ? sx : sy);
-                    }
-                    p.cand_center[static_cast<size_t>(cur.cs) * 3 + lane] = c;
-                }
-            }
+            tc_epilogue(p, cur, v, j, lane);
             cur = nx;
             if (p.dbg && tid == 0) {
                 long long* o = p.dbg + blockIdx.x * 16;
@@ -410,6 +421,231 @@ refine_tc_kernel(const TcParams p) {
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem_base, 64);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// v2: A operand through TMEM.
+//
+// v1 is bound by shared-memory bandwidth: every 128x32 A k-block is written by cp.async, read and re-written by
+// the hi/lo split, and read twice more by the tensor core (hi and lo operands) for only 16..32 output columns.
+// Here the tensor core reads A from TMEM instead.  Three producer groups of 4 warps take k-blocks round-robin;
+// a group gathers its k-block with coalesced cp.async into a private 3-stage smem ring, then every thread reads
+// ITS row (thread = row = TMEM lane; conflict-free thanks to the 128-B swizzle), splits hi/lo in registers and
+// writes both with tcgen05.st into a 4-slot TMEM ring.  Shared-memory traffic per tile drops from ~640 KB to
+// 256 KB (+ the tiny B panel reads).  The MMA warp issues tcgen05.mma with [a_tmem] operands; two epilogue groups
+// drain the double-buffered accumulators as in v1.
+constexpr int T2_PGROUPS = 3;                   // producer groups (4 warps each)
+constexpr int T2_STAGES = 3;                    // smem stages per group
+constexpr int T2_SLOTS = 4;                     // TMEM A slots (64 columns each: 32 hi + 32 lo)
+constexpr int T2_EG = 3;                        // epilogue groups: tile i -> group i % 3, accumulator i % 3
+constexpr int T2_RB = 2 * T2_EG;                // row-pointer buffers: rows are set up 2 own tiles (= 6 tiles) ahead
+constexpr int T2_FIRST_PRODUCER = TC_EPI_WARPS * T2_EG;                         // warp 12
+constexpr int T2_MMA_WARP = T2_FIRST_PRODUCER + 4 * T2_PGROUPS;                // warp 24
+constexpr int T2_THREADS = 32 * (T2_MMA_WARP + 1);
+constexpr int T2_TMEM_COLS = 512;
+constexpr int T2_D_COL = 0;                     // accumulators: T2_EG x 32 columns
+constexpr int T2_A_COL = 32 * T2_EG;            // A ring: 4 slots x 64 columns
+constexpr int T2_SMEM = 1024 + T2_PGROUPS * T2_STAGES * TC_A_BYTES + 2 * TC_B_BYTES;
+
+__global__ void __launch_bounds__(T2_THREADS, 1)
+refine_tc2_kernel(const TcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    unsigned char* sA = base;                                              // [group][stage] k-block tiles
+    unsigned char* sB = sA + T2_PGROUPS * T2_STAGES * TC_A_BYTES;          // per k-block: 16 hi rows then 16 lo rows
+    __shared__ uint64_t a_full[T2_SLOTS], a_empty[T2_SLOTS];               // producers -> MMA, MMA -> producers
+    __shared__ uint64_t acc_full[T2_EG], acc_free[T2_EG], rows_ready[T2_RB];
+    __shared__ uint32_t tmem_base;
+    __shared__ const float* s_rowptr[T2_RB][128];   // row pointers are produced T2_RB tiles ahead of their epilogue
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long kernel_t0 = clock64();
+    const int J = p.J;
+    const int n_valid = __ldg(p.n_valid);
+    const int n_groups = (n_valid + 3) >> 2;
+    const int n_tiles = J * n_groups;
+    const int t0 = static_cast<int>(static_cast<long long>(n_tiles) * blockIdx.x / gridDim.x);
+    const int t1 = static_cast<int>(static_cast<long long>(n_tiles) * (blockIdx.x + 1) / gridDim.x);
+    if (t0 >= t1) return;
+    const int my_tiles = t1 - t0;
+    const int total_kb = my_tiles * TC_KB;
+
+    if (tid == 0) {
+        for (int s = 0; s < T2_SLOTS; ++s) { tc::mbar_init(&a_full[s], 4); tc::mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < T2_EG; ++s) { tc::mbar_init(&acc_full[s], 1); tc::mbar_init(&acc_free[s], TC_EPI_WARPS); }
+        for (int s = 0; s < T2_RB; ++s) tc::mbar_init(&rows_ready[s], TC_EPI_WARPS);
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) tc::tmem_alloc(&tmem_base, T2_TMEM_COLS);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem0 = tmem_base;
+    const uint32_t sB_u = tc::smem_u32(sB);
+
+    if (warp == T2_MMA_WARP) {
+        // ===== MMA issuer warp (also owns the B panels) ================================================================
+        constexpr uint32_t idesc32 = tc::instr_desc_tf32(128, 2 * TC_N);   // A_hi x [B_hi ; B_lo]  -> D[:, 0:32]
+        constexpr uint32_t idesc16 = tc::instr_desc_tf32(128, TC_N);       // A_lo x  B_hi          -> D[:, 0:16]
+        int g = 0, cur_j = -1;
+        long long m_w = 0, m_i = 0, m_b = 0, m_f = 0;
+        for (int i = 0; i < my_tiles; ++i) {
+            const uint32_t dcol = tmem0 + T2_D_COL + (i % T2_EG) * 32;
+            const long long tb0 = clock64();
+            const int j = (t0 + i) / n_groups;
+            if (j != cur_j) {
+                // new joint: every earlier MMA must have finished reading the old panels
+                if (g > 0) tc::mbar_wait(&a_empty[(g - 1) % T2_SLOTS], ((g - 1) / T2_SLOTS) & 1);
+                const unsigned char* src = p.bpanel + static_cast<size_t>(j) * 2 * TC_B_BYTES;
+                for (int c = lane; c < 2 * TC_B_BYTES / 16; c += 32) tc::cp_async16(sB_u + c * 16, src + c * 16, true);
+                tc::cp_async_commit();
+                tc::cp_async_wait<0>();
+                tc::fence_proxy_async();
+                __syncwarp();
+                cur_j = j;
+            }
+            const long long tb1 = clock64();
+            if (i >= T2_EG) tc::mbar_wait(&acc_free[i % T2_EG], ((i / T2_EG) - 1) & 1);   // epilogue of tile i-EG has drained this buffer
+            const long long tb2 = clock64();
+            m_b += tb1 - tb0; m_f += tb2 - tb1;
+            for (int kb = 0; kb < TC_KB; ++kb, ++g) {
+                const int slot = g % T2_SLOTS;
+                const long long c0 = clock64();
+                tc::mbar_wait(&a_full[slot], (g / T2_SLOTS) & 1);
+                tc::tc_fence_after();
+                const long long c1 = clock64();
+                m_w += c1 - c0;
+                const uint32_t a_hi = tmem0 + T2_A_COL + slot * 64, a_lo = a_hi + 32;
+                const uint32_t b_pk = sB_u + kb * TC_BK_BYTES;
+                if (p.split & 1) {
+                    tc::umma_kblock_3xtf32_ts(dcol, a_hi, a_lo, tc::smem_desc_sw128(b_pk), idesc32, idesc16, kb != 0);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc::umma_tf32_ts_elect(dcol, a_hi + k * 8, tc::smem_desc_sw128(b_pk + k * 32), idesc16, (kb | k) != 0);
+                }
+                tc::umma_commit_elect(&a_empty[slot]);
+                if (kb == TC_KB - 1) tc::umma_commit_elect(&acc_full[i % T2_EG]);
+                m_i += clock64() - c1;
+            }
+        }
+        if (p.dbg && lane == 0) { long long* o = p.dbg + blockIdx.x * 16; o[0] = m_w; o[1] = m_i; o[2] = m_f; o[14] = m_b; }
+    } else if (warp >= T2_FIRST_PRODUCER) {
+        // ===== producer groups: gather (cp.async, coalesced) -> own row from smem -> hi/lo -> TMEM ====================
+        const int pg = (warp - T2_FIRST_PRODUCER) >> 2;          // group: handles k-blocks g with g % 3 == pg
+        const int qw = warp & 3;                                 // TMEM lane quadrant (T2_FIRST_PRODUCER % 4 == 0)
+        const int gt = (qw << 5) | lane;                         // thread within the group = row it owns
+        const uint32_t sG_u = tc::smem_u32(sA) + pg * T2_STAGES * TC_A_BYTES;
+        unsigned char* sG = sA + pg * T2_STAGES * TC_A_BYTES;
+        const int bar_id = 1 + pg;
+        const int my_n = (total_kb - pg + T2_PGROUPS - 1) / T2_PGROUPS;   // number of k-blocks of this group
+        // coalesced gather mapping: chunk c = gt + 128 * it  ->  row c >> 3, 16-B chunk c & 7
+        auto gather = [&](int n) {
+            const int g = pg + n * T2_PGROUPS;
+            const int i = g / TC_KB, kb = g - i * TC_KB, st = n % T2_STAGES;
+            if (kb < T2_PGROUPS) tc::mbar_wait(&rows_ready[i % T2_RB], (i / T2_RB) & 1);   // first k-block of tile i seen by this group
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int row = (gt >> 3) + 16 * it, ch = gt & 7;
+                const float* src = s_rowptr[i % T2_RB][row];
+                tc::cp_async16_ca(sG_u + st * TC_A_BYTES + tc::swz128(row, ch), src ? src + kb * 32 + ch * 4 : p.wpack, src != nullptr);
+            }
+        };
+        for (int n = 0; n < T2_STAGES - 1; ++n) { if (n < my_n) gather(n); tc::cp_async_commit(); }
+        long long d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0;
+        for (int n = 0; n < my_n; ++n) {
+            const int g = pg + n * T2_PGROUPS;
+            const int slot = g % T2_SLOTS, st = n % T2_STAGES;
+            const long long c0 = clock64();
+            tc::cp_async_wait<T2_STAGES - 2>();                  // this thread's chunks of k-block n have landed
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // ... and everybody else's in the group
+            const long long c1 = clock64();
+            float hi[32];
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                const float4 a = *reinterpret_cast<const float4*>(sG + st * TC_A_BYTES + tc::swz128(gt, ch));
+                hi[4 * ch] = a.x; hi[4 * ch + 1] = a.y; hi[4 * ch + 2] = a.z; hi[4 * ch + 3] = a.w;
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // stage `st` may be overwritten from here on
+            const long long c2 = clock64();
+            if (n + T2_STAGES - 1 < my_n) gather(n + T2_STAGES - 1);     // into stage (n + 2) % 3 == (n - 1) % 3, read last step
+            tc::cp_async_commit();
+            const long long c3 = clock64();
+            if (g >= T2_SLOTS) tc::mbar_wait(&a_empty[slot], ((g / T2_SLOTS) - 1) & 1);   // MMAs of k-block g-4 done with this TMEM slot
+            tc::tc_fence_after();
+            const long long c4 = clock64();
+            const uint32_t taddr = tmem0 + (static_cast<uint32_t>(qw * 32) << 16) + T2_A_COL + slot * 64;
+            tc::tmem_st32(taddr, hi);
+            if (p.split & 1) {
+                float lo[32];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) lo[e] = hi[e] - tc::tf32_hi(hi[e]);
+                tc::tmem_st32(taddr + 32, lo);
+            }
+            tc::tmem_st_wait();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&a_full[slot]);
+            d0 += c1 - c0; d1 += c2 - c1; d2 += c3 - c2; d3 += c4 - c3; d4 += clock64() - c4;
+        }
+        tc::cp_async_wait<0>();
+        if (p.dbg && pg == 0 && gt == 0) { long long* o = p.dbg + blockIdx.x * 16; o[3] = d0; o[4] = d1; o[5] = d2; o[6] = d3; o[7] = d4; o[8] = my_n; }
+    } else {
+        // ===== epilogue / row-setup warps: thread t <-> row t = (item warp, head lane>>2, corner lane&3) ===========
+        const int e = warp / TC_EPI_WARPS;          // epilogue group
+        const int rt = tid - e * 32 * TC_EPI_WARPS; // row of the tile this thread owns (= TMEM lane)
+        const int qw = warp % TC_EPI_WARPS;         // TMEM lane quadrant this warp may read
+        // this group's tiles are e, e+EG, e+2EG, ...; their row state is prepared two of them (= 2*EG tiles) ahead
+        RowState cur{}, nx1{};
+        if (e < my_tiles) {
+            cur = setup_row(p, t0 + e, n_groups, n_valid, rt);
+            s_rowptr[e][rt] = cur.ptr;
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&rows_ready[e]);
+        }
+        if (e + T2_EG < my_tiles) {
+            nx1 = setup_row(p, t0 + e + T2_EG, n_groups, n_valid, rt);
+            s_rowptr[e + T2_EG][rt] = nx1.ptr;
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&rows_ready[e + T2_EG]);
+        }
+#pragma unroll 1
+        for (int i = e; i < my_tiles; i += T2_EG) {
+            const int tile = t0 + i;
+            const int j = tile / n_groups;
+            const long long e0 = clock64();
+            tc::mbar_wait(&acc_full[e], (i / T2_EG) & 1);
+            tc::tc_fence_after();
+            const long long e1 = clock64();
+            float v[16], v2[16];
+            const uint32_t taddr = tmem0 + (static_cast<uint32_t>(qw * 32) << 16) + T2_D_COL + e * 32;
+            tc::tmem_ld16(taddr, v);
+            if (p.split & 1) {
+                tc::tmem_ld16(taddr + TC_N, v2);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) v[k] += v2[k];
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&acc_free[e]);
+            // tile i+2EG reuses tile i's pointer buffer: every gather of tile i was issued before its MMAs completed
+            RowState nx2{};
+            if (i + T2_RB < my_tiles) {
+                nx2 = setup_row(p, tile + T2_RB, n_groups, n_valid, rt);
+                s_rowptr[i % T2_RB][rt] = nx2.ptr;
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&rows_ready[i % T2_RB]);
+            }
+            tc_epilogue(p, cur, v, j, lane);
+            cur = nx1;
+            nx1 = nx2;
+            if (p.dbg && tid == 0) { long long* o = p.dbg + blockIdx.x * 16; o[9] += e1 - e0; o[10] += clock64() - e1; }
+        }
+    }
+    if (p.dbg && tid == 0) p.dbg[blockIdx.x * 16 + 13] = clock64() - kernel_t0;
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, T2_TMEM_COLS);
 }
 
 // [J][17][C] packed weights -> per joint [8 k-blocks][32 rows = 16 hi + 16 lo][128 B swizzled]
@@ -474,7 +710,17 @@ extern "C" int das_refine_tc(const das_levels* d_levels, const das_levels* h_lev
         DAS_CUDA_CHECK(cudaFuncSetAttribute(refine_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
         attr_done = true;
     }
-    refine_tc_kernel<<<kSMs, TC_THREADS, TC_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+    static bool attr2_done = false;
+    if (!attr2_done) {
+        DAS_CUDA_CHECK(cudaFuncSetAttribute(refine_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
+        attr2_done = true;
+    }
+    if (split & 16) {        // v1 (A operand from shared memory), kept for comparison
+        p.split = split & 15;
+        refine_tc_kernel<<<kSMs, TC_THREADS, TC_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+    } else {
+        refine_tc2_kernel<<<kSMs, T2_THREADS, T2_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+    }
     DAS_CUDA_CHECK(cudaGetLastError());
     return DAS_OK;
 }

@@ -82,6 +82,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 32 bit x 32 columns store: thread t of warp w writes TMEM lane 32*(w%4)+t, columns [col, col+32)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+        "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+        "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+        "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- UMMA descriptors --------------------------------------------------------------------------------
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart (cute::UMMA::SmemDescriptor)
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
@@ -139,6 +156,47 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
         "elect.sync _|q, 0xffffffff;\n\t"
         "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
         "}" ::"r"(smem_u32(bar))
+        : "memory");
+}
+
+// A operand from TMEM (lane = row, one 32-bit column per K element), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+    const uint32_t acc = accumulate ? 1u : 0u;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+// One k-block (4 k-steps of K = 8) of the 3xTF32 scheme in a single issue burst, A from TMEM:
+//   D[:, 0:n32] (+)= A_hi[k] x [B_hi ; B_lo][k]     (idesc32)      D[:, 0:n16] += A_lo[k] x B_hi[k]   (idesc16)
+// a_hi / a_lo: TMEM column addresses of the 32 hi / lo columns; db0: smem descriptor of the B k-block (k-step 0).
+__device__ __forceinline__ void umma_kblock_3xtf32_ts(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint64_t db0,
+                                                       uint32_t idesc32, uint32_t idesc16, bool accumulate_first) {
+    const uint32_t acc = accumulate_first ? 1u : 0u;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b64 d1, d2, d3;\n\t"
+        ".reg .b32 h1, h2, h3, l1, l2, l3;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "add.s64 d1, %3, 2;\n\t add.s64 d2, %3, 4;\n\t add.s64 d3, %3, 6;\n\t"      // +32 B per k-step (>> 4)
+        "add.u32 h1, %1, 8;\n\t add.u32 h2, %1, 16;\n\t add.u32 h3, %1, 24;\n\t"
+        "add.u32 l1, %2, 8;\n\t add.u32 l2, %2, 16;\n\t add.u32 l3, %2, 24;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %3, %4, p;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %3, %5, 1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [h1], d1, %4, 1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [l1], d1, %5, 1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [h2], d2, %4, 1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [l2], d2, %5, 1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [h3], d3, %4, 1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [l3], d3, %5, 1;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_hi), "r"(a_lo), "l"(db0), "r"(idesc32), "r"(idesc16), "r"(acc)
         : "memory");
 }
 

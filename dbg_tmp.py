@@ -15,5 +15,5 @@ lib.das_tc_set_debug_buffer(C.c_void_p(dbg.data_ptr()))
 for _ in range(3): plan.run(use_graph=False)
 torch.cuda.synchronize(); dbg.zero_(); plan.run(use_graph=False); torch.cuda.synchronize()
 d=dbg.cpu().numpy().astype(np.float64)
-names=['mma:wait_full','mma:issue','mma:wait_accfree','prod:wait_consumed','prod:gather','prod:cpasync_wait','prod:split','prod:fence_arrive','prod:n_kb','epi:wait_accfull','epi:tmem_ld','epi:setup','epi:math','cta:total']
+names=['mma:wait_afull','mma:issue','mma:wait_accfree','pg0:cpwait+bar','pg0:lds+bar','pg0:gather_issue','pg0:wait_aempty','pg0:tmem_st+arrive','pg0:n_kb','epi0:wait_accfull','epi0:rest','-','-','cta:total','mma:bpanel']
 for i,n in enumerate(names): print(f'{n:22s} mean {d[:,i].mean():10.0f}  max {d[:,i].max():10.0f}')

@@ -190,8 +190,8 @@ int das_plan_run(das_plan* plan, void* stream, int32_t mode);
 int das_plan_stage_ms(das_plan* plan, float* ms);
 /* all out_* buffers are carved from one device block (one D2H, or one NCCL all-gather across ranks) */
 int das_plan_output_block(const das_plan* plan, void** ptr, int64_t* bytes);
-/* refinement implementation: 0 = fp32 SIMT (default), 1 = tensor cores 3xTF32 (feat_channels = 256,
- * num_heads = 4), 2 = tensor cores, single TF32 pass. Call before the first run. */
+/* refinement implementation: 0 = fp32 SIMT, 1 = tensor cores 3xTF32 (default when feat_channels = 256 and
+ * num_heads = 4), 2 = tensor cores, single TF32 pass (looser accuracy). Call before the first run. */
 int das_plan_set_refine_mode(das_plan* plan, int32_t mode);
 int das_plan_buffers(const das_plan* plan, das_buffers* out, int32_t* cand_slots, int32_t* out_slots);
 int64_t das_plan_kernel_launches(const das_plan* plan);   /* kernels enqueued by das_plan_run so far */

@@ -13,7 +13,8 @@ def tf32_trunc(x):
     return (x.view(torch.int32) & -8192).view(torch.float32)
 
 
-@pytest.mark.parametrize("N,K,split", [(16, 32, 0), (16, 256, 0), (32, 256, 0), (16, 256, 1), (32, 256, 1), (32, 128, 1)])
+@pytest.mark.parametrize("N,K,split", [(16, 32, 0), (16, 256, 0), (32, 256, 0), (16, 256, 1), (32, 256, 1), (32, 128, 1),
+                                       (16, 64, 2), (32, 256, 2), (16, 256, 3), (32, 256, 3)])   # split & 2: A operand through TMEM
 def test_tcgen05_tile_gemm(N, K, split):
     lib = _lib.load()
     g = torch.Generator(device="cuda").manual_seed(5)
@@ -25,7 +26,7 @@ def test_tcgen05_tile_gemm(N, K, split):
     torch.cuda.synchronize()
     exact = A.double() @ B.double().T
     scale = (A.double().abs() @ B.double().abs().T)
-    if split:
+    if split & 1:
         # 3xTF32: only the lo*lo term (2^-22 relative) and fp32 accumulation are missing
         assert float(((D.double() - exact).abs() / scale).max()) < 2e-6
     else:
