@@ -283,7 +283,7 @@ def run_b200(args):
     value = world * B * args.steps / (ms / 1e3)
 
     # ---- per-stage device times (graph replay with event nodes at the stage boundaries) -----------
-    stage = np.zeros(4)
+    stage = np.zeros(5)
     n_prof = max(min(args.steps, 200), 5)
     for i in range(3):
         plans[i % n_sets].run(stage_events=True)
@@ -294,19 +294,27 @@ def run_b200(args):
         torch.cuda.synchronize()
         stage += np.array(p.stage_ms())
     stage /= n_prof
-    t_refine_ms = float(stage[2])
     J, K, C = head.num_joints, w["K"], head.feat_channels
-    rows_per_item = 1 + 4 + 2 * head.num_heads * 4
-    alg_bytes = B * K * J * rows_per_item * C * 4                      # 37*K*J feature rows of C*4 B
+    mode = plans[0].refine_mode
+    if mode == 0:
+        kernel, rows_per_item = "refine_sparse_kernel (fp32 SIMT: phases 1-3)", 1 + 4 + 2 * head.num_heads * 4
+    else:
+        kernel = "refine_tc2_kernel (tcgen05 %s: sampling phase, 32 rows per item)" % ("3xTF32" if mode == 1 else "TF32")
+        rows_per_item = 2 * head.num_heads * 4
+    t_refine_ms = float(stage[3])
+    alg_bytes = B * K * J * rows_per_item * C * 4                      # feature rows of C*4 B per (centre, joint)
+    path_bytes = B * (2 * 4 * w["h"] * w["w"]) + B * K * J * 37 * C * 4
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (t_refine_ms / 1e3) / 1e9
-    roofline = dict(bound="hbm", kernel="refine_sparse_kernel", achieved=achieved, peak=peak, unit="GB/s",
+    roofline = dict(bound="hbm", kernel=kernel, achieved=achieved, peak=peak, unit="GB/s",
                     frac=achieved / peak, traffic=ncu_traffic(), peak_source=peak_src,
                     algorithmic_bytes_per_launch=alg_bytes, kernel_ms=t_refine_ms,
-                    stage_ms=dict(score_topk=float(stage[0]), dense_layers=float(stage[1]),
-                                  refine_assemble=t_refine_ms, nms_backproject=float(stage[3])),
-                    path_frac=(B * (2 * 4 * w["h"] * w["w"]) + alg_bytes) / (float(stage.sum()) / 1e3) / 1e9 / peak,
-                    how=f"CUDA-event nodes inside the replayed graph, mean of {n_prof} replays with a sync between them")
+                    stage_ms=dict(score_topk=float(stage[0]), dense_layers=float(stage[1]), refine_phase12=float(stage[2]),
+                                  refine_assemble=t_refine_ms, nms_backproject=float(stage[4])),
+                    path=dict(algorithmic_bytes=path_bytes, ms=float(stage.sum()),
+                              frac=path_bytes / (float(stage.sum()) / 1e3) / 1e9 / peak,
+                              note="whole decode (scan 2*4*H*W + 37 feature rows per (centre, joint)) over the summed stage times"),
+                    how=f"CUDA-event nodes inside the replayed graph (single stream), mean of {n_prof} replays with a sync between them")
 
     # ---- end to end through the host-buffer C-ABI entry: pinned host inputs, H2D + decode + D2H ---
     e2e = None

@@ -304,6 +304,7 @@ static int enqueue(das_plan* p, cudaStream_t st, int* n_launch, bool events) {
         const float* w = p->wpack[c.num_layers - 1];
         DAS_TRY(das_refine_heads(p->d_levels, &p->bound, &c, w, prev, p->buf.cand_score, p->buf.cand_index, p->CT,
                                  p->item_heads, p->valid_list, p->work_counter, st));
+        DAS_TRY(mark(3));
         DAS_TRY(das_refine_tc(p->d_levels, &p->bound, &c, w, p->tc_panels, prev, p->d_scale_xy, p->buf.cand_index, p->CT,
                               p->item_heads, p->valid_list, p->work_counter + 1, p->buf.cand_pose, p->buf.cand_center,
                               p->refine_mode == 1 ? 1 : (p->refine_mode == 2 ? 0 : p->refine_mode - 2), st));
@@ -313,12 +314,13 @@ static int enqueue(das_plan* p, cudaStream_t st, int* n_launch, bool events) {
                                            p->d_scale_xy, p->buf.cand_score, p->buf.cand_index, p->CT, p->buf.cand_pose,
                                            p->buf.cand_center, p->work_counter, st));
         ++n;
+        DAS_TRY(mark(3));
     }
-    DAS_TRY(mark(3));
+    DAS_TRY(mark(4));
     DAS_TRY(das_nms_backproject(&c, p->B, p->CT, p->buf.cand_score, p->buf.cand_pose, p->buf.cand_center, p->d_cam,
                                 p->buf, st));
     ++n;
-    DAS_TRY(mark(4));
+    DAS_TRY(mark(5));
     *n_launch = n;
     return DAS_OK;
 }
@@ -368,7 +370,8 @@ extern "C" int das_plan_run(das_plan* p, void* stream, int32_t mode) {
     return DAS_OK;
 }
 
-// Milliseconds of each stage of the last mode-2 replay: {score_topk, dense layers, refine+assemble, nms+backproject}.
+// Milliseconds of each stage of the last mode-2 replay: {score_topk, dense layers, refine phases 1-2 (0 in SIMT mode),
+// refine + assemble, nms+backproject}.
 // The caller must have synchronised the stream.
 extern "C" int das_plan_stage_ms(das_plan* p, float* ms) {
     using namespace das;

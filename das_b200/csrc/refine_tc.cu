@@ -1,5 +1,5 @@
 // Stage 3+4 on the tensor cores: the sampling phase of the sparse last-layer refinement as a gathered
-// 3xTF32 GEMM (tcgen05.mma kind::tf32, accumulator in TMEM), for C = 256, num_heads = 4.
+// 3xTF32 GEMM (tcgen05.mma kind::tf32, A operand and accumulator in TMEM), for C = 256, num_heads = 4.
 //
 // Reference semantics: recursive_update.py:186-197 (gate / value / confidence 1x1 projections and the gated
 // blend), :34-82 + :9-31 (bilinear sampling with zero padding, softmax over the 2*nh heads), das_head.py:252-262
@@ -8,45 +8,37 @@
 // rows (8 heads x 4 bilinear corners) times that joint's 9 projection rows -- a real dense contraction once
 // items of the SAME joint are batched:
 //
-//   tile   = 4 items of one joint = 128 gathered feature rows  (A: 128 x 256, fp32 as tf32 hi/lo)
+//   tile   = 4 items of one joint = 128 gathered feature rows  (A: 128 x 256, fp32 split into tf32 hi/lo)
 //   B      = that joint's {gate 3, value 3, conf 3} rows, zero-padded to N = 16, pre-split into hi/lo and
-//            pre-swizzled on the host side of the kernel (das_pack_tc_panels)
-//   D      = A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T   (3xTF32: fp32-level accuracy, fp32 accumulation in TMEM)
+//            pre-swizzled by das_pack_tc_panels; per k-block the 16 hi rows are followed by the 16 lo rows
+//   D      = A_hi [B_hi;B_lo]^T (N = 32)  +  A_lo B_hi^T (N = 16, into the first 16 columns)
+//            -> 3xTF32: fp32-level accuracy, fp32 accumulation in TMEM, 2 MMAs per K = 8 step
 //
-// One CTA (16 warps) per SM walks a contiguous range of tiles.  Rows are gathered k-block by k-block
-// (32 channels = one 128-B swizzle span) with cp.async into a 7-stage ring, 3 k-blocks ahead and across tile
-// boundaries; every thread splits the chunks it copied itself (hi stays in place -- the tensor core drops the
-// low mantissa bits -- lo goes to a 4-deep side ring); a dedicated warp issues 8 MMAs per k-block and
-// commits them to the stage's mbarrier.  Epilogue: thread t owns TMEM lane t = row t (item, head, corner):
-// bias, sigmoid gate, blend with the previous offset, bilinear weight / zero padding, corner sum (2 shuffles),
-// softmax over the 8 heads (3 shuffles), eval tail, assembly.
+// One CTA per SM walks a contiguous range of tiles, warp-specialised (measured design history in DESIGN.md):
+//   3 producer groups (4 warps each; k-blocks round-robin) gather their k-block with coalesced cp.async into a
+//                     private 3-stage smem ring; then every thread reads ITS row (thread = row = TMEM lane, conflict-
+//                     free thanks to the 128-B swizzle), splits hi/lo in registers and tcgen05.st's both into a
+//                     4-slot TMEM ring -- the tensor core never reads A from shared memory
+//   MMA warp          one fused burst of 8 tcgen05.mma per k-block (~47 cycles each: an M=128,K=8 tcgen05.mma costs
+//                     ~50 cycles for any N <= 64, A from smem or TMEM alike), tcgen05.commit to the slot's mbarrier;
+//                     also (re)loads the B panels when the joint changes
+//   3 epilogue groups (4 warps each; thread = row) drain the triple-buffered accumulators: bias, sigmoid gate, blend
+//                     with the previous offset, bilinear weight / zero padding, corner sum (2 shuffles), softmax
+//                     over the 8 heads (3 shuffles), eval tail, assembly; they also prepare the row pointers and
+//                     per-row state 6 tiles ahead and prefetch those rows into L2
 #include "refine_common.cuh"
 #include "tc_common.cuh"
 
 namespace das {
 
-constexpr int TC_EPI_WARPS = 4;                 // one epilogue group = 4 warps = the 128 TMEM lanes (row setup + epilogue)
-constexpr int TC_EPI_GROUPS = 2;                // group e handles tiles e, e+2, ... with TMEM buffer / pointer buffer e
-constexpr int TC_PRODUCER_WARPS = 12;           // gather + hi/lo split: warps 8.. whose id % 4 != 3
-constexpr int TC_FIRST_PRODUCER = TC_EPI_WARPS * TC_EPI_GROUPS;
-// Warp w is scheduled by SM sub-partition w % 4.  Sub-partition 3 hosts only the MMA issuer (warp 11), the two
-// mostly-sleeping quadrant-3 epilogue warps (3, 7) and idle filler warps, so the single-thread tcgen05.mma issue
-// stream does not compete with the producers for issue slots.
-constexpr int TC_MMA_WARP = 11;
-constexpr int TC_WARPS = 24;
-constexpr int TC_THREADS = 32 * TC_WARPS;
-constexpr int TC_NS = 7;                       // A_hi ring stages
-constexpr int TC_PD = 3;                       // prefetch distance in k-blocks
-constexpr int TC_NLO = 4;                      // A_lo buffers = how many k-blocks the producers may run ahead of the MMAs
-static_assert(TC_NS - TC_PD == TC_NLO, "ring reuse distance and A_lo depth must agree");
-constexpr int TC_N = 16;                       // MMA N: 9 projection rows + zero padding
-constexpr int TC_KB = 8;                       // k-blocks of 32 channels (C = 256)
+constexpr int TC_EPI_WARPS = 4;                 // one epilogue / producer group = 4 warps = the 128 TMEM lanes
+constexpr int TC_N = 16;                        // MMA N: 9 projection rows + zero padding
+constexpr int TC_KB = 8;                        // k-blocks of 32 channels (C = 256)
 constexpr int TC_C = 256;
 constexpr int TC_NH = 4;
-constexpr int TC_A_BYTES = 128 * 128;          // one k-block of 128 rows
-constexpr int TC_B_BYTES = TC_KB * TC_N * 128; // hi or lo rows of one joint: 16 KB (a joint's panel = 2x that)
-constexpr int TC_BK_BYTES = 2 * TC_N * 128;    // panel bytes per k-block: 16 hi rows followed by 16 lo rows
-constexpr int TC_SMEM = 1024 + TC_NS * TC_A_BYTES + TC_NLO * TC_A_BYTES + 2 * TC_B_BYTES;
+constexpr int TC_A_BYTES = 128 * 128;           // one k-block of 128 rows
+constexpr int TC_B_BYTES = TC_KB * TC_N * 128;  // hi or lo rows of one joint: 16 KB (a joint's panel = 2x that)
+constexpr int TC_BK_BYTES = 2 * TC_N * 128;     // panel bytes per k-block: 16 hi rows followed by 16 lo rows
 constexpr int TC_NOUT = 2 * TC_NH + 9;
 constexpr int TC_OGATE = 2 * TC_NH;
 
@@ -200,240 +192,6 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const RowState& c
         }
     }}
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
-refine_tc_kernel(const TcParams p) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    unsigned char* sA = base;                                   // TC_NS stages of A_hi
-    unsigned char* sAl = sA + TC_NS * TC_A_BYTES;               // TC_NLO buffers of A_lo
-    unsigned char* sB = sAl + TC_NLO * TC_A_BYTES;              // per k-block: 16 hi rows then 16 lo rows
-    __shared__ uint64_t full[TC_NS], empty[TC_NS];              // producers -> MMA warp, MMA warp -> producers
-    __shared__ uint64_t acc_full[2], acc_free[2], rows_ready[2];// MMA -> epilogue, epilogue -> MMA, epilogue -> producers
-    __shared__ uint32_t tmem_base;
-    __shared__ const float* s_rowptr[2][128];
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long kernel_t0 = clock64();
-    const int J = p.J;
-    const int n_valid = __ldg(p.n_valid);
-    const int n_groups = (n_valid + 3) >> 2;
-    const int n_tiles = J * n_groups;
-    const int t0 = static_cast<int>(static_cast<long long>(n_tiles) * blockIdx.x / gridDim.x);
-    const int t1 = static_cast<int>(static_cast<long long>(n_tiles) * (blockIdx.x + 1) / gridDim.x);
-    if (t0 >= t1) return;
-    const int my_tiles = t1 - t0;
-
-    if (tid == 0) {
-        for (int s = 0; s < TC_NS; ++s) { tc::mbar_init(&full[s], TC_PRODUCER_WARPS); tc::mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { tc::mbar_init(&acc_full[s], 1); tc::mbar_init(&acc_free[s], TC_EPI_WARPS); tc::mbar_init(&rows_ready[s], TC_EPI_WARPS); }
-        tc::mbar_fence_init();
-    }
-    if (warp == 0) tc::tmem_alloc(&tmem_base, 64);
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    const uint32_t tmem_d = tmem_base;
-    const uint32_t sA_u = tc::smem_u32(sA), sAl_u = tc::smem_u32(sAl), sB_u = tc::smem_u32(sB);
-
-    if (warp == TC_MMA_WARP) {
-        // ===== MMA issuer warp =====================================================================================
-        constexpr uint32_t idesc32 = tc::instr_desc_tf32(128, 2 * TC_N);   // A_hi x [B_hi ; B_lo]  -> D[:, 0:32]
-        constexpr uint32_t idesc16 = tc::instr_desc_tf32(128, TC_N);       // A_lo x  B_hi          -> D[:, 0:16]
-        int g = 0;
-        long long dbg_a = 0, dbg_b = 0, dbg_c = 0;   // wait full | issue | wait acc_free
-        for (int i = 0; i < my_tiles; ++i) {
-            const uint32_t dcol = tmem_d + (i & 1) * 32;
-            { const long long c0 = clock64();
-              if (i >= 2) tc::mbar_wait(&acc_free[i & 1], ((i >> 1) - 1) & 1);   // epilogue of tile i-2 has drained this buffer
-              dbg_c += clock64() - c0; }
-            for (int kb = 0; kb < TC_KB; ++kb, ++g) {
-                const int st = g % TC_NS;
-                const long long c0 = clock64();
-                tc::mbar_wait(&full[st], (g / TC_NS) & 1);
-                tc::tc_fence_after();
-                const long long c1 = clock64();
-                dbg_a += c1 - c0;
-                if (!(p.split & 2)) {            // (bit 1: timing experiment without MMAs)
-                    const uint32_t a_hi = sA_u + st * TC_A_BYTES, a_lo = sAl_u + (g % TC_NLO) * TC_A_BYTES;
-                    const uint32_t b_pk = sB_u + kb * TC_BK_BYTES;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t da = tc::smem_desc_sw128(a_hi + k * 32);
-                        const uint64_t db = tc::smem_desc_sw128(b_pk + k * 32);
-                        if (p.split & 1) {
-                            tc::umma_tf32_elect(dcol, da, db, idesc32, (kb | k) != 0);
-                            tc::umma_tf32_elect(dcol, tc::smem_desc_sw128(a_lo + k * 32), db, idesc16, true);
-                        } else {
-                            tc::umma_tf32_elect(dcol, da, db, idesc16, (kb | k) != 0);
-                        }
-                    }
-                }
-                tc::umma_commit_elect(&empty[st]);
-                if (kb == TC_KB - 1) tc::umma_commit_elect(&acc_full[i & 1]);
-                __syncwarp();
-                dbg_b += clock64() - c1;
-            }
-        }
-        if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 16 + 0] = dbg_a; p.dbg[blockIdx.x * 16 + 1] = dbg_b; p.dbg[blockIdx.x * 16 + 2] = dbg_c; }
-    } else if (warp >= TC_FIRST_PRODUCER && (warp & 3) == 3) {
-        // filler warps of sub-partition 3: nothing to do
-    } else if (warp >= TC_FIRST_PRODUCER) {
-        // ===== producer warps: gather feature rows (cp.async), split hi/lo, hand k-blocks to the MMA warp ===========
-        const int ptid = (((warp - TC_FIRST_PRODUCER) >> 2) * 3 + (warp & 3)) * 32 + lane;
-        constexpr int NPT = 32 * TC_PRODUCER_WARPS;
-        constexpr int NIT = (1024 + NPT - 1) / NPT;
-        const int total_kb = my_tiles * TC_KB;
-        auto wait_consumed = [&](int g) { tc::mbar_wait(&empty[g % TC_NS], (g / TC_NS) & 1); };
-        // this thread always handles the same (row, 16-B chunk) pairs: chunk c = ptid + NPT * it
-        uint32_t soff[NIT];
-        const float* rp[2][NIT];     // feature-row pointers (+ chunk offset) of the tile being gathered, per pointer buffer
-#pragma unroll
-        for (int it = 0; it < NIT; ++it) {
-            const int c = ptid + NPT * it;
-            soff[it] = tc::swz128((c & 1023) >> 3, c & 7);
-            rp[0][it] = rp[1][it] = nullptr;
-        }
-        // stage k-block gi (tile gi / 8) into ring slot gi % NS
-        auto gather = [&](int gi) {
-            const int i = gi / TC_KB, kb = gi - i * TC_KB, st = gi % TC_NS;
-            if (kb == 0) {
-                tc::mbar_wait(&rows_ready[i & 1], (i >> 1) & 1);   // row pointers of tile i are in s_rowptr[i & 1]
-#pragma unroll
-                for (int it = 0; it < NIT; ++it) {
-                    const int c = ptid + NPT * it;
-                    const float* src = (c < 1024) ? s_rowptr[i & 1][c >> 3] : nullptr;
-                    if (i & 1) rp[1][it] = src ? src + (c & 7) * 4 : nullptr; else rp[0][it] = src ? src + (c & 7) * 4 : nullptr;
-                }
-            }
-#pragma unroll
-            for (int it = 0; it < NIT; ++it) {
-                const int c = ptid + NPT * it;
-                if (c < 1024) {
-                    const float* src = (i & 1) ? rp[1][it] : rp[0][it];
-                    tc::cp_async16_ca(sA_u + st * TC_A_BYTES + soff[it], src ? src + kb * 32 : p.wpack, src != nullptr);
-                }
-            }
-        };
-        for (int gi = 0; gi < TC_PD && gi < total_kb; ++gi) { gather(gi); tc::cp_async_commit(); }
-        for (int gi = total_kb; gi < TC_PD; ++gi) tc::cp_async_commit();
-        int cur_j = -1;
-        long long d_wc = 0, d_g = 0, d_w = 0, d_s = 0, d_f = 0;   // wait consumed | gather (incl. rows_ready) | cp.async wait | split | fence+arrive
-        for (int g = 0; g < total_kb; ++g) {
-            const int i = g / TC_KB, kb = g - i * TC_KB, st = g % TC_NS;
-            const long long c0 = clock64();
-            // k-block g-NLO consumed => ring slot (g+PD)%NS and A_lo[g%NLO] are free again
-            if (g >= TC_NLO) wait_consumed(g - TC_NLO);
-            const long long c1 = clock64();
-            if (g + TC_PD < total_kb) gather(g + TC_PD);
-            tc::cp_async_commit();             // possibly empty: keeps the group count uniform
-            const long long c2 = clock64();
-            if (kb == 0) {
-                const int j = (t0 + i) / n_groups;
-                if (j != cur_j) {
-                    // new joint: its panels replace the old ones once every earlier MMA has finished reading them
-                    if (g > 0) wait_consumed(g - 1);
-                    const unsigned char* src = p.bpanel + static_cast<size_t>(j) * 2 * TC_B_BYTES;
-                    for (int c = ptid; c < 2 * TC_B_BYTES / 16; c += NPT) tc::cp_async16(sB_u + c * 16, src + c * 16, true);
-                    tc::cp_async_commit();
-                    tc::cp_async_wait<0>();
-                    cur_j = j;
-                }
-            }
-            tc::cp_async_wait<TC_PD>();        // this thread's chunks of k-block g have landed
-            const long long c3 = clock64();
-            if ((p.split & 1) && !(p.split & 4)) {
-#pragma unroll
-                for (int it = 0; it < NIT; ++it) {
-                    const int c = ptid + NPT * it;
-                    if (c < 1024) {
-                        const uint32_t off = soff[it];
-                        const float4 a = *reinterpret_cast<const float4*>(sA + st * TC_A_BYTES + off);
-                        float4 lo;
-                        lo.x = a.x - tc::tf32_hi(a.x); lo.y = a.y - tc::tf32_hi(a.y);
-                        lo.z = a.z - tc::tf32_hi(a.z); lo.w = a.w - tc::tf32_hi(a.w);
-                        *reinterpret_cast<float4*>(sAl + (g % TC_NLO) * TC_A_BYTES + off) = lo;
-                    }
-                }
-            }
-            const long long c4 = clock64();
-            if (!(p.split & 8)) tc::fence_proxy_async();     // bit 3: timing experiment only
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&full[st]);
-            const long long c5 = clock64();
-            d_wc += c1 - c0; d_g += c2 - c1; d_w += c3 - c2; d_s += c4 - c3; d_f += c5 - c4;
-        }
-        tc::cp_async_wait<0>();
-        if (p.dbg && ptid == 0) {
-            long long* o = p.dbg + blockIdx.x * 16;
-            o[3] = d_wc; o[4] = d_g; o[5] = d_w; o[6] = d_s; o[7] = d_f; o[8] = total_kb;
-        }
-    } else {
-        // ===== epilogue / row-setup warps: thread t <-> row t = (item warp, head lane>>2, corner lane&3) ===========
-        const int e = warp / TC_EPI_WARPS;          // epilogue group: tiles e, e+2, ...; buffers e
-        const int rt = tid - e * 32 * TC_EPI_WARPS; // row of the tile this thread owns (= TMEM lane)
-        const int qw = warp % TC_EPI_WARPS;         // TMEM lane quadrant this warp may read
-        RowState cur{};
-        if (e < my_tiles) {
-            cur = setup_row(p, t0 + e, n_groups, n_valid, rt);
-            s_rowptr[e][rt] = cur.ptr;
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&rows_ready[e]);
-        }
-#pragma unroll 1
-        for (int i = e; i < my_tiles; i += TC_EPI_GROUPS) {
-            const int tile = t0 + i;
-            const int j = tile / n_groups;
-            const long long e0 = clock64();
-            tc::mbar_wait(&acc_full[i & 1], (i >> 1) & 1);
-            tc::tc_fence_after();
-            const long long e1 = clock64();
-            float v[16], v2[16];
-            const uint32_t taddr = tmem_d + (static_cast<uint32_t>(qw * 32) << 16) + (i & 1) * 32;
-            tc::tmem_ld16(taddr, v);
-            if (p.split & 1) {
-                tc::tmem_ld16(taddr + TC_N, v2);
-#pragma unroll
-                for (int k = 0; k < 9; ++k) v[k] += v2[k];
-            }
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&acc_free[i & 1]);
-            // next-but-one tile: its rows reuse this tile's pointer buffer (every gather of this tile was issued
-            // before its MMAs could complete); start the dependent loads now, they overlap the math below
-            const long long e2 = clock64();
-            RowState nx{};
-            if (i + 2 < my_tiles) {
-                nx = setup_row(p, tile + 2, n_groups, n_valid, rt);
-                s_rowptr[e][rt] = nx.ptr;
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&rows_ready[e]);
-            }
-            const long long e3 = clock64();
-            tc_epilogue(p, cur, v, j, lane);
-            cur = nx;
-            if (p.dbg && tid == 0) {
-                long long* o = p.dbg + blockIdx.x * 16;
-                o[9] += e1 - e0; o[10] += e2 - e1; o[11] += e3 - e2; o[12] += clock64() - e3;
-            }
-        }
-    }
-    if (p.dbg && tid == 0) p.dbg[blockIdx.x * 16 + 13] = clock64() - kernel_t0;
-    tc::tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_base, 64);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// v2: A operand through TMEM.
-//
-// v1 is bound by shared-memory bandwidth: every 128x32 A k-block is written by cp.async, read and re-written by
-// the hi/lo split, and read twice more by the tensor core (hi and lo operands) for only 16..32 output columns.
-// Here the tensor core reads A from TMEM instead.  Three producer groups of 4 warps take k-blocks round-robin;
-// a group gathers its k-block with coalesced cp.async into a private 3-stage smem ring, then every thread reads
-// ITS row (thread = row = TMEM lane; conflict-free thanks to the 128-B swizzle), splits hi/lo in registers and
-// writes both with tcgen05.st into a 4-slot TMEM ring.  Shared-memory traffic per tile drops from ~640 KB to
-// 256 KB (+ the tiny B panel reads).  The MMA warp issues tcgen05.mma with [a_tmem] operands; two epilogue groups
-// drain the double-buffered accumulators as in v1.
 constexpr int T2_PGROUPS = 3;                   // producer groups (4 warps each)
 constexpr int T2_STAGES = 3;                    // smem stages per group
 constexpr int T2_SLOTS = 4;                     // TMEM A slots (64 columns each: 32 hi + 32 lo)
@@ -705,22 +463,12 @@ extern "C" int das_refine_tc(const das_levels* d_levels, const das_levels* h_lev
     p.CT = cand_slots; p.J = cfg->num_joints; p.root = cfg->root_idx; p.nms_pre = cfg->nms_pre; p.layer = cfg->num_layers - 1;
     p.split = split; p.depth_factor = cfg->depth_factor; p.z_norm = cfg->z_norm;
     p.dbg = g_tc_dbg;
-    static bool attr_done = false;
-    if (!attr_done) {
-        DAS_CUDA_CHECK(cudaFuncSetAttribute(refine_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-        attr_done = true;
-    }
     static bool attr2_done = false;
     if (!attr2_done) {
         DAS_CUDA_CHECK(cudaFuncSetAttribute(refine_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
         attr2_done = true;
     }
-    if (split & 16) {        // v1 (A operand from shared memory), kept for comparison
-        p.split = split & 15;
-        refine_tc_kernel<<<kSMs, TC_THREADS, TC_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
-    } else {
-        refine_tc2_kernel<<<kSMs, T2_THREADS, T2_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
-    }
+    refine_tc2_kernel<<<kSMs, T2_THREADS, T2_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
     DAS_CUDA_CHECK(cudaGetLastError());
     return DAS_OK;
 }

@@ -131,6 +131,8 @@ class DecodePlan:
             if refine_mode is not None:      # 0 fp32 SIMT, 1 tcgen05 3xTF32 (default when supported), 2 tcgen05 TF32
                 _lib.check(self.lib.das_plan_set_refine_mode(self._plan, int(refine_mode)), "das_plan_set_refine_mode")
         self.cand_slots, self.out_slots = ct.value, p.value
+        self.refine_mode = (int(refine_mode) if refine_mode is not None else
+                            (1 if (refine and feat_channels == 256 and num_heads == 4) else 0))
         B, CT, P, J = self.batch, ct.value, p.value, num_joints
         dev = self.device
         self.t = dict(
@@ -254,8 +256,9 @@ class DecodePlan:
             _lib.check(self.lib.das_plan_run(self._plan, _stream_ptr(self.device), mode), "das_plan_run")
 
     def stage_ms(self) -> List[float]:
-        """[score_topk, dense layers, refine+assemble, nms+backproject] of the last stage_events run."""
-        arr = (C.c_float * 4)()
+        """[score_topk, dense layers, refine phases 1-2 (tensor-core mode only), refine+assemble, nms+backproject]
+        of the last stage_events run."""
+        arr = (C.c_float * 5)()
         _lib.check(self.lib.das_plan_stage_ms(self._plan, arr), "das_plan_stage_ms")
         return [float(x) for x in arr]
 

@@ -36,7 +36,7 @@ extern "C" {
 #define DAS_MAX_JOINTS 32
 #define DAS_MAX_NMS_PRE 2048  /* per-level top-k capacity (reference configs use 1000) */
 #define DAS_CAM_DOUBLES 18    /* K[0,:3], K[1,:3], R row-major 3x3, t[3] */
-#define DAS_NUM_STAGES 4      /* score_topk | dense layers | refine+assemble | nms+backproject */
+#define DAS_NUM_STAGES 5      /* score_topk | dense layers | refine phases 1-2 (tensor-core mode) | refine + assemble | nms+backproject */
 
 typedef enum das_status {
     DAS_OK = 0,

@@ -1,4 +1,4 @@
-import sys, os, ctypes as C; sys.path.insert(0,'.'); sys.path.insert(0,'tests')
+import sys, os, ctypes as C; import os as _os; _r=_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))); sys.path.insert(0,_r); sys.path.insert(0,_os.path.join(_r,'tests'))
 import torch, numpy as np
 from das_b200 import synth, _lib
 import util
