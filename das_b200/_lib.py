@@ -87,6 +87,8 @@ SIGNATURES = {
     "das_tc_selftest": (C.c_int, [_VP, _VP, _VP, C.c_int32, C.c_int32, C.c_int32, _VP]),
     "das_tc_mma_bench": (C.c_int, [C.c_int32, C.c_int32, _VP, _VP]),
     "das_plan_h2d_bytes": (C.c_int64, [_VP]),
+    "das_plan_set_host_mode": (C.c_int, [_VP, C.c_int32]),
+    "das_plan_h2d_explicit_bytes": (C.c_int64, [_VP]),
     "das_plan_d2h_bytes": (C.c_int64, [_VP]),
 }
 

@@ -46,6 +46,8 @@ struct das_plan {
     // host-entry staging
     das_levels staging{};
     bool staging_ready = false;
+    int host_mode = 0;                // das_plan_run_host: 0 = bulk H2D of every map, 1 = sparse maps read in place (zero copy)
+    int64_t h2d_explicit = 0;         // bytes das_plan_run_host copies explicitly per call in the current host_mode
     int64_t h2d_bytes = 0, d2h_bytes = 0;
     unsigned char* out_block = nullptr;   // all out_* buffers live in this one allocation (one D2H / one all-gather)
     size_t out_block_bytes = 0;
@@ -410,6 +412,15 @@ extern "C" int das_plan_buffers(const das_plan* p, das_buffers* out, int32_t* ca
 
 extern "C" int64_t das_plan_kernel_launches(const das_plan* p) { return p ? p->launches : 0; }
 extern "C" int64_t das_plan_h2d_bytes(const das_plan* p) { return p ? p->h2d_bytes : 0; }
+// bytes the last das_plan_run_host call moved with explicit copies (host_mode 1 reads the sparse maps in place)
+extern "C" int64_t das_plan_h2d_explicit_bytes(const das_plan* p) { return p ? p->h2d_explicit : 0; }
+extern "C" int das_plan_set_host_mode(das_plan* p, int32_t mode) {
+    using namespace das;
+    DAS_REQUIRE(p, DAS_ERR_ARG, "null plan");
+    DAS_REQUIRE(mode == 0 || mode == 1, DAS_ERR_ARG, "host mode %d", mode);
+    p->host_mode = mode;
+    return DAS_OK;
+}
 extern "C" int64_t das_plan_d2h_bytes(const das_plan* p) { return p ? p->d2h_bytes : 0; }
 
 extern "C" int das_plan_run_host(das_plan* p, const das_levels* levels, const float* scale_xy, const double* cam,
@@ -421,40 +432,73 @@ extern "C" int das_plan_run_host(das_plan* p, const das_levels* levels, const fl
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t B = p->B, J = p->cfg.num_joints, C = p->cfg.feat_channels;
     const int L = p->cfg.refine ? p->cfg.num_layers : 0;
+    // host_mode 1: the decode touches every cell of the centre / centerness logits but only ~5 % of the pose and
+    // feature maps (K cells and their bilinear corners per image).  Pinned host memory is device-addressable
+    // (unified addressing), so those sparse maps are read IN PLACE over PCIe by the gather kernels instead of being
+    // copied wholesale; only the logit planes are staged.
+    bool zero_copy = p->host_mode == 1;
+    const float* dev_alias[DAS_MAX_LEVELS][1 + DAS_MAX_LAYERS] = {};
+    if (zero_copy) {
+        for (int l = 0; l < p->shape.n_levels && zero_copy; ++l) {
+            const das_level_desc& h = levels->lv[l];
+            const void* srcs[1 + DAS_MAX_LAYERS] = {h.pose};
+            for (int k = 0; k < L; ++k) srcs[1 + k] = h.feats[k];
+            for (int k = 0; k < 1 + L; ++k) {
+                cudaPointerAttributes at{};
+                if (!srcs[k] || cudaPointerGetAttributes(&at, srcs[k]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+                    cudaGetLastError();
+                    zero_copy = false;      // pageable memory: fall back to staging copies
+                    break;
+                }
+                dev_alias[l][k] = static_cast<const float*>(at.devicePointer);
+            }
+        }
+    }
     if (!p->staging_ready) {
         p->staging = p->shape;
         for (int l = 0; l < p->shape.n_levels; ++l) {
             const size_t hw = static_cast<size_t>(p->shape.lv[l].H) * p->shape.lv[l].W;
-            float *a = nullptr, *b = nullptr, *c = nullptr;
+            float *a = nullptr, *b = nullptr;
             DAS_TRY(dev_alloc(&a, B * hw));
             DAS_TRY(dev_alloc(&b, B * hw));
-            DAS_TRY(dev_alloc(&c, B * hw * (3 + 6 * J)));
-            p->staging.lv[l].cls = a; p->staging.lv[l].ctr = b; p->staging.lv[l].pose = c;
+            p->staging.lv[l].cls = a; p->staging.lv[l].ctr = b; p->staging.lv[l].pose = nullptr;
             for (int k = 0; k < DAS_MAX_LAYERS; ++k) p->staging.lv[l].feats[k] = nullptr;
-            for (int k = 0; k < L; ++k) {
-                float* f = nullptr;
-                DAS_TRY(dev_alloc(&f, B * hw * C));
-                p->staging.lv[l].feats[k] = f;
-            }
         }
         p->staging_ready = true;
     }
+    das_levels run = p->staging;
+    int64_t copied = 0;
     for (int l = 0; l < p->shape.n_levels; ++l) {
         const das_level_desc& h = levels->lv[l];
-        das_level_desc& d = p->staging.lv[l];
+        das_level_desc& d = run.lv[l];
         DAS_REQUIRE(h.H == d.H && h.W == d.W && h.stride == d.stride, DAS_ERR_ARG, "run_host: level %d shape differs", l);
         DAS_REQUIRE(h.cls && h.ctr && h.pose, DAS_ERR_ARG, "run_host: level %d has a null map", l);
         const size_t hw = static_cast<size_t>(h.H) * h.W;
         d.scale_offset = h.scale_offset; d.scale_depth = h.scale_depth; d.scale_uv = h.scale_uv; d.scale_d = h.scale_d;
         DAS_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(d.cls), h.cls, B * hw * 4, cudaMemcpyHostToDevice, st));
         DAS_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(d.ctr), h.ctr, B * hw * 4, cudaMemcpyHostToDevice, st));
-        DAS_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(d.pose), h.pose, B * hw * (3 + 6 * J) * 4, cudaMemcpyHostToDevice, st));
-        for (int k = 0; k < L; ++k) {
-            DAS_REQUIRE(h.feats[k], DAS_ERR_ARG, "run_host: level %d layer %d feature map is null", l, k);
-            DAS_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(d.feats[k]), h.feats[k], B * hw * C * 4, cudaMemcpyHostToDevice, st));
+        copied += static_cast<int64_t>(B * hw * 8);
+        if (zero_copy) {
+            d.pose = dev_alias[l][0];
+            for (int k = 0; k < L; ++k) d.feats[k] = dev_alias[l][1 + k];
+        } else {
+            // lazily allocated bulk staging for the sparse maps
+            das_level_desc& sd = p->staging.lv[l];
+            if (!sd.pose) { float* c = nullptr; DAS_TRY(dev_alloc(&c, B * hw * (3 + 6 * J))); sd.pose = c; }
+            DAS_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(sd.pose), h.pose, B * hw * (3 + 6 * J) * 4, cudaMemcpyHostToDevice, st));
+            copied += static_cast<int64_t>(B * hw * (3 + 6 * J) * 4);
+            d.pose = sd.pose;
+            for (int k = 0; k < L; ++k) {
+                DAS_REQUIRE(h.feats[k], DAS_ERR_ARG, "run_host: level %d layer %d feature map is null", l, k);
+                if (!sd.feats[k]) { float* f = nullptr; DAS_TRY(dev_alloc(&f, B * hw * C)); sd.feats[k] = f; }
+                DAS_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(sd.feats[k]), h.feats[k], B * hw * C * 4, cudaMemcpyHostToDevice, st));
+                copied += static_cast<int64_t>(B * hw * C * 4);
+                d.feats[k] = sd.feats[k];
+            }
         }
     }
-    DAS_TRY(das_plan_bind(p, &p->staging, st));
+    p->h2d_explicit = copied + static_cast<int64_t>(B) * (2 * 4 + DAS_CAM_DOUBLES * 8);
+    DAS_TRY(das_plan_bind(p, &run, st));
     DAS_TRY(das_plan_set_metas(p, scale_xy, cam, st));
     DAS_TRY(das_plan_run(p, st, 1));
     const size_t P = p->P;

@@ -415,7 +415,7 @@ extern "C" int das_refine_heads(const das_levels* d_levels, const das_levels* h_
     DAS_REQUIRE(items < (1ll << 31), DAS_ERR_CAPACITY, "too many work items");
     p.n_items = static_cast<int>(items);
     DAS_CUDA_CHECK(cudaMemsetAsync(counters, 0, 2 * sizeof(int32_t), st));
-    refine_sparse_kernel<8, 4, 3, true><<<kSMs * 3, RS_WARPS * 32, 0, st>>>(p);
+    refine_sparse_kernel<8, 4, 4, true><<<kSMs * 4, RS_WARPS * 32, 0, st>>>(p);
     DAS_CUDA_CHECK(cudaGetLastError());
     return DAS_OK;
 }

@@ -291,6 +291,15 @@ class DecodePlan:
         """Typed views into a copy of an output block (this rank's, or one gathered from a peer rank)."""
         return block_views(block, self.batch, self.out_slots, self.cfg.num_joints)
 
+    def set_host_mode(self, zero_copy: bool):
+        """run_host policy: False = bulk H2D of every map; True = copy only the logit planes and let the gather
+        kernels read the (sparsely used) pose / feature maps in place from pinned host memory."""
+        _lib.check(self.lib.das_plan_set_host_mode(self._plan, int(bool(zero_copy))), "das_plan_set_host_mode")
+
+    @property
+    def h2d_explicit_bytes(self) -> int:
+        return int(self.lib.das_plan_h2d_explicit_bytes(self._plan))
+
     @property
     def kernel_launches(self) -> int:
         return int(self.lib.das_plan_kernel_launches(self._plan))

@@ -203,6 +203,11 @@ int64_t das_plan_kernel_launches(const das_plan* plan);   /* kernels enqueued by
 int das_plan_run_host(das_plan* plan, const das_levels* levels, const float* scale_xy,
                       const double* cam, das_buffers host_out, void* stream);
 int64_t das_plan_h2d_bytes(const das_plan* plan);
+/* das_plan_run_host transfer policy: 0 = bulk H2D copy of every input map (default); 1 = only the logit planes are
+ * copied, the pose and feature maps (of which the decode touches ~5 %) are read in place from PINNED host memory
+ * by the gather kernels (falls back to 0 for pageable memory). */
+int das_plan_set_host_mode(das_plan* plan, int32_t mode);
+int64_t das_plan_h2d_explicit_bytes(const das_plan* plan);   /* bytes explicitly copied by the last run_host */
 int64_t das_plan_d2h_bytes(const das_plan* plan);
 
 /* ---- diagnostics ------------------------------------------------------------------------------- */

@@ -238,6 +238,23 @@ def test_host_entry_equals_device_entry():
     for g, h in zip(got, res):
         assert g["scores"] == h["scores"] and torch.equal(g["poses"].cpu(), h["poses"]) and torch.equal(g["poses_cam"].cpu(), h["poses_cam"])
     assert plan.h2d_bytes > 3 * 24 * 40 * 256 * 4 and plan.d2h_bytes > 0
+    assert plan.h2d_explicit_bytes == plan.h2d_bytes
+    # zero-copy policy: only the logit planes are copied, pose / feature maps are read in place from pinned memory
+    plan.set_host_mode(True)
+    out2 = plan.alloc_host_out()
+    plan.run_host(host_levels, case["metas"], out2)
+    assert plan.h2d_explicit_bytes < plan.h2d_bytes // 20
+    for k in out:
+        assert torch.equal(out[k], out2[k]), k
+    # pageable inputs silently fall back to staging copies
+    pageable = [dict(cls=lv["cls"].clone(), ctr=lv["ctr"].clone(), pose=lv["pose_raw"].clone(),
+                     feats=[f.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2) for f in lv["feats"]], scales=lv["scales"])
+                for lv in case["levels"]]
+    out3 = plan.alloc_host_out()
+    plan.run_host(pageable, case["metas"], out3)
+    assert plan.h2d_explicit_bytes == plan.h2d_bytes
+    for k in out:
+        assert torch.equal(out[k], out3[k]), k
 
 
 def test_drop_in_head_api():
