@@ -29,8 +29,15 @@ sys.path.insert(0, ROOT)
 
 from das_b200 import synth  # noqa: E402
 
-WORKLOAD = dict(name="panoptic_decode_B64_J15_128x208_K10_L1", batch=64, h=128, w=208, stride=8, K=10,
-                head=synth.PANOPTIC)
+WORKLOADS = {
+    # BASELINE config #2 (the metric's configuration) -- the default
+    "panoptic": dict(name="panoptic_decode_B64_J15_128x208_K10_L1", batch=64, h=128, w=208, stride=8, K=10, head=synth.PANOPTIC),
+    # BASELINE config #3: MuPoTS-shaped, 17 joints, 3 refinement layers (2 dense + 1 sparse), K=20
+    "mupots": dict(name="mupots_decode_B64_J17_128x208_K20_L3", batch=64, h=128, w=208, stride=8, K=20, head=synth.MUPOTS17),
+    # BASELINE config #4: crowded scene, 256x416 map, K=64
+    "crowded": dict(name="crowded_decode_B32_J15_256x416_K64_L1", batch=32, h=256, w=416, stride=8, K=64, head=synth.PANOPTIC),
+}
+WORKLOAD = dict(WORKLOADS["panoptic"])
 TEST_CFG = dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)
 METRIC = "decoded_images_per_sec"
 UNIT = "images/s"
@@ -208,7 +215,8 @@ def run_b200(args):
     metas = synth.make_metas(B, w["h"], w["w"], stride=w["stride"], seed=1236 + rank)
     plans, keep = [], []
     for s in range(n_sets):
-        levels = synth.make_levels(head, B, w["h"], w["w"], seed=1234 + 17 * s + 1000 * rank, device=dev, peaks=16)
+        levels = synth.make_levels(head, B, w["h"], w["w"], seed=1234 + 17 * s + 1000 * rank, device=dev,
+                                   peaks=max(16, (3 * w["K"]) // 2))
         plan = DecodePlan(num_joints=head.num_joints, root_idx=head.root_idx, depth_factor=head.depth_factor,
                           z_norm=head.z_norm, strides=head.strides, level_sizes=[(w["h"], w["w"])], batch=B,
                           test_cfg=TEST_CFG, num_heads=head.num_heads, feat_channels=head.feat_channels,
@@ -303,7 +311,8 @@ def run_b200(args):
         rows_per_item = 2 * head.num_heads * 4
     t_refine_ms = float(stage[3])
     alg_bytes = B * K * J * rows_per_item * C * 4                      # feature rows of C*4 B per (centre, joint)
-    path_bytes = B * (2 * 4 * w["h"] * w["w"]) + B * K * J * 37 * C * 4
+    dense_bytes = (head.num_layers - 1) * B * w["h"] * w["w"] * (C * 4 + (3 + 3 * J) * 4)   # SURVEY 8(d) dense layers
+    path_bytes = B * (2 * 4 * w["h"] * w["w"]) + B * K * J * 37 * C * 4 + dense_bytes
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (t_refine_ms / 1e3) / 1e9
     roofline = dict(bound="hbm", kernel=kernel, achieved=achieved, peak=peak, unit="GB/s",
@@ -373,7 +382,7 @@ def run_b200(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["name"], "images_per_gpu": B, "J": J, "map": f"{w['h']}x{w['w']}", "K": K,
-                       "refine_layers": head.num_layers, "feat_channels": C, "test_cfg": TEST_CFG,
+                       "refine_layers": head.num_layers, "feat_channels": C, "test_cfg": dict(TEST_CFG),
                        "algorithm": "sparse last-layer refinement at the selected centres (SURVEY 8.0 divergence B)",
                        "l2": f"{n_sets} distinct input sets of {plans[0].h2d_bytes / 1e9:.2f} GB rotated round-robin "
                              f"(each far larger than the 126 MB L2)",
@@ -405,7 +414,12 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="panoptic", choices=sorted(WORKLOADS),
+                    help="panoptic = BASELINE config #2 (the metric; default); mupots = #3; crowded = #4")
     args = ap.parse_args()
+    WORKLOAD.clear()
+    WORKLOAD.update(WORKLOADS[args.workload])
+    TEST_CFG.update(nms_pre=WORKLOAD["K"], nms_post=WORKLOAD["K"])
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -68,8 +68,11 @@ SIGNATURES = {
     "das_tc_set_debug_buffer": (C.c_int, [_VP]),
     "das_tc_panel_bytes": (C.c_int64, [C.POINTER(DecodeCfg)]),
     "das_plan_set_refine_mode": (C.c_int, [_VP, C.c_int32]),
-    "das_refine_dense_layer": (C.c_int, [_VP, C.POINTER(Levels), C.c_int32, C.c_int32, C.POINTER(DecodeCfg), _VP, _VP,
+    "das_refine_dense_layer": (C.c_int, [_VP, C.POINTER(Levels), C.c_int32, C.c_int32, C.POINTER(DecodeCfg), _VP, _VP, _VP,
                                          _VP, _VP, _VP]),
+    "das_dense_project_tc": (C.c_int, [_VP, C.POINTER(Levels), C.c_int32, C.c_int32, C.POINTER(DecodeCfg), _VP, _VP, _VP, _VP, _VP]),
+    "das_pack_dense_panels": (C.c_int, [C.POINTER(DecodeCfg), _VP, _VP, _VP]),
+    "das_dense_panel_bytes": (C.c_int64, [C.POINTER(DecodeCfg)]),
     "das_nms_backproject": (C.c_int, [C.POINTER(DecodeCfg), C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, Buffers, _VP]),
     "das_pack_weights": (C.c_int, [C.POINTER(DecodeCfg)] + [_VP] * 10),
     "das_packed_weight_floats": (C.c_int64, [C.POINTER(DecodeCfg)]),

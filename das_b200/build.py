@@ -10,7 +10,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libdas_decode.so")
-SOURCES = ["plan.cu", "score_topk.cu", "refine_sparse.cu", "refine_dense.cu", "nms_backproject.cu", "tc_selftest.cu", "refine_tc.cu"]
+SOURCES = ["plan.cu", "score_topk.cu", "refine_sparse.cu", "refine_dense.cu", "nms_backproject.cu", "tc_selftest.cu", "refine_tc.cu", "dense_project_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--fmad=true",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I", os.path.join(ROOT, "include"), "-I", CSRC]

@@ -39,7 +39,8 @@ struct das_plan {
     unsigned char* tc_panels = nullptr;
     float* item_heads = nullptr;
     int32_t* valid_list = nullptr;
-    // dense layers (num_layers > 1): ping-pong NHWC [B,H,W,3J] maps per level + projection scratch
+    unsigned char* dense_panels[DAS_MAX_LAYERS] = {};   // tensor-core panels of the dense layers (0..L-2)
+    // dense layers (num_layers > 1): ping-pong joint-major [B][J][HW][4] maps per level + projection scratch [B][J][HW][16]
     float* uvd_map[2][DAS_MAX_LEVELS] = {};
     float* proj = nullptr;
     const float** d_prev_ptrs = nullptr;
@@ -166,10 +167,12 @@ extern "C" int das_plan_create(const das_decode_cfg* cfg, const das_levels* shap
             for (int l = 0; l < shape->n_levels; ++l) {
                 const size_t hw = static_cast<size_t>(shape->lv[l].H) * shape->lv[l].W;
                 max_hw = std::max(max_hw, hw);
-                A(dev_alloc(&p->uvd_map[0][l], B * hw * 3 * J));
-                if (cfg->num_layers > 2) A(dev_alloc(&p->uvd_map[1][l], B * hw * 3 * J));
+                A(dev_alloc(&p->uvd_map[0][l], B * hw * 4 * J));          // joint-major [B][J][HW][4]
+                if (cfg->num_layers > 2) A(dev_alloc(&p->uvd_map[1][l], B * hw * 4 * J));
             }
-            A(dev_alloc(&p->proj, B * max_hw * (2 * cfg->num_heads + 6) * J));
+            A(dev_alloc(&p->proj, B * max_hw * (2 * cfg->num_heads + 8) * J));
+            if (cfg->feat_channels == 256 && cfg->num_heads == 4)
+                for (int k = 0; k < cfg->num_layers - 1; ++k) A(dev_alloc(&p->dense_panels[k], static_cast<size_t>(das_dense_panel_bytes(cfg))));
             A(dev_alloc(&p->d_prev_ptrs, DAS_MAX_LEVELS));
         }
     }
@@ -216,6 +219,7 @@ extern "C" void das_plan_destroy(das_plan* p) {
                     p->proj, p->d_prev_ptrs, p->tc_panels, p->item_heads, p->valid_list};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (int k = 0; k < DAS_MAX_LAYERS; ++k) if (p->wpack[k]) cudaFree(p->wpack[k]);
+    for (int k = 0; k < DAS_MAX_LAYERS; ++k) if (p->dense_panels[k]) cudaFree(p->dense_panels[k]);
     for (int i = 0; i < 2; ++i)
         for (int l = 0; l < DAS_MAX_LEVELS; ++l) if (p->uvd_map[i][l]) cudaFree(p->uvd_map[i][l]);
     if (p->staging_ready) {
@@ -239,6 +243,7 @@ extern "C" int das_plan_set_weights(das_plan* p, int32_t layer, const float* so_
     DAS_REQUIRE(layer >= 0 && layer < p->cfg.num_layers, DAS_ERR_ARG, "layer=%d of %d", layer, p->cfg.num_layers);
     DAS_TRY(das_pack_weights(&p->cfg, so_w, so_b, sc_w, sc_b, uw_w, uw_b, uv_w, uv_b, p->wpack[layer], stream));
     if (layer == p->cfg.num_layers - 1 && p->tc_panels) DAS_TRY(das_pack_tc_panels(&p->cfg, p->wpack[layer], p->tc_panels, stream));
+    if (layer < p->cfg.num_layers - 1 && p->dense_panels[layer]) DAS_TRY(das_pack_dense_panels(&p->cfg, p->wpack[layer], p->dense_panels[layer], stream));
     return DAS_OK;
 }
 
@@ -294,7 +299,8 @@ static int enqueue(das_plan* p, cudaStream_t st, int* n_launch, bool events) {
             const float* in = nullptr;
             for (int k = 0; k < c.num_layers - 1; ++k) {
                 float* outm = p->uvd_map[k & 1][l];
-                DAS_TRY(das_refine_dense_layer(p->d_levels, &p->bound, l, k, &c, p->wpack[k], in, outm, p->proj, st));
+                DAS_TRY(das_refine_dense_layer(p->d_levels, &p->bound, l, k, &c, p->wpack[k],
+                                               p->refine_mode != 0 ? p->dense_panels[k] : nullptr, in, outm, p->proj, st));
                 n += 2;
                 in = outm;
             }

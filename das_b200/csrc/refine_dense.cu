@@ -19,9 +19,9 @@ constexpr int DP_WARPS = 8;
 struct DenseParams {
     const das_levels* lv;
     const float* wpack;
-    const float* uvd_in;   // nullptr -> scaled raw uvd from lv.pose (layer 0); else NHWC [B,HW,3J]
-    float* uvd_out;        // NHWC [B,HW,3J]
-    float* proj;           // [B,HW,J,PW]
+    const float* uvd_in;   // nullptr -> scaled raw uvd from lv.pose (layer 0); else joint-major [B][J][HW][4]
+    float* uvd_out;        // joint-major [B][J][HW][4] (u, v, d, -)
+    float* proj;           // two joint-major planes: S [B][J][HW][8], then OC [B][J][HW][8] = {O 3, conf 3, -, -}
     int level, layer, J, root, B;
 };
 
@@ -29,7 +29,7 @@ template <int CPL, int NH>
 __global__ void __launch_bounds__(DP_WARPS * 32)
 dense_project_kernel(const DenseParams p) {
     constexpr int C = CPL * 32;
-    constexpr int NOUT = 2 * NH + 9, PW = 2 * NH + 6;
+    constexpr int NOUT = 2 * NH + 9;
     constexpr int O_GATE = 2 * NH, O_VAL = 2 * NH + 3, O_CONF = 2 * NH + 6;
     const das_level_desc& d = p.lv->lv[p.level];
     const int HW = d.H * d.W, J = p.J;
@@ -65,23 +65,25 @@ dense_project_kernel(const DenseParams p) {
                 res[o] = reduce8_permuted(acc) + __ldg(Bj + o);
             }
             if (!live) continue;
-            float* out = p.proj + (static_cast<size_t>(cell) * J + j) * PW;
-            // the quad of lanes owning this cell shares the 14 stores: lane q writes S[2q], S[2q+1] and dim q
+            const size_t rec = ((static_cast<size_t>(b) * J + j) * HW + pix) * 8;
+            float* outS = p.proj + rec;
+            float* outOC = p.proj + static_cast<size_t>(p.B) * J * HW * 8 + rec;
+            // the quad of lanes owning this cell shares the stores: lane q writes S[2q], S[2q+1] and dim q
 #pragma unroll
             for (int o = 0; o < 2 * NH; ++o)
-                if ((o >> 1) == q) out[o] = res[o];
+                if ((o >> 1) == q) outS[o] = res[o];
             if (q < 3) {
                 const float rg = q == 0 ? res[O_GATE] : (q == 1 ? res[O_GATE + 1] : res[O_GATE + 2]);
                 const float rn = q == 0 ? res[O_VAL] : (q == 1 ? res[O_VAL + 1] : res[O_VAL + 2]);
                 const float rc = q == 0 ? res[O_CONF] : (q == 1 ? res[O_CONF + 1] : res[O_CONF + 2]);
                 float prev;
-                if (p.uvd_in) prev = __ldg(p.uvd_in + static_cast<size_t>(cell) * 3 * J + 3 * j + q);
+                if (p.uvd_in) prev = __ldg(p.uvd_in + ((static_cast<size_t>(b) * J + j) * HW + pix) * 4 + q);
                 else if (q == 2 && j == p.root) prev = 0.f;
                 else prev = __ldg(d.pose + (static_cast<size_t>(b) * (3 + 6 * J) + 3 + 3 * j + q) * HW + pix) *
                             (q < 2 ? d.scale_uv : d.scale_d);
                 const float gate = sigmoid_acc(rg);
-                out[2 * NH + q] = rc;                                                       // confidence logits
-                out[2 * NH + 3 + q] = __fadd_rn(__fmul_rn(1.0f - gate, prev), __fmul_rn(gate, rn));  // blended offset
+                outOC[q] = __fadd_rn(__fmul_rn(1.0f - gate, prev), __fmul_rn(gate, rn));  // blended offset
+                outOC[3 + q] = rc;                                                       // confidence logits
             }
         }
     }
@@ -90,22 +92,25 @@ dense_project_kernel(const DenseParams p) {
 template <int NH>
 __global__ void __launch_bounds__(256)
 dense_sample_kernel(const DenseParams p) {
-    constexpr int PW = 2 * NH + 6;
+    static_assert(NH == 4, "record layout below is for 2*NH = 8 sampling offsets");
+    // two planes of 32-B records (4 cells per 128-B line): S = the 8 sampling offsets, OC = {O.x,O.y,O.z,cf.x,cf.y,cf.z,-,-}
     const das_level_desc& d = p.lv->lv[p.level];
     const int H = d.H, W = d.W, HW = H * W, J = p.J;
     const float fW = static_cast<float>(W), fH = static_cast<float>(H);
     const long long total = static_cast<long long>(p.B) * HW * J;
     for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
          t += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int j = static_cast<int>(t % J);
-        const long long cell = t / J;
-        const int b = static_cast<int>(cell / HW);
-        const int pix = static_cast<int>(cell - static_cast<long long>(b) * HW);
+        // joint-major thread order: a warp covers 32 consecutive cells of ONE joint, whose records are contiguous and
+        // whose bilinear taps overlap -> coalesced record loads, L1 hits on the taps
+        const int pix = static_cast<int>(t % HW);
+        const long long bj = t / HW;                 // b * J + j
+        const int j = static_cast<int>(bj % J);
         const int y = pix / W, x = pix - y * W;
-        const float* __restrict__ pj = p.proj + static_cast<size_t>(b) * HW * J * PW + static_cast<size_t>(j) * PW;
-        auto at = [&](int px) { return pj + static_cast<size_t>(px) * J * PW; };
-        const float* me = at(pix);
-        const float ox = me[2 * NH + 3], oy = me[2 * NH + 4];
+        const float4* __restrict__ pS = reinterpret_cast<const float4*>(p.proj + static_cast<size_t>(bj) * HW * 8);
+        const float4* __restrict__ pOC = reinterpret_cast<const float4*>(p.proj + (static_cast<size_t>(p.B) * J + bj) * HW * 8);
+        (void)j;
+        const float4 s0 = __ldg(pS + 2 * pix), s1 = __ldg(pS + 2 * pix + 1), om = __ldg(pOC + 2 * pix);
+        const float ox = om.x, oy = om.y;
         float hx[2 * NH], hy[2 * NH];
         {
             const Corner ct = make_corner(sample_coord(x, ox, fW), sample_coord(y, oy, fH), W, H);
@@ -116,16 +121,20 @@ dense_sample_kernel(const DenseParams p) {
             for (int k = 0; k < 4; ++k) {
                 if (!corner_ok(ct, k, W, H)) continue;
                 const float wk = corner_wgt(ct, k);
-                const float* c = at(corner_pix(ct, k, W));
-#pragma unroll
-                for (int o = 0; o < 2 * NH; ++o) s[o] = __fadd_rn(s[o], __fmul_rn(c[o], wk));
+                const float4* c = pS + 2 * corner_pix(ct, k, W);
+                const float4 a0 = __ldg(c), a1 = __ldg(c + 1);
+                s[0] = __fadd_rn(s[0], __fmul_rn(a0.x, wk)); s[1] = __fadd_rn(s[1], __fmul_rn(a0.y, wk));
+                s[2] = __fadd_rn(s[2], __fmul_rn(a0.z, wk)); s[3] = __fadd_rn(s[3], __fmul_rn(a0.w, wk));
+                s[4] = __fadd_rn(s[4], __fmul_rn(a1.x, wk)); s[5] = __fadd_rn(s[5], __fmul_rn(a1.y, wk));
+                s[6] = __fadd_rn(s[6], __fmul_rn(a1.z, wk)); s[7] = __fadd_rn(s[7], __fmul_rn(a1.w, wk));
             }
+            const float sm[2 * NH] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
             for (int h = 0; h < NH; ++h) {
                 hx[h] = s[2 * h] + ox;
                 hy[h] = s[2 * h + 1] + oy;
-                hx[NH + h] = me[2 * h];
-                hy[NH + h] = me[2 * h + 1];
+                hx[NH + h] = sm[2 * h];
+                hy[NH + h] = sm[2 * h + 1];
             }
         }
         float hv[2 * NH][3], hc[2 * NH][3];
@@ -137,19 +146,19 @@ dense_sample_kernel(const DenseParams p) {
             for (int k = 0; k < 4; ++k) {
                 if (!corner_ok(ch, k, W, H)) continue;
                 const float wk = corner_wgt(ch, k);
-                const float* c = at(corner_pix(ch, k, W)) + 2 * NH;
-#pragma unroll
-                for (int e = 0; e < 3; ++e) {
-                    cf[e] = __fadd_rn(cf[e], __fmul_rn(c[e], wk));
-                    v[e] = __fadd_rn(v[e], __fmul_rn(c[3 + e], wk));
-                }
+                const float4* c = pOC + 2 * corner_pix(ch, k, W);
+                const float4 oo = __ldg(c), cc = __ldg(c + 1);      // {O.x,O.y,O.z,cf.x} {cf.y,cf.z,-,-}
+                cf[0] = __fadd_rn(cf[0], __fmul_rn(oo.w, wk)); cf[1] = __fadd_rn(cf[1], __fmul_rn(cc.x, wk));
+                cf[2] = __fadd_rn(cf[2], __fmul_rn(cc.y, wk));
+                v[0] = __fadd_rn(v[0], __fmul_rn(oo.x, wk)); v[1] = __fadd_rn(v[1], __fmul_rn(oo.y, wk));
+                v[2] = __fadd_rn(v[2], __fmul_rn(oo.z, wk));
             }
             hv[h][0] = v[0] + hx[h];
             hv[h][1] = v[1] + hy[h];
             hv[h][2] = v[2];
             hc[h][0] = cf[0]; hc[h][1] = cf[1]; hc[h][2] = cf[2];
         }
-        float* out = p.uvd_out + static_cast<size_t>(cell) * 3 * J + 3 * j;
+        float res[3];
 #pragma unroll
         for (int e = 0; e < 3; ++e) {
             float m = hc[0][e];
@@ -161,16 +170,22 @@ dense_sample_kernel(const DenseParams p) {
             float o = 0.f;
 #pragma unroll
             for (int h = 0; h < 2 * NH; ++h) o += hv[h][e] * (ex[h] / se);
-            out[e] = o;
+            res[e] = o;
         }
+        reinterpret_cast<float4*>(p.uvd_out)[static_cast<size_t>(bj) * HW + pix] = make_float4(res[0], res[1], res[2], 0.f);
     }
 }
 
 }  // namespace das
 
+extern "C" int das_dense_project_tc(const das_levels* d_levels, const das_levels* h_levels, int32_t level, int32_t layer,
+                                    const das_decode_cfg* cfg, const float* weights, const void* panels,
+                                    const float* uvd_in, float* proj, void* stream);
+
 extern "C" int das_refine_dense_layer(const das_levels* d_levels, const das_levels* h_levels, int32_t level,
                                       int32_t layer, const das_decode_cfg* cfg, const float* weights,
-                                      const float* uvd_in, float* uvd_out, float* proj, void* stream) {
+                                      const void* tc_panels, const float* uvd_in, float* uvd_out, float* proj,
+                                      void* stream) {
     using namespace das;
     DAS_REQUIRE(d_levels && h_levels && cfg && weights && uvd_out && proj, DAS_ERR_ARG, "das_refine_dense_layer: null pointer");
     DAS_REQUIRE(level >= 0 && level < h_levels->n_levels, DAS_ERR_ARG, "level=%d", level);
@@ -183,6 +198,10 @@ extern "C" int das_refine_dense_layer(const das_levels* d_levels, const das_leve
     p.level = level; p.layer = layer; p.J = cfg->num_joints; p.root = cfg->root_idx; p.B = h_levels->batch;
     const long long cells = static_cast<long long>(h_levels->batch) * h_levels->lv[level].H * h_levels->lv[level].W;
     const int grid1 = static_cast<int>(std::min<long long>((cells / 8 + DP_WARPS) / DP_WARPS, 4LL * kSMs));
+    if (tc_panels && cfg->feat_channels == 256) {
+        const int st_ = das_dense_project_tc(d_levels, h_levels, level, layer, cfg, weights, tc_panels, uvd_in, proj, stream);
+        if (st_ != DAS_OK) return st_;
+    } else
     switch (cfg->feat_channels) {
         case 128: dense_project_kernel<4, 4><<<grid1, DP_WARPS * 32, 0, st>>>(p); break;
         case 256: dense_project_kernel<8, 4><<<grid1, DP_WARPS * 32, 0, st>>>(p); break;

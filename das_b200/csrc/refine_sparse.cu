@@ -29,7 +29,7 @@ constexpr int RS_WARPS = 8;  // warps per CTA
 struct RefineParams {
     const das_levels* lv;
     const float* wpack;            // [J][NOUT][C] then [J][NOUT] biases
-    const float* const* prev_uvd;  // nullptr or device array [n_levels] of NHWC [B,H,W,3J]
+    const float* const* prev_uvd;  // nullptr or device array [n_levels] of joint-major maps [B][J][HW][4] (u, v, d, -)
     const float* scale_xy;         // [B,2]
     const float* cand_score;
     const int32_t* cand_index;
@@ -78,14 +78,14 @@ refine_sparse_kernel(const RefineParams p) {
         const float* __restrict__ F = d.feats[p.layer] + static_cast<size_t>(b) * HW * C;
         const float* __restrict__ pose = d.pose + static_cast<size_t>(b) * (3 + 6 * J) * HW;
         const float* __restrict__ prev = p.prev_uvd ? p.prev_uvd[l] : nullptr;
-        if (prev) prev += static_cast<size_t>(b) * HW * 3 * J;
+        if (prev) prev += (static_cast<size_t>(b) * J + j) * HW * 4;
         const float* __restrict__ Wj = p.wpack + static_cast<size_t>(j) * NOUT * C;
         const float* __restrict__ Bj = p.wpack + static_cast<size_t>(J) * NOUT * C + j * NOUT;
         const float fW = static_cast<float>(W), fH = static_cast<float>(H);
 
         // previous-layer offset of joint j, dim k at cell `pix` (das_head.py:243-249 for layer 0)
         auto prev_at = [&](int pix, int k) -> float {
-            if (prev) return __ldg(prev + static_cast<size_t>(pix) * 3 * J + 3 * j + k);
+            if (prev) return __ldg(prev + static_cast<size_t>(pix) * 4 + k);
             if (k == 2 && j == p.root) return 0.0f;
             const float raw = __ldg(pose + static_cast<size_t>(3 + 3 * j + k) * HW + pix);
             return raw * (k < 2 ? d.scale_uv : d.scale_d);

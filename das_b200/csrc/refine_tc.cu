@@ -107,8 +107,8 @@ __device__ __forceinline__ RowState setup_row(const TcParams& p, int tile, int n
     for (int q = 0; q < TC_C * 4 / 128; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(r.ptr + q * 32));
     const float* prev = p.prev_uvd ? p.prev_uvd[l] : nullptr;
     if (prev) {
-        const float* q = prev + (static_cast<size_t>(b) * HW + pix) * 3 * J + 3 * j;
-        r.prev0 = __ldg(q); r.prev1 = __ldg(q + 1); r.prev2 = __ldg(q + 2);
+        const float4 q = __ldg(reinterpret_cast<const float4*>(prev) + (static_cast<size_t>(b) * J + j) * HW + pix);
+        r.prev0 = q.x; r.prev1 = q.y; r.prev2 = q.z;
     } else {
         const float* q = d.pose + (static_cast<size_t>(b) * (3 + 6 * J) + 3 + 3 * j) * HW + pix;
         r.prev0 = __ldg(q) * d.scale_uv;

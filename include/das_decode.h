@@ -118,7 +118,7 @@ int das_score_topk(const das_levels* d_levels, const das_levels* h_levels, int32
 
 /* Stage 3+4(+eval tail): gather at the selected cells, sparse last-layer refinement, assembly.
  * weights: das_pack_weights() layout of the LAST layer; prev_uvd: NULL (use scaled raw uvd of
- * lv.pose) or [n_levels] device pointers to NHWC [B,H,W,3J] maps produced by dense layers.
+ * lv.pose) or [n_levels] device pointers to joint-major [B][J][HW][4] maps produced by dense layers.
  * scale_xy: [B,2] device (img_metas['scale_factor'][:2]). */
 int das_gather_refine_assemble(const das_levels* d_levels, const das_levels* h_levels,
                                const das_decode_cfg* cfg, const float* weights,
@@ -147,12 +147,19 @@ int64_t das_tc_panel_bytes(const das_decode_cfg* cfg);
 /* profiling aid: per-CTA cycle counters of das_refine_tc's warp roles ([148][16] int64 device buffer; NULL = off) */
 int das_tc_set_debug_buffer(long long* dev_buf);
 
-/* One dense refinement layer over a whole level (layers 1..L-1 when num_layers > 1).
- * uvd_in NULL -> scaled raw uvd from lv.pose.  uvd_out NHWC [B,H,W,3J]. proj: scratch
- * [B,H,W,14J] fp32. */
+/* One dense refinement layer over a whole level (layers 1..L-1 when num_layers > 1): 1x1 projection + gated
+ * blend into proj (scratch [B][J][HW][16] fp32), then the progressive sampling into uvd_out (joint-major
+ * [B][J][HW][4] = u, v, d, pad).  uvd_in NULL -> scaled raw uvd from lv.pose.  tc_panels: das_pack_dense_panels() image of this layer's packed
+ * weights -> the projection runs on the tensor cores (tcgen05 3xTF32; feat_channels = 256, num_heads = 4);
+ * NULL -> fp32 SIMT projection. */
 int das_refine_dense_layer(const das_levels* d_levels, const das_levels* h_levels, int32_t level,
                            int32_t layer, const das_decode_cfg* cfg, const float* weights,
-                           const float* uvd_in, float* uvd_out, float* proj, void* stream);
+                           const void* tc_panels, const float* uvd_in, float* uvd_out, float* proj, void* stream);
+int das_dense_project_tc(const das_levels* d_levels, const das_levels* h_levels, int32_t level, int32_t layer,
+                         const das_decode_cfg* cfg, const float* weights, const void* panels,
+                         const float* uvd_in, float* proj, void* stream);
+int das_pack_dense_panels(const das_decode_cfg* cfg, const float* packed_weights, void* panels, void* stream);
+int64_t das_dense_panel_bytes(const das_decode_cfg* cfg);
 
 /* Stage 5: score_thr, OKS-NMS, nms_post, output packing, depth de-norm + back-projection.
  * cam: [B,DAS_CAM_DOUBLES] device doubles. */

@@ -15,13 +15,14 @@ from test_gpu_parity import compare, TOL, GOLDEN
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("mode", [None, 0], ids=["tensor_core", "simt"])
 @pytest.mark.parametrize("layers,J,root", [(2, 15, 2), (3, 17, 14), (2, 21, 14)])
-def test_multi_layer_refinement_matches_oracle(layers, J, root):
+def test_multi_layer_refinement_matches_oracle(layers, J, root, mode):
     cfg = synth.HeadConfig(num_joints=J, root_idx=root, depth_factor=1.0, z_norm=50.0, num_layers=layers)
     tc = dict(nms_pre=20, nms_post=20, nms_thr=0.9, score_thr=0.0)
     case = util.make_case(cfg, 2, 28, 36, seed=600 + layers, scales=(1.05, 0.95, 1.1, 0.9))
     ref, _ = util.run_oracle(case, tc)
-    plan, got = util.run_gpu(case, tc, refine=True)
+    plan, got = util.run_gpu(case, tc, refine=True, refine_mode=mode)
     compare(plan, got, ref, util.rank_margin_ulps(case["levels"], 20))
 
 
