@@ -39,7 +39,8 @@ class DecodeCfg(C.Structure):
                 ("nms_pre", C.c_int32), ("nms_post", C.c_int32),
                 ("nms_thr", C.c_float), ("score_thr", C.c_float),
                 ("peak_kernel", C.c_int32), ("refine", C.c_int32),
-                ("dataset_depth_factor", C.c_double)]
+                ("dataset_depth_factor", C.c_double),
+                ("nms_soft", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class Buffers(C.Structure):

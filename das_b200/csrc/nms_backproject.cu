@@ -22,7 +22,7 @@ constexpr int NM_MAX_CAND = 8192;
 constexpr int NM_MATRIX_N = 64;   // up to this many candidates: all-pairs OKS + bitmask greedy
 
 struct NmsParams {
-    int B, CT, P, J, root, nms_post;
+    int B, CT, P, J, root, nms_post, soft;
     float nms_thr, score_thr;
     double ddf;
     const float* cand_score;
@@ -74,6 +74,7 @@ nms_backproject_kernel(const NmsParams p) {
     __shared__ int s_n, s_kept;
     __shared__ unsigned long long s_mask[NM_MATRIX_N];
     __shared__ int s_keep[NM_MATRIX_N];
+    int* s_keep_soft = reinterpret_cast<int*>(area + CT) + CT + (CT + 3) / 4;   // after order[] and dead[]: kept slots of the soft path
 
     const int b = blockIdx.x, tid = threadIdx.x, J = p.J;
     const float* __restrict__ score = p.cand_score + static_cast<size_t>(b) * CT;
@@ -162,7 +163,48 @@ nms_backproject_kernel(const NmsParams p) {
         }
 
         const int limit = min(p.nms_post, n);
-        if (n <= NM_MATRIX_N) {
+        if (p.soft) {
+            // ---- soft OKS-NMS (pose_nms.py:129-194, gaussian rescoring): repeatedly take the best remaining
+            // candidate and multiply every other remaining score by exp(-oks^2 / thr) (float32 like NumPy's).
+            // `keys` is reused as the float32 working scores; ties go to the lower slot.
+            float* cur = reinterpret_cast<float*>(keys);
+            __shared__ unsigned long long s_best;
+            for (int i = tid; i < n; i += NT) { cur[i] = score[order[i]]; dead[i] = 0; }
+            __syncthreads();
+            const int grp = tid >> 5, gl = tid & 31;
+            for (int k = 0; k < limit; ++k) {
+                if (tid == 0) s_best = 0ull;
+                __syncthreads();
+                unsigned long long mine = 0ull;
+                for (int i = tid; i < n; i += NT)
+                    if (!dead[i]) {
+                        // positive floats order like their bit patterns; lower sorted position (= lower slot on ties) wins
+                        const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(cur[i])) << 32) |
+                                                       (0xFFFFFFFFu - static_cast<unsigned>(i));
+                        mine = key > mine ? key : mine;
+                    }
+                if (mine) atomicMax(&s_best, mine | (1ull << 63));
+                __syncthreads();
+                const unsigned long long best = s_best;
+                if (!best) break;
+                const int bi = static_cast<int>(0xFFFFFFFFu - static_cast<unsigned>(best & 0xFFFFFFFFull));
+                const int ci = order[bi];
+                __syncthreads();
+                if (tid == 0) { s_keep_soft[k] = ci; dead[bi] = 1; }
+                kept = k + 1;
+                for (int j = grp; j < n; j += NT / 32) {
+                    if (dead[j] || j == bi) continue;
+                    const int cj = order[j];
+                    const float v = oks_pair<32>(pose + static_cast<size_t>(ci) * J * 3, pose + static_cast<size_t>(cj) * J * 3,
+                                                 area[ci], area[cj], J, gl);
+                    if (gl == 0) cur[j] = __fmul_rn(cur[j], expf(__fdiv_rn(-__fmul_rn(v, v), p.nms_thr)));
+                }
+                __syncthreads();
+            }
+            __syncthreads();
+            for (int k = tid; k < kept; k += NT) kept_list[k] = s_keep_soft[k];
+            __syncthreads();
+        } else if (n <= NM_MATRIX_N) {
             // ---- all pairs in parallel, then a 64-bit mask greedy pass by one thread ---------------
             if (tid < n) s_mask[tid] = 0ull;
             __syncthreads();
@@ -307,22 +349,22 @@ extern "C" int das_nms_backproject(const das_decode_cfg* cfg, int32_t batch, int
     DAS_REQUIRE(cfg->num_joints >= 1 && cfg->num_joints <= DAS_MAX_JOINTS, DAS_ERR_CAPACITY, "num_joints=%d", cfg->num_joints);
     NmsParams p{};
     p.B = batch; p.CT = cand_slots; p.P = das_output_slots(cand_slots, cfg->nms_post);
-    p.J = cfg->num_joints; p.root = cfg->root_idx; p.nms_post = cfg->nms_post;
+    p.J = cfg->num_joints; p.root = cfg->root_idx; p.nms_post = cfg->nms_post; p.soft = cfg->nms_soft;
     p.nms_thr = cfg->nms_thr; p.score_thr = cfg->score_thr;
     p.ddf = cfg->dataset_depth_factor == 0.0 ? 1.0 : cfg->dataset_depth_factor;
     p.cand_score = cand_score; p.cand_pose = cand_pose; p.cand_center = cand_center; p.cam = cam;
     p.out = out;
     int n2 = 1;
     while (n2 < cand_slots) n2 <<= 1;
-    const size_t smem = static_cast<size_t>(n2) * 8 + static_cast<size_t>(cand_slots) * (4 + 4 + 1) + 16;
+    const size_t smem = static_cast<size_t>(n2) * 8 + static_cast<size_t>(cand_slots) * (4 + 4 + 1 + 4) + 32;
     static bool attr_done = false;
     if (!attr_done) {
         DAS_CUDA_CHECK(cudaFuncSetAttribute(nms_backproject_kernel<NM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            NM_MAX_CAND * 8 + NM_MAX_CAND * 9 + 16));
+                                            NM_MAX_CAND * 8 + NM_MAX_CAND * 13 + 32));
         attr_done = true;
     }
     // few candidates (the usual case): 8 warps keep the ~20 block barriers of this latency-bound kernel cheap
-    if (cand_slots <= 128) nms_backproject_kernel<256><<<batch, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    if (cand_slots <= 32) nms_backproject_kernel<256><<<batch, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
     else nms_backproject_kernel<NM_THREADS><<<batch, NM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
     DAS_CUDA_CHECK(cudaGetLastError());
     return DAS_OK;

@@ -205,6 +205,8 @@ constexpr int T2_D_COL = 0;                     // accumulators: T2_EG x 32 colu
 constexpr int T2_A_COL = 32 * T2_EG;            // A ring: 4 slots x 64 columns
 constexpr int T2_SMEM = 1024 + T2_PGROUPS * T2_STAGES * TC_A_BYTES + 2 * TC_B_BYTES;
 
+// PROF: per-role cycle counters into p.dbg (tools/tc_role_cycles.py); the production instantiation carries none.
+template <bool PROF>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 refine_tc2_kernel(const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -217,7 +219,7 @@ refine_tc2_kernel(const TcParams p) {
     __shared__ const float* s_rowptr[T2_RB][128];   // row pointers are produced T2_RB tiles ahead of their epilogue
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long kernel_t0 = clock64();
+    const long long kernel_t0 = (PROF ? clock64() : 0ll);
     const int J = p.J;
     const int n_valid = __ldg(p.n_valid);
     const int n_groups = (n_valid + 3) >> 2;
@@ -249,7 +251,7 @@ refine_tc2_kernel(const TcParams p) {
         long long m_w = 0, m_i = 0, m_b = 0, m_f = 0;
         for (int i = 0; i < my_tiles; ++i) {
             const uint32_t dcol = tmem0 + T2_D_COL + (i % T2_EG) * 32;
-            const long long tb0 = clock64();
+            const long long tb0 = (PROF ? clock64() : 0ll);
             const int j = (t0 + i) / n_groups;
             if (j != cur_j) {
                 // new joint: every earlier MMA must have finished reading the old panels
@@ -262,16 +264,16 @@ refine_tc2_kernel(const TcParams p) {
                 __syncwarp();
                 cur_j = j;
             }
-            const long long tb1 = clock64();
+            const long long tb1 = (PROF ? clock64() : 0ll);
             if (i >= T2_EG) tc::mbar_wait(&acc_free[i % T2_EG], ((i / T2_EG) - 1) & 1);   // epilogue of tile i-EG has drained this buffer
-            const long long tb2 = clock64();
+            const long long tb2 = (PROF ? clock64() : 0ll);
             m_b += tb1 - tb0; m_f += tb2 - tb1;
             for (int kb = 0; kb < TC_KB; ++kb, ++g) {
                 const int slot = g % T2_SLOTS;
-                const long long c0 = clock64();
+                const long long c0 = (PROF ? clock64() : 0ll);
                 tc::mbar_wait(&a_full[slot], (g / T2_SLOTS) & 1);
                 tc::tc_fence_after();
-                const long long c1 = clock64();
+                const long long c1 = (PROF ? clock64() : 0ll);
                 m_w += c1 - c0;
                 const uint32_t a_hi = tmem0 + T2_A_COL + slot * 64, a_lo = a_hi + 32;
                 const uint32_t b_pk = sB_u + kb * TC_BK_BYTES;
@@ -284,10 +286,10 @@ refine_tc2_kernel(const TcParams p) {
                 }
                 tc::umma_commit_elect(&a_empty[slot]);
                 if (kb == TC_KB - 1) tc::umma_commit_elect(&acc_full[i % T2_EG]);
-                m_i += clock64() - c1;
+                m_i += (PROF ? clock64() : 0ll) - c1;
             }
         }
-        if (p.dbg && lane == 0) { long long* o = p.dbg + blockIdx.x * 16; o[0] = m_w; o[1] = m_i; o[2] = m_f; o[14] = m_b; }
+        if (PROF && p.dbg && lane == 0) { long long* o = p.dbg + blockIdx.x * 16; o[0] = m_w; o[1] = m_i; o[2] = m_f; o[14] = m_b; }
     } else if (warp >= T2_FIRST_PRODUCER) {
         // ===== producer groups: gather (cp.async, coalesced) -> own row from smem -> hi/lo -> TMEM ====================
         const int pg = (warp - T2_FIRST_PRODUCER) >> 2;          // group: handles k-blocks g with g % 3 == pg
@@ -314,10 +316,10 @@ refine_tc2_kernel(const TcParams p) {
         for (int n = 0; n < my_n; ++n) {
             const int g = pg + n * T2_PGROUPS;
             const int slot = g % T2_SLOTS, st = n % T2_STAGES;
-            const long long c0 = clock64();
+            const long long c0 = (PROF ? clock64() : 0ll);
             tc::cp_async_wait<T2_STAGES - 2>();                  // this thread's chunks of k-block n have landed
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // ... and everybody else's in the group
-            const long long c1 = clock64();
+            const long long c1 = (PROF ? clock64() : 0ll);
             float hi[32];
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) {
@@ -325,13 +327,13 @@ refine_tc2_kernel(const TcParams p) {
                 hi[4 * ch] = a.x; hi[4 * ch + 1] = a.y; hi[4 * ch + 2] = a.z; hi[4 * ch + 3] = a.w;
             }
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // stage `st` may be overwritten from here on
-            const long long c2 = clock64();
+            const long long c2 = (PROF ? clock64() : 0ll);
             if (n + T2_STAGES - 1 < my_n) gather(n + T2_STAGES - 1);     // into stage (n + 2) % 3 == (n - 1) % 3, read last step
             tc::cp_async_commit();
-            const long long c3 = clock64();
+            const long long c3 = (PROF ? clock64() : 0ll);
             if (g >= T2_SLOTS) tc::mbar_wait(&a_empty[slot], ((g / T2_SLOTS) - 1) & 1);   // MMAs of k-block g-4 done with this TMEM slot
             tc::tc_fence_after();
-            const long long c4 = clock64();
+            const long long c4 = (PROF ? clock64() : 0ll);
             const uint32_t taddr = tmem0 + (static_cast<uint32_t>(qw * 32) << 16) + T2_A_COL + slot * 64;
             tc::tmem_st32(taddr, hi);
             if (p.split & 1) {
@@ -344,10 +346,10 @@ refine_tc2_kernel(const TcParams p) {
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&a_full[slot]);
-            d0 += c1 - c0; d1 += c2 - c1; d2 += c3 - c2; d3 += c4 - c3; d4 += clock64() - c4;
+            d0 += c1 - c0; d1 += c2 - c1; d2 += c3 - c2; d3 += c4 - c3; d4 += (PROF ? clock64() : 0ll) - c4;
         }
         tc::cp_async_wait<0>();
-        if (p.dbg && pg == 0 && gt == 0) { long long* o = p.dbg + blockIdx.x * 16; o[3] = d0; o[4] = d1; o[5] = d2; o[6] = d3; o[7] = d4; o[8] = my_n; }
+        if (PROF && p.dbg && pg == 0 && gt == 0) { long long* o = p.dbg + blockIdx.x * 16; o[3] = d0; o[4] = d1; o[5] = d2; o[6] = d3; o[7] = d4; o[8] = my_n; }
     } else {
         // ===== epilogue / row-setup warps: thread t <-> row t = (item warp, head lane>>2, corner lane&3) ===========
         const int e = warp / TC_EPI_WARPS;          // epilogue group
@@ -371,10 +373,10 @@ refine_tc2_kernel(const TcParams p) {
         for (int i = e; i < my_tiles; i += T2_EG) {
             const int tile = t0 + i;
             const int j = tile / n_groups;
-            const long long e0 = clock64();
+            const long long e0 = (PROF ? clock64() : 0ll);
             tc::mbar_wait(&acc_full[e], (i / T2_EG) & 1);
             tc::tc_fence_after();
-            const long long e1 = clock64();
+            const long long e1 = (PROF ? clock64() : 0ll);
             float v[16], v2[16];
             const uint32_t taddr = tmem0 + (static_cast<uint32_t>(qw * 32) << 16) + T2_D_COL + e * 32;
             tc::tmem_ld16(taddr, v);
@@ -397,10 +399,10 @@ refine_tc2_kernel(const TcParams p) {
             tc_epilogue(p, cur, v, j, lane);
             cur = nx1;
             nx1 = nx2;
-            if (p.dbg && tid == 0) { long long* o = p.dbg + blockIdx.x * 16; o[9] += e1 - e0; o[10] += clock64() - e1; }
+            if (PROF && p.dbg && tid == 0) { long long* o = p.dbg + blockIdx.x * 16; o[9] += e1 - e0; o[10] += (PROF ? clock64() : 0ll) - e1; }
         }
     }
-    if (p.dbg && tid == 0) p.dbg[blockIdx.x * 16 + 13] = clock64() - kernel_t0;
+    if (PROF && p.dbg && tid == 0) p.dbg[blockIdx.x * 16 + 13] = (PROF ? clock64() : 0ll) - kernel_t0;
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem_base, T2_TMEM_COLS);
@@ -465,10 +467,12 @@ extern "C" int das_refine_tc(const das_levels* d_levels, const das_levels* h_lev
     p.dbg = g_tc_dbg;
     static bool attr2_done = false;
     if (!attr2_done) {
-        DAS_CUDA_CHECK(cudaFuncSetAttribute(refine_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
+        DAS_CUDA_CHECK(cudaFuncSetAttribute(refine_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
+        DAS_CUDA_CHECK(cudaFuncSetAttribute(refine_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
         attr2_done = true;
     }
-    refine_tc2_kernel<<<kSMs, T2_THREADS, T2_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+    if (p.dbg) refine_tc2_kernel<true><<<kSMs, T2_THREADS, T2_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+    else refine_tc2_kernel<false><<<kSMs, T2_THREADS, T2_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
     DAS_CUDA_CHECK(cudaGetLastError());
     return DAS_OK;
 }

@@ -52,9 +52,15 @@ def _stream_ptr(device) -> C.c_void_p:
 
 def _check_f32(t: torch.Tensor, what: str):
     if t.dtype != torch.float32:
-        raise TypeError(f"{what}: expected float32, got {t.dtype} (fp16 I/O is SURVEY 8(f) rank 3)")
+        raise TypeError(f"{what}: expected float32 at the C ABI, got {t.dtype}")
     if not t.is_cuda:
         raise RuntimeError(f"{what}: the decode path only runs on CUDA tensors")
+
+
+def _to_f32(t: torch.Tensor) -> torch.Tensor:
+    """fp16 / bf16 head outputs (the reference's fp16 mode, das_head.py:180,218 + exp_panoptic.py:222) are up-cast at
+    the boundary exactly like mmcv's force_fp32 does before get_poses; the kernels compute in fp32."""
+    return t if t.dtype == torch.float32 else t.float()
 
 
 _BLOCK_SPEC = (("out_count", torch.int32, 0), ("out_score", torch.float32, 1), ("out_slot", torch.int32, 1),
@@ -97,9 +103,7 @@ class DecodePlan:
         self.device = torch.device(device)
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        nms_type = test_cfg.get("nms_type", "hard")
-        if nms_type != "hard":
-            raise NotImplementedError("nms_type != 'hard' (soft_oks_nms) is SURVEY 8(f) rank 3, not built yet")
+        nms_type = test_cfg.get("nms_type", "hard")       # anything but 'hard' selects soft_oks_nms (das_head.py:784-790)
         nms_post = test_cfg.get("nms_post", -1)
         self.cfg = DecodeCfg(num_joints=num_joints, root_idx=root_idx, num_heads=num_heads,
                              feat_channels=feat_channels, num_layers=num_layers,
@@ -110,7 +114,7 @@ class DecodePlan:
                              nms_thr=float(test_cfg.get("nms_thr", 0.9)),
                              score_thr=float(test_cfg.get("score_thr", 0.0)),
                              peak_kernel=int(peak_kernel), refine=int(bool(refine)),
-                             dataset_depth_factor=float(dataset_depth_factor))
+                             dataset_depth_factor=float(dataset_depth_factor), nms_soft=int(nms_type != "hard"))
         self.batch = int(batch)
         self.strides = [int(s) for s in strides]
         self.level_sizes = [(int(h), int(w)) for h, w in level_sizes]
@@ -408,10 +412,10 @@ class DASHeadB200:
         levels = []
         for l in range(num_levels):
             assert cls_scores[l].shape[-2:] == pose_preds[l].shape[-2:]
-            d = dict(cls=cls_scores[l].detach(), ctr=centernesses[l].detach(), pose=pose_preds[l].detach(),
-                     scales=self.scales[l])
+            d = dict(cls=_to_f32(cls_scores[l].detach()), ctr=_to_f32(centernesses[l].detach()),
+                     pose=_to_f32(pose_preds[l].detach()), scales=self.scales[l])
             if refine:
-                d["feats"] = [f.detach() for f in refine_feats[l]]
+                d["feats"] = [_to_f32(f.detach()) for f in refine_feats[l]]
             levels.append(d)
         plan.bind(levels)
         plan.set_metas(img_metas)

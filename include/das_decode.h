@@ -79,6 +79,8 @@ typedef struct das_decode_cfg {
     int32_t peak_kernel;     /* 0/1: reference behaviour; 3: north-star 3x3 max-pool peak mask */
     int32_t refine;          /* 1: pose maps are raw, run refinement + eval tail; 0: maps are final */
     double dataset_depth_factor; /* cmupanoptic_mono_dataset.py:399 (dataset-side factor, 1.0) */
+    int32_t nms_soft;        /* test_cfg.nms_type != 'hard': soft_oks_nms (pose_nms.py:129-194, das_head.py:789-790) */
+    int32_t reserved_;
 } das_decode_cfg;
 
 /* Device buffers of one decode.  CT = candidate slots per image (das_candidate_slots()),

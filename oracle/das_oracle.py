@@ -205,6 +205,25 @@ def oks_nms(scores, kpts, areas, thr, stable: bool = False):
     return np.array(keep)
 
 
+def soft_oks_nms(scores, kpts, areas, thr, max_dets, stable: bool = False):
+    """Gaussian soft OKS-NMS (pose_nms.py:129-194): nothing is removed; after every pick the remaining
+    scores are multiplied by exp(-oks^2 / thr) (float32) and the best one is taken next."""
+    if len(scores) == 0:
+        return np.zeros(0, dtype=np.int64)
+    order = np.argsort(-scores.astype(np.float64), kind="stable") if stable else scores.argsort()[::-1]
+    cur = scores[order]
+    keep = []
+    while len(order) > 0 and len(keep) < max_dets:
+        i = order[0]
+        ovr = oks_to_head(kpts[i], kpts[order[1:]], areas[i], areas[order[1:]])
+        order = order[1:]
+        cur = cur[1:] * np.exp(-ovr ** 2 / thr)
+        tmp = np.argsort(-cur.astype(np.float64), kind="stable") if stable else cur.argsort()[::-1]
+        order, cur = order[tmp], cur[tmp]
+        keep.append(i)
+    return np.array(keep)
+
+
 # --------------------------------------------------------------------------
 # decode (das_head.py:653-796)
 # --------------------------------------------------------------------------
@@ -272,10 +291,12 @@ def decode_image(cls_l, pose_l, ctr_l, strides, scale_factor, cfg, num_joints,
         lo = poses[..., :2].min(1)[0]
         areas = (hi - lo).prod(-1).numpy()
         kp = torch.cat([poses[..., :2], torch.ones_like(poses[..., :1])], -1).reshape(len(poses), -1).numpy()
-        if cfg.get("nms_type", "hard") != "hard":
-            raise NotImplementedError("soft_oks_nms is SURVEY 8(f) rank 3 (not built yet)")
-        keep = oks_nms(scores.numpy(), kp, areas, cfg.get("nms_thr", 0.9), stable=stable).tolist()
-        keep = keep[:cfg.get("nms_post", 100)]
+        if cfg.get("nms_type", "hard") == "hard":
+            keep = oks_nms(scores.numpy(), kp, areas, cfg.get("nms_thr", 0.9), stable=stable).tolist()
+            keep = keep[:cfg.get("nms_post", 100)]
+        else:                                           # das_head.py:789-790
+            keep = soft_oks_nms(scores.numpy(), kp, areas, cfg.get("nms_thr", 0.9), cfg.get("nms_post", 100),
+                                stable=stable).tolist()
         scores, poses, centres, lvls, idxs = scores[keep], poses[keep], centres[keep], lvls[keep], idxs[keep]
     out = dict(scores=scores, poses=poses, vis=torch.ones(poses.shape[:2]), centers=centres,
                level=lvls, index=idxs)

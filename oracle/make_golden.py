@@ -43,6 +43,8 @@ CASES = {
                     dict(nms_pre=20, nms_post=20, nms_thr=0.9, score_thr=0.0)),
     "coherent_nms": (P, 2, 32, 48, 1241, 12, (1.0, 1.0, 1.0, 1.0),
                      dict(nms_pre=30, nms_post=30, nms_thr=0.9, score_thr=0.0), dict(coherent=8)),
+    "soft_nms": (P, 2, 32, 48, 1242, 12, (1.0, 1.0, 1.0, 1.0),
+                 dict(nms_pre=30, nms_post=12, nms_thr=0.9, score_thr=0.0, nms_type="soft"), dict(coherent=8)),
     "reference_cfg_nms1000": (P, 1, 40, 72, 1240, 24, (1.0, 1.0, 1.0, 1.0),
                               dict(nms_across_levels=False, nms_pre=1000, nms_post=100, nms_thr=0.9, score_thr=0.07)),
 }

@@ -361,3 +361,31 @@ def test_tensor_core_refinement_with_threshold_and_pyramid():
     ref, _ = util.run_oracle(case, tc)
     plan, got = util.run_gpu(case, tc, refine=True, refine_mode=1)
     compare(plan, got, ref, util.rank_margin_ulps(case["levels"], 60, 0.05))
+
+
+def test_soft_oks_nms_matches_oracle():
+    """test_cfg.nms_type != 'hard' -> soft_oks_nms (pose_nms.py:129-194): rescoring changes the order, nothing is dropped."""
+    tc = dict(nms_pre=30, nms_post=12, nms_thr=0.9, score_thr=0.0, nms_type="soft")
+    case = util.make_case(P, 3, 32, 48, seed=81, peaks=12, coherent=8)
+    ref, _ = util.run_oracle(case, tc)
+    plan, got = util.run_gpu(case, tc, refine=True)
+    hard, _ = util.run_oracle(case, dict(tc, nms_type="hard"))
+    assert any(a["index"].tolist() != b["index"].tolist() for a, b in zip(ref, hard)), "case does not exercise the rescoring"
+    compare(plan, got, ref, util.rank_margin_ulps(case["levels"], 30))
+    for g in got:
+        assert len(g["scores"]) == 12
+
+
+def test_fp16_head_outputs_are_upcast_at_the_boundary():
+    tc = dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)
+    case = util.make_case(P, 2, 24, 40, seed=91)
+    dl = synth.levels_to(case["levels"], "cuda")
+    head = DASHeadB200(num_joints=15, strides=[8], depth_factor=20, z_norm=50, root_idx=2, test_cfg=tc)
+    head.load_refine_weights(synth.layers_to(case["layers"], "cuda"))
+    half = lambda t: t.half()
+    a = head.get_poses([half(lv["cls"]) for lv in dl], [half(lv["pose_raw"]) for lv in dl], [half(lv["ctr"]) for lv in dl],
+                       [[half(f) for f in lv["feats"]] for lv in dl], case["metas"])
+    b = head.get_poses([half(lv["cls"]).float() for lv in dl], [half(lv["pose_raw"]).float() for lv in dl],
+                       [half(lv["ctr"]).float() for lv in dl], [[half(f).float() for f in lv["feats"]] for lv in dl], case["metas"])
+    for x, y in zip(a, b):
+        assert x["scores"] == y["scores"] and torch.equal(x["poses"], y["poses"])

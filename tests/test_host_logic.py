@@ -60,11 +60,8 @@ def test_product_path_fails_loudly_without_cuda():
 def test_head_rejects_unsupported_config_keys():
     with pytest.raises(AssertionError):
         H.DASHeadB200(num_classes=2, num_joints=15, root_idx=2)
-    head = H.DASHeadB200(num_joints=15, strides=(8,), root_idx=2, test_cfg=dict(nms_type="soft", nms_pre=10, nms_post=10))
-    if not torch.cuda.is_available():
-        with pytest.raises((NotImplementedError, RuntimeError)):
-            head.get_poses([torch.zeros(1, 1, 4, 4)], [torch.zeros(1, 93, 4, 4)], [torch.zeros(1, 1, 4, 4)],
-                           synth.make_metas(1, 4, 4))
+    with pytest.raises(AssertionError):
+        H.DASHeadB200(num_joints=15, root_idx=2, recursive_update=dict(dim=2))
 
 
 def test_product_package_never_imports_the_oracle():
