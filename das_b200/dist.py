@@ -43,3 +43,37 @@ def merge_results(per_rank_results: Sequence[Sequence[dict]]) -> List[dict]:
     for r in per_rank_results:
         merged.extend(r)
     return merged
+
+
+# ---- drop-in for the CLI flow: mmdet multi_gpu_test + collect_results (reference tools/test.py:201-206) ------------
+def sampler_indices(size: int, world: int, rank: int) -> List[int]:
+    """Dataset indices a rank sees under the reference's test DistributedSampler (shuffle=False): the index list is
+    padded by wrapping to a multiple of `world`, rank r takes r, r+world, ..."""
+    total = -(-size // world) * world
+    idx = list(range(size)) + list(range(total - size))
+    return idx[rank:total:world]
+
+
+def interleave_results(per_rank_results: Sequence[Sequence[dict]], size: int) -> List[dict]:
+    """Re-order per-rank result lists into dataset order exactly like mmdet's collect_results:
+    zip the parts, flatten, drop the sampler padding."""
+    ordered = []
+    for group in zip(*per_rank_results):
+        ordered.extend(group)
+    return ordered[:size]
+
+
+def collect_results(plan, local_results_block: torch.Tensor, local_metas: Sequence[dict], world: int, rank: int,
+                    size: int, all_metas: Sequence[Sequence[dict]] = None):
+    """Pickle-free replacement of collect_results_gpu: ONE all-gather of the packed output blocks, then rank 0 rebuilds
+    the per-image dicts of every rank and interleaves them into dataset order.  `all_metas[r]` are rank r's img_metas
+    (filenames); if omitted only rank-local metas are known and file names are taken from `local_metas` on rank 0 only."""
+    gathered = gather_blocks(local_results_block, world)
+    if rank != 0:
+        return None
+    parts = []
+    for r in range(world):
+        views = plan.views_of_block(gathered[r])
+        metas = all_metas[r] if all_metas is not None else local_metas
+        parts.append(plan.results(metas, src=views))
+    return interleave_results(parts, size)

@@ -73,3 +73,12 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f"{f} imports the oracle"
+
+
+def test_sampler_order_and_interleave_match_multi_gpu_test():
+    for size in (1, 5, 8, 13):
+        for world in (1, 2, 4):
+            parts = [[dict(i=i) for i in ddist.sampler_indices(size, world, r)] for r in range(world)]
+            assert all(len(p) == len(parts[0]) for p in parts)
+            merged = ddist.interleave_results(parts, size)
+            assert [m["i"] for m in merged] == list(range(size))
