@@ -62,9 +62,10 @@ SIGNATURES = {
     "das_score_topk": (C.c_int, [_VP, C.POINTER(Levels), C.c_int32, C.c_int32, _VP, _VP, C.c_int32, _VP, _VP]),
     "das_gather_refine_assemble": (C.c_int, [_VP, C.POINTER(Levels), C.POINTER(DecodeCfg), _VP, _VP, _VP, _VP, _VP,
                                              C.c_int32, _VP, _VP, _VP, _VP]),
-    "das_refine_heads": (C.c_int, [_VP, C.POINTER(Levels), C.POINTER(DecodeCfg), _VP, _VP, _VP, _VP, C.c_int32, _VP, _VP, _VP, _VP]),
-    "das_refine_tc": (C.c_int, [_VP, C.POINTER(Levels), C.POINTER(DecodeCfg), _VP, _VP, _VP, _VP, _VP, C.c_int32, _VP, _VP, _VP,
-                                _VP, _VP, C.c_int32, _VP]),
+    "das_refine_heads": (C.c_int, [_VP, C.POINTER(Levels), C.POINTER(DecodeCfg), _VP, _VP, _VP, _VP, _VP, C.c_int32,
+                                   _VP, _VP, _VP, _VP, _VP, _VP]),
+    "das_refine_tc": (C.c_int, [_VP, C.POINTER(Levels), C.POINTER(DecodeCfg), _VP, _VP, C.c_int32, _VP, _VP, _VP, _VP, _VP,
+                                C.c_int32, _VP]),
     "das_pack_tc_panels": (C.c_int, [C.POINTER(DecodeCfg), _VP, _VP, _VP]),
     "das_tc_set_debug_buffer": (C.c_int, [_VP]),
     "das_tc_panel_bytes": (C.c_int64, [C.POINTER(DecodeCfg)]),

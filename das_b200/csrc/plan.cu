@@ -37,7 +37,8 @@ struct das_plan {
     // tensor-core refinement (C = 256, nh = 4)
     int refine_mode = 0;              // 0 SIMT, 1 tcgen05 3xTF32, 2 tcgen05 single TF32
     unsigned char* tc_panels = nullptr;
-    float* item_heads = nullptr;
+    float* item_heads = nullptr;      // row records [B*CT*J][32][8]
+    float* item_asm = nullptr;        // item records [B*CT*J][8]
     int32_t* valid_list = nullptr;
     unsigned char* dense_panels[DAS_MAX_LAYERS] = {};   // tensor-core panels of the dense layers (0..L-2)
     // dense layers (num_layers > 1): ping-pong joint-major [B][J][HW][4] maps per level + projection scratch [B][J][HW][16]
@@ -159,7 +160,8 @@ extern "C" int das_plan_create(const das_decode_cfg* cfg, const das_levels* shap
             // das_plan_set_refine_mode(plan, 0) selects the fp32 SIMT kernel
             p->refine_mode = 1;
             A(dev_alloc(&p->tc_panels, static_cast<size_t>(das_tc_panel_bytes(cfg))));
-            A(dev_alloc(&p->item_heads, B * CT * J * 16));
+            A(dev_alloc(&p->item_heads, B * CT * J * 32 * 8));
+            A(dev_alloc(&p->item_asm, B * CT * J * 8));
             A(dev_alloc(&p->valid_list, B * CT));
         }
         if (cfg->num_layers > 1) {
@@ -216,7 +218,7 @@ extern "C" void das_plan_destroy(das_plan* p) {
     for (cudaEvent_t e : p->ev) if (e) cudaEventDestroy(e);
     void* ptrs[] = {p->d_levels, p->buf.cand_score, p->buf.cand_index, p->buf.cand_pose, p->buf.cand_center,
                     p->out_block, p->scratch, p->work_counter, p->d_scale_xy, p->d_cam,
-                    p->proj, p->d_prev_ptrs, p->tc_panels, p->item_heads, p->valid_list};
+                    p->proj, p->d_prev_ptrs, p->tc_panels, p->item_heads, p->item_asm, p->valid_list};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (int k = 0; k < DAS_MAX_LAYERS; ++k) if (p->wpack[k]) cudaFree(p->wpack[k]);
     for (int k = 0; k < DAS_MAX_LAYERS; ++k) if (p->dense_panels[k]) cudaFree(p->dense_panels[k]);
@@ -310,11 +312,11 @@ static int enqueue(das_plan* p, cudaStream_t st, int* n_launch, bool events) {
     DAS_TRY(mark(2));
     if (c.refine && p->refine_mode != 0) {
         const float* w = p->wpack[c.num_layers - 1];
-        DAS_TRY(das_refine_heads(p->d_levels, &p->bound, &c, w, prev, p->buf.cand_score, p->buf.cand_index, p->CT,
-                                 p->item_heads, p->valid_list, p->work_counter, st));
+        DAS_TRY(das_refine_heads(p->d_levels, &p->bound, &c, w, prev, p->d_scale_xy, p->buf.cand_score, p->buf.cand_index, p->CT,
+                                 p->item_heads, p->item_asm, p->buf.cand_center, p->valid_list, p->work_counter, st));
         DAS_TRY(mark(3));
-        DAS_TRY(das_refine_tc(p->d_levels, &p->bound, &c, w, p->tc_panels, prev, p->d_scale_xy, p->buf.cand_index, p->CT,
-                              p->item_heads, p->valid_list, p->work_counter + 1, p->buf.cand_pose, p->buf.cand_center,
+        DAS_TRY(das_refine_tc(p->d_levels, &p->bound, &c, w, p->tc_panels, p->CT, p->item_heads, p->item_asm, p->valid_list,
+                              p->work_counter + 1, p->buf.cand_pose,
                               p->refine_mode == 1 ? 1 : (p->refine_mode == 2 ? 0 : p->refine_mode - 2), st));
         n += 2;
     } else {

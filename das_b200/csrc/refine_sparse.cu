@@ -36,7 +36,8 @@ struct RefineParams {
     float* cand_pose;
     float* cand_center;
     int* work_counter;             // [0] work queue head, [1] number of valid candidates (heads-only mode)
-    float* item_heads;             // heads-only mode: [B*CT*J][16] = hx[8], hy[8]
+    float* item_heads;             // heads-only mode: row records [B*CT*J][32 rows][8 floats] (see TcRowRec in refine_tc.cu)
+    float* item_asm;               // heads-only mode: per-item assembly record [B*CT*J][8] = {Px, Py, zq, sx, sy, stride, -, -}
     int32_t* valid_list;           // heads-only mode: candidate slots (b*CT+slot) that pass score_thr
     int CT, J, root, nms_pre, layer;
     float depth_factor, z_norm, score_thr;
@@ -149,15 +150,47 @@ refine_sparse_kernel(const RefineParams p) {
         }
 
         if constexpr (HEADS_ONLY) {
-            // phases 1-2 only: hand the 2*NH sampling offsets to the tensor-core kernel (refine_tc.cu)
+            // phases 1-2 only.  Everything the tensor-core kernel (refine_tc.cu) needs per gathered row is prepared
+            // here, one lane per row (head = lane >> 2, corner = lane & 3): feature-row pointer (null = zero
+            // padding), bilinear weight, previous offset at that cell, the head's sampling offset.
+            static_assert(NH == 4, "32 rows per item = 8 heads x 4 corners");
+            {
+                const int h = lane >> 2, ck2 = lane & 3;
+                float hxv = hx[0], hyv = hy[0];
+#pragma unroll
+                for (int i = 1; i < 2 * NH; ++i) { hxv = (h == i) ? hx[i] : hxv; hyv = (h == i) ? hy[i] : hyv; }
+                const Corner c = make_corner(sample_coord(x, hxv, fW), sample_coord(y, hyv, fH), W, H);
+                const bool ok = corner_ok(c, ck2, W, H);
+                const int pix = ok ? corner_pix(c, ck2, W) : 0;
+                const float* ptr = ok ? F + static_cast<size_t>(pix) * C : nullptr;
+                const float wk = ok ? corner_wgt(c, ck2) : 0.f;
+                float pv0 = 0.f, pv1 = 0.f, pv2 = 0.f;
+                if (ok) { pv0 = prev_at(pix, 0); pv1 = prev_at(pix, 1); pv2 = prev_at(pix, 2); }
+                const unsigned long long pb = reinterpret_cast<unsigned long long>(ptr);
+                float4* dst = reinterpret_cast<float4*>(p.item_heads + (static_cast<size_t>(item) * 32 + lane) * 8);
+                dst[0] = make_float4(__uint_as_float(static_cast<unsigned>(pb)), __uint_as_float(static_cast<unsigned>(pb >> 32)), wk, pv0);
+                dst[1] = make_float4(pv1, pv2, hxv, hyv);
+            }
             if (lane == 0) {
-                float4* dst = reinterpret_cast<float4*>(p.item_heads + static_cast<size_t>(item) * 16);
-                static_assert(NH == 4, "item_heads layout is hx[8], hy[8]");
-                dst[0] = make_float4(hx[0], hx[1], hx[2], hx[3]);
-                dst[1] = make_float4(hx[4], hx[5], hx[6], hx[7]);
-                dst[2] = make_float4(hy[0], hy[1], hy[2], hy[3]);
-                dst[3] = make_float4(hy[4], hy[5], hy[6], hy[7]);
-                if (j == 0) p.valid_list[atomicAdd(p.work_counter + 1, 1)] = cs;
+                // eval-tail / assembly inputs of this item (das_head.py:254-262, 725-743), and the centre for joint 0
+                const float sx = __ldg(p.scale_xy + 2 * b), sy = __ldg(p.scale_xy + 2 * b + 1);
+                const float qf = sqrtf(sx * sy);
+                const float st = static_cast<float>(d.stride), half = static_cast<float>(d.stride / 2);
+                float z = __ldg(pose + 2 * static_cast<size_t>(HW) + idx) * d.scale_depth;
+                z = __fdiv_rn(z, p.depth_factor);
+                const float zq = __fmul_rn(z, qf);
+                const float Px = static_cast<float>(x) * st + half, Py = static_cast<float>(y) * st + half;
+                float4* a = reinterpret_cast<float4*>(p.item_asm + static_cast<size_t>(item) * 8);
+                a[0] = make_float4(Px, Py, zq, sx);
+                a[1] = make_float4(sy, st, 0.f, 0.f);
+                if (j == 0) {
+                    const float offx = __ldg(pose + idx) * d.scale_offset;
+                    const float offy = __ldg(pose + static_cast<size_t>(HW) + idx) * d.scale_offset;
+                    p.cand_center[static_cast<size_t>(cs) * 3 + 0] = __fdiv_rn(__fsub_rn(Px, offx), sx);
+                    p.cand_center[static_cast<size_t>(cs) * 3 + 1] = __fdiv_rn(__fsub_rn(Py, offy), sy);
+                    p.cand_center[static_cast<size_t>(cs) * 3 + 2] = zq;
+                    p.valid_list[atomicAdd(p.work_counter + 1, 1)] = cs;
+                }
             }
             continue;
         }
@@ -392,23 +425,27 @@ extern "C" int das_gather_refine_assemble(const das_levels* d_levels, const das_
     return DAS_OK;
 }
 
-// Phases 1-2 of the sparse refinement only (feeds das_refine_tc): writes the 2*nh sampling offsets of every
-// (candidate, joint) item to item_heads[item][16] and the candidates passing score_thr to valid_list;
-// counters[0] is the work-queue head, counters[1] receives the number of valid candidates.
+// Phases 1-2 of the sparse refinement only (feeds das_refine_tc): per (candidate, joint) item it writes the 32 row
+// records of the sampling phase (row_records [item][32][8 floats]: feature-row pointer, bilinear weight, previous
+// offset, head offset), the item's assembly record (item_records [item][8]) and, for joint 0, the centre and the
+// candidate's entry in valid_list; counters[0] is the work-queue head, counters[1] receives the number of valid
+// candidates.
 extern "C" int das_refine_heads(const das_levels* d_levels, const das_levels* h_levels, const das_decode_cfg* cfg,
-                                const float* weights, const float* const* prev_uvd, const float* cand_score,
-                                const int32_t* cand_index, int32_t cand_slots, float* item_heads,
+                                const float* weights, const float* const* prev_uvd, const float* scale_xy,
+                                const float* cand_score, const int32_t* cand_index, int32_t cand_slots,
+                                float* row_records, float* item_records, float* cand_center,
                                 int32_t* valid_list, int32_t* counters, void* stream) {
     using namespace das;
-    DAS_REQUIRE(d_levels && h_levels && cfg && weights && cand_score && cand_index && item_heads && valid_list && counters,
-                DAS_ERR_ARG, "das_refine_heads: null pointer");
+    DAS_REQUIRE(d_levels && h_levels && cfg && weights && scale_xy && cand_score && cand_index && row_records && item_records &&
+                cand_center && valid_list && counters, DAS_ERR_ARG, "das_refine_heads: null pointer");
     DAS_REQUIRE(cfg->feat_channels == 256 && cfg->num_heads == 4, DAS_ERR_UNSUPPORTED,
                 "das_refine_heads is built for feat_channels=256, num_heads=4");
     DAS_REQUIRE(cfg->num_joints >= 1 && cfg->num_joints <= DAS_MAX_JOINTS, DAS_ERR_CAPACITY, "num_joints=%d", cfg->num_joints);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     RefineParams p{};
     p.lv = d_levels; p.wpack = weights; p.prev_uvd = prev_uvd; p.cand_score = cand_score; p.cand_index = cand_index;
-    p.work_counter = counters; p.item_heads = item_heads; p.valid_list = valid_list;
+    p.work_counter = counters; p.item_heads = row_records; p.item_asm = item_records; p.valid_list = valid_list;
+    p.scale_xy = scale_xy; p.cand_center = cand_center;
     p.CT = cand_slots; p.J = cfg->num_joints; p.root = cfg->root_idx; p.nms_pre = cfg->nms_pre; p.layer = cfg->num_layers - 1;
     p.depth_factor = cfg->depth_factor; p.z_norm = cfg->z_norm; p.score_thr = cfg->score_thr;
     const long long items = static_cast<long long>(h_levels->batch) * cand_slots * cfg->num_joints;

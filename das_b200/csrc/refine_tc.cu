@@ -46,15 +46,12 @@ struct TcParams {
     const das_levels* lv;
     const float* wpack;              // biases live behind the [J][17][C] weights
     const unsigned char* bpanel;     // [J][2][TC_B_BYTES] swizzled hi / lo panels
-    const float* const* prev_uvd;
-    const float* scale_xy;
-    const int32_t* cand_index;
-    const float* item_heads;         // [B*CT*J][16]: hx[8], hy[8]
+    const float* item_heads;         // row records [B*CT*J][32][8 floats] written by das_refine_heads
+    const float* item_asm;           // assembly records [B*CT*J][8] = {Px, Py, zq, sx, sy, stride, -, -}
     const int32_t* valid_list;       // candidates that survive score_thr, any order
     const int32_t* n_valid;
     float* cand_pose;
-    float* cand_center;
-    int CT, J, root, nms_pre, layer, split;
+    int CT, J, root, split;
     float depth_factor, z_norm;
     long long* dbg;                  // optional [gridDim.x][16] cycle counters (profiling builds of the host code)
 };
@@ -62,58 +59,30 @@ struct TcParams {
 struct RowState {                    // what thread t keeps about row t of a tile until its epilogue
     const float* ptr;                // feature row, nullptr = outside the map / padding row
     float wk, prev0, prev1, prev2, hxv, hyv;
-    float z, sx, sy;                 // eval-tail inputs of the item (root depth, image scale), fetched early
-    int cs, idx, lvl;
+    int cs;
     bool item_ok;
 };
 
+// Row t of tile `tile`: (item = t >> 5, head = (t >> 2) & 7, corner = t & 3).  The phase-1/2 kernel (das_refine_heads)
+// has already resolved every row to a 32-byte record; setting a row up is two dependent loads.
 __device__ __forceinline__ RowState setup_row(const TcParams& p, int tile, int n_groups, int n_valid, int tid) {
     RowState r;
     const int j = tile / n_groups, g = tile - j * n_groups;
-    const int li = tid >> 5, h = (tid >> 2) & 7, ck = tid & 3;
-    const int vi = g * 4 + li;
+    const int vi = g * 4 + (tid >> 5);
     r.item_ok = vi < n_valid;
     r.cs = r.item_ok ? __ldg(p.valid_list + vi) : 0;
-    r.ptr = nullptr; r.wk = 0.f; r.prev0 = r.prev1 = r.prev2 = 0.f; r.hxv = r.hyv = 0.f; r.idx = 0; r.lvl = 0;
-    r.z = 0.f; r.sx = r.sy = 1.f;
+    r.ptr = nullptr; r.wk = 0.f; r.prev0 = r.prev1 = r.prev2 = 0.f; r.hxv = r.hyv = 0.f;
     if (!r.item_ok) return r;
-    const das_levels* __restrict__ lvp = p.lv;
-    const int b = r.cs / p.CT, slot = r.cs - b * p.CT;
-    int l = 0, s0 = 0;
-    for (; l < lvp->n_levels - 1; ++l) {
-        const int ns = level_slots(lvp->lv[l].H * lvp->lv[l].W, p.nms_pre);
-        if (slot < s0 + ns) break;
-        s0 += ns;
-    }
-    r.lvl = l;
-    const das_level_desc& d = lvp->lv[l];
-    const int H = d.H, W = d.W, HW = H * W, J = p.J;
-    r.idx = __ldg(p.cand_index + r.cs);
-    const int y = r.idx / W, x = r.idx - y * W;
-    r.z = __ldg(d.pose + (static_cast<size_t>(b) * (3 + 6 * J) + 2) * HW + r.idx);
-    r.sx = __ldg(p.scale_xy + 2 * b);
-    r.sy = __ldg(p.scale_xy + 2 * b + 1);
-    const float* heads = p.item_heads + (static_cast<size_t>(r.cs) * J + j) * 16;
-    r.hxv = __ldg(heads + h);
-    r.hyv = __ldg(heads + 8 + h);
-    const Corner c = make_corner(sample_coord(x, r.hxv, static_cast<float>(W)), sample_coord(y, r.hyv, static_cast<float>(H)), W, H);
-    if (!corner_ok(c, ck, W, H)) return r;
-    const int pix = corner_pix(c, ck, W);
-    r.wk = corner_wgt(c, ck);
-    r.ptr = d.feats[p.layer] + (static_cast<size_t>(b) * HW + pix) * TC_C;
-    // the producers gather this row one to two tiles from now: pull its 8 lines into L2 already, so that a
-    // k-block's arrival is bounded by L2 latency instead of by its slowest DRAM miss
+    const float4* rec = reinterpret_cast<const float4*>(p.item_heads) + ((static_cast<size_t>(r.cs) * p.J + j) * 32 + (tid & 31)) * 2;
+    const float4 a = __ldg(rec), c = __ldg(rec + 1);
+    r.ptr = reinterpret_cast<const float*>(static_cast<unsigned long long>(__float_as_uint(a.x)) |
+                                           (static_cast<unsigned long long>(__float_as_uint(a.y)) << 32));
+    r.wk = a.z; r.prev0 = a.w; r.prev1 = c.x; r.prev2 = c.y; r.hxv = c.z; r.hyv = c.w;
+    if (r.ptr) {
+        // the producers gather this row a few tiles from now: pull its 8 lines into L2 already, so that a k-block's
+        // arrival is bounded by L2 latency instead of by its slowest DRAM miss
 #pragma unroll
-    for (int q = 0; q < TC_C * 4 / 128; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(r.ptr + q * 32));
-    const float* prev = p.prev_uvd ? p.prev_uvd[l] : nullptr;
-    if (prev) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(prev) + (static_cast<size_t>(b) * J + j) * HW + pix);
-        r.prev0 = q.x; r.prev1 = q.y; r.prev2 = q.z;
-    } else {
-        const float* q = d.pose + (static_cast<size_t>(b) * (3 + 6 * J) + 3 + 3 * j) * HW + pix;
-        r.prev0 = __ldg(q) * d.scale_uv;
-        r.prev1 = __ldg(q + HW) * d.scale_uv;
-        r.prev2 = (j == p.root) ? 0.f : __ldg(q + 2 * static_cast<size_t>(HW)) * d.scale_d;
+        for (int q = 0; q < TC_C * 4 / 128; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(r.ptr + q * 32));
     }
     return r;
 }
@@ -162,35 +131,17 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const RowState& c
         out[k] = o;
     }
     if (cur.item_ok && lane < 3) {
-        // eval tail + assembly (das_head.py:254-262, 725-743)
-        const das_level_desc& d = p.lv->lv[cur.lvl];
-        const int W = d.W, HW = d.H * d.W;
-        const int b = cur.cs / p.CT;
-        const int y = cur.idx / W, x = cur.idx - y * W;
-        const float* pose = d.pose + static_cast<size_t>(b) * (3 + 6 * J) * HW;
-        const float sx = cur.sx, sy = cur.sy;
-        const float qf = sqrtf(sx * sy);
-        const float stf = static_cast<float>(d.stride), half = static_cast<float>(d.stride / 2);
-        float z = cur.z * d.scale_depth;
-        z = __fdiv_rn(z, p.depth_factor);
-        const float zq = __fmul_rn(z, qf);
+        // eval tail + assembly (das_head.py:254-262, 725-743) from the item's record {Px, Py, zq, sx, sy, stride}
+        const float4* ar = reinterpret_cast<const float4*>(p.item_asm) + (static_cast<size_t>(cur.cs) * J + j) * 2;
+        const float4 a0 = __ldg(ar), a1 = __ldg(ar + 1);
         const float o = lane == 0 ? out[0] : (lane == 1 ? out[1] : out[2]);
         float r;
-        if (lane == 0) r = __fdiv_rn(__fadd_rn(__fmul_rn(o, stf), static_cast<float>(x) * stf + half), sx);
-        else if (lane == 1) r = __fdiv_rn(__fadd_rn(__fmul_rn(o, stf), static_cast<float>(y) * stf + half), sy);
-        else r = __fadd_rn((j == p.root) ? 0.0f : __fmul_rn(o, p.z_norm), zq);
+        if (lane == 0) r = __fdiv_rn(__fadd_rn(__fmul_rn(o, a1.y), a0.x), a0.w);
+        else if (lane == 1) r = __fdiv_rn(__fadd_rn(__fmul_rn(o, a1.y), a0.y), a1.x);
+        else r = __fadd_rn((j == p.root) ? 0.0f : __fmul_rn(o, p.z_norm), a0.z);
         p.cand_pose[(static_cast<size_t>(cur.cs) * J + j) * 3 + lane] = r;
-        if (j == 0) {
-            float c;
-            if (lane == 2) c = zq;
-            else {
-                const float off = __ldg(pose + static_cast<size_t>(lane) * HW + cur.idx) * d.scale_offset;
-                const float P = static_cast<float>(lane == 0 ? x : y) * stf + half;
-                c = __fdiv_rn(__fsub_rn(P, off), lane == 0 ? sx : sy);
-            }
-            p.cand_center[static_cast<size_t>(cur.cs) * 3 + lane] = c;
-        }
-    }}
+    }
+}
 
 constexpr int T2_PGROUPS = 3;                   // producer groups (4 warps each)
 constexpr int T2_STAGES = 3;                    // smem stages per group
@@ -449,20 +400,19 @@ extern "C" int das_pack_tc_panels(const das_decode_cfg* cfg, const float* packed
 }
 
 extern "C" int das_refine_tc(const das_levels* d_levels, const das_levels* h_levels, const das_decode_cfg* cfg,
-                             const float* weights, const void* panels, const float* const* prev_uvd,
-                             const float* scale_xy, const int32_t* cand_index, int32_t cand_slots,
-                             const float* item_heads, const int32_t* valid_list, const int32_t* n_valid,
-                             float* cand_pose, float* cand_center, int32_t split, void* stream) {
+                             const float* weights, const void* panels, int32_t cand_slots,
+                             const float* row_records, const float* item_records, const int32_t* valid_list,
+                             const int32_t* n_valid, float* cand_pose, int32_t split, void* stream) {
     using namespace das;
-    DAS_REQUIRE(d_levels && h_levels && cfg && weights && panels && scale_xy && cand_index && item_heads && valid_list &&
-                n_valid && cand_pose && cand_center, DAS_ERR_ARG, "das_refine_tc: null pointer");
+    DAS_REQUIRE(d_levels && h_levels && cfg && weights && panels && row_records && item_records && valid_list && n_valid &&
+                cand_pose, DAS_ERR_ARG, "das_refine_tc: null pointer");
     DAS_REQUIRE(cfg->feat_channels == TC_C && cfg->num_heads == TC_NH, DAS_ERR_UNSUPPORTED,
                 "tensor-core refinement is built for feat_channels=256, num_heads=4");
     TcParams p{};
-    p.lv = d_levels; p.wpack = weights; p.bpanel = static_cast<const unsigned char*>(panels); p.prev_uvd = prev_uvd;
-    p.scale_xy = scale_xy; p.cand_index = cand_index; p.item_heads = item_heads; p.valid_list = valid_list; p.n_valid = n_valid;
-    p.cand_pose = cand_pose; p.cand_center = cand_center;
-    p.CT = cand_slots; p.J = cfg->num_joints; p.root = cfg->root_idx; p.nms_pre = cfg->nms_pre; p.layer = cfg->num_layers - 1;
+    p.lv = d_levels; p.wpack = weights; p.bpanel = static_cast<const unsigned char*>(panels);
+    p.item_heads = row_records; p.item_asm = item_records; p.valid_list = valid_list; p.n_valid = n_valid;
+    p.cand_pose = cand_pose;
+    p.CT = cand_slots; p.J = cfg->num_joints; p.root = cfg->root_idx;
     p.split = split; p.depth_factor = cfg->depth_factor; p.z_norm = cfg->z_norm;
     p.dbg = g_tc_dbg;
     static bool attr2_done = false;

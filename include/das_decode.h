@@ -130,20 +130,22 @@ int das_gather_refine_assemble(const das_levels* d_levels, const das_levels* h_l
                                void* stream);
 
 /* Tensor-core variant of stage 3+4 (feat_channels = 256, num_heads = 4), two launches:
- *   das_refine_heads  phases 1-2 per (candidate, joint): sampling offsets -> item_heads [B*CT*J][16],
+ *   das_refine_heads  phases 1-2 per (candidate, joint) item: the 32 row records of the sampling phase
+ *                     (row_records [B*CT*J][32][8 floats]: feature-row pointer, bilinear weight, previous offset,
+ *                     head offset), the item's assembly record (item_records [B*CT*J][8]), the centre (joint 0),
  *                     surviving candidates -> valid_list, counters[1] = their number (counters: 2 int32)
  *   das_refine_tc     the 32 sampled rows per item as a gathered tcgen05 GEMM (split=1: 3xTF32, fp32-level
  *                     accuracy; split=0: one TF32 pass) + gate/blend/softmax epilogue, eval tail, assembly.
  * panels: das_pack_tc_panels() image of the last layer's packed weights (das_tc_panel_bytes() bytes). */
 int das_refine_heads(const das_levels* d_levels, const das_levels* h_levels, const das_decode_cfg* cfg,
-                     const float* weights, const float* const* prev_uvd, const float* cand_score,
-                     const int32_t* cand_index, int32_t cand_slots, float* item_heads,
+                     const float* weights, const float* const* prev_uvd, const float* scale_xy,
+                     const float* cand_score, const int32_t* cand_index, int32_t cand_slots,
+                     float* row_records, float* item_records, float* cand_center,
                      int32_t* valid_list, int32_t* counters, void* stream);
 int das_refine_tc(const das_levels* d_levels, const das_levels* h_levels, const das_decode_cfg* cfg,
-                  const float* weights, const void* panels, const float* const* prev_uvd,
-                  const float* scale_xy, const int32_t* cand_index, int32_t cand_slots,
-                  const float* item_heads, const int32_t* valid_list, const int32_t* n_valid,
-                  float* cand_pose, float* cand_center, int32_t split, void* stream);
+                  const float* weights, const void* panels, int32_t cand_slots,
+                  const float* row_records, const float* item_records, const int32_t* valid_list,
+                  const int32_t* n_valid, float* cand_pose, int32_t split, void* stream);
 int das_pack_tc_panels(const das_decode_cfg* cfg, const float* packed_weights, void* panels, void* stream);
 int64_t das_tc_panel_bytes(const das_decode_cfg* cfg);
 /* profiling aid: per-CTA cycle counters of das_refine_tc's warp roles ([148][16] int64 device buffer; NULL = off) */
