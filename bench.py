@@ -354,7 +354,7 @@ def run_b200(args):
 
         el_bulk, bytes_bulk = time_host(False)
         el_zc, bytes_zc = time_host(True)
-        sparse_ub = B * K * J * 37 * C * 4 + B * K * (3 + J * 33 * 3) * 32     # feature rows + 32-B sectors of the pose gathers
+        sparse_ub = B * K * J * 37 * C * 4 + (B * K * (3 + J * 33 * 3) * 32 if head.num_layers == 1 else 0)   # rows + pose sectors
         e2e = dict(value=world * B * n_e2e / el_zc, unit=UNIT, h2d_bytes_per_step=int(bytes_zc + sparse_ub),
                    d2h_bytes_per_step=plans[0].d2h_bytes, steps=n_e2e, ms_per_step=el_zc / n_e2e * 1e3,
                    h2d_explicit_bytes=int(bytes_zc), h2d_in_place_bytes_upper_bound=int(sparse_ub),

@@ -445,6 +445,9 @@ extern "C" int das_plan_run_host(das_plan* p, const das_levels* levels, const fl
     // (unified addressing), so those sparse maps are read IN PLACE over PCIe by the gather kernels instead of being
     // copied wholesale; only the logit planes are staged.
     bool zero_copy = p->host_mode == 1;
+    // dense layers (num_layers > 1) read every cell of the pose map and of the feature maps of layers 0..L-2: those
+    // are bulk-copied in either mode; only maps that are touched sparsely are read in place
+    const bool pose_sparse = L <= 1;
     const float* dev_alias[DAS_MAX_LEVELS][1 + DAS_MAX_LAYERS] = {};
     if (zero_copy) {
         for (int l = 0; l < p->shape.n_levels && zero_copy; ++l) {
@@ -486,23 +489,25 @@ extern "C" int das_plan_run_host(das_plan* p, const das_levels* levels, const fl
         DAS_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(d.cls), h.cls, B * hw * 4, cudaMemcpyHostToDevice, st));
         DAS_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(d.ctr), h.ctr, B * hw * 4, cudaMemcpyHostToDevice, st));
         copied += static_cast<int64_t>(B * hw * 8);
-        if (zero_copy) {
+        das_level_desc& sd = p->staging.lv[l];      // bulk staging, allocated lazily
+        if (zero_copy && pose_sparse) {
             d.pose = dev_alias[l][0];
-            for (int k = 0; k < L; ++k) d.feats[k] = dev_alias[l][1 + k];
         } else {
-            // lazily allocated bulk staging for the sparse maps
-            das_level_desc& sd = p->staging.lv[l];
             if (!sd.pose) { float* c = nullptr; DAS_TRY(dev_alloc(&c, B * hw * (3 + 6 * J))); sd.pose = c; }
             DAS_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(sd.pose), h.pose, B * hw * (3 + 6 * J) * 4, cudaMemcpyHostToDevice, st));
             copied += static_cast<int64_t>(B * hw * (3 + 6 * J) * 4);
             d.pose = sd.pose;
-            for (int k = 0; k < L; ++k) {
-                DAS_REQUIRE(h.feats[k], DAS_ERR_ARG, "run_host: level %d layer %d feature map is null", l, k);
-                if (!sd.feats[k]) { float* f = nullptr; DAS_TRY(dev_alloc(&f, B * hw * C)); sd.feats[k] = f; }
-                DAS_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(sd.feats[k]), h.feats[k], B * hw * C * 4, cudaMemcpyHostToDevice, st));
-                copied += static_cast<int64_t>(B * hw * C * 4);
-                d.feats[k] = sd.feats[k];
+        }
+        for (int k = 0; k < L; ++k) {
+            DAS_REQUIRE(h.feats[k], DAS_ERR_ARG, "run_host: level %d layer %d feature map is null", l, k);
+            if (zero_copy && k == L - 1) {          // the last layer is evaluated sparsely at the selected centres
+                d.feats[k] = dev_alias[l][1 + k];
+                continue;
             }
+            if (!sd.feats[k]) { float* f = nullptr; DAS_TRY(dev_alloc(&f, B * hw * C)); sd.feats[k] = f; }
+            DAS_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(sd.feats[k]), h.feats[k], B * hw * C * 4, cudaMemcpyHostToDevice, st));
+            copied += static_cast<int64_t>(B * hw * C * 4);
+            d.feats[k] = sd.feats[k];
         }
     }
     p->h2d_explicit = copied + static_cast<int64_t>(B) * (2 * 4 + DAS_CAM_DOUBLES * 8);
