@@ -10,6 +10,21 @@ namespace das {
 
 constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs
 
+// cudaFuncSetAttribute is per device: each launcher remembers which devices it has configured, so a
+// process that drives several GPUs (one plan per device) sets the attribute on each of them.
+struct DeviceOnce {
+    unsigned long long done[4] = {0, 0, 0, 0};
+    bool need() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess) return true;
+        d &= 255;
+        const unsigned long long bit = 1ull << (d & 63);
+        const bool first = !(done[d >> 6] & bit);
+        done[d >> 6] |= bit;
+        return first;
+    }
+};
+
 void set_error(const char* fmt, ...);
 
 #define DAS_CUDA_CHECK(expr)                                                              \

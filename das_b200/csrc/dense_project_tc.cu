@@ -276,10 +276,9 @@ extern "C" int das_dense_project_tc(const das_levels* d_levels, const das_levels
     p.level = level; p.layer = layer; p.J = cfg->num_joints; p.root = cfg->root_idx; p.B = h_levels->batch;
     p.Q = (cfg->num_joints + DT_JG - 1) / DT_JG;
     DAS_REQUIRE(p.Q <= kSMs, DAS_ERR_CAPACITY, "too many joint groups");
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_done;
+    if (attr_done.need()) {
         DAS_CUDA_CHECK(cudaFuncSetAttribute(dense_project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
-        attr_done = true;
     }
     const int grid = (kSMs / p.Q) * p.Q;
     dense_project_tc_kernel<<<grid, DT_THREADS, DT_SMEM, static_cast<cudaStream_t>(stream)>>>(p);

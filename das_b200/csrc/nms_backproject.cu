@@ -357,11 +357,10 @@ extern "C" int das_nms_backproject(const das_decode_cfg* cfg, int32_t batch, int
     int n2 = 1;
     while (n2 < cand_slots) n2 <<= 1;
     const size_t smem = static_cast<size_t>(n2) * 8 + static_cast<size_t>(cand_slots) * (4 + 4 + 1 + 4) + 32;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_done;
+    if (attr_done.need()) {
         DAS_CUDA_CHECK(cudaFuncSetAttribute(nms_backproject_kernel<NM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             NM_MAX_CAND * 8 + NM_MAX_CAND * 13 + 32));
-        attr_done = true;
     }
     // few candidates (the usual case): 8 warps keep the ~20 block barriers of this latency-bound kernel cheap
     if (cand_slots <= 32) nms_backproject_kernel<256><<<batch, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);

@@ -28,6 +28,7 @@ struct das_plan {
     das_levels bound{};        // last bound inputs (device pointers)
     das_levels* d_levels = nullptr;
     int B = 0, CT = 0, P = 0, hw_sum = 0;
+    int device = 0;            // the plan's buffers live here; run/bind must be called with this device current
     das_buffers buf{};
     uint32_t* scratch = nullptr;
     int32_t* work_counter = nullptr;
@@ -101,16 +102,18 @@ extern "C" int das_plan_create(const das_decode_cfg* cfg, const das_levels* shap
         DAS_REQUIRE(cfg->feat_channels == 128 || cfg->feat_channels == 256 || cfg->feat_channels == 512, DAS_ERR_UNSUPPORTED,
                     "feat_channels=%d: only 128/256/512 are built", cfg->feat_channels);
     }
+    for (int l = 0; l < shape->n_levels; ++l)
+        DAS_REQUIRE(shape->lv[l].H > 0 && shape->lv[l].W > 0 && shape->lv[l].stride > 0, DAS_ERR_ARG, "level %d: bad shape", l);
+    int device = 0;
+    DAS_CUDA_CHECK(cudaGetDevice(&device));
     das_plan* p = new (std::nothrow) das_plan();
     DAS_REQUIRE(p, DAS_ERR_ARG, "out of host memory");
     p->cfg = *cfg;
     p->shape = *shape;
     p->bound = *shape;
     p->B = shape->batch;
-    for (int l = 0; l < shape->n_levels; ++l) {
-        DAS_REQUIRE(shape->lv[l].H > 0 && shape->lv[l].W > 0 && shape->lv[l].stride > 0, DAS_ERR_ARG, "level %d: bad shape", l);
-        p->hw_sum += shape->lv[l].H * shape->lv[l].W;
-    }
+    p->device = device;
+    for (int l = 0; l < shape->n_levels; ++l) p->hw_sum += shape->lv[l].H * shape->lv[l].W;
     p->CT = das_candidate_slots(shape, cfg->nms_pre);
     p->P = das_output_slots(p->CT, cfg->nms_post);
     if (p->CT > 8192) {
@@ -356,6 +359,9 @@ extern "C" int das_plan_run(das_plan* p, void* stream, int32_t mode) {
     DAS_REQUIRE(p, DAS_ERR_ARG, "null plan");
     DAS_REQUIRE(mode >= 0 && mode <= 2, DAS_ERR_ARG, "mode=%d", mode);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int cur_device = -1;
+    DAS_CUDA_CHECK(cudaGetDevice(&cur_device));
+    DAS_REQUIRE(cur_device == p->device, DAS_ERR_ARG, "plan was created on device %d but device %d is current", p->device, cur_device);
     if (p->launches == 0) {
         if (p->cfg.refine && p->cfg.num_layers > 1) {
             const float* host_prev[DAS_MAX_LEVELS] = {};

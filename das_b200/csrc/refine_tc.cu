@@ -415,11 +415,10 @@ extern "C" int das_refine_tc(const das_levels* d_levels, const das_levels* h_lev
     p.CT = cand_slots; p.J = cfg->num_joints; p.root = cfg->root_idx;
     p.split = split; p.depth_factor = cfg->depth_factor; p.z_norm = cfg->z_norm;
     p.dbg = g_tc_dbg;
-    static bool attr2_done = false;
-    if (!attr2_done) {
+    static DeviceOnce attr2_done;
+    if (attr2_done.need()) {
         DAS_CUDA_CHECK(cudaFuncSetAttribute(refine_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
         DAS_CUDA_CHECK(cudaFuncSetAttribute(refine_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
-        attr2_done = true;
     }
     if (p.dbg) refine_tc2_kernel<true><<<kSMs, T2_THREADS, T2_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
     else refine_tc2_kernel<false><<<kSMs, T2_THREADS, T2_SMEM, static_cast<cudaStream_t>(stream)>>>(p);

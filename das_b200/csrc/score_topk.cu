@@ -353,11 +353,10 @@ extern "C" int das_score_topk(const das_levels* d_levels, const das_levels* h_le
     }
     DAS_REQUIRE(total == cand_slots, DAS_ERR_ARG, "cand_slots=%d but levels give %d", cand_slots, total);
     const size_t smem = TK_LIST_CAP * sizeof(uint64_t) + (peak ? TK_TILE_FLOATS * sizeof(float) : 0);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_done;
+    if (attr_done.need()) {
         DAS_CUDA_CHECK(cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             static_cast<int>(TK_LIST_CAP * sizeof(uint64_t) + TK_TILE_FLOATS * sizeof(float))));
-        attr_done = true;
     }
     const int grid = h_levels->batch * h_levels->n_levels;
     score_topk_kernel<<<grid, TK_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(

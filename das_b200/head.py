@@ -388,20 +388,21 @@ class DASHeadB200:
             self._plans[key] = p
         return p
 
-    def get_poses(self, cls_scores, pose_preds, centernesses, *rest, cfg=None, rescale=None):
-        """Reference call: get_poses(cls_scores, pose_preds, centernesses, img_metas, cfg=None, rescale=None)
-        with pose_preds already refined + eval-tailed (das_head.py:264-267 outputs).
-        Extended call: get_poses(cls_scores, raw_pose_preds, centernesses, refine_feats, img_metas, ...)
-        where refine_feats[level] is the list of per-layer feature maps; refinement then runs on the GPU."""
+    @staticmethod
+    def _split_rest(rest, cfg):
+        """(img_metas[, cfg[, rescale]]) as the reference takes them, or (refine_feats, img_metas) for the extended call."""
         if len(rest) == 1:
-            refine_feats, img_metas = None, rest[0]
-        elif len(rest) == 2 and isinstance(rest[1], (list, tuple)) and (len(rest[1]) == 0 or isinstance(rest[1][0], dict)):
-            refine_feats, img_metas = rest
-        elif len(rest) >= 2:                      # positional cfg / rescale like the reference allows
-            refine_feats, img_metas = None, rest[0]
-            cfg = rest[1] if cfg is None else cfg
-        else:
-            raise TypeError("get_poses() missing img_metas")
+            return None, rest[0], cfg
+        if len(rest) == 2 and isinstance(rest[1], (list, tuple)) and (len(rest[1]) == 0 or isinstance(rest[1][0], dict)):
+            return rest[0], rest[1], cfg
+        if len(rest) >= 2:                        # positional cfg / rescale like the reference allows
+            return None, rest[0], rest[1] if cfg is None else cfg
+        raise TypeError("get_poses() missing img_metas")
+
+    def decode_to_device(self, cls_scores, pose_preds, centernesses, *rest, cfg=None, rescale=None) -> DecodePlan:
+        """get_poses without the device->host read: enqueues the decode on the current stream and returns the plan
+        whose `output_block()` / `views_of_block()` hold the padded pose lists on the device (same arguments)."""
+        refine_feats, img_metas, cfg = self._split_rest(rest, cfg)
         assert len(cls_scores) == len(pose_preds) == len(centernesses)
         cfg = self.test_cfg if cfg is None else dict(cfg)
         num_levels = len(cls_scores)
@@ -420,6 +421,16 @@ class DASHeadB200:
         plan.bind(levels)
         plan.set_metas(img_metas)
         plan.run()
+        return plan
+
+    def get_poses(self, cls_scores, pose_preds, centernesses, *rest, cfg=None, rescale=None):
+        """Reference call: get_poses(cls_scores, pose_preds, centernesses, img_metas, cfg=None, rescale=None)
+        with pose_preds already refined + eval-tailed (das_head.py:264-267 outputs).
+        Extended call: get_poses(cls_scores, raw_pose_preds, centernesses, refine_feats, img_metas, ...)
+        where refine_feats[level] is the list of per-layer feature maps; refinement then runs on the GPU.
+        Returns the reference's list of per-image dicts (das_head.py:680-687) plus 'poses_cam' / 'poses_world'."""
+        img_metas = self._split_rest(rest, cfg)[1]
+        plan = self.decode_to_device(cls_scores, pose_preds, centernesses, *rest, cfg=cfg, rescale=rescale)
         return plan.results(img_metas)
 
     def simple_test_decode(self, outs, img_metas, rescale=False):

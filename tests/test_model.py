@@ -1,0 +1,196 @@
+"""the image -> decode-input network (das_b200/model.py).
+
+CPU: MSPNBackbone against the reference's own MSPN2 (golden made by oracle/make_model_golden.py from the reference
+source under mmcv shims), BatchNorm folding, the checkpoint key map, output layout.
+GPU: model outputs decoded by the CUDA path vs the oracle decode of the very same maps."""
+import ast
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from das_b200 import model as M
+from oracle.model_fixture import synthetic_image, synthetic_state
+
+GOLDEN_DIR = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load_backbone_from_reference_keys(net: M.MSPNBackbone, state):
+    mine = net.state_dict()
+    seen = set()
+    for k, v in state.items():
+        loc = M.reference_key_to_local("backbone." + k)
+        assert loc is not None and loc.startswith("backbone."), k
+        loc = loc[len("backbone."):]
+        assert loc in mine, (k, loc)
+        assert mine[loc].shape == v.shape, (k, loc)
+        mine[loc].copy_(v)
+        seen.add(loc)
+    left = [k for k in mine if k not in seen and not k.endswith("num_batches_tracked")]
+    assert not left, left[:5]
+
+
+@pytest.fixture(scope="module")
+def mspn_golden():
+    z = np.load(os.path.join(GOLDEN_DIR, "mspn_small.npz"))
+    keys = [str(k) for k in z["keys"]]
+    shapes = [tuple(int(v) for v in str(s).split(",")) if str(s) else () for s in z["shapes"]]
+    cfg = ast.literal_eval(str(z["cfg"]))
+    img = ast.literal_eval(str(z["img"]))
+    outs = [torch.from_numpy(z[f"out{i}"]) for i in range(4)]
+    return keys, shapes, cfg, img, outs
+
+
+def test_backbone_matches_reference_mspn2(mspn_golden):
+    keys, shapes, cfg, img, want = mspn_golden
+    torch.manual_seed(0)
+    net = M.MSPNBackbone(unit_channels=cfg["unit_channels"], num_stages=cfg["num_stages"],
+                         num_blocks=tuple(cfg["num_blocks"])).eval()
+    with torch.no_grad():
+        _load_backbone_from_reference_keys(net, synthetic_state(keys, shapes))
+        x = synthetic_image(**img)
+        got = net(x)
+        assert len(got) == 4
+        for g, w in zip(got, want):
+            assert g.shape == w.shape
+            scale = float(w.abs().max())
+            assert float((g - w).abs().max()) <= 2e-5 * scale, (float((g - w).abs().max()), scale)
+        # BatchNorm folded into the convolutions: same function up to fp32 re-association
+        for m in net.modules():
+            if isinstance(m, M.ConvUnit):
+                m.fold_batchnorm()
+        assert not any(isinstance(m, torch.nn.BatchNorm2d) for m in net.modules())
+        folded = net(x.contiguous(memory_format=torch.channels_last))
+        for g, w in zip(folded, want):
+            assert float((g - w).abs().max()) <= 2e-4 * float(w.abs().max())
+
+
+def _tiny_net(num_layers=1, J=15):
+    torch.manual_seed(5)
+    return M.DASNet(num_joints=J, backbone=dict(unit_channels=64, num_stages=2, num_blocks=(1, 1, 1, 1)),
+                    fpn_channels=64, num_layers=num_layers)
+
+
+def test_network_outputs_have_the_decode_layout():
+    J = 15
+    net = _tiny_net(num_layers=2, J=J)
+    ref = net.eval()
+    x = synthetic_image(2, 96, 128, seed=3)
+    with torch.no_grad():
+        before = ref(x)
+        net.prepare_inference()
+        cls, pose, ctr, feats = net(x)
+    assert len(cls) == len(pose) == len(ctr) == len(feats) == 4
+    for l, s in enumerate((8, 16, 32, 64)):
+        h, w = -(-96 // s), -(-128 // s)
+        assert tuple(cls[l].shape) == (2, 1, h, w) and cls[l].dtype == torch.float32 and cls[l].is_contiguous()
+        assert tuple(ctr[l].shape) == (2, 1, h, w)
+        assert tuple(pose[l].shape) == (2, 3 + 6 * J, h, w) and pose[l].is_contiguous()
+        assert len(feats[l]) == 2
+        for f in feats[l]:
+            assert tuple(f.shape) == (2, 64, h, w) and f.dtype == torch.float32
+            assert f.is_contiguous(memory_format=torch.channels_last)
+        # folding BatchNorm does not change the function
+        assert torch.allclose(cls[l], before[0][l], atol=1e-4, rtol=1e-4)
+        assert torch.allclose(pose[l], before[1][l], atol=1e-4, rtol=1e-4)
+        assert torch.allclose(feats[l][1], before[3][l][1], atol=1e-3, rtol=1e-3)
+    w = net.refine_weights()
+    assert len(w) == 2 and tuple(w[0]["so_w"].shape) == (J * 4 * 2, 64) and tuple(w[1]["uv_b"].shape) == (3 * J,)
+    assert net.level_scales() == [(1.0, 1.0, 1.0, 1.0)] * 4
+
+
+def test_reference_checkpoint_keys_map_onto_the_network():
+    """Key names as the reference modules register them (das_head.py:103-175, anchor_free...:100-198,
+    recursive_update.py:166-180,243-249, mmdet FPN lateral_convs/fpn_convs, mspn_mmpose.py)."""
+    net = _tiny_net()
+    mine = net.state_dict()
+    cases = {
+        "backbone.top.top.0.conv.weight": "backbone.stem.conv.weight",
+        "backbone.top.top.0.bn.running_var": "backbone.stem.norm.running_var",
+        "backbone.multi_stage_mspn.1.downsample.layer3.0.downsample.bn.bias": "backbone.stages.1.encoder.2.0.shortcut.norm.bias",
+        "backbone.multi_stage_mspn.0.downsample.layer1.0.conv2.weight": "backbone.stages.0.encoder.0.0.spatial.conv.weight",
+        "backbone.multi_stage_mspn.0.upsample.up4.cross_conv.conv.weight": "backbone.stages.0.decoder.3.to_next.conv.weight",
+        "backbone.multi_stage_mspn.0.upsample.up2.out_skip2.bn.weight": "backbone.stages.0.decoder.1.skip_dec.norm.weight",
+        "neck.lateral_convs.0.conv.weight": "neck.lateral.0.conv.weight",
+        "neck.fpn_convs.2.bn.weight": "neck.smooth.2.norm.weight",
+        "neck.fpn_convs.3.conv.weight": "neck.extra.0.conv.weight",
+        "bbox_head.cls_convs.0.conv.bias": "towers.cls_tower.0.conv.bias",
+        "bbox_head.cls_convs.0.gn.weight": "towers.cls_tower.0.norm.weight",
+        "bbox_head.pose_convs.1.conv.conv_offset.weight": "towers.pose_tower.1.offset_mask.weight",
+        "bbox_head.conv_cls.bias": "towers.cls_out.1.bias",
+        "bbox_head.conv_reg_prevs.1.0.gn.bias": "towers.depth_out.0.norm.bias",
+        "bbox_head.conv_poses.0.weight": "towers.uvd_out.1.weight",
+        "bbox_head.conv_centerness_prev.0.conv.weight": "towers.centerness_out.0.conv.weight",
+        "bbox_head.recursive_update_branch.reduction.gn.weight": "towers.reduction.norm.weight",
+        "bbox_head.recursive_update_branch.layer_0.next_level_offset.sampling_offset.weight": "towers.layers.0.sampling_offset.weight",
+        "bbox_head.recursive_update_branch.layer_0.next_level_offset.update_feat_conv.conv.conv_offset.bias": "towers.layers.0.update.offset_mask.bias",
+        "bbox_head.recursive_update_branch.layer_0.next_level_offset.update_feat_conv.gn.bias": "towers.layers.0.update.norm.bias",
+    }
+    for ref, want in cases.items():
+        assert M.reference_key_to_local(ref) == want, ref
+        assert want in mine, want
+    assert M.reference_key_to_local("bbox_head.scales.2.1.scale") == "scales"
+    assert M.reference_key_to_local("bbox_head.loss_cls.something") is None
+
+    # a DCNv2 pack's own weight sits where a plain unit has `.conv`: the loader resolves it against the module tree
+    sd = {"module.bbox_head.reg_convs.1.conv.weight": torch.full_like(mine["towers.reg_tower.1.weight"], 0.25),
+          "module.bbox_head.scales.1.2.scale": torch.tensor(1.5),
+          "module.backbone.top.top.0.bn.num_batches_tracked": torch.tensor(7)}
+    missing, unknown = net.load_reference_state_dict(sd, strict=False)
+    assert not unknown
+    assert float(net.towers.reg_tower[1].weight.detach().mean()) == 0.25
+    assert net.level_scales()[1][2] == 1.5
+    assert "towers.reg_tower.1.weight" not in missing and "backbone.stem.conv.weight" in missing
+    with pytest.raises(KeyError):
+        net.load_reference_state_dict({"bbox_head.unheard_of.weight": torch.zeros(1)})
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("num_layers,dtype", [(1, None), (2, None), (1, torch.bfloat16)])
+def test_network_to_poses_matches_oracle_decode(num_layers, dtype):
+    """image -> DASNet -> DASHeadB200.get_poses (CUDA) against the oracle decode of the very same raw maps."""
+    from das_b200 import synth
+    from das_b200.head import DASHeadB200
+    from oracle import das_oracle as O
+    from util import rank_margin_ulps, rel_err
+
+    J, B = 15, 3
+    strides = (8, 16, 32, 64)
+    test_cfg = dict(nms_pre=12, nms_post=20, nms_thr=0.9, score_thr=0.0)
+    torch.manual_seed(11)
+    net = M.DASNet(num_joints=J, backbone=dict(unit_channels=256, num_stages=2, num_blocks=(1, 1, 1, 1)),
+                   num_layers=num_layers)
+    with torch.no_grad():      # a random-init network is nearly flat: widen the predictors so ranks are well separated
+        for branch, gain in ((net.towers.cls_out, 40.0), (net.towers.centerness_out, 20.0), (net.towers.uvd_out, 30.0),
+                             (net.towers.offset_out, 10.0), (net.towers.depth_out, 10.0)):
+            branch[1].weight.mul_(gain)
+        net.towers.depth_out[1].bias.fill_(3.0)
+        net.scales.copy_(torch.tensor([[1.0, 1.1, 0.9, 1.2]]).repeat(4, 1))
+    net = net.cuda().prepare_inference(dtype)
+    img = synthetic_image(B, 256, 320, seed=21).cuda()
+    with torch.no_grad():
+        outs = net(img)
+    cls, pose, ctr, feats = outs
+    head = DASHeadB200(1, 256, num_joints=J, strides=strides, depth_factor=20, z_norm=50, root_idx=2,
+                       recursive_update=dict(num_heads=4, feat_channels=256, num_layers=num_layers), test_cfg=test_cfg)
+    head.scales = net.level_scales()
+    head.load_refine_weights(net.refine_weights())
+    metas = synth.make_metas(B, cls[0].shape[-2], cls[0].shape[-1], stride=8, seed=9)
+    got = head.get_poses(*outs, metas)
+
+    levels = [dict(cls=cls[l].cpu(), ctr=ctr[l].cpu(), pose_raw=pose[l].cpu(), feats=[f.cpu() for f in feats[l]],
+                   stride=strides[l], scales=head.scales[l]) for l in range(4)]
+    if rank_margin_ulps(levels, test_cfg["nms_pre"]) < 16:
+        pytest.skip("model-produced scores tie within 16 ulp at a rank boundary")
+    layers = [{k: v.cpu() for k, v in lw.items()} for lw in net.refine_weights()]
+    head_cfg = dict(num_joints=J, root_idx=2, depth_factor=20.0, z_norm=50.0, strides=list(strides), num_heads=4,
+                    feat_channels=256, num_layers=num_layers, dim=3)
+    want, _ = O.decode_full(levels, layers, metas, head_cfg, test_cfg)
+    assert sum(len(w["scores"]) for w in want) > 0
+    for g, w in zip(got, want):
+        assert len(g["scores"]) == len(w["scores"])
+        assert np.allclose(g["scores"], w["scores"], rtol=1e-6, atol=0)
+        assert rel_err(g["poses"].cpu().numpy(), w["poses"].numpy()) < 2e-4
+        assert rel_err(g["centers"].cpu().numpy(), w["centers"].numpy()) < 2e-4
+        assert rel_err(g["poses_cam"].cpu().numpy(), w["poses_cam"], floor=10.0) < 2e-4
