@@ -39,8 +39,13 @@ class ConvUnit(nn.Module):
         self.conv = nn.Conv2d(cin, cout, k, stride, k // 2, bias=(norm is None) if bias is None else bias)
         self.norm = nn.BatchNorm2d(cout) if norm == "bn" else nn.GroupNorm(32, cout) if norm == "gn" else None
         self.act = act
+        self.fused = False          # set by DASNet.prepare_inference on CUDA
 
     def forward(self, x):
+        x = x.to(self.conv.weight.dtype)
+        if self.fused and self.act and self.norm is None and x.is_cuda:
+            c = self.conv       # cuDNN's fused conv + bias + ReLU: no separate bias-add / ReLU passes over the map
+            return torch.cudnn_convolution_relu(x, c.weight, c.bias, c.stride, c.padding, c.dilation, 1)
         x = self.conv(x)
         if self.norm is not None:
             x = self.norm(x)
@@ -78,15 +83,20 @@ class DeformUnit(nn.Module):
         nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
         self.bias = nn.Parameter(torch.zeros(cout)) if bias else None
         self.norm = nn.GroupNorm(32, cout)
+        self.tf32 = False           # set by DASNet.prepare_inference: the column GEMM on TF32 tensor cores
 
     def forward(self, x):
         from torchvision.ops import deform_conv2d
-        with torch.autocast(x.device.type, enabled=False):
-            x = x.float()
-            om = self.offset_mask(x)
-            first, second, mask = torch.chunk(om, 3, dim=1)
+        x = x.float()
+        om = self.offset_mask(x)
+        first, second, mask = torch.chunk(om, 3, dim=1)
+        was = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = was or self.tf32
+        try:
             y = deform_conv2d(x, torch.cat((first, second), 1), self.weight, self.bias, padding=1, mask=torch.sigmoid(mask))
-            return F.relu(self.norm(y), inplace=True)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = was
+        return F.relu(self.norm(y), inplace=True)
 
 
 # ------------------------------------------------------------------------------------------ backbone
@@ -101,10 +111,18 @@ class Bottleneck(nn.Module):
         self.spatial = ConvUnit(mid, mid, 3, stride)
         self.expand = ConvUnit(mid, cout, 1, act=False)
         self.shortcut = ConvUnit(cin, cout, 1, stride, act=False) if (stride != 1 or cin != cout) else None
+        self.tail_bias = None       # expand bias (+ shortcut bias) once BatchNorm is folded (prepare_inference)
 
     def forward(self, x):
-        y = self.expand(self.spatial(self.reduce(x)))
-        y = y + (x if self.shortcut is None else self.shortcut(x))
+        h = self.spatial(self.reduce(x))
+        if self.tail_bias is not None and h.is_cuda:
+            # relu(expand(h) + identity) as ONE cuDNN call: conv + residual add + bias + ReLU
+            e = self.expand.conv
+            x = x.to(e.weight.dtype)
+            z = x if self.shortcut is None else F.conv2d(x, self.shortcut.conv.weight, None, self.shortcut.conv.stride)
+            return torch.cudnn_convolution_add_relu(h, e.weight, z, 1.0, self.tail_bias, e.stride, e.padding, e.dilation, 1)
+        y = self.expand(h)
+        y = y + (x.to(y.dtype) if self.shortcut is None else self.shortcut(x))
         return F.relu(y, inplace=True)
 
 
@@ -120,13 +138,24 @@ class UpUnit(nn.Module):
         self.skip_enc = ConvUnit(cin, cin, 1) if feeds_next else None
         self.skip_dec = ConvUnit(width, cin, 1) if feeds_next else None
         self.to_next = ConvUnit(width, stem, 1) if (feeds_next and rung == n_rungs - 1) else None
+        self.merge_bias = None      # lateral bias (+ from_coarse bias) once BatchNorm is folded (prepare_inference)
 
     def forward(self, enc, coarse):
-        y = self.lateral(enc)
-        if self.from_coarse is not None:
-            up = F.interpolate(coarse, size=enc.shape[-2:], mode="bilinear", align_corners=True)
-            y = y + self.from_coarse(up)
-        y = F.relu(y, inplace=True)
+        if self.merge_bias is not None and enc.is_cuda:
+            l = self.lateral.conv
+            enc = enc.to(l.weight.dtype)
+            if self.from_coarse is None:
+                y = torch.cudnn_convolution_relu(enc, l.weight, self.merge_bias, l.stride, l.padding, l.dilation, 1)
+            else:
+                up = F.interpolate(coarse, size=enc.shape[-2:], mode="bilinear", align_corners=True)
+                z = F.conv2d(up.to(l.weight.dtype), self.from_coarse.conv.weight, None)
+                y = torch.cudnn_convolution_add_relu(enc, l.weight, z, 1.0, self.merge_bias, l.stride, l.padding, l.dilation, 1)
+        else:
+            y = self.lateral(enc)
+            if self.from_coarse is not None:
+                up = F.interpolate(coarse, size=enc.shape[-2:], mode="bilinear", align_corners=True)
+                y = y + self.from_coarse(up)
+            y = F.relu(y, inplace=True)
         s1 = self.skip_enc(enc) if self.skip_enc is not None else None
         s2 = self.skip_dec(y) if self.skip_dec is not None else None
         nxt = self.to_next(y) if self.to_next is not None else None
@@ -294,14 +323,17 @@ class DASTowers(nn.Module):
 
     def forward(self, x):
         cls_feat, reg_feat, pose_feat = self.cls_tower(x), self.reg_tower(x), self.pose_tower(x)
-        cls = self.cls_out(cls_feat).float()
-        ctr = self.centerness_out(reg_feat).float()
-        off, dep, uvd = self.offset_out(reg_feat), self.depth_out(reg_feat), self.uvd_out(pose_feat)
+
+        def predict(branch, feat):                # 3x3+GN+ReLU unit in the network dtype, the 1x1 predictor always in fp32
+            return branch[1](branch[0](feat).float())
+        cls = predict(self.cls_out, cls_feat)
+        ctr = predict(self.centerness_out, reg_feat)
+        off, dep, uvd = predict(self.offset_out, reg_feat), predict(self.depth_out, reg_feat), predict(self.uvd_out, pose_feat)
         if self.with_sigma:
-            sig = self.sigma_out(pose_feat)
+            sig = predict(self.sigma_out, pose_feat)
         else:                                     # sigma is never read at test time (das_head.py:732)
             sig = uvd.new_zeros(uvd.shape)
-        pose = torch.cat((off, dep, uvd, sig), 1).float().contiguous()
+        pose = torch.cat((off, dep, uvd, sig), 1).contiguous()
         f = self.reduction(pose_feat)
         feats = []
         for layer in self.layers:
@@ -330,18 +362,33 @@ class DASNet(nn.Module):
                                 num_layers, num_heads, with_sigma=with_sigma)
         # learnable per-level Scale factors for (offset, depth, uv, d), init 1 (das_head.py:171-173)
         self.scales = nn.Parameter(torch.ones(len(self.strides), 4))
-        self.autocast_dtype: Optional[torch.dtype] = None
+        self.compute_dtype: Optional[torch.dtype] = None
 
     @torch.no_grad()
     def prepare_inference(self, dtype: Optional[torch.dtype] = None):
-        """eval mode, BatchNorm folded, weights in channels-last; `dtype=torch.bfloat16` runs the convolutions under
-        autocast (predictor maps and refinement features are still produced in fp32)."""
+        """eval mode, BatchNorm folded, channels-last weights, cuDNN fused conv+bias(+residual)+ReLU calls, DCNv2 column
+        GEMMs on TF32 tensor cores; `dtype=torch.bfloat16` stores and runs the plain convolutions in bf16 (the 1x1
+        predictors, DCNv2 and the refinement features stay fp32)."""
         self.eval()
         for m in self.modules():
             if isinstance(m, ConvUnit):
                 m.fold_batchnorm()
         self.to(memory_format=torch.channels_last)
-        self.autocast_dtype = dtype
+        self.compute_dtype = dtype
+        for m in self.modules():
+            if isinstance(m, ConvUnit):
+                m.fused = True
+                if dtype is not None:
+                    m.to(dtype)                   # conv (+ GroupNorm affine) in the network dtype; predictors / DCNv2 stay fp32
+            elif isinstance(m, DeformUnit):
+                m.tf32 = True
+        for m in self.modules():
+            if isinstance(m, Bottleneck):
+                b = m.expand.conv.bias
+                m.tail_bias = (b if m.shortcut is None else b + m.shortcut.conv.bias).detach().clone()
+            elif isinstance(m, UpUnit):
+                b = m.lateral.conv.bias
+                m.merge_bias = (b if m.from_coarse is None else b + m.from_coarse.conv.bias).detach().clone()
         return self
 
     def level_scales(self) -> List[Tuple[float, float, float, float]]:
@@ -353,10 +400,8 @@ class DASNet(nn.Module):
 
     def forward(self, img):
         img = img.contiguous(memory_format=torch.channels_last)
-        with torch.autocast(img.device.type, dtype=self.autocast_dtype or torch.bfloat16,
-                            enabled=self.autocast_dtype is not None):
-            pyramid = self.neck(self.backbone(img))
-            per_level = [self.towers(x) for x in pyramid]
+        pyramid = self.neck(self.backbone(img))
+        per_level = [self.towers(x) for x in pyramid]
         cls, pose, ctr, feats = (list(t) for t in zip(*per_level))
         return cls, pose, ctr, feats
 

@@ -194,3 +194,33 @@ def test_network_to_poses_matches_oracle_decode(num_layers, dtype):
         assert rel_err(g["poses"].cpu().numpy(), w["poses"].numpy()) < 2e-4
         assert rel_err(g["centers"].cpu().numpy(), w["centers"].numpy()) < 2e-4
         assert rel_err(g["poses_cam"].cpu().numpy(), w["poses_cam"], floor=10.0) < 2e-4
+
+
+@pytest.mark.gpu
+def test_fused_inference_path_matches_plain_modules():
+    """prepare_inference (BatchNorm folded, cuDNN fused conv+bias(+residual)+ReLU, TF32 DCNv2 GEMM, optional bf16)
+    computes the same function as the plain module graph."""
+    torch.manual_seed(4)
+    net = M.DASNet(backbone=dict(unit_channels=128, num_stages=2, num_blocks=(2, 1, 1, 1)), fpn_channels=128).cuda().eval()
+    with torch.no_grad():
+        for m in net.modules():      # non-trivial BatchNorm statistics and deformable offsets
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1)
+                m.running_var.uniform_(0.5, 1.5)
+                m.bias.normal_(0, 0.1)
+            if isinstance(m, M.DeformUnit):
+                m.offset_mask.weight.normal_(0, 0.01)
+        x = synthetic_image(2, 192, 256, seed=8).cuda()
+        plain = net(x)
+        net.prepare_inference()
+        fused = net(x)
+
+        def worst(a, b):
+            return max(float((p - q).abs().max()) / max(float(q.abs().max()), 1e-6) for p, q in zip(a, b))
+        assert any(m.tail_bias is not None for m in net.modules() if isinstance(m, M.Bottleneck))
+        assert worst(fused[0], plain[0]) < 1e-2 and worst(fused[1], plain[1]) < 1e-2
+        assert worst([f[0] for f in fused[3]], [f[0] for f in plain[3]]) < 1e-2
+        net.prepare_inference(torch.bfloat16)
+        low = net(x)
+        assert low[0][0].dtype == torch.float32 and low[3][0][0].dtype == torch.float32
+        assert worst([f[0] for f in low[3]], [f[0] for f in plain[3]]) < 0.15
