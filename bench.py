@@ -151,9 +151,53 @@ def time_cpu_baseline(budget_s=15.0, chunk=4):
         el = time.perf_counter() - t0
         if el >= budget_s or n >= 64:
             break
-    return dict(value=n / el, unit=UNIT, cores=torch.get_num_threads(), kind="port",
-                sample=f"{n} images of the {WORKLOAD['name']} workload in chunks of {chunk} "
-                       f"(dense refinement + eval tail + get_poses + OKS-NMS + back-projection), {el:.1f} s")
+    out = dict(value=n / el, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+               sample=f"{n} images of the {WORKLOAD['name']} workload in chunks of {chunk} "
+                      f"(dense refinement + eval tail + get_poses + OKS-NMS + back-projection), {el:.1f} s")
+    out["split_ms_per_image"] = cpu_split(levels, layers, metas, chunk)
+    if torch.cuda.is_available():
+        out["eager_gpu"] = time_eager_gpu(layers, chunk)
+    return out
+
+
+def cpu_split(levels, layers, metas, chunk):
+    """where the host time goes -- dense refinement + eval tail / get_poses incl. OKS-NMS / back-projection."""
+    from oracle import das_oracle as O
+    hc = WORKLOAD["head"].as_dict()
+    t0 = time.perf_counter()
+    pps = [O.head_eval_tail(lv["pose_raw"], lv["feats"], layers, lv["scales"], num_joints=hc["num_joints"],
+                            num_heads=hc["num_heads"], root_idx=hc["root_idx"], depth_factor=hc["depth_factor"],
+                            z_norm=hc["z_norm"], stride=lv["stride"]) for lv in levels]
+    t1 = time.perf_counter()
+    res = O.get_poses([lv["cls"] for lv in levels], pps, [lv["ctr"] for lv in levels], metas, TEST_CFG,
+                      [lv["stride"] for lv in levels], hc["num_joints"])
+    t2 = time.perf_counter()
+    for r, m in zip(res, metas):
+        O.backproject(r["poses"].numpy(), m["cam"]["K"], m["cam"]["R"], m["cam"]["t"], hc["root_idx"])
+    t3 = time.perf_counter()
+    return dict(refinement_and_tail=(t1 - t0) / chunk * 1e3, get_poses_and_nms=(t2 - t1) / chunk * 1e3,
+                backprojection=(t3 - t2) / chunk * 1e3)
+
+
+def time_eager_gpu(layers, chunk, budget_s=6.0):
+    """SURVEY 8(d) secondary baseline: the same reference-order algorithm (dense refinement in eager PyTorch, per-image
+    python decode with host NumPy OKS-NMS and its .cpu() syncs) with the tensors on the B200."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    levels, metas = make_cpu_sample(chunk, 99)
+    levels = synth.levels_to(levels, dev)
+    layers = synth.layers_to(layers, dev)
+    cpu_reference_step(levels, layers, metas, WORKLOAD["head"])
+    torch.cuda.synchronize()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        cpu_reference_step(levels, layers, metas, WORKLOAD["head"])
+        torch.cuda.synchronize()
+        n += chunk
+        el = time.perf_counter() - t0
+        if el >= budget_s or n >= 256:
+            break
+    return dict(value=n / el, unit=UNIT, kind="port, eager PyTorch on the GPU",
+                sample=f"{n} images in chunks of {chunk}, {el:.1f} s")
 
 
 def run_reference(args):

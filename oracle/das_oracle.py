@@ -40,18 +40,18 @@ COCO17_SIGMAS = np.array([.26, .25, .25, .35, .35, .79, .79, .72, .72, .62, .62,
 # --------------------------------------------------------------------------
 # point grid
 # --------------------------------------------------------------------------
-def point_grid(h: int, w: int, stride: int, dtype=torch.float32) -> torch.Tensor:
+def point_grid(h: int, w: int, stride: int, dtype=torch.float32, device=None) -> torch.Tensor:
     """[H*W, 2] image-space anchor of every cell, raster order i = y*W + x.
 
     das_head.py:276-278: (x*stride, y*stride) + stride // 2.
     """
-    ys, xs = torch.meshgrid(torch.arange(h, dtype=dtype), torch.arange(w, dtype=dtype), indexing="ij")
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=dtype, device=device), torch.arange(w, dtype=dtype, device=device), indexing="ij")
     return torch.stack((xs.reshape(-1) * stride, ys.reshape(-1) * stride), dim=-1) + stride // 2
 
 
-def cell_centres(h: int, w: int, dtype=torch.float32) -> torch.Tensor:
+def cell_centres(h: int, w: int, dtype=torch.float32, device=None) -> torch.Tensor:
     """[2, H, W] feature-space cell centres (x+0.5, y+0.5); recursive_update.py:211-218."""
-    ys, xs = torch.meshgrid(torch.arange(h, dtype=dtype), torch.arange(w, dtype=dtype), indexing="ij")
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=dtype, device=device), torch.arange(w, dtype=dtype, device=device), indexing="ij")
     return torch.stack((xs, ys), dim=0) + 0.5
 
 
@@ -90,7 +90,7 @@ def progressive_sample(uvd, samp_off, joint_conf, num_joints: int, num_heads: in
     b = uvd.shape[0]
     h, w = uvd.shape[-2:]
     bj = b * num_joints
-    pts = cell_centres(h, w, uvd.dtype)
+    pts = cell_centres(h, w, uvd.dtype, uvd.device)
     wh = uvd.new_tensor([w, h]).view(1, 2, 1, 1)
 
     uvd = uvd.view(bj, dim, h, w)
@@ -240,11 +240,11 @@ def decode_image(cls_l, pose_l, ctr_l, strides, scale_factor, cfg, num_joints,
     all_c, all_p, all_s, all_lvl, all_idx = [], [], [], [], []
     for lvl, (cls, pose, ctr, stride) in enumerate(zip(cls_l, pose_l, ctr_l, strides)):
         h, w = cls.shape[-2:]
-        pts = point_grid(h, w, stride, pose.dtype)
+        pts = point_grid(h, w, stride, pose.dtype, pose.device)
         sc = cls.permute(1, 2, 0).reshape(-1, 1).sigmoid()
         ct = ctr.permute(1, 2, 0).reshape(-1).sigmoid()
         pp = pose.permute(1, 2, 0).reshape(-1, pose.shape[0])
-        idx = torch.arange(h * w)
+        idx = torch.arange(h * w, device=pose.device)
         if nms_pre > 0 and sc.shape[0] > nms_pre:
             rank = (sc * ct[:, None]).max(dim=1)[0]
             if peak_kernel and peak_kernel > 1:
@@ -274,7 +274,7 @@ def decode_image(cls_l, pose_l, ctr_l, strides, scale_factor, cfg, num_joints,
         all_c.append(centre)
         all_p.append(joints)
         all_s.append(sc[:, 0] * ct)
-        all_lvl.append(torch.full((len(idx),), lvl, dtype=torch.int64))
+        all_lvl.append(torch.full((len(idx),), lvl, dtype=torch.int64, device=pose.device))
         all_idx.append(idx.to(torch.int64))
     centres, poses = torch.cat(all_c), torch.cat(all_p)
     scores, lvls, idxs = torch.cat(all_s), torch.cat(all_lvl), torch.cat(all_idx)
@@ -289,16 +289,16 @@ def decode_image(cls_l, pose_l, ctr_l, strides, scale_factor, cfg, num_joints,
     if nms_post > 0 and len(scores) > 0:
         hi = poses[..., :2].max(1)[0]
         lo = poses[..., :2].min(1)[0]
-        areas = (hi - lo).prod(-1).numpy()
-        kp = torch.cat([poses[..., :2], torch.ones_like(poses[..., :1])], -1).reshape(len(poses), -1).numpy()
+        areas = (hi - lo).prod(-1).cpu().numpy()
+        kp = torch.cat([poses[..., :2], torch.ones_like(poses[..., :1])], -1).reshape(len(poses), -1).cpu().numpy()
         if cfg.get("nms_type", "hard") == "hard":
-            keep = oks_nms(scores.numpy(), kp, areas, cfg.get("nms_thr", 0.9), stable=stable).tolist()
+            keep = oks_nms(scores.cpu().numpy(), kp, areas, cfg.get("nms_thr", 0.9), stable=stable).tolist()
             keep = keep[:cfg.get("nms_post", 100)]
         else:                                           # das_head.py:789-790
-            keep = soft_oks_nms(scores.numpy(), kp, areas, cfg.get("nms_thr", 0.9), cfg.get("nms_post", 100),
+            keep = soft_oks_nms(scores.cpu().numpy(), kp, areas, cfg.get("nms_thr", 0.9), cfg.get("nms_post", 100),
                                 stable=stable).tolist()
         scores, poses, centres, lvls, idxs = scores[keep], poses[keep], centres[keep], lvls[keep], idxs[keep]
-    out = dict(scores=scores, poses=poses, vis=torch.ones(poses.shape[:2]), centers=centres,
+    out = dict(scores=scores, poses=poses, vis=torch.ones(poses.shape[:2], device=poses.device), centers=centres,
                level=lvls, index=idxs)
     out.update(cand)
     return out
@@ -314,7 +314,7 @@ def get_poses(cls_scores, pose_preds, centernesses, img_metas, cfg, strides, num
                          [c[b] for c in centernesses], strides, meta["scale_factor"], cfg,
                          num_joints, stable=stable, peak_kernel=peak_kernel)
         r["image_paths"] = [meta.get("filename", "")]
-        r["scores_list"] = r["scores"].numpy().tolist()
+        r["scores_list"] = r["scores"].cpu().numpy().tolist()
         res.append(r)
     return res
 
@@ -366,6 +366,6 @@ def decode_full(levels, layers, img_metas, head_cfg, test_cfg, stable: bool = Fa
     for r, meta in zip(res, img_metas):
         cam = meta.get("cam")
         if cam is not None:
-            r["poses_cam"], r["poses_world"] = backproject(r["poses"].numpy(), cam["K"], cam["R"], cam["t"],
+            r["poses_cam"], r["poses_world"] = backproject(r["poses"].cpu().numpy(), cam["K"], cam["R"], cam["t"],
                                                            head_cfg["root_idx"])
     return res, pose_preds
