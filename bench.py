@@ -36,6 +36,8 @@ WORKLOADS = {
     "mupots": dict(name="mupots_decode_B64_J17_128x208_K20_L3", batch=64, h=128, w=208, stride=8, K=20, head=synth.MUPOTS17),
     # BASELINE config #4: crowded scene, 256x416 map, K=64
     "crowded": dict(name="crowded_decode_B32_J15_256x416_K64_L1", batch=32, h=256, w=416, stride=8, K=64, head=synth.PANOPTIC),
+    # BASELINE config #1: one image (latency-bound: judge ms_per_step, not the roofline fraction)
+    "single": dict(name="single_image_decode_B1_J15_128x208_K10_L1", batch=1, h=128, w=208, stride=8, K=10, head=synth.PANOPTIC),
     # BASELINE config #5: images through the whole network (run_model); h, w are IMAGE sizes here
     "e2e_model": dict(name="e2e_model_B16_per_gpu_1024x1664_J15_K10_L1", batch=16, h=1024, w=1664, stride=8, K=10, head=synth.PANOPTIC),
 }
@@ -382,8 +384,8 @@ def run_b200(args):
         host_out = plans[0].alloc_host_out(pinned=True)
         n_e2e = max(min(args.steps, args.e2e_steps), 1)
 
-        def time_host(zero_copy):
-            plans[0].set_host_mode(zero_copy)
+        def time_host(zero_copy, row_cache=True):
+            plans[0].set_host_mode(zero_copy, row_cache)
             for _ in range(2):
                 plans[0].run_host(host_levels, metas, host_out)
             barrier()
@@ -399,14 +401,17 @@ def run_b200(args):
             return el, plans[0].h2d_explicit_bytes
 
         el_bulk, bytes_bulk = time_host(False)
+        el_nc, _ = time_host(True, False)
         el_zc, bytes_zc = time_host(True)
         sparse_ub = B * K * J * 37 * C * 4 + (B * K * (3 + J * 33 * 3) * 32 if head.num_layers == 1 else 0)   # rows + pose sectors
         e2e = dict(value=world * B * n_e2e / el_zc, unit=UNIT, h2d_bytes_per_step=int(bytes_zc + sparse_ub),
                    d2h_bytes_per_step=plans[0].d2h_bytes, steps=n_e2e, ms_per_step=el_zc / n_e2e * 1e3,
                    h2d_explicit_bytes=int(bytes_zc), h2d_in_place_bytes_upper_bound=int(sparse_ub),
-                   api="das_plan_run_host, host_mode 1: pinned host inputs; logit planes H2D-copied, pose / feature maps read "
-                       "in place over PCIe by the gather kernels (the decode touches ~5 % of them) -> graph replay -> D2H of "
-                       "the packed pose lists",
+                   api="das_plan_run_host, host_mode 2: pinned host inputs; logit planes H2D-copied, pose / feature maps read "
+                       "in place over PCIe by the gather kernels (the decode touches ~5 % of them), every distinct row of the "
+                       "sampling phase copied once into a device row cache -> graph replay -> D2H of the packed pose lists",
+                   no_row_cache=dict(value=world * B * n_e2e / el_nc, ms_per_step=el_nc / n_e2e * 1e3,
+                                     api="das_plan_run_host, host_mode 1: as above without the row-cache pass"),
                    bulk_copy=dict(value=world * B * n_e2e / el_bulk, ms_per_step=el_bulk / n_e2e * 1e3,
                                   h2d_bytes_per_step=int(bytes_bulk),
                                   api="das_plan_run_host, host_mode 0: every input map H2D-copied (2.39 GB per step)"))
@@ -581,7 +586,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="panoptic", choices=sorted(WORKLOADS),
-                    help="panoptic = BASELINE config #2 (the metric; default); mupots = #3; crowded = #4; e2e_model = #5 (network + decode)")
+                    help="panoptic = BASELINE config #2 (the metric; default); single = #1 (B=1 latency); mupots = #3; crowded = #4; e2e_model = #5 (network + decode)")
     args = ap.parse_args()
     WORKLOAD.clear()
     WORKLOAD.update(WORKLOADS[args.workload])

@@ -67,6 +67,8 @@ SIGNATURES = {
     "das_refine_tc": (C.c_int, [_VP, C.POINTER(Levels), C.POINTER(DecodeCfg), _VP, _VP, C.c_int32, _VP, _VP, _VP, _VP, _VP,
                                 C.c_int32, _VP]),
     "das_pack_tc_panels": (C.c_int, [C.POINTER(DecodeCfg), _VP, _VP, _VP]),
+    "das_refine_row_cache": (C.c_int, [C.POINTER(DecodeCfg), _VP, _VP, _VP, _VP, C.c_int32, _VP, C.c_int32, _VP]),
+    "das_row_cache_table_bytes": (C.c_int64, [C.c_int32]),
     "das_tc_set_debug_buffer": (C.c_int, [_VP]),
     "das_tc_panel_bytes": (C.c_int64, [C.POINTER(DecodeCfg)]),
     "das_plan_set_refine_mode": (C.c_int, [_VP, C.c_int32]),

@@ -67,6 +67,16 @@ __device__ __forceinline__ int block_sum_1024(int v, int* red /* >= 33 ints smem
 
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+// One 256-bit read-only load (LDG.E.256, sm_100+): a 32-byte record in a single request instead of two 128-bit ones.
+struct F8 { float4 lo, hi; };
+__device__ __forceinline__ F8 ldg_f8(const float4* p32) {
+    F8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+                 : "l"(p32));
+    return r;
+}
+
 // streaming 128-bit load that does not pollute L1 (score planes are read once per pass)
 __device__ __forceinline__ float4 ldg_f4_stream(const float* p) {
     float4 r;

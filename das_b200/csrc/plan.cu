@@ -2,6 +2,7 @@
 // replay -- score scan + top-k, (dense layers 1..L-1,) sparse last-layer refinement + assembly,
 // OKS-NMS + back-projection -- plus the host-buffer entry used for end-to-end measurements.
 #include <algorithm>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -49,7 +50,12 @@ struct das_plan {
     // host-entry staging
     das_levels staging{};
     bool staging_ready = false;
-    int host_mode = 0;                // das_plan_run_host: 0 = bulk H2D of every map, 1 = sparse maps read in place (zero copy)
+    int host_mode = 0;                // das_plan_run_host: 0 = bulk H2D of every map, 1 = sparse maps read in place (zero copy),
+                                      // 2 = zero copy + device row cache in front of the tensor-core sampling phase
+    bool rc_active = false;           // the row-cache pass is part of the enqueued / captured work
+    void* rc_table = nullptr;
+    float* rc_rows = nullptr;
+    int rc_bits = 0, rc_cap = 0;
     int64_t h2d_explicit = 0;         // bytes das_plan_run_host copies explicitly per call in the current host_mode
     int64_t h2d_bytes = 0, d2h_bytes = 0;
     unsigned char* out_block = nullptr;   // all out_* buffers live in this one allocation (one D2H / one all-gather)
@@ -223,6 +229,8 @@ extern "C" void das_plan_destroy(das_plan* p) {
                     p->out_block, p->scratch, p->work_counter, p->d_scale_xy, p->d_cam,
                     p->proj, p->d_prev_ptrs, p->tc_panels, p->item_heads, p->item_asm, p->valid_list};
     for (void* q : ptrs) if (q) cudaFree(q);
+    if (p->rc_table) cudaFree(p->rc_table);
+    if (p->rc_rows) cudaFree(p->rc_rows);
     for (int k = 0; k < DAS_MAX_LAYERS; ++k) if (p->wpack[k]) cudaFree(p->wpack[k]);
     for (int k = 0; k < DAS_MAX_LAYERS; ++k) if (p->dense_panels[k]) cudaFree(p->dense_panels[k]);
     for (int i = 0; i < 2; ++i)
@@ -318,6 +326,11 @@ static int enqueue(das_plan* p, cudaStream_t st, int* n_launch, bool events) {
         DAS_TRY(das_refine_heads(p->d_levels, &p->bound, &c, w, prev, p->d_scale_xy, p->buf.cand_score, p->buf.cand_index, p->CT,
                                  p->item_heads, p->item_asm, p->buf.cand_center, p->valid_list, p->work_counter, st));
         DAS_TRY(mark(3));
+        if (p->rc_active) {
+            DAS_TRY(das_refine_row_cache(&c, p->item_heads, p->valid_list, p->work_counter + 1, p->rc_table, p->rc_bits,
+                                         p->rc_rows, p->rc_cap, st));
+            ++n;
+        }
         DAS_TRY(das_refine_tc(p->d_levels, &p->bound, &c, w, p->tc_panels, p->CT, p->item_heads, p->item_asm, p->valid_list,
                               p->work_counter + 1, p->buf.cand_pose,
                               p->refine_mode == 1 ? 1 : (p->refine_mode == 2 ? 0 : p->refine_mode - 2), st));
@@ -431,8 +444,34 @@ extern "C" int64_t das_plan_h2d_explicit_bytes(const das_plan* p) { return p ? p
 extern "C" int das_plan_set_host_mode(das_plan* p, int32_t mode) {
     using namespace das;
     DAS_REQUIRE(p, DAS_ERR_ARG, "null plan");
-    DAS_REQUIRE(mode == 0 || mode == 1, DAS_ERR_ARG, "host mode %d", mode);
+    DAS_REQUIRE(mode >= 0 && mode <= 2, DAS_ERR_ARG, "host mode %d", mode);
     p->host_mode = mode;
+    return DAS_OK;
+}
+
+// Switch the row-cache pass on/off for the following runs (buffers are allocated on first use; a captured graph that
+// was built with the other setting is dropped and re-captured by the next das_plan_run).
+static int set_row_cache(das_plan* p, bool on) {
+    using namespace das;
+    on = on && p->cfg.refine && p->refine_mode != 0 && p->tc_panels;
+    if (on && !p->rc_table) {
+        const long long records = static_cast<long long>(p->B) * p->CT * p->cfg.num_joints * 32;
+        int bits = 10;
+        while (bits < 26 && (1ll << bits) < 2 * records) ++bits;
+        long long cap = std::min<long long>(records, 262144);
+        if (const char* e = std::getenv("DAS_ROW_CACHE_ROWS")) cap = std::max<long long>(1, std::min<long long>(records, std::atoll(e)));
+        unsigned char* t = nullptr;
+        DAS_TRY(dev_alloc(&t, static_cast<size_t>(das_row_cache_table_bytes(bits))));
+        p->rc_table = t;
+        DAS_TRY(dev_alloc(&p->rc_rows, static_cast<size_t>(cap) * p->cfg.feat_channels));
+        p->rc_bits = bits;
+        p->rc_cap = static_cast<int>(cap);
+    }
+    if (on != p->rc_active) {
+        p->rc_active = on;
+        if (p->exec) { cudaGraphExecDestroy(p->exec); p->exec = nullptr; }
+        if (p->exec_prof) { cudaGraphExecDestroy(p->exec_prof); p->exec_prof = nullptr; }
+    }
     return DAS_OK;
 }
 extern "C" int64_t das_plan_d2h_bytes(const das_plan* p) { return p ? p->d2h_bytes : 0; }
@@ -450,7 +489,7 @@ extern "C" int das_plan_run_host(das_plan* p, const das_levels* levels, const fl
     // feature maps (K cells and their bilinear corners per image).  Pinned host memory is device-addressable
     // (unified addressing), so those sparse maps are read IN PLACE over PCIe by the gather kernels instead of being
     // copied wholesale; only the logit planes are staged.
-    bool zero_copy = p->host_mode == 1;
+    bool zero_copy = p->host_mode >= 1;
     // dense layers (num_layers > 1) read every cell of the pose map and of the feature maps of layers 0..L-2: those
     // are bulk-copied in either mode; only maps that are touched sparsely are read in place
     const bool pose_sparse = L <= 1;
@@ -483,6 +522,7 @@ extern "C" int das_plan_run_host(das_plan* p, const das_levels* levels, const fl
         }
         p->staging_ready = true;
     }
+    DAS_TRY(set_row_cache(p, zero_copy && p->host_mode == 2));
     das_levels run = p->staging;
     int64_t copied = 0;
     for (int l = 0; l < p->shape.n_levels; ++l) {

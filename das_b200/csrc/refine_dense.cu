@@ -109,7 +109,8 @@ dense_sample_kernel(const DenseParams p) {
         const float4* __restrict__ pS = reinterpret_cast<const float4*>(p.proj + static_cast<size_t>(bj) * HW * 8);
         const float4* __restrict__ pOC = reinterpret_cast<const float4*>(p.proj + (static_cast<size_t>(p.B) * J + bj) * HW * 8);
         (void)j;
-        const float4 s0 = __ldg(pS + 2 * pix), s1 = __ldg(pS + 2 * pix + 1), om = __ldg(pOC + 2 * pix);
+        const F8 sp = ldg_f8(pS + 2 * pix);
+        const float4 s0 = sp.lo, s1 = sp.hi, om = __ldg(pOC + 2 * pix);
         const float ox = om.x, oy = om.y;
         float hx[2 * NH], hy[2 * NH];
         {
@@ -122,7 +123,8 @@ dense_sample_kernel(const DenseParams p) {
                 if (!corner_ok(ct, k, W, H)) continue;
                 const float wk = corner_wgt(ct, k);
                 const float4* c = pS + 2 * corner_pix(ct, k, W);
-                const float4 a0 = __ldg(c), a1 = __ldg(c + 1);
+                const F8 a = ldg_f8(c);
+                const float4 a0 = a.lo, a1 = a.hi;
                 s[0] = __fadd_rn(s[0], __fmul_rn(a0.x, wk)); s[1] = __fadd_rn(s[1], __fmul_rn(a0.y, wk));
                 s[2] = __fadd_rn(s[2], __fmul_rn(a0.z, wk)); s[3] = __fadd_rn(s[3], __fmul_rn(a0.w, wk));
                 s[4] = __fadd_rn(s[4], __fmul_rn(a1.x, wk)); s[5] = __fadd_rn(s[5], __fmul_rn(a1.y, wk));
@@ -147,7 +149,8 @@ dense_sample_kernel(const DenseParams p) {
                 if (!corner_ok(ch, k, W, H)) continue;
                 const float wk = corner_wgt(ch, k);
                 const float4* c = pOC + 2 * corner_pix(ch, k, W);
-                const float4 oo = __ldg(c), cc = __ldg(c + 1);      // {O.x,O.y,O.z,cf.x} {cf.y,cf.z,-,-}
+                const F8 rec = ldg_f8(c);                          // {O.x,O.y,O.z,cf.x} {cf.y,cf.z,-,-}
+                const float4 oo = rec.lo, cc = rec.hi;
                 cf[0] = __fadd_rn(cf[0], __fmul_rn(oo.w, wk)); cf[1] = __fadd_rn(cf[1], __fmul_rn(cc.x, wk));
                 cf[2] = __fadd_rn(cf[2], __fmul_rn(cc.y, wk));
                 v[0] = __fadd_rn(v[0], __fmul_rn(oo.x, wk)); v[1] = __fadd_rn(v[1], __fmul_rn(oo.y, wk));

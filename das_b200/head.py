@@ -295,10 +295,12 @@ class DecodePlan:
         """Typed views into a copy of an output block (this rank's, or one gathered from a peer rank)."""
         return block_views(block, self.batch, self.out_slots, self.cfg.num_joints)
 
-    def set_host_mode(self, zero_copy: bool):
+    def set_host_mode(self, zero_copy: bool, row_cache: bool = True):
         """run_host policy: False = bulk H2D of every map; True = copy only the logit planes and let the gather
-        kernels read the (sparsely used) pose / feature maps in place from pinned host memory."""
-        _lib.check(self.lib.das_plan_set_host_mode(self._plan, int(bool(zero_copy))), "das_plan_set_host_mode")
+        kernels read the (sparsely used) pose / feature maps in place from pinned host memory; `row_cache` adds the
+        pass that copies every distinct feature row of the sampling phase to the device once."""
+        mode = (2 if row_cache else 1) if zero_copy else 0
+        _lib.check(self.lib.das_plan_set_host_mode(self._plan, mode), "das_plan_set_host_mode")
 
     @property
     def h2d_explicit_bytes(self) -> int:

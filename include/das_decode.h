@@ -147,6 +147,15 @@ int das_refine_tc(const das_levels* d_levels, const das_levels* h_levels, const 
                   const float* row_records, const float* item_records, const int32_t* valid_list,
                   const int32_t* n_valid, float* cand_pose, int32_t split, void* stream);
 int das_pack_tc_panels(const das_decode_cfg* cfg, const float* packed_weights, void* panels, void* stream);
+/* Host zero-copy mode only (feature maps read in place from pinned host memory): between das_refine_heads and
+ * das_refine_tc, copy every DISTINCT row the row records point at into `rows` ([max_rows][256] floats, device) once and
+ * re-point the records at the copies, so PCIe carries each row once (on device memory L2 already gives that re-use).
+ * table: das_row_cache_table_bytes(table_bits) bytes of device scratch, cleared here; 2^table_bits should be at least
+ * twice the number of row records.  A full row buffer leaves the remaining records pointing at the host. */
+int das_refine_row_cache(const das_decode_cfg* cfg, float* row_records, const int32_t* valid_list,
+                         const int32_t* n_valid, void* table, int32_t table_bits, float* rows, int32_t max_rows,
+                         void* stream);
+int64_t das_row_cache_table_bytes(int32_t table_bits);
 int64_t das_tc_panel_bytes(const das_decode_cfg* cfg);
 /* profiling aid: per-CTA cycle counters of das_refine_tc's warp roles ([148][16] int64 device buffer; NULL = off) */
 int das_tc_set_debug_buffer(long long* dev_buf);
@@ -216,7 +225,8 @@ int das_plan_run_host(das_plan* plan, const das_levels* levels, const float* sca
 int64_t das_plan_h2d_bytes(const das_plan* plan);
 /* das_plan_run_host transfer policy: 0 = bulk H2D copy of every input map (default); 1 = only the logit planes are
  * copied, the pose and feature maps (of which the decode touches ~5 %) are read in place from PINNED host memory
- * by the gather kernels (falls back to 0 for pageable memory). */
+ * by the gather kernels (falls back to 0 for pageable memory); 2 = as 1, plus das_refine_row_cache in front of the
+ * tensor-core sampling phase so that every distinct feature row crosses PCIe once. */
 int das_plan_set_host_mode(das_plan* plan, int32_t mode);
 int64_t das_plan_h2d_explicit_bytes(const das_plan* plan);   /* bytes explicitly copied by the last run_host */
 int64_t das_plan_d2h_bytes(const das_plan* plan);

@@ -246,6 +246,21 @@ def test_host_entry_equals_device_entry():
     assert plan.h2d_explicit_bytes < plan.h2d_bytes // 20
     for k in out:
         assert torch.equal(out[k], out2[k]), k
+    # ... without the row cache, with a row cache too small for the distinct rows, and back to the cached default:
+    # the same bits every time (a full cache leaves the remaining records pointing at the host rows)
+    for row_cache, cap in ((False, None), (True, "7"), (True, None)):
+        if cap is not None:
+            os.environ["DAS_ROW_CACHE_ROWS"] = cap
+        p2 = util.make_plan(case, tc, refine=True)
+        os.environ.pop("DAS_ROW_CACHE_ROWS", None)
+        p2.set_host_mode(True, row_cache=row_cache)
+        o = p2.alloc_host_out()
+        for _ in range(3):                     # eager first run, then graph capture + replay
+            for t in o.values():
+                t.zero_()
+            p2.run_host(host_levels, case["metas"], o)
+            for k in out:
+                assert torch.equal(out[k], o[k]), (row_cache, cap, k)
     # pageable inputs silently fall back to staging copies
     pageable = [dict(cls=lv["cls"].clone(), ctr=lv["ctr"].clone(), pose=lv["pose_raw"].clone(),
                      feats=[f.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2) for f in lv["feats"]], scales=lv["scales"])
