@@ -51,6 +51,11 @@ class Buffers(C.Structure):
                 ("out_cam", C.c_void_p), ("out_world", C.c_void_p)]
 
 
+class RowCache(C.Structure):
+    _fields_ = [("table", C.c_void_p), ("rows", C.c_void_p), ("cand_rows", C.c_void_p),
+                ("table_bits", C.c_int32), ("max_rows", C.c_int32)]
+
+
 # every symbol include/das_decode.h declares: (restype, argtypes)
 _VP = C.c_void_p
 SIGNATURES = {
@@ -63,12 +68,15 @@ SIGNATURES = {
     "das_gather_refine_assemble": (C.c_int, [_VP, C.POINTER(Levels), C.POINTER(DecodeCfg), _VP, _VP, _VP, _VP, _VP,
                                              C.c_int32, _VP, _VP, _VP, _VP]),
     "das_refine_heads": (C.c_int, [_VP, C.POINTER(Levels), C.POINTER(DecodeCfg), _VP, _VP, _VP, _VP, _VP, C.c_int32,
-                                   _VP, _VP, _VP, _VP, _VP, _VP]),
+                                   _VP, _VP, _VP, _VP, _VP, C.POINTER(RowCache), _VP]),
     "das_refine_tc": (C.c_int, [_VP, C.POINTER(Levels), C.POINTER(DecodeCfg), _VP, _VP, C.c_int32, _VP, _VP, _VP, _VP, _VP,
                                 C.c_int32, _VP]),
     "das_pack_tc_panels": (C.c_int, [C.POINTER(DecodeCfg), _VP, _VP, _VP]),
-    "das_refine_row_cache": (C.c_int, [C.POINTER(DecodeCfg), _VP, _VP, _VP, _VP, C.c_int32, _VP, C.c_int32, _VP]),
+    "das_refine_row_cache": (C.c_int, [C.POINTER(DecodeCfg), _VP, _VP, _VP, C.POINTER(RowCache), _VP]),
     "das_row_cache_table_bytes": (C.c_int64, [C.c_int32]),
+    "das_row_cache_clear": (C.c_int, [C.POINTER(RowCache), _VP]),
+    "das_refine_cand_rows": (C.c_int, [_VP, C.POINTER(Levels), C.POINTER(DecodeCfg), _VP, _VP, C.c_int32,
+                                       C.POINTER(RowCache), _VP]),
     "das_tc_set_debug_buffer": (C.c_int, [_VP]),
     "das_tc_panel_bytes": (C.c_int64, [C.POINTER(DecodeCfg)]),
     "das_plan_set_refine_mode": (C.c_int, [_VP, C.c_int32]),

@@ -44,6 +44,12 @@ void set_error(const char* fmt, ...);
         }                                 \
     } while (0)
 
+#define DAS_TRY(expr)                 \
+    do {                              \
+        int _s = (expr);              \
+        if (_s != DAS_OK) return _s;  \
+    } while (0)
+
 __host__ __device__ __forceinline__ int level_slots(int hw, int nms_pre) {
     // das_head.py:716-717: top-k only `if nms_pre > 0 and N > nms_pre`, else every cell passes through
     return (nms_pre > 0 && hw > nms_pre) ? nms_pre : hw;

@@ -53,9 +53,7 @@ struct das_plan {
     int host_mode = 0;                // das_plan_run_host: 0 = bulk H2D of every map, 1 = sparse maps read in place (zero copy),
                                       // 2 = zero copy + device row cache in front of the tensor-core sampling phase
     bool rc_active = false;           // the row-cache pass is part of the enqueued / captured work
-    void* rc_table = nullptr;
-    float* rc_rows = nullptr;
-    int rc_bits = 0, rc_cap = 0;
+    das_row_cache rc{};               // allocated on first use
     int64_t h2d_explicit = 0;         // bytes das_plan_run_host copies explicitly per call in the current host_mode
     int64_t h2d_bytes = 0, d2h_bytes = 0;
     unsigned char* out_block = nullptr;   // all out_* buffers live in this one allocation (one D2H / one all-gather)
@@ -86,12 +84,6 @@ static int dev_alloc(T** p, size_t n) {
     DAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T)));
     return DAS_OK;
 }
-
-#define DAS_TRY(expr)                 \
-    do {                              \
-        int _s = (expr);              \
-        if (_s != DAS_OK) return _s;  \
-    } while (0)
 
 extern "C" int das_plan_create(const das_decode_cfg* cfg, const das_levels* shape, das_plan** out) {
     using namespace das;
@@ -229,8 +221,9 @@ extern "C" void das_plan_destroy(das_plan* p) {
                     p->out_block, p->scratch, p->work_counter, p->d_scale_xy, p->d_cam,
                     p->proj, p->d_prev_ptrs, p->tc_panels, p->item_heads, p->item_asm, p->valid_list};
     for (void* q : ptrs) if (q) cudaFree(q);
-    if (p->rc_table) cudaFree(p->rc_table);
-    if (p->rc_rows) cudaFree(p->rc_rows);
+    if (p->rc.table) cudaFree(p->rc.table);
+    if (p->rc.rows) cudaFree(p->rc.rows);
+    if (p->rc.cand_rows) cudaFree(p->rc.cand_rows);
     for (int k = 0; k < DAS_MAX_LAYERS; ++k) if (p->wpack[k]) cudaFree(p->wpack[k]);
     for (int k = 0; k < DAS_MAX_LAYERS; ++k) if (p->dense_panels[k]) cudaFree(p->dense_panels[k]);
     for (int i = 0; i < 2; ++i)
@@ -323,12 +316,17 @@ static int enqueue(das_plan* p, cudaStream_t st, int* n_launch, bool events) {
     DAS_TRY(mark(2));
     if (c.refine && p->refine_mode != 0) {
         const float* w = p->wpack[c.num_layers - 1];
+        if (p->rc_active) {         // host zero-copy mode: every distinct feature row crosses PCIe once
+            DAS_TRY(das_row_cache_clear(&p->rc, st));
+            DAS_TRY(das_refine_cand_rows(p->d_levels, &p->bound, &c, p->buf.cand_score, p->buf.cand_index, p->CT, &p->rc, st));
+            ++n;
+        }
         DAS_TRY(das_refine_heads(p->d_levels, &p->bound, &c, w, prev, p->d_scale_xy, p->buf.cand_score, p->buf.cand_index, p->CT,
-                                 p->item_heads, p->item_asm, p->buf.cand_center, p->valid_list, p->work_counter, st));
+                                 p->item_heads, p->item_asm, p->buf.cand_center, p->valid_list, p->work_counter,
+                                 p->rc_active ? &p->rc : nullptr, st));
         DAS_TRY(mark(3));
         if (p->rc_active) {
-            DAS_TRY(das_refine_row_cache(&c, p->item_heads, p->valid_list, p->work_counter + 1, p->rc_table, p->rc_bits,
-                                         p->rc_rows, p->rc_cap, st));
+            DAS_TRY(das_refine_row_cache(&c, p->item_heads, p->valid_list, p->work_counter + 1, &p->rc, st));
             ++n;
         }
         DAS_TRY(das_refine_tc(p->d_levels, &p->bound, &c, w, p->tc_panels, p->CT, p->item_heads, p->item_asm, p->valid_list,
@@ -454,18 +452,19 @@ extern "C" int das_plan_set_host_mode(das_plan* p, int32_t mode) {
 static int set_row_cache(das_plan* p, bool on) {
     using namespace das;
     on = on && p->cfg.refine && p->refine_mode != 0 && p->tc_panels;
-    if (on && !p->rc_table) {
-        const long long records = static_cast<long long>(p->B) * p->CT * p->cfg.num_joints * 32;
+    if (on && !p->rc.table) {
+        const long long records = static_cast<long long>(p->B) * p->CT * p->cfg.num_joints * (32 + 4);
         int bits = 10;
         while (bits < 26 && (1ll << bits) < 2 * records) ++bits;
         long long cap = std::min<long long>(records, 262144);
         if (const char* e = std::getenv("DAS_ROW_CACHE_ROWS")) cap = std::max<long long>(1, std::min<long long>(records, std::atoll(e)));
         unsigned char* t = nullptr;
         DAS_TRY(dev_alloc(&t, static_cast<size_t>(das_row_cache_table_bytes(bits))));
-        p->rc_table = t;
-        DAS_TRY(dev_alloc(&p->rc_rows, static_cast<size_t>(cap) * p->cfg.feat_channels));
-        p->rc_bits = bits;
-        p->rc_cap = static_cast<int>(cap);
+        p->rc.table = t;
+        DAS_TRY(dev_alloc(&p->rc.rows, static_cast<size_t>(cap) * p->cfg.feat_channels));
+        DAS_TRY(dev_alloc(&p->rc.cand_rows, static_cast<size_t>(p->B) * p->CT * p->cfg.feat_channels));
+        p->rc.table_bits = bits;
+        p->rc.max_rows = static_cast<int>(cap);
     }
     if (on != p->rc_active) {
         p->rc_active = on;

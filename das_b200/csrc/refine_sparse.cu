@@ -21,6 +21,7 @@
 #include <algorithm>
 
 #include "refine_common.cuh"
+#include "row_cache.cuh"
 
 namespace das {
 
@@ -42,9 +43,10 @@ struct RefineParams {
     int CT, J, root, nms_pre, layer;
     float depth_factor, z_norm, score_thr;
     int n_items;
+    RowCacheView rc;               // heads-only mode, host zero-copy: device row cache (keys == nullptr: off)
 };
 
-template <int CPL, int NH, int MINB, bool HEADS_ONLY>
+template <int CPL, int NH, int MINB, bool HEADS_ONLY, bool ROW_CACHE = false>
 __global__ void __launch_bounds__(RS_WARPS * 32, MINB)
 refine_sparse_kernel(const RefineParams p) {
     constexpr int C = CPL * 32;
@@ -96,7 +98,8 @@ refine_sparse_kernel(const RefineParams p) {
         float S[2 * NH];
         float O[3];
         {
-            const Row<CPL> f = load_row<CPL>(F + static_cast<size_t>(idx) * C, lane, true);
+            const float* prow = (ROW_CACHE && p.rc.cand_rows) ? p.rc.cand_rows + static_cast<size_t>(cs) * C : F + static_cast<size_t>(idx) * C;
+            const Row<CPL> f = load_row<CPL>(prow, lane, true);
             float acc[2 * NH + 6];
 #pragma unroll
             for (int o = 0; o < 2 * NH + 6; ++o) {
@@ -125,7 +128,23 @@ refine_sparse_kernel(const RefineParams p) {
             for (int k = 0; k < 4; ++k) {
                 const bool ok = corner_ok(ct, k, W, H);
                 const float wk = ok ? corner_wgt(ct, k) : 0.f;
-                const Row<CPL> f = load_row<CPL>(F + static_cast<size_t>(ok ? corner_pix(ct, k, W) : 0) * C, lane, ok);
+                const float* rowp = F + static_cast<size_t>(ok ? corner_pix(ct, k, W) : 0) * C;
+                const Row<CPL> f = load_row<CPL>(rowp, lane, ok);
+                if constexpr (ROW_CACHE) {
+                    if (p.rc.keys && ok) {       // host zero-copy mode: the sampling phase mostly wants these very rows again
+                        int slot = -1;
+                        uint32_t hh;
+                        bool won = false;
+                        if (lane == 0) won = row_cache_insert(p.rc, reinterpret_cast<unsigned long long>(rowp), hh, slot);
+                        won = __shfl_sync(FULL, won, 0);
+                        slot = __shfl_sync(FULL, slot, 0);
+                        if (won && slot >= 0) {
+#pragma unroll
+                            for (int q = 0; q < CPL / 4; ++q)
+                                *reinterpret_cast<float4*>(p.rc.rows + static_cast<size_t>(slot) * C + q * 128 + 4 * lane) = f.v[q];
+                        }
+                    }
+                }
                 wsum += wk;
 #pragma unroll
                 for (int q = 0; q < CPL / 4; ++q) {
@@ -434,7 +453,7 @@ extern "C" int das_refine_heads(const das_levels* d_levels, const das_levels* h_
                                 const float* weights, const float* const* prev_uvd, const float* scale_xy,
                                 const float* cand_score, const int32_t* cand_index, int32_t cand_slots,
                                 float* row_records, float* item_records, float* cand_center,
-                                int32_t* valid_list, int32_t* counters, void* stream) {
+                                int32_t* valid_list, int32_t* counters, const das_row_cache* rc, void* stream) {
     using namespace das;
     DAS_REQUIRE(d_levels && h_levels && cfg && weights && scale_xy && cand_score && cand_index && row_records && item_records &&
                 cand_center && valid_list && counters, DAS_ERR_ARG, "das_refine_heads: null pointer");
@@ -451,8 +470,50 @@ extern "C" int das_refine_heads(const das_levels* d_levels, const das_levels* h_
     const long long items = static_cast<long long>(h_levels->batch) * cand_slots * cfg->num_joints;
     DAS_REQUIRE(items < (1ll << 31), DAS_ERR_CAPACITY, "too many work items");
     p.n_items = static_cast<int>(items);
+    p.rc = row_cache_view(rc);
     DAS_CUDA_CHECK(cudaMemsetAsync(counters, 0, 2 * sizeof(int32_t), st));
-    refine_sparse_kernel<8, 4, 4, true><<<kSMs * 4, RS_WARPS * 32, 0, st>>>(p);
+    if (p.rc.keys) refine_sparse_kernel<8, 4, 4, true, true><<<kSMs * 4, RS_WARPS * 32, 0, st>>>(p);
+    else refine_sparse_kernel<8, 4, 4, true><<<kSMs * 4, RS_WARPS * 32, 0, st>>>(p);
+    DAS_CUDA_CHECK(cudaGetLastError());
+    return DAS_OK;
+}
+
+// Host zero-copy mode: F(p) of every candidate above score_thr -> rc->cand_rows[b*CT+slot][C], once per candidate
+// instead of once per (candidate, joint) warp of das_refine_heads.
+namespace das {
+__global__ void __launch_bounds__(256)
+cand_rows_kernel(const das_levels* __restrict__ lvp, const float* __restrict__ cand_score, const int32_t* __restrict__ cand_index,
+                 int CT, int n_cand, int nms_pre, int layer, int C, float score_thr, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    for (int cs = blockIdx.x * 8 + (threadIdx.x >> 5); cs < n_cand; cs += gridDim.x * 8) {
+        if (score_thr > 0.f && !(__ldg(cand_score + cs) > score_thr)) continue;
+        const int b = cs / CT, slot = cs - b * CT;
+        int l = 0, s0 = 0;
+        for (; l < lvp->n_levels - 1; ++l) {
+            const int ns = level_slots(lvp->lv[l].H * lvp->lv[l].W, nms_pre);
+            if (slot < s0 + ns) break;
+            s0 += ns;
+        }
+        const das_level_desc& d = lvp->lv[l];
+        const int idx = __ldg(cand_index + cs);
+        if (idx < 0) continue;
+        const float4* src = reinterpret_cast<const float4*>(d.feats[layer] + (static_cast<size_t>(b) * d.H * d.W + idx) * C);
+        float4* dst = reinterpret_cast<float4*>(out + static_cast<size_t>(cs) * C);
+        for (int q = lane; q < C / 4; q += 32) dst[q] = __ldg(src + q);
+    }
+}
+}  // namespace das
+
+extern "C" int das_refine_cand_rows(const das_levels* d_levels, const das_levels* h_levels, const das_decode_cfg* cfg,
+                                    const float* cand_score, const int32_t* cand_index, int32_t cand_slots,
+                                    const das_row_cache* rc, void* stream) {
+    using namespace das;
+    DAS_REQUIRE(d_levels && h_levels && cfg && cand_score && cand_index && rc && rc->cand_rows, DAS_ERR_ARG,
+                "das_refine_cand_rows: null pointer");
+    const int n = h_levels->batch * cand_slots;
+    cand_rows_kernel<<<std::min(kSMs * 4, (n + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_levels, cand_score, cand_index, cand_slots, n, cfg->nms_pre, cfg->num_layers - 1, cfg->feat_channels, cfg->score_thr,
+        rc->cand_rows);
     DAS_CUDA_CHECK(cudaGetLastError());
     return DAS_OK;
 }

@@ -27,6 +27,7 @@
 //                     over the 8 heads (3 shuffles), eval tail, assembly; they also prepare the row pointers and
 //                     per-row state 6 tiles ahead and prefetch those rows into L2
 #include "refine_common.cuh"
+#include "row_cache.cuh"
 #include "tc_common.cuh"
 
 namespace das {
@@ -405,57 +406,26 @@ namespace das {
 // although the 32 rows of neighbouring heads / joints / candidates are mostly the same few rows (on device memory L2
 // absorbs that 10x re-use; sysmem reads are not deduplicated the same way: measured 117 MB per 64-image batch for
 // ~31 MB of distinct rows).  This pass runs between the two refinement kernels: every distinct row address is inserted
-// into an open-addressing hash set, the inserting lane's warp copies that row ONCE into a device-resident row buffer,
-// and every record is re-pointed at the copy.  A full buffer just leaves the remaining records pointing at the host.
-struct RowCacheParams {
-    float* row_records;
-    const int32_t* valid_list;
-    const int32_t* n_valid;
-    unsigned long long* keys;   // [mask + 1], all-ones = empty
-    int32_t* slots;             // [mask + 1], -1 = not assigned yet, -2 = buffer full
-    int32_t* counter;           // starts at -1 (the whole table is cleared with 0xFF bytes)
-    float* rows;                // [cap][TC_C]
-    uint32_t mask;
-    int cap, J;
-};
-
+// into an open-addressing hash set (row_cache.cuh), the inserting lane's warp copies that row ONCE into a
+// device-resident row buffer, and every record is re-pointed at the copy.  Rows the heads kernel already left in the
+// cache are found, not fetched again.  A full buffer just leaves the remaining records pointing at the host.
 __global__ void __launch_bounds__(256)
-row_cache_kernel(const RowCacheParams p) {
-    constexpr unsigned long long EMPTY = ~0ull;
+row_cache_kernel(float* row_records, const int32_t* valid_list, const int32_t* n_valid, int J, const RowCacheView rc) {
     const int lane = threadIdx.x & 31;
-    const int n_items = *p.n_valid * p.J;
+    const int n_items = *n_valid * J;
     for (int it = blockIdx.x * 8 + (threadIdx.x >> 5); it < n_items; it += gridDim.x * 8) {
-        const int cs = __ldg(p.valid_list + it / p.J);
-        const int j = it % p.J;
-        float4* rec = reinterpret_cast<float4*>(p.row_records) + ((static_cast<size_t>(cs) * p.J + j) * 32 + lane) * 2;
+        const int cs = __ldg(valid_list + it / J);
+        const int j = it % J;
+        float4* rec = reinterpret_cast<float4*>(row_records) + ((static_cast<size_t>(cs) * J + j) * 32 + lane) * 2;
         float4 a = *rec;
         const unsigned long long ptr = static_cast<unsigned long long>(__float_as_uint(a.x)) |
                                        (static_cast<unsigned long long>(__float_as_uint(a.y)) << 32);
         int slot = -1;
         bool won = false;
         uint32_t h = 0;
-        if (ptr) {
-            h = static_cast<uint32_t>(((ptr >> 10) * 0x9E3779B97F4A7C15ull) >> 40) & p.mask;   // rows are 1 KB apart
-            while (true) {
-                const unsigned long long old = atomicCAS(p.keys + h, EMPTY, ptr);
-                if (old == EMPTY) {
-                    won = true;
-                    const int sl = atomicAdd(p.counter, 1) + 1;
-                    slot = sl < p.cap ? sl : -2;
-                    atomicExch(p.slots + h, slot);     // published before anything else: waiters below only need this
-                    break;
-                }
-                if (old == ptr) break;
-                h = (h + 1) & p.mask;
-            }
-        }
+        if (ptr) won = row_cache_insert(rc, ptr, h, slot);
         __syncwarp();
-        if (ptr && !won) {
-            volatile int32_t* sl = p.slots + h;
-            int v;
-            while ((v = *sl) == -1) {}
-            slot = v;
-        }
+        if (ptr && !won) slot = row_cache_wait(rc, h);
         unsigned todo = __ballot_sync(0xffffffffu, won && slot >= 0);
         while (todo) {
             const int src = __ffs(todo) - 1;
@@ -464,12 +434,12 @@ row_cache_kernel(const RowCacheParams p) {
             const int ss = __shfl_sync(0xffffffffu, slot, src);
             const float4* s4 = reinterpret_cast<const float4*>(sp) + lane * 2;        // 32 lanes x 32 B = one row
             const float4 v0 = __ldg(s4), v1 = __ldg(s4 + 1);
-            float4* d4 = reinterpret_cast<float4*>(p.rows + static_cast<size_t>(ss) * TC_C) + lane * 2;
+            float4* d4 = reinterpret_cast<float4*>(rc.rows + static_cast<size_t>(ss) * TC_C) + lane * 2;
             d4[0] = v0;
             d4[1] = v1;
         }
         if (slot >= 0) {
-            const unsigned long long np = reinterpret_cast<unsigned long long>(p.rows + static_cast<size_t>(slot) * TC_C);
+            const unsigned long long np = reinterpret_cast<unsigned long long>(rc.rows + static_cast<size_t>(slot) * TC_C);
             a.x = __uint_as_float(static_cast<uint32_t>(np));
             a.y = __uint_as_float(static_cast<uint32_t>(np >> 32));
             *rec = a;
@@ -478,31 +448,37 @@ row_cache_kernel(const RowCacheParams p) {
 }
 }  // namespace das
 
-extern "C" int das_refine_row_cache(const das_decode_cfg* cfg, float* row_records, const int32_t* valid_list,
-                                    const int32_t* n_valid, void* table, int32_t table_bits, float* rows, int32_t max_rows,
-                                    void* stream) {
+static int check_row_cache(const das_row_cache* rc, const char* who) {
     using namespace das;
-    DAS_REQUIRE(cfg && row_records && valid_list && n_valid && table && rows, DAS_ERR_ARG, "das_refine_row_cache: null pointer");
-    DAS_REQUIRE(cfg->feat_channels == TC_C, DAS_ERR_UNSUPPORTED, "the row cache is built for feat_channels=256");
-    DAS_REQUIRE(table_bits >= 10 && table_bits <= 26 && max_rows >= 1, DAS_ERR_ARG, "row cache: table_bits=%d max_rows=%d",
-                table_bits, max_rows);
-    const size_t n = static_cast<size_t>(1) << table_bits;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    DAS_CUDA_CHECK(cudaMemsetAsync(table, 0xFF, das_row_cache_table_bytes(table_bits), st));
-    RowCacheParams p{};
-    p.row_records = row_records; p.valid_list = valid_list; p.n_valid = n_valid;
-    p.keys = static_cast<unsigned long long*>(table);
-    p.slots = reinterpret_cast<int32_t*>(p.keys + n);
-    p.counter = p.slots + n;
-    p.rows = rows; p.mask = static_cast<uint32_t>(n - 1); p.cap = max_rows; p.J = cfg->num_joints;
-    row_cache_kernel<<<kSMs * 4, 256, 0, st>>>(p);
-    DAS_CUDA_CHECK(cudaGetLastError());
+    DAS_REQUIRE(rc && rc->table && rc->rows, DAS_ERR_ARG, "%s: null row cache", who);
+    DAS_REQUIRE(rc->table_bits >= 10 && rc->table_bits <= 26 && rc->max_rows >= 1, DAS_ERR_ARG, "%s: table_bits=%d max_rows=%d",
+                who, rc->table_bits, rc->max_rows);
     return DAS_OK;
 }
 
 extern "C" int64_t das_row_cache_table_bytes(int32_t table_bits) {
     if (table_bits < 10 || table_bits > 26) return 0;
     return (static_cast<int64_t>(1) << table_bits) * 12 + 64;      // keys (8 B) + slots (4 B) + the row counter
+}
+
+extern "C" int das_row_cache_clear(const das_row_cache* rc, void* stream) {
+    using namespace das;
+    DAS_TRY(check_row_cache(rc, "das_row_cache_clear"));
+    DAS_CUDA_CHECK(cudaMemsetAsync(rc->table, 0xFF, static_cast<size_t>(das_row_cache_table_bytes(rc->table_bits)),
+                                   static_cast<cudaStream_t>(stream)));
+    return DAS_OK;
+}
+
+extern "C" int das_refine_row_cache(const das_decode_cfg* cfg, float* row_records, const int32_t* valid_list,
+                                    const int32_t* n_valid, const das_row_cache* rc, void* stream) {
+    using namespace das;
+    DAS_REQUIRE(cfg && row_records && valid_list && n_valid, DAS_ERR_ARG, "das_refine_row_cache: null pointer");
+    DAS_TRY(check_row_cache(rc, "das_refine_row_cache"));
+    DAS_REQUIRE(cfg->feat_channels == TC_C, DAS_ERR_UNSUPPORTED, "the row cache is built for feat_channels=256");
+    row_cache_kernel<<<kSMs * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(row_records, valid_list, n_valid, cfg->num_joints,
+                                                                            row_cache_view(rc));
+    DAS_CUDA_CHECK(cudaGetLastError());
+    return DAS_OK;
 }
 
 extern "C" int das_refine_tc(const das_levels* d_levels, const das_levels* h_levels, const das_decode_cfg* cfg,

@@ -129,6 +129,15 @@ int das_gather_refine_assemble(const das_levels* d_levels, const das_levels* h_l
                                float* cand_pose, float* cand_center, int32_t* work_counter,
                                void* stream);
 
+/* Device row cache of the host zero-copy mode; see das_refine_row_cache below. */
+typedef struct das_row_cache {
+    void* table;        /* das_row_cache_table_bytes(table_bits) bytes of device memory */
+    float* rows;        /* [max_rows][feat_channels] device */
+    float* cand_rows;   /* [B*CT][feat_channels] device, or NULL */
+    int32_t table_bits;
+    int32_t max_rows;
+} das_row_cache;
+
 /* Tensor-core variant of stage 3+4 (feat_channels = 256, num_heads = 4), two launches:
  *   das_refine_heads  phases 1-2 per (candidate, joint) item: the 32 row records of the sampling phase
  *                     (row_records [B*CT*J][32][8 floats]: feature-row pointer, bilinear weight, previous offset,
@@ -141,21 +150,30 @@ int das_refine_heads(const das_levels* d_levels, const das_levels* h_levels, con
                      const float* weights, const float* const* prev_uvd, const float* scale_xy,
                      const float* cand_score, const int32_t* cand_index, int32_t cand_slots,
                      float* row_records, float* item_records, float* cand_center,
-                     int32_t* valid_list, int32_t* counters, void* stream);
+                     int32_t* valid_list, int32_t* counters, const das_row_cache* rc /* NULL = off */,
+                     void* stream);
 int das_refine_tc(const das_levels* d_levels, const das_levels* h_levels, const das_decode_cfg* cfg,
                   const float* weights, const void* panels, int32_t cand_slots,
                   const float* row_records, const float* item_records, const int32_t* valid_list,
                   const int32_t* n_valid, float* cand_pose, int32_t split, void* stream);
 int das_pack_tc_panels(const das_decode_cfg* cfg, const float* packed_weights, void* panels, void* stream);
-/* Host zero-copy mode only (feature maps read in place from pinned host memory): between das_refine_heads and
- * das_refine_tc, copy every DISTINCT row the row records point at into `rows` ([max_rows][256] floats, device) once and
- * re-point the records at the copies, so PCIe carries each row once (on device memory L2 already gives that re-use).
- * table: das_row_cache_table_bytes(table_bits) bytes of device scratch, cleared here; 2^table_bits should be at least
- * twice the number of row records.  A full row buffer leaves the remaining records pointing at the host. */
-int das_refine_row_cache(const das_decode_cfg* cfg, float* row_records, const int32_t* valid_list,
-                         const int32_t* n_valid, void* table, int32_t table_bits, float* rows, int32_t max_rows,
-                         void* stream);
+/* Row cache for the host zero-copy mode (feature maps read in place from pinned HOST memory).  On device memory L2
+ * absorbs the ~10x re-use of feature rows between heads / joints / candidates; reads of host memory are not
+ * deduplicated that way, so these passes make every distinct row cross PCIe once:
+ *   das_row_cache_clear    empties the table (before das_refine_cand_rows / das_refine_heads of a batch)
+ *   das_refine_cand_rows   copies F(p) of every candidate above score_thr into rc->cand_rows (read by all J joints)
+ *   das_refine_heads(rc)   reads F(p) from rc->cand_rows and leaves the target-corner rows it fetched in the cache
+ *   das_refine_row_cache   between das_refine_heads and das_refine_tc: copies every still-missing DISTINCT row the row
+ *                          records point at into rc->rows and re-points the records at the copies.
+ * A full row buffer leaves the remaining records pointing at the host.  2^table_bits should be at least twice the
+ * number of row records (B*CT*J*32). */
 int64_t das_row_cache_table_bytes(int32_t table_bits);
+int das_row_cache_clear(const das_row_cache* rc, void* stream);
+int das_refine_cand_rows(const das_levels* d_levels, const das_levels* h_levels, const das_decode_cfg* cfg,
+                         const float* cand_score, const int32_t* cand_index, int32_t cand_slots,
+                         const das_row_cache* rc, void* stream);
+int das_refine_row_cache(const das_decode_cfg* cfg, float* row_records, const int32_t* valid_list,
+                         const int32_t* n_valid, const das_row_cache* rc, void* stream);
 int64_t das_tc_panel_bytes(const das_decode_cfg* cfg);
 /* profiling aid: per-CTA cycle counters of das_refine_tc's warp roles ([148][16] int64 device buffer; NULL = off) */
 int das_tc_set_debug_buffer(long long* dev_buf);
