@@ -129,21 +129,40 @@ refine_sparse_kernel(const RefineParams p) {
                 const bool ok = corner_ok(ct, k, W, H);
                 const float wk = ok ? corner_wgt(ct, k) : 0.f;
                 const float* rowp = F + static_cast<size_t>(ok ? corner_pix(ct, k, W) : 0) * C;
-                const Row<CPL> f = load_row<CPL>(rowp, lane, ok);
+                Row<CPL> f;
                 if constexpr (ROW_CACHE) {
-                    if (p.rc.keys && ok) {       // host zero-copy mode: the sampling phase mostly wants these very rows again
-                        int slot = -1;
-                        uint32_t hh;
-                        bool won = false;
-                        if (lane == 0) won = row_cache_insert(p.rc, reinterpret_cast<unsigned long long>(rowp), hh, slot);
+                    // host zero-copy mode: neighbouring candidates and the sampling phase want these very rows again, so
+                    // whoever asks first fetches the row over PCIe into the device row buffer and publishes it; everybody
+                    // else waits for that copy instead of fetching the row a second time
+                    const float* src = rowp;
+                    int slot = -1;
+                    uint32_t hh = 0;
+                    bool won = false;
+                    if (p.rc.keys && ok) {
+                        if (lane == 0) {
+                            won = row_cache_insert(p.rc, reinterpret_cast<unsigned long long>(rowp), hh, slot, false);
+                            if (!won) slot = row_cache_wait(p.rc, hh);
+                        }
                         won = __shfl_sync(FULL, won, 0);
                         slot = __shfl_sync(FULL, slot, 0);
-                        if (won && slot >= 0) {
-#pragma unroll
-                            for (int q = 0; q < CPL / 4; ++q)
-                                *reinterpret_cast<float4*>(p.rc.rows + static_cast<size_t>(slot) * C + q * 128 + 4 * lane) = f.v[q];
-                        }
+                        if (!won && slot >= 0) src = p.rc.rows + static_cast<size_t>(slot) * C;
                     }
+                    if (src == rowp) {
+                        f = load_row<CPL>(rowp, lane, ok);
+                    } else {                                  // written by another SM during this kernel: no .nc path
+#pragma unroll
+                        for (int q = 0; q < CPL / 4; ++q) f.v[q] = __ldcg(reinterpret_cast<const float4*>(src + q * 128 + 4 * lane));
+                    }
+                    if (won && slot >= 0) {
+#pragma unroll
+                        for (int q = 0; q < CPL / 4; ++q)
+                            *reinterpret_cast<float4*>(p.rc.rows + static_cast<size_t>(slot) * C + q * 128 + 4 * lane) = f.v[q];
+                        __threadfence();       // every lane's part of the row is visible device-wide before the slot is
+                        __syncwarp();
+                        if (lane == 0) row_cache_publish(p.rc, hh, slot);
+                    }
+                } else {
+                    f = load_row<CPL>(rowp, lane, ok);
                 }
                 wsum += wk;
 #pragma unroll

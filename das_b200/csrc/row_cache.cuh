@@ -33,8 +33,12 @@ inline RowCacheView row_cache_view(const das_row_cache* rc) {
 
 // Insert `ptr` (never 0).  Returns true if this thread created the entry: then `slot` is its row-buffer slot (or -2
 // when the buffer is full) and is already published.  Otherwise the entry exists at `h`; its slot may still be -1
-// for a few cycles (row_cache_wait).  The row DATA of a slot is only guaranteed complete after the inserting kernel.
-__device__ __forceinline__ bool row_cache_insert(const RowCacheView& rc, unsigned long long ptr, uint32_t& h, int& slot) {
+// for a while (row_cache_wait).  With publish = true the row DATA of a slot is only guaranteed complete after the
+// inserting kernel has finished.
+// publish = false: the caller fills the row first and then calls row_cache_publish, so that a thread that finds the
+// entry (row_cache_wait) may read the row's DATA in the same kernel; a full buffer (-2) is always published at once.
+__device__ __forceinline__ bool row_cache_insert(const RowCacheView& rc, unsigned long long ptr, uint32_t& h, int& slot,
+                                                 bool publish = true) {
     constexpr unsigned long long EMPTY = ~0ull;
     h = static_cast<uint32_t>(((ptr >> 10) * 0x9E3779B97F4A7C15ull) >> 40) & rc.mask;   // rows are >= 512 B apart
     while (true) {
@@ -42,12 +46,17 @@ __device__ __forceinline__ bool row_cache_insert(const RowCacheView& rc, unsigne
         if (old == EMPTY) {
             const int sl = atomicAdd(rc.counter, 1) + 1;
             slot = sl < rc.cap ? sl : -2;
-            atomicExch(rc.slots + h, slot);
+            if (publish || slot < 0) atomicExch(rc.slots + h, slot);
             return true;
         }
         if (old == ptr) { slot = -1; return false; }
         h = (h + 1) & rc.mask;
     }
+}
+
+__device__ __forceinline__ void row_cache_publish(const RowCacheView& rc, uint32_t h, int slot) {
+    __threadfence();                       // the row's stores before the slot becomes visible
+    atomicExch(rc.slots + h, slot);
 }
 
 __device__ __forceinline__ int row_cache_wait(const RowCacheView& rc, uint32_t h) {

@@ -272,6 +272,25 @@ def test_host_entry_equals_device_entry():
         assert torch.equal(out[k], out3[k]), k
 
 
+def test_host_row_cache_with_heavy_row_sharing():
+    """Coherent fields: neighbouring candidates point at the same joints, so many warps ask for the same feature rows at
+    the same time -- the first fetches, the others wait for its copy.  Must stay bit-equal to the device entry."""
+    tc = dict(nms_pre=30, nms_post=30, nms_thr=0.9, score_thr=0.0)
+    case = util.make_case(P, 8, 64, 96, seed=77, coherent=8, peaks=6)
+    plan, _ = util.run_gpu(case, tc, refine=True)
+    want = plan.output_block().clone()
+    host_levels = [dict(cls=lv["cls"].pin_memory(), ctr=lv["ctr"].pin_memory(), pose=lv["pose_raw"].pin_memory(),
+                        feats=[f.permute(0, 2, 3, 1).contiguous().pin_memory().permute(0, 3, 1, 2) for f in lv["feats"]],
+                        scales=lv["scales"]) for lv in case["levels"]]
+    plan.set_host_mode(True)
+    out = plan.alloc_host_out()
+    ref = plan.views_of_block(want.cpu())
+    for _ in range(6):
+        plan.run_host(host_levels, case["metas"], out)
+        for k, v in ref.items():
+            assert torch.equal(out[k], v), k
+
+
 def test_drop_in_head_api():
     """DASHeadB200.get_poses with the reference signature and return structure (das_head.py:653-688)."""
     tc = dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)
