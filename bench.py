@@ -251,6 +251,7 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # NCCL's version / debug lines: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     w, head = WORKLOAD, WORKLOAD["head"]
     B = w["batch"]
@@ -284,26 +285,65 @@ def run_b200(args):
     # 64-CTA top-k and NMS kernels of one batch overlap the refinement of another.
     n_streams = max(1, min(args.streams, n_sets))
     streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)] if n_streams > 1 else [torch.cuda.current_stream(dev)]
-    gathered_s = [torch.empty((world, blocks[0].numel()), dtype=torch.uint8, device=dev) for _ in range(n_sets)] if world > 1 else None
+
+    # N > 1: result collection = one all-gather of the ranks' packed pose lists.  It is latency-bound (~0.6 MB per rank and
+    # step), so the blocks of `n_sets` consecutive steps are staged contiguously and gathered by ONE collective on its own
+    # stream: the collective of round r overlaps the decodes of round r+1.
+    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    decoded = [torch.cuda.Event() for _ in range(n_sets)]
+    gathered_ev = [None]
+    nb = blocks[0].numel()
+    staging = torch.empty((n_sets, nb), dtype=torch.uint8, device=dev) if world > 1 else None
+    gathered = torch.empty((world, n_sets, nb), dtype=torch.uint8, device=dev) if world > 1 else None
+    pending = [0]
+    gathers = [0]
+
+    def flush(n):
+        for k in range(n):
+            comm_stream.wait_event(decoded[k])
+        with torch.cuda.stream(comm_stream):
+            if n == n_sets:
+                dist.all_gather_into_tensor(gathered.view(-1), staging.view(-1))
+            else:               # tail of a run whose step count is not a multiple of n_sets
+                tmp = torch.empty((world, n, nb), dtype=torch.uint8, device=dev)
+                dist.all_gather_into_tensor(tmp.view(-1), staging[:n].reshape(-1))
+            gathered_ev[0] = torch.cuda.Event()
+            gathered_ev[0].record(comm_stream)
+        pending[0] = 0
+        gathers[0] += 1
 
     def step(i):
         k = i % n_sets
-        with torch.cuda.stream(streams[k % n_streams]):
+        st = streams[k % n_streams]
+        with torch.cuda.stream(st):
             plans[k].run(use_graph=True)
-            if world > 1:       # the final small pose lists: one all-gather of the packed output block
-                dist.all_gather_into_tensor(gathered_s[k].view(-1), blocks[k])
+            if world > 1:
+                if gathered_ev[0] is not None:
+                    st.wait_event(gathered_ev[0])      # the previous round's gather must have read the staging buffer
+                staging[k].copy_(blocks[k], non_blocking=True)
+                decoded[k].record(st)
+        if world > 1:
+            pending[0] += 1
+            if pending[0] == n_sets:
+                flush(n_sets)
 
     def fork():
+        cur = torch.cuda.current_stream(dev)
         if n_streams > 1:
-            cur = torch.cuda.current_stream(dev)
             for st in streams:
                 st.wait_stream(cur)
+        if comm_stream is not None:
+            comm_stream.wait_stream(cur)
 
     def join():
+        cur = torch.cuda.current_stream(dev)
+        if world > 1 and pending[0]:
+            flush(pending[0])
         if n_streams > 1:
-            cur = torch.cuda.current_stream(dev)
             for st in streams:
                 cur.wait_stream(st)
+        if comm_stream is not None:
+            cur.wait_stream(comm_stream)
 
     def barrier():
         if world > 1:
@@ -438,7 +478,7 @@ def run_b200(args):
                        "l2": f"{n_sets} distinct input sets of {plans[0].h2d_bytes / 1e9:.2f} GB rotated round-robin "
                              f"(each far larger than the 126 MB L2)",
                        "streams": n_streams,
-                       "parallelism": f"dp{world} batch-sharded, one NCCL all-gather of the packed pose lists per step"
+                       "parallelism": f"dp{world} batch-sharded; result collection: one NCCL all-gather of the packed pose lists of every {n_sets} steps, on its own stream"
                                       if world > 1 else "single GPU"},
             "clocks": clocks, "gpu_launches": int(launches) * world, "roofline": roofline,
         }
@@ -465,6 +505,7 @@ def run_model(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     w = WORKLOAD
     B, H, W, J, K = w["batch"], w["h"], w["w"], 15, w["K"]
