@@ -48,6 +48,28 @@ UNIT = "images/s"
 
 
 # ------------------------------------------------------------------------------------------------
+_JSON_FD = None
+
+
+def guard_stdout():
+    """stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner under NCCL_DEBUG) are
+    sent to stderr for the whole run, and emit() writes the result to the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -57,12 +79,17 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, enabled: bool = True):
+        """index: one GPU index or a list of them (one poller for all GPUs of the job: NVML queries from one poller per
+        rank measurably slowed every rank's launches at N = 8)."""
+        self.index = ",".join(str(i) for i in index) if isinstance(index, (list, tuple)) else str(index)
+        self.rows, self.proc, self.enabled = [], None, enabled
 
     def start(self):
+        if not self.enabled:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.index, f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
@@ -226,7 +253,7 @@ def run_reference(args):
     value = sample_b * args.steps / el
     cores = torch.get_num_threads()
     sample = f"{sample_b} images per step of the {WORKLOAD['name']} workload, torch CPU threads={cores}"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": el / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -236,7 +263,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    })
 
 
 # ------------------------------------------------------------------------------------------------
@@ -257,7 +284,7 @@ def run_b200(args):
     B = w["batch"]
     n_sets = args.input_sets
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(list(range(world)) if world > 1 else local_rank, enabled=rank == 0)
     sampler.start()
 
     layers = synth.make_layers(head, seed=1235, device=dev)
@@ -486,7 +513,7 @@ def run_b200(args):
             out["e2e"] = e2e
         if cpu is not None:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -511,7 +538,7 @@ def run_model(args):
     B, H, W, J, K = w["batch"], w["h"], w["w"], 15, w["K"]
     strides = (8, 16, 32, 64)
     dtype = None if os.environ.get("DAS_MODEL_DTYPE", "bf16") == "tf32" else torch.bfloat16
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(list(range(world)) if world > 1 else local_rank, enabled=rank == 0)
     sampler.start()
     torch.manual_seed(1238)
     net = DASNet(num_joints=J, strides=strides)
@@ -590,7 +617,7 @@ def run_model(args):
     sampler.stop()
     clocks = sampler.summary(t_wall0, t_wall1)
     if rank == 0:
-        print(json.dumps({
+        emit({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 convolutions (fp32 DCNv2 / GroupNorm / predictor outputs), f32 decode" if dtype else "tf32 convolutions, f32 decode",
@@ -607,7 +634,7 @@ def run_model(args):
                     "api": "DASNet(img) -> DASHeadB200.get_poses(*outs, img_metas): pinned host images in, result dicts out",
                     "people_last_step": n_people},
             "cpu_baseline": None,
-        }), flush=True)
+        })
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -629,12 +656,13 @@ def main():
     ap.add_argument("--workload", default="panoptic", choices=sorted(WORKLOADS),
                     help="panoptic = BASELINE config #2 (the metric; default); single = #1 (B=1 latency); mupots = #3; crowded = #4; e2e_model = #5 (network + decode)")
     args = ap.parse_args()
+    guard_stdout()
     WORKLOAD.clear()
     WORKLOAD.update(WORKLOADS[args.workload])
     TEST_CFG.update(nms_pre=WORKLOAD["K"], nms_post=WORKLOAD["K"])
     if args.workload == "e2e_model":
         if args.impl == "reference":      # mmcv / mmdet are absent: the reference network cannot run here
-            print(json.dumps({"impl": "reference", "unavailable": "the reference network needs mmcv-full/mmdet (not installed); only its decode is restated"}))
+            emit({"impl": "reference", "unavailable": "the reference network needs mmcv-full/mmdet (not installed); only its decode is restated"})
             return
         if args.steps == 300:
             args.steps = 10
