@@ -53,6 +53,7 @@ struct das_plan {
     int host_mode = 0;                // das_plan_run_host: 0 = bulk H2D of every map, 1 = sparse maps read in place (zero copy),
                                       // 2 = zero copy + device row cache in front of the tensor-core sampling phase
     bool rc_active = false;           // the row-cache pass is part of the enqueued / captured work
+    bool in_host_call = false;        // das_plan_bind is being called by das_plan_run_host
     das_row_cache rc{};               // allocated on first use
     int64_t h2d_explicit = 0;         // bytes das_plan_run_host copies explicitly per call in the current host_mode
     int64_t h2d_bytes = 0, d2h_bytes = 0;
@@ -253,9 +254,12 @@ extern "C" int das_plan_set_weights(das_plan* p, int32_t layer, const float* so_
     return DAS_OK;
 }
 
+static int set_row_cache(das_plan* p, bool on);
+
 extern "C" int das_plan_bind(das_plan* p, const das_levels* levels, void* stream) {
     using namespace das;
     DAS_REQUIRE(p && levels, DAS_ERR_ARG, "das_plan_bind: null pointer");
+    if (!p->in_host_call) DAS_TRY(set_row_cache(p, false));   // device-resident inputs: L2 already gives the row re-use
     DAS_REQUIRE(levels->n_levels == p->shape.n_levels && levels->batch == p->shape.batch, DAS_ERR_ARG,
                 "bind: n_levels/batch (%d/%d) differ from the plan (%d/%d)", levels->n_levels, levels->batch,
                 p->shape.n_levels, p->shape.batch);
@@ -556,7 +560,10 @@ extern "C" int das_plan_run_host(das_plan* p, const das_levels* levels, const fl
         }
     }
     p->h2d_explicit = copied + static_cast<int64_t>(B) * (2 * 4 + DAS_CAM_DOUBLES * 8);
-    DAS_TRY(das_plan_bind(p, &run, st));
+    p->in_host_call = true;
+    const int bound = das_plan_bind(p, &run, st);
+    p->in_host_call = false;
+    DAS_TRY(bound);
     DAS_TRY(das_plan_set_metas(p, scale_xy, cam, st));
     DAS_TRY(das_plan_run(p, st, 1));
     const size_t P = p->P;
