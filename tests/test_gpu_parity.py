@@ -272,11 +272,15 @@ def test_host_entry_equals_device_entry():
         assert torch.equal(out[k], out3[k]), k
 
 
-def test_host_row_cache_with_heavy_row_sharing():
+@pytest.mark.parametrize("cfg,tc,kw", [
+    (P, dict(nms_pre=30, nms_post=30, nms_thr=0.9, score_thr=0.0), dict(coherent=8, peaks=6)),
+    (dataclasses.replace(P, strides=(8, 16, 32, 64)), dict(nms_pre=40, nms_post=30, nms_thr=0.9, score_thr=0.05), dict(peaks=24)),
+], ids=["coherent", "pyramid4_score_thr"])
+def test_host_row_cache_with_heavy_row_sharing(cfg, tc, kw):
     """Coherent fields: neighbouring candidates point at the same joints, so many warps ask for the same feature rows at
-    the same time -- the first fetches, the others wait for its copy.  Must stay bit-equal to the device entry."""
-    tc = dict(nms_pre=30, nms_post=30, nms_thr=0.9, score_thr=0.0)
-    case = util.make_case(P, 8, 64, 96, seed=77, coherent=8, peaks=6)
+    the same time -- the first fetches, the others wait for its copy.  Must stay bit-equal to the device entry
+    (also on a 4-level pyramid with candidates dropped by score_thr)."""
+    case = util.make_case(cfg, 8, 64, 96, seed=77, **kw)
     plan, _ = util.run_gpu(case, tc, refine=True)
     want = plan.output_block().clone()
     host_levels = [dict(cls=lv["cls"].pin_memory(), ctr=lv["ctr"].pin_memory(), pose=lv["pose_raw"].pin_memory(),

@@ -224,3 +224,28 @@ def test_fused_inference_path_matches_plain_modules():
         low = net(x)
         assert low[0][0].dtype == torch.float32 and low[3][0][0].dtype == torch.float32
         assert worst([f[0] for f in low[3]], [f[0] for f in plain[3]]) < 0.15
+
+
+def test_fpn_top_down_path_matches_torchvision_fpn():
+    """The lateral / nearest-upsample / 3x3 part of FPNNeck against torchvision's FeaturePyramidNetwork on shared weights
+    (the published FPN algorithm; mmdet's own FPN is not in the reference tree).  The extra level is 'on_output':
+    a stride-2 3x3 conv of the last output."""
+    from collections import OrderedDict
+    from torchvision.ops import FeaturePyramidNetwork
+    torch.manual_seed(2)
+    neck = M.FPNNeck(in_channels=(16, 24, 32, 40), out_channels=8, start_level=1, num_outs=4, norm=None).eval()
+    ref = FeaturePyramidNetwork([24, 32, 40], 8).eval()
+    with torch.no_grad():
+        for i in range(3):
+            ref.inner_blocks[i][0].weight.copy_(neck.lateral[i].conv.weight)
+            ref.inner_blocks[i][0].bias.copy_(neck.lateral[i].conv.bias)
+            ref.layer_blocks[i][0].weight.copy_(neck.smooth[i].conv.weight)
+            ref.layer_blocks[i][0].bias.copy_(neck.smooth[i].conv.bias)
+        feats = [torch.randn(2, c, 40 >> i, 56 >> i) for i, c in enumerate((16, 24, 32, 40))]
+        got = neck(feats)
+        want = list(ref(OrderedDict((str(i), f) for i, f in enumerate(feats[1:]))).values())
+        assert len(got) == 4
+        for g, w in zip(got[:3], want):
+            assert torch.allclose(g, w, atol=1e-5, rtol=1e-5)
+        extra = torch.nn.functional.conv2d(got[2], neck.extra[0].conv.weight, neck.extra[0].conv.bias, stride=2, padding=1)
+        assert torch.allclose(got[3], extra, atol=1e-6)
