@@ -90,7 +90,7 @@ class ClockSampler:
             return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", self.index, f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -643,7 +643,8 @@ def run_model(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=None,
+                    help="timed steps (default: 4000 decode steps = ~0.3 s on one B200; 20 for --impl reference; 10 for e2e_model)")
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--input-sets", type=int, default=4)
@@ -656,6 +657,8 @@ def main():
     ap.add_argument("--workload", default="panoptic", choices=sorted(WORKLOADS),
                     help="panoptic = BASELINE config #2 (the metric; default); single = #1 (B=1 latency); mupots = #3; crowded = #4; e2e_model = #5 (network + decode)")
     args = ap.parse_args()
+    if args.steps is None and args.workload != "e2e_model":
+        args.steps = 20 if args.impl == "reference" else (4000 if args.workload in ("panoptic", "single", "crowded") else 300)
     guard_stdout()
     WORKLOAD.clear()
     WORKLOAD.update(WORKLOADS[args.workload])
@@ -664,7 +667,7 @@ def main():
         if args.impl == "reference":      # mmcv / mmdet are absent: the reference network cannot run here
             emit({"impl": "reference", "unavailable": "the reference network needs mmcv-full/mmdet (not installed); only its decode is restated"})
             return
-        if args.steps == 300:
+        if args.steps is None:
             args.steps = 10
         run_model(args)
     elif args.impl == "reference":
