@@ -59,6 +59,25 @@ __device__ __forceinline__ float oks_pair(const float* pg, const float* pd, floa
     return static_cast<float>(t / static_cast<double>(J));
 }
 
+// Hard NMS only needs the DECISION oks > thr.  A float32 estimate of the same expression (error ~1e-6) settles every pair
+// whose estimate is below thr - 0.05 -- in practice all pairs of distinct people -- and only the others pay for the
+// reference's float64 divide / exp chain, so the decision is still the exact one.  Must be called by all 32 lanes; the
+// exact path is taken warp-wide when any of the warp's groups needs it (the float64 butterfly uses full-warp shuffles).
+template <int G>
+__device__ __forceinline__ bool oks_over(const float* pg, const float* pd, float ag, float ad, int J, int gl, float thr) {
+    float t = 0.f;
+    if (gl < J) {
+        const float dx = pd[3 * gl] - pg[3 * gl], dy = pd[3 * gl + 1] - pg[3 * gl + 1];
+        const float e = (dx * dx + dy * dy) / static_cast<float>(oks_var(gl, J)) / ((ag + ad) * 0.5f + 2.220446049250313e-16f) * 0.5f;
+        t = __expf(-e);
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    const bool maybe = !(t / static_cast<float>(J) < thr - 0.05f);      // NaN-safe: anything odd goes to the exact path
+    if (!__any_sync(0xffffffffu, maybe)) return false;
+    return oks_pair<G>(pg, pd, ag, ad, J, gl) > thr;
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT, 1)
 nms_backproject_kernel(const NmsParams p) {
@@ -222,9 +241,9 @@ nms_backproject_kernel(const NmsParams p) {
                         j = i + 1 + rem;
                     }
                     const int ci = order[i], cj = order[live ? j : 1 % max(n, 1)];
-                    const float v = oks_pair<16>(pose + static_cast<size_t>(ci) * J * 3, pose + static_cast<size_t>(cj) * J * 3,
-                                                 area[ci], area[cj], J, gl);
-                    if (live && gl == 0 && v > p.nms_thr) atomicOr(&s_mask[i], 1ull << j);
+                    const bool over = oks_over<16>(pose + static_cast<size_t>(ci) * J * 3, pose + static_cast<size_t>(cj) * J * 3,
+                                                   area[ci], area[cj], J, gl, p.nms_thr);
+                    if (live && gl == 0 && over) atomicOr(&s_mask[i], 1ull << j);
                 }
             } else {
                 const int grp = tid >> 5, gl = tid & 31;
@@ -233,9 +252,9 @@ nms_backproject_kernel(const NmsParams p) {
                     while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
                     const int j = i + 1 + rem;
                     const int ci = order[i], cj = order[j];
-                    const float v = oks_pair<32>(pose + static_cast<size_t>(ci) * J * 3, pose + static_cast<size_t>(cj) * J * 3,
-                                                 area[ci], area[cj], J, gl);
-                    if (gl == 0 && v > p.nms_thr) atomicOr(&s_mask[i], 1ull << j);
+                    const bool over = oks_over<32>(pose + static_cast<size_t>(ci) * J * 3, pose + static_cast<size_t>(cj) * J * 3,
+                                                   area[ci], area[cj], J, gl, p.nms_thr);
+                    if (gl == 0 && over) atomicOr(&s_mask[i], 1ull << j);
                 }
             }
             __syncthreads();
@@ -269,9 +288,9 @@ nms_backproject_kernel(const NmsParams p) {
                 for (int j = i + 1 + grp; j < n; j += NT / 32) {
                     if (dead[j]) continue;             // warp-uniform
                     const int cj = order[j];
-                    const float v = oks_pair<32>(pose + static_cast<size_t>(ci) * J * 3, pose + static_cast<size_t>(cj) * J * 3,
-                                                 area[ci], area[cj], J, gl);
-                    if (gl == 0 && v > p.nms_thr) dead[j] = 1;
+                    const bool over = oks_over<32>(pose + static_cast<size_t>(ci) * J * 3, pose + static_cast<size_t>(cj) * J * 3,
+                                                   area[ci], area[cj], J, gl, p.nms_thr);
+                    if (gl == 0 && over) dead[j] = 1;
                 }
                 __syncthreads();
             }
