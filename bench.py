@@ -270,7 +270,6 @@ def run_reference(args):
 def run_b200(args):
     import torch.distributed as dist
     from das_b200.head import DecodePlan
-    from das_b200 import dist as ddist
 
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():

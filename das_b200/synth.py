@@ -12,7 +12,7 @@ benchmarks where 1.7 GB of features per batch would take too long on the host).
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List, Sequence
 
 import numpy as np

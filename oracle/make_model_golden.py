@@ -9,7 +9,6 @@ Writes tests/golden/mspn_small.npz: state_dict key/shape list, the input recipe,
 import os
 import re
 import sys
-import types
 
 import numpy as np
 import torch

@@ -1,11 +1,9 @@
 """GPU: recursive_update.num_layers > 1 -- dense layers 1..L-1 followed by the sparse last layer,
 against the oracle (which runs every layer densely like the reference) and the L=3 golden vectors."""
-import dataclasses
 import os
 
 import numpy as np
 import pytest
-import torch
 
 import util
 from das_b200 import synth

@@ -7,7 +7,6 @@ margin >= 16 ulp (the CPU reference's own fp32 sigmoid is only accurate to ~2 ul
 scores within 8 ulp; 3D joint coordinates within 1e-4 relative to their magnitude (floor 1 unit).
 """
 import dataclasses
-import glob
 import os
 
 import numpy as np

@@ -82,3 +82,28 @@ def test_sampler_order_and_interleave_match_multi_gpu_test():
             assert all(len(p) == len(parts[0]) for p in parts)
             merged = ddist.interleave_results(parts, size)
             assert [m["i"] for m in merged] == list(range(size))
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference`: exactly one JSON line on stdout with the contract's keys (the reference algorithm on
+    the host cores; on a multi-rank launch only rank 0 prints)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="0", LOCAL_RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, env=env, check=True).stdout
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "decoded_images_per_sec" and d["unit"] == "images/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    # a non-zero rank of a torchrun launch exits without output
+    env["RANK"] = "1"
+    silent = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                            capture_output=True, text=True, timeout=600, env=env, check=True).stdout
+    assert silent.strip() == ""
