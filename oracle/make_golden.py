@@ -47,6 +47,13 @@ CASES = {
                  dict(nms_pre=30, nms_post=12, nms_thr=0.9, score_thr=0.0, nms_type="soft"), dict(coherent=8)),
     "reference_cfg_nms1000": (P, 1, 40, 72, 1240, 24, (1.0, 1.0, 1.0, 1.0),
                               dict(nms_across_levels=False, nms_pre=1000, nms_post=100, nms_thr=0.9, score_thr=0.07)),
+    # SURVEY 8(c) edge cases: nms_post absent -> the NMS block is skipped (das_head.py:770-772); nothing above score_thr
+    # (N == 0, :772); uv offsets scaled 6x so most sampling targets fall outside the map (zero padding, recursive_update.py:25)
+    "no_nms_post": (P, 2, 24, 40, 1243, 12, (1.0, 1.0, 1.0, 1.0), dict(nms_pre=12, nms_thr=0.9, score_thr=0.02)),
+    "none_above_thr": (P, 2, 24, 40, 1244, 12, (1.0, 1.0, 1.0, 1.0),
+                       dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.9999)),
+    "border_targets": (P, 2, 16, 20, 1245, 10, (1.0, 1.0, 6.0, 1.0),
+                       dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)),
 }
 
 
