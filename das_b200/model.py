@@ -415,7 +415,7 @@ class DASNet(nn.Module):
         loaded, unknown = set(), []
         for key, val in state.items():
             k = key[7:] if key.startswith("module.") else key
-            if k.endswith("num_batches_tracked"):
+            if k.endswith("num_batches_tracked") or k.startswith(_TRAINING_ONLY):
                 continue
             tgt = reference_key_to_local(k, n_lateral=len(self.neck.lateral))
             if tgt is not None and tgt not in mine:      # a DCNv2 pack keeps its own weight/bias where a plain unit has .conv
@@ -439,6 +439,8 @@ class DASNet(nn.Module):
         return missing, unknown
 
 
+# training-only state of the reference head: the RLE loss's normalising flows (das_head.py:94-98) and loss modules
+_TRAINING_ONLY = ("bbox_head.flow2d", "bbox_head.flow3d", "bbox_head.loss_")
 _UNIT = {"conv": "conv", "bn": "norm", "gn": "norm"}
 _BLOCK = {"conv1": "reduce.conv", "bn1": "reduce.norm", "conv2": "spatial.conv", "bn2": "spatial.norm",
           "conv3": "expand.conv", "bn3": "expand.norm"}

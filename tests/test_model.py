@@ -249,3 +249,40 @@ def test_fpn_top_down_path_matches_torchvision_fpn():
             assert torch.allclose(g, w, atol=1e-5, rtol=1e-5)
         extra = torch.nn.functional.conv2d(got[2], neck.extra[0].conv.weight, neck.extra[0].conv.bias, stride=2, padding=1)
         assert torch.allclose(got[3], extra, atol=1e-6)
+
+
+def test_every_reference_checkpoint_key_is_consumed():
+    """tests/golden/reference_state_keys.json = the state_dict keys and shapes of the reference's Panoptic model, taken
+    from the reference's own MSPN2 / DASHead sources (oracle/make_state_keys.py).  Loading a checkpoint with exactly those
+    keys must fill EVERY parameter and buffer of DASNet, with no unmapped key besides the training-only flows."""
+    import json
+    import zlib
+    keys = json.load(open(os.path.join(GOLDEN_DIR, "reference_state_keys.json")))
+    assert sum(k.startswith("bbox_head.flow") for k in keys) > 0          # real checkpoints carry the RLE flows
+    state = {}
+    for k, shape in keys.items():
+        if k.endswith("num_batches_tracked"):
+            state["module." + k] = torch.tensor(0)
+        else:       # a value unique to the key, so a parameter landing in the wrong place is caught below
+            state["module." + k] = torch.full(shape, float(zlib.crc32(k.encode()) % 9973) / 9973.0 + 0.5)
+    net = M.DASNet(with_sigma=True)
+    missing, unknown = net.load_reference_state_dict({"state_dict": state}, strict=True)
+    assert missing == [] and unknown == []
+    mine = net.state_dict()
+
+    def val(k):
+        return float(zlib.crc32(k.encode()) % 9973) / 9973.0 + 0.5
+    spot = {
+        "backbone.multi_stage_mspn.1.downsample.layer4.2.conv3.weight": "backbone.stages.1.encoder.3.2.expand.conv.weight",
+        "backbone.multi_stage_mspn.0.upsample.up3.out_skip1.bn.running_var": "backbone.stages.0.decoder.2.skip_enc.norm.running_var",
+        "neck.fpn_convs.3.conv.weight": "neck.extra.0.conv.weight",
+        "bbox_head.reg_convs.1.conv.weight": "towers.reg_tower.1.weight",
+        "bbox_head.reg_convs.1.conv.conv_offset.bias": "towers.reg_tower.1.offset_mask.bias",
+        "bbox_head.conv_pose_prevs.1.0.gn.weight": "towers.sigma_out.0.norm.weight",
+        "bbox_head.recursive_update_branch.layer_0.next_level_offset.update_weight.bias": "towers.layers.0.update_weight.bias",
+        "bbox_head.recursive_update_branch.layer_0.next_level_offset.update_feat_conv.conv.weight": "towers.layers.0.update.weight",
+    }
+    for ref, loc in spot.items():
+        assert ref in keys, ref
+        assert torch.all(mine[loc] == val(ref)), (ref, loc)
+    assert abs(net.level_scales()[2][3] - val("bbox_head.scales.2.3.scale")) < 1e-6
