@@ -14,10 +14,14 @@ What it mirrors (behaviour, not code):
   * DASNet            <- DAS.extract_feat + bbox_head forward (detectors/das.py:74-79)
 
 Parity status: MSPNBackbone is pinned against the reference's own MSPN2 source executed under mmcv shims
-(oracle/make_model_golden.py -> tests/golden/mspn_small.npz).  FPN and the towers have no runnable reference here
-(mmdet / mmcv's DCNv2 op are absent): they are restated and only self-consistency-tested; DCNv2 is
-torchvision.ops.deform_conv2d with mmcv's (o1, o2, mask) channel split -- offset ordering vs mmcv is unverified.
-`load_reference_state_dict` maps the reference's checkpoint keys onto these modules.
+(oracle/make_model_golden.py -> tests/golden/mspn_small.npz).  DASTowers is pinned against the reference head's own
+forward code (das_head.py:180-230 + the RecursiveUpdateBranch conv part) executed under shims
+(oracle/make_state_keys.py -> tests/golden/das_head_small.npz), with ONE substitution: mmcv's DCNv2 CUDA op is absent, so
+both sides use torchvision.ops.deform_conv2d with mmcv's (o1, o2, mask) channel split -- the wiring, GroupNorm / bias
+conventions and the key map are pinned, the DCNv2 kernel's offset ordering vs mmcv is not.  FPN (mmdet, not in the tree)
+is restated from the published algorithm and checked against torchvision's FeaturePyramidNetwork.
+`load_reference_state_dict` maps the reference's checkpoint keys onto these modules (all 1200 keys of the Panoptic
+model, tests/golden/reference_state_keys.json).
 """
 from __future__ import annotations
 

@@ -31,6 +31,15 @@ class DCNv2Pack(nn.Module):
         self.weight = nn.Parameter(torch.zeros(cout, cin, k, k))
         self.bias = nn.Parameter(torch.zeros(cout)) if bias else None
         self.conv_offset = nn.Conv2d(cin, 3 * k * k, k, padding=padding)
+        self.padding = padding
+
+    def forward(self, x):
+        """mmcv's documented pack forward: one conv predicts (o1, o2, mask); offset = cat(o1, o2); mask = sigmoid(mask).
+        The deformable convolution itself is torchvision's here (mmcv's CUDA op is absent) -- so this pins the WIRING of
+        the towers, not the DCNv2 kernel."""
+        from torchvision.ops import deform_conv2d
+        o1, o2, mask = torch.chunk(self.conv_offset(x), 3, dim=1)
+        return deform_conv2d(x, torch.cat((o1, o2), dim=1), self.weight, self.bias, padding=self.padding, mask=torch.sigmoid(mask))
 
 
 class ConvModule(nn.Module):
@@ -47,6 +56,12 @@ class ConvModule(nn.Module):
                 self.gn = nn.GroupNorm(norm_cfg["num_groups"], cout)
             else:
                 self.bn = nn.BatchNorm2d(cout)
+        self.relu = act_cfg is not None
+
+    def forward(self, x):
+        x = self.conv(x)
+        x = self.gn(x) if hasattr(self, "gn") else self.bn(x) if hasattr(self, "bn") else x
+        return torch.relu(x) if self.relu else x
 
 
 class Scale(nn.Module):
@@ -94,7 +109,33 @@ def fpn_keys(n_lateral=3, n_out=4, ch=256):
     return keys
 
 
+def make_head_golden():
+    """Conv part of the reference head's forward (das_head.py:180-230, recursive_update.py:186-188, 250-252) on one small
+    feature map, with weights from the shared synthetic recipe -> tests/golden/das_head_small.npz."""
+    import numpy as np
+    from model_fixture import synthetic_state
+    head = reference_head().eval()
+    sd = head.state_dict()
+    keys = [k for k in sd if not k.startswith(("flow", "loss_"))]
+    full = synthetic_state(["bbox_head." + k for k in keys], [tuple(sd[k].shape) for k in keys])
+    head.load_state_dict({k: full["bbox_head." + k] for k in keys}, strict=False)
+    g = torch.Generator().manual_seed(91)
+    x = torch.randn(2, 256, 12, 16, generator=g)
+    with torch.no_grad():
+        cls, pose, cls_feat, reg_feat, pose_feat = head._forward_single(x)
+        ctr = head._forward_centerness(cls_feat, reg_feat)
+        f0 = head.recursive_update_branch.reduction(pose_feat)
+        f1 = f0 + head.recursive_update_branch.layer_0.next_level_offset._update_feat(f0)
+    out = os.path.join(os.path.dirname(OUT), "das_head_small.npz")
+    np.savez_compressed(out, cls=cls.numpy(), pose=pose.numpy(), ctr=ctr.numpy(), feat=f1.numpy(),
+                        keys=np.array(["bbox_head." + k for k in keys]),
+                        shapes=np.array([",".join(map(str, sd[k].shape)) for k in keys]))
+    print("wrote", os.path.normpath(out), os.path.getsize(out) // 1024, "KiB;", float(cls.abs().mean()), float(pose.abs().mean()),
+          float(f1.abs().mean()))
+
+
 def main():
+    make_head_golden()
     MSPN2 = G.load_reference_mspn()
     bb = MSPN2(unit_channels=256, num_stages=2, num_units=4, num_blocks=[3, 4, 6, 3], norm_cfg=dict(type="SyncBN"))
     keys = {"backbone." + k: list(v.shape) for k, v in bb.state_dict().items()}

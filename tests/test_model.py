@@ -286,3 +286,22 @@ def test_every_reference_checkpoint_key_is_consumed():
         assert ref in keys, ref
         assert torch.all(mine[loc] == val(ref)), (ref, loc)
     assert abs(net.level_scales()[2][3] - val("bbox_head.scales.2.3.scale")) < 1e-6
+
+
+def test_towers_match_reference_head_forward():
+    """tests/golden/das_head_small.npz = conv part of the reference DASHead's own forward code (das_head.py:180-230,
+    recursive_update.py:186-188, 250-252) executed under mmcv shims with torchvision's deform_conv2d as the DCNv2 op
+    (oracle/make_state_keys.py): pins the tower wiring, the GN / bias conventions and the key map; not mmcv's DCNv2 kernel."""
+    z = np.load(os.path.join(GOLDEN_DIR, "das_head_small.npz"))
+    keys = [str(k) for k in z["keys"]]
+    shapes = [tuple(int(v) for v in str(s).split(",")) if str(s) else () for s in z["shapes"]]
+    net = M.DASNet(backbone=dict(unit_channels=256, num_stages=1, num_blocks=(1, 1, 1, 1)), with_sigma=True).eval()
+    missing, unknown = net.load_reference_state_dict(synthetic_state(keys, shapes), strict=False)
+    assert unknown == [] and not any(m.startswith("towers.") for m in missing)
+    x = torch.randn(2, 256, 12, 16, generator=torch.Generator().manual_seed(91))
+    with torch.no_grad():
+        cls, pose, ctr, feats = net.towers(x)
+    for name, got in (("cls", cls), ("pose", pose), ("ctr", ctr), ("feat", feats[0])):
+        want = torch.from_numpy(z[name])
+        assert got.shape == want.shape, name
+        assert float((got - want).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max())), (name, float((got - want).abs().max()))
