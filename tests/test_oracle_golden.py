@@ -12,7 +12,7 @@ from oracle import make_golden as G
 from oracle import ref_extract as R
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-MODEL_FIXTURES = {"mspn_small"}          # tests/test_model.py (made by oracle/make_model_golden.py)
+MODEL_FIXTURES = {"mspn_small", "das_head_small"}      # tests/test_model.py (oracle/make_model_golden.py, make_state_keys.py)
 NAMES = sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
                if n not in MODEL_FIXTURES)
 
