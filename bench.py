@@ -656,6 +656,14 @@ def main():
     ap.add_argument("--workload", default="panoptic", choices=sorted(WORKLOADS),
                     help="panoptic = BASELINE config #2 (the metric; default); single = #1 (B=1 latency); mupots = #3; crowded = #4; e2e_model = #5 (network + decode)")
     args = ap.parse_args()
+    if args.gpus > 1 and "RANK" not in os.environ and args.impl != "reference":
+        # `python bench.py --gpus N` without a launcher: start one rank per GPU ourselves (what the driver's torchrun does)
+        import socket
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                                  "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:])
     if args.steps is None and args.workload != "e2e_model":
         args.steps = 20 if args.impl == "reference" else (4000 if args.workload in ("panoptic", "single", "crowded") else 300)
     guard_stdout()
