@@ -234,12 +234,15 @@ class DecodePlan:
         cam = np.zeros((B, _lib.CAM_DOUBLES), dtype=np.float64)
         cams = [m.get("cam") for m in img_metas]
         if all(c is not None and "R" in c and "t" in c for c in cams):
-            K = np.array([c["K"] for c in cams], dtype=np.float64)          # np.array over a list of equal-shape arrays
-            cam[:, 0:3] = K[:, 0, :3]                                        # is the cheapest way to gather them
-            cam[:, 3:6] = K[:, 1, :3]
-            cam[:, 6:15] = np.array([c["R"] for c in cams], dtype=np.float64).reshape(B, 9)
-            cam[:, 15:18] = np.array([c["t"] for c in cams], dtype=np.float64).reshape(B, 3)
-            return sxy, cam
+            try:
+                K = np.array([c["K"] for c in cams], dtype=np.float64)      # np.array over a list of equal-shape arrays
+                cam[:, 0:3] = K[:, 0, :3]                                    # is the cheapest way to gather them
+                cam[:, 3:6] = K[:, 1, :3]
+                cam[:, 6:15] = np.array([c["R"] for c in cams], dtype=np.float64).reshape(B, 9)
+                cam[:, 15:18] = np.array([c["t"] for c in cams], dtype=np.float64).reshape(B, 3)
+                return sxy, cam
+            except (ValueError, IndexError):     # images with differently shaped K (2x3 next to 3x3): general path
+                pass
         for b, c in enumerate(cams):                 # mixed / partial camera entries: the general path
             if c is None:
                 K, R, t = np.eye(3), np.eye(3), np.zeros(3)

@@ -107,3 +107,35 @@ def test_bench_reference_arm_prints_one_json_line():
     silent = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                             capture_output=True, text=True, timeout=600, env=env, check=True).stdout
     assert silent.strip() == ""
+
+
+def test_get_poses_argument_forms():
+    """The three call forms get_poses accepts: the reference's (img_metas[, cfg[, rescale]]) and the extended
+    (refine_feats, img_metas) one (das_head.py:653-659; detectors/das.py:78 splats the head outputs)."""
+    from das_b200.head import DASHeadB200
+    metas = [dict(scale_factor=np.ones(4, np.float32), filename="a.jpg")]
+    feats = [[object()]]
+    sr = DASHeadB200._split_rest
+    assert sr((metas,), None) == (None, metas, None)
+    assert sr((metas, dict(nms_pre=5)), None) == (None, metas, dict(nms_pre=5))        # positional cfg
+    assert sr((metas, dict(nms_pre=5), True), None) == (None, metas, dict(nms_pre=5))  # positional cfg, rescale
+    assert sr((metas, None, True), dict(nms_pre=7)) == (None, metas, dict(nms_pre=7))
+    assert sr((feats, metas), None) == (feats, metas, None)                            # extended call
+    assert sr((feats, []), None) == (feats, [], None)                                  # empty batch
+    with pytest.raises(TypeError):
+        sr((), None)
+
+
+def test_pack_metas_fast_and_general_paths_agree():
+    from das_b200 import synth
+    from das_b200.head import DecodePlan
+    metas = synth.make_metas(5, 16, 20, stride=8, seed=3)
+    s1, c1 = DecodePlan.pack_metas(metas)
+    partial = [dict(m) for m in metas]
+    partial[2] = dict(scale_factor=metas[2]["scale_factor"], filename="x")            # no camera -> identity K, R; t = 0
+    s2, c2 = DecodePlan.pack_metas(partial)
+    assert np.array_equal(s1, s2) and s1.dtype == np.float32 and s1.flags["C_CONTIGUOUS"] and s1.shape == (5, 2)
+    assert np.array_equal(np.delete(c1, 2, 0), np.delete(c2, 2, 0))
+    assert c2[2].tolist() == [1, 0, 0, 0, 1, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0]
+    two_by_three = [dict(m, cam=dict(K=m["cam"]["K"][:2], R=m["cam"]["R"], t=m["cam"]["t"])) for m in metas]   # MuPoTS K is 2x3
+    assert np.array_equal(DecodePlan.pack_metas(two_by_three)[1], c1)
