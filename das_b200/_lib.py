@@ -51,6 +51,14 @@ class Buffers(C.Structure):
                 ("out_cam", C.c_void_p), ("out_world", C.c_void_p)]
 
 
+MAX_PEERS = 15
+
+
+class PeerBlocks(C.Structure):
+    _fields_ = [("n", C.c_int32), ("reserved_", C.c_int32), ("delta", C.c_int64 * MAX_PEERS),
+                ("seq", C.c_void_p), ("ticket", C.c_void_p)]
+
+
 class RowCache(C.Structure):
     _fields_ = [("table", C.c_void_p), ("rows", C.c_void_p), ("cand_rows", C.c_void_p),
                 ("table_bits", C.c_int32), ("max_rows", C.c_int32)]
@@ -60,6 +68,7 @@ class RowCache(C.Structure):
 _VP = C.c_void_p
 SIGNATURES = {
     "das_version": (C.c_char_p, []),
+    "das_abi_struct_sizes": (None, [_i32p]),
     "das_last_error": (C.c_char_p, []),
     "das_level_slots": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
     "das_candidate_slots": (C.c_int32, [C.POINTER(Levels), C.c_int32]),
@@ -86,6 +95,14 @@ SIGNATURES = {
     "das_pack_dense_panels": (C.c_int, [C.POINTER(DecodeCfg), _VP, _VP, _VP]),
     "das_dense_panel_bytes": (C.c_int64, [C.POINTER(DecodeCfg)]),
     "das_nms_backproject": (C.c_int, [C.POINTER(DecodeCfg), C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, Buffers, _VP]),
+    "das_nms_backproject_peers": (C.c_int, [C.POINTER(DecodeCfg), C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, Buffers,
+                                            C.POINTER(PeerBlocks), _VP]),
+    "das_plan_set_output_block": (C.c_int, [_VP, _VP, C.c_int64]),
+    "das_plan_set_peer_blocks": (C.c_int, [_VP, C.c_int32, C.POINTER(_VP)]),
+    "das_ipc_alloc": (C.c_int, [C.c_int64, C.POINTER(_VP), C.c_char_p]),
+    "das_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(_VP)]),
+    "das_ipc_close": (C.c_int, [_VP]),
+    "das_ipc_free": (C.c_int, [_VP]),
     "das_pack_weights": (C.c_int, [C.POINTER(DecodeCfg)] + [_VP] * 10),
     "das_packed_weight_floats": (C.c_int64, [C.POINTER(DecodeCfg)]),
     "das_plan_create": (C.c_int, [C.POINTER(DecodeCfg), C.POINTER(Levels), C.POINTER(_VP)]),
@@ -105,6 +122,7 @@ SIGNATURES = {
     "das_plan_set_host_mode": (C.c_int, [_VP, C.c_int32]),
     "das_plan_h2d_explicit_bytes": (C.c_int64, [_VP]),
     "das_plan_d2h_bytes": (C.c_int64, [_VP]),
+    "das_plan_row_cache_stats": (C.c_int, [_VP, _i32p]),
 }
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libdas_decode.so")
@@ -120,18 +138,29 @@ def lib_path() -> str:
 
 
 def load():
-    """Load libdas_decode.so (building it when absent and nvcc exists). Raises if impossible."""
+    """Load libdas_decode.so, (re)building it first when it is absent or older than its sources / the header and nvcc
+    exists (a stale library would be bound with new ctypes struct layouts: silent corruption).  The library also
+    reports the sizes of the by-value structs it was compiled with; a mismatch with the ctypes mirrors raises."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.isfile(LIB_PATH):
-        from . import build as _build
-        _build.build()
+    from . import build as _build
+    if _build._stale():
+        if os.path.isfile(_build.NVCC):
+            _build.build()
+        elif not os.path.isfile(LIB_PATH):
+            raise DasError(f"{LIB_PATH} is missing and nvcc ({_build.NVCC}) is not available to build it")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here = header and library disagree
         fn.restype = res
         fn.argtypes = args
+    sizes = (C.c_int32 * 4)()
+    lib.das_abi_struct_sizes(sizes)
+    mine = [C.sizeof(Levels), C.sizeof(DecodeCfg), C.sizeof(Buffers), C.sizeof(RowCache)]
+    if list(sizes) != mine:
+        raise DasError(f"ABI mismatch: library struct sizes {list(sizes)} != ctypes mirrors {mine}; rebuild with "
+                       "python -m das_b200.build --force")
     _lib = lib
     return lib
 

@@ -30,7 +30,18 @@ struct NmsParams {
     const float* cand_center;
     const double* cam;
     das_buffers out;
+    das_peer_blocks peers;     // n == 0: local stores only
 };
+
+// Every output value goes to the local block and, when peers are configured, to the same offset of every peer's copy
+// of this rank's block (NVLink P2P stores, fire-and-forget): the result all-gather is fused into the kernel that
+// produces the results ("only the final small pose lists are gathered over NVLink").
+template <typename T>
+__device__ __forceinline__ void store_all(const das_peer_blocks& pe, T* local, T v) {
+    *local = v;
+    for (int q = 0; q < pe.n; ++q)
+        *reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(local) + pe.delta[q]) = v;
+}
 
 __device__ __forceinline__ double oks_var(int j, int J) {
     // pose_nms.py:65-73: vars = (sigmas * 2) ** 2
@@ -311,7 +322,8 @@ nms_backproject_kernel(const NmsParams p) {
 
     // ---- outputs -----------------------------------------------------------------------------------
     const das_buffers& o = p.out;
-    if (tid == 0) o.out_count[b] = kept;
+    const das_peer_blocks& pe = p.peers;
+    if (tid == 0) store_all(pe, o.out_count + b, kept);
     const double* __restrict__ cam = p.cam + static_cast<size_t>(b) * DAS_CAM_DOUBLES;
     const double K00 = cam[0], K01 = cam[1], K02 = cam[2], K10 = cam[3], K11 = cam[4], K12 = cam[5];
     const double* R = cam + 6;
@@ -327,9 +339,9 @@ nms_backproject_kernel(const NmsParams p) {
     for (int k = tid; k < P; k += NT) {
         const bool live = k < kept;
         const int c = live ? kept_list[k] : 0;
-        o.out_score[static_cast<size_t>(b) * P + k] = live ? score[c] : 0.f;
-        o.out_slot[static_cast<size_t>(b) * P + k] = live ? c : -1;
-        for (int d = 0; d < 3; ++d) o.out_center[(static_cast<size_t>(b) * P + k) * 3 + d] = live ? center[c * 3 + d] : 0.f;
+        store_all(pe, o.out_score + static_cast<size_t>(b) * P + k, live ? score[c] : 0.f);
+        store_all(pe, o.out_slot + static_cast<size_t>(b) * P + k, live ? c : -1);
+        for (int d = 0; d < 3; ++d) store_all(pe, o.out_center + (static_cast<size_t>(b) * P + k) * 3 + d, live ? center[c * 3 + d] : 0.f);
     }
     for (int e = tid; e < P * J; e += NT) {
         const int k = e / J, j = e - k * J;
@@ -338,7 +350,7 @@ nms_backproject_kernel(const NmsParams p) {
             const int c = kept_list[k];
             const float* pc = pose + static_cast<size_t>(c) * J * 3;
             const float fx = pc[3 * j], fy = pc[3 * j + 1], fz = pc[3 * j + 2];
-            o.out_pose[ob] = fx; o.out_pose[ob + 1] = fy; o.out_pose[ob + 2] = fz;
+            store_all(pe, o.out_pose + ob, fx); store_all(pe, o.out_pose + ob + 1, fy); store_all(pe, o.out_pose + ob + 2, fz);
             const double zr = static_cast<double>(pc[3 * p.root + 2]);
             double Z = zr * nd + (static_cast<double>(fz) - zr);
             Z *= p.ddf;
@@ -346,13 +358,28 @@ nms_backproject_kernel(const NmsParams p) {
             const double a = (K11 * X0 - K01 * X1) / detK;
             const double bb = (-K10 * X0 + K00 * X1) / detK;
             const double cx = a * Z, cy = bb * Z, cz = Z;
-            o.out_cam[ob] = cx; o.out_cam[ob + 1] = cy; o.out_cam[ob + 2] = cz;
+            store_all(pe, o.out_cam + ob, cx); store_all(pe, o.out_cam + ob + 1, cy); store_all(pe, o.out_cam + ob + 2, cz);
             const double dx = cx - T[0], dy = cy - T[1], dz = cz - T[2];
-            o.out_world[ob] = (c00 * dx + c01 * dy + c02 * dz) / detR;
-            o.out_world[ob + 1] = (c10 * dx + c11 * dy + c12 * dz) / detR;
-            o.out_world[ob + 2] = (c20 * dx + c21 * dy + c22 * dz) / detR;
+            store_all(pe, o.out_world + ob, (c00 * dx + c01 * dy + c02 * dz) / detR);
+            store_all(pe, o.out_world + ob + 1, (c10 * dx + c11 * dy + c12 * dz) / detR);
+            store_all(pe, o.out_world + ob + 2, (c20 * dx + c21 * dy + c22 * dz) / detR);
         } else {
-            for (int d = 0; d < 3; ++d) { o.out_pose[ob + d] = 0.f; o.out_cam[ob + d] = 0.0; o.out_world[ob + d] = 0.0; }
+            for (int d = 0; d < 3; ++d) { store_all(pe, o.out_pose + ob + d, 0.f); store_all(pe, o.out_cam + ob + d, 0.0); store_all(pe, o.out_world + ob + d, 0.0); }
+        }
+    }
+    if (pe.n > 0 && pe.seq) {
+        // publish: the last CTA to finish bumps the block's sequence number on every peer, after every CTA's stores have
+        // been made visible system-wide -- a consumer on the peer that sees seq == s may read step s's results
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            const int ticket = atomicAdd(pe.ticket, 1);
+            if (ticket == static_cast<int>(gridDim.x) - 1) {
+                *pe.ticket = 0;
+                const int sq = *pe.seq + 1;
+                __threadfence_system();
+                store_all(pe, pe.seq, sq);
+            }
         }
     }
 }
@@ -366,8 +393,15 @@ extern "C" int32_t das_output_slots(int32_t cand_slots, int32_t nms_post) {
 extern "C" int das_nms_backproject(const das_decode_cfg* cfg, int32_t batch, int32_t cand_slots,
                                    const float* cand_score, const float* cand_pose, const float* cand_center,
                                    const double* cam, das_buffers out, void* stream) {
+    return das_nms_backproject_peers(cfg, batch, cand_slots, cand_score, cand_pose, cand_center, cam, out, nullptr, stream);
+}
+
+extern "C" int das_nms_backproject_peers(const das_decode_cfg* cfg, int32_t batch, int32_t cand_slots,
+                                         const float* cand_score, const float* cand_pose, const float* cand_center,
+                                         const double* cam, das_buffers out, const das_peer_blocks* peers, void* stream) {
     using namespace das;
     DAS_REQUIRE(cfg && cand_score && cand_pose && cand_center && cam, DAS_ERR_ARG, "das_nms_backproject: null pointer");
+    DAS_REQUIRE(!peers || (peers->n >= 0 && peers->n <= DAS_MAX_PEERS), DAS_ERR_ARG, "das_nms_backproject: %d peers", peers ? peers->n : 0);
     DAS_REQUIRE(out.out_count && out.out_score && out.out_slot && out.out_pose && out.out_center && out.out_cam && out.out_world,
                 DAS_ERR_ARG, "das_nms_backproject: null output pointer");
     DAS_REQUIRE(batch >= 1 && cand_slots >= 1, DAS_ERR_ARG, "batch=%d cand_slots=%d", batch, cand_slots);
@@ -380,6 +414,7 @@ extern "C" int das_nms_backproject(const das_decode_cfg* cfg, int32_t batch, int
     p.ddf = cfg->dataset_depth_factor == 0.0 ? 1.0 : cfg->dataset_depth_factor;
     p.cand_score = cand_score; p.cand_pose = cand_pose; p.cand_center = cand_center; p.cam = cam;
     p.out = out;
+    if (peers) p.peers = *peers;
     int n2 = 1;
     while (n2 < cand_slots) n2 <<= 1;
     const size_t smem = static_cast<size_t>(n2) * 8 + static_cast<size_t>(cand_slots) * (4 + 4 + 1 + 4) + 32;

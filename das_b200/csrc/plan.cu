@@ -58,7 +58,10 @@ struct das_plan {
     int64_t h2d_explicit = 0;         // bytes das_plan_run_host copies explicitly per call in the current host_mode
     int64_t h2d_bytes = 0, d2h_bytes = 0;
     unsigned char* out_block = nullptr;   // all out_* buffers live in this one allocation (one D2H / one all-gather)
-    size_t out_block_bytes = 0;
+    unsigned char* own_block = nullptr;   // the plan's own allocation (out_block may point at a caller-owned block instead)
+    size_t out_block_bytes = 0;           // packed outputs; a 256-byte trailer with the sequence word follows
+    size_t out_off[7] = {};               // byte offsets of count | score | slot | pose | center | cam | world
+    das_peer_blocks peers{};              // fused result all-gather (das_plan_set_peer_blocks)
     // graph
     cudaGraphExec_t exec = nullptr;
     cudaGraphExec_t exec_prof = nullptr;   // same graph with event-record nodes between the stages
@@ -70,6 +73,9 @@ struct das_plan {
 
 extern "C" const char* das_version(void) { return "das-b200 0.1 (sm_100a)"; }
 extern "C" const char* das_last_error(void) { return das::g_err; }
+extern "C" void das_abi_struct_sizes(int32_t out[4]) {
+    out[0] = sizeof(das_levels); out[1] = sizeof(das_decode_cfg); out[2] = sizeof(das_buffers); out[3] = sizeof(das_row_cache);
+}
 
 extern "C" int32_t das_level_slots(int32_t H, int32_t W, int32_t nms_pre) { return das::level_slots(H * W, nms_pre); }
 
@@ -78,6 +84,17 @@ extern "C" int32_t das_candidate_slots(const das_levels* lv, int32_t nms_pre) {
     int t = 0;
     for (int l = 0; l < lv->n_levels; ++l) t += das::level_slots(lv->lv[l].H * lv->lv[l].W, nms_pre);
     return t;
+}
+
+static void point_outputs(das_plan* p, unsigned char* q) {
+    p->out_block = q;
+    p->buf.out_count = reinterpret_cast<int32_t*>(q + p->out_off[0]);
+    p->buf.out_score = reinterpret_cast<float*>(q + p->out_off[1]);
+    p->buf.out_slot = reinterpret_cast<int32_t*>(q + p->out_off[2]);
+    p->buf.out_pose = reinterpret_cast<float*>(q + p->out_off[3]);
+    p->buf.out_center = reinterpret_cast<float*>(q + p->out_off[4]);
+    p->buf.out_cam = reinterpret_cast<double*>(q + p->out_off[5]);
+    p->buf.out_world = reinterpret_cast<double*>(q + p->out_off[6]);
 }
 
 template <typename T>
@@ -139,16 +156,12 @@ extern "C" int das_plan_create(const das_decode_cfg* cfg, const das_levels* shap
         const size_t o_cam = up(o_center + B * P * 3 * 4);
         const size_t o_world = up(o_cam + B * P * J * 3 * 8);
         p->out_block_bytes = up(o_world + B * P * J * 3 * 8);
-        A(dev_alloc(&p->out_block, p->out_block_bytes));
+        const size_t offs[7] = {o_count, o_score, o_slot, o_pose, o_center, o_cam, o_world};
+        std::memcpy(p->out_off, offs, sizeof(offs));
+        A(dev_alloc(&p->own_block, p->out_block_bytes + 256));
         if (s == DAS_OK) {
-            unsigned char* q = p->out_block;
-            p->buf.out_count = reinterpret_cast<int32_t*>(q + o_count);
-            p->buf.out_score = reinterpret_cast<float*>(q + o_score);
-            p->buf.out_slot = reinterpret_cast<int32_t*>(q + o_slot);
-            p->buf.out_pose = reinterpret_cast<float*>(q + o_pose);
-            p->buf.out_center = reinterpret_cast<float*>(q + o_center);
-            p->buf.out_cam = reinterpret_cast<double*>(q + o_cam);
-            p->buf.out_world = reinterpret_cast<double*>(q + o_world);
+            if (cudaMemset(p->own_block + p->out_block_bytes, 0, 256) != cudaSuccess) s = DAS_ERR_CUDA;
+            point_outputs(p, p->own_block);
         }
     }
     A(dev_alloc(&p->scratch, B * static_cast<size_t>(p->hw_sum)));
@@ -219,7 +232,7 @@ extern "C" void das_plan_destroy(das_plan* p) {
     if (p->exec_prof) cudaGraphExecDestroy(p->exec_prof);
     for (cudaEvent_t e : p->ev) if (e) cudaEventDestroy(e);
     void* ptrs[] = {p->d_levels, p->buf.cand_score, p->buf.cand_index, p->buf.cand_pose, p->buf.cand_center,
-                    p->out_block, p->scratch, p->work_counter, p->d_scale_xy, p->d_cam,
+                    p->own_block, p->scratch, p->work_counter, p->d_scale_xy, p->d_cam,
                     p->proj, p->d_prev_ptrs, p->tc_panels, p->item_heads, p->item_asm, p->valid_list};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->rc.table) cudaFree(p->rc.table);
@@ -335,7 +348,7 @@ static int enqueue(das_plan* p, cudaStream_t st, int* n_launch, bool events) {
         }
         DAS_TRY(das_refine_tc(p->d_levels, &p->bound, &c, w, p->tc_panels, p->CT, p->item_heads, p->item_asm, p->valid_list,
                               p->work_counter + 1, p->buf.cand_pose,
-                              p->refine_mode == 1 ? 1 : (p->refine_mode == 2 ? 0 : p->refine_mode - 2), st));
+                              p->refine_mode == 1 ? 1 : 0, st));
         n += 2;
     } else {
         DAS_TRY(das_gather_refine_assemble(p->d_levels, &p->bound, &c, c.refine ? p->wpack[c.num_layers - 1] : nullptr, prev,
@@ -345,8 +358,8 @@ static int enqueue(das_plan* p, cudaStream_t st, int* n_launch, bool events) {
         DAS_TRY(mark(3));
     }
     DAS_TRY(mark(4));
-    DAS_TRY(das_nms_backproject(&c, p->B, p->CT, p->buf.cand_score, p->buf.cand_pose, p->buf.cand_center, p->d_cam,
-                                p->buf, st));
+    DAS_TRY(das_nms_backproject_peers(&c, p->B, p->CT, p->buf.cand_score, p->buf.cand_pose, p->buf.cand_center, p->d_cam,
+                                      p->buf, p->peers.n > 0 ? &p->peers : nullptr, st));
     ++n;
     DAS_TRY(mark(5));
     *n_launch = n;
@@ -386,13 +399,14 @@ extern "C" int das_plan_run(das_plan* p, void* stream, int32_t mode) {
         for (cudaEvent_t& e : p->ev) DAS_CUDA_CHECK(cudaEventCreate(&e));
     }
     if (mode == 0 || p->launches == 0) {
-        // the very first run is always eager: module loading and cudaFuncSetAttribute must not land inside a capture
+        // the very first run is always eager (module loading and cudaFuncSetAttribute must not land inside a capture);
+        // the graph is captured by the next call, so no call runs the decode twice
         int n = 0;
         DAS_TRY(enqueue(p, st, &n, false));
         p->launches_per_run = n;
         p->launches += n;
-        if (mode == 0) return DAS_OK;
-        DAS_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (mode != 2) return DAS_OK;
+        DAS_CUDA_CHECK(cudaStreamSynchronize(st));      // profiling replay requested on a fresh plan: capture right away
     }
     cudaGraphExec_t* ex = (mode == 2) ? &p->exec_prof : &p->exec;
     if (!*ex) DAS_TRY(capture(p, ex, mode == 2));
@@ -420,10 +434,87 @@ extern "C" int das_plan_output_block(const das_plan* p, void** ptr, int64_t* byt
     return DAS_OK;
 }
 
+static void drop_graphs(das_plan* p) {
+    if (p->exec) { cudaGraphExecDestroy(p->exec); p->exec = nullptr; }
+    if (p->exec_prof) { cudaGraphExecDestroy(p->exec_prof); p->exec_prof = nullptr; }
+}
+
+extern "C" int das_plan_set_output_block(das_plan* p, void* block, int64_t bytes) {
+    using namespace das;
+    DAS_REQUIRE(p, DAS_ERR_ARG, "null plan");
+    if (!block) {                                  // back to the plan's own allocation
+        point_outputs(p, p->own_block);
+    } else {
+        DAS_REQUIRE((reinterpret_cast<uintptr_t>(block) & 255) == 0, DAS_ERR_ARG, "output block must be 256-byte aligned");
+        DAS_REQUIRE(bytes >= static_cast<int64_t>(p->out_block_bytes + 256), DAS_ERR_ARG,
+                    "output block of %lld bytes is smaller than the %lld the plan needs", static_cast<long long>(bytes),
+                    static_cast<long long>(p->out_block_bytes + 256));
+        DAS_CUDA_CHECK(cudaMemset(static_cast<unsigned char*>(block) + p->out_block_bytes, 0, 256));
+        point_outputs(p, static_cast<unsigned char*>(block));
+    }
+    p->peers = das_peer_blocks{};                  // peer deltas were relative to the old block
+    drop_graphs(p);
+    return DAS_OK;
+}
+
+extern "C" int das_plan_set_peer_blocks(das_plan* p, int32_t n_peers, void* const* peer_blocks) {
+    using namespace das;
+    DAS_REQUIRE(p, DAS_ERR_ARG, "null plan");
+    DAS_REQUIRE(n_peers >= 0 && n_peers <= DAS_MAX_PEERS && (n_peers == 0 || peer_blocks), DAS_ERR_ARG, "n_peers=%d (max %d)",
+                n_peers, DAS_MAX_PEERS);
+    das_peer_blocks pb{};
+    pb.n = n_peers;
+    for (int q = 0; q < n_peers; ++q) {
+        DAS_REQUIRE(peer_blocks[q] && (reinterpret_cast<uintptr_t>(peer_blocks[q]) & 255) == 0, DAS_ERR_ARG, "peer block %d is null or unaligned", q);
+        pb.delta[q] = static_cast<int64_t>(reinterpret_cast<intptr_t>(peer_blocks[q]) - reinterpret_cast<intptr_t>(p->out_block));
+    }
+    if (n_peers > 0) {
+        pb.seq = reinterpret_cast<int32_t*>(p->out_block + p->out_block_bytes);
+        pb.ticket = p->work_counter + 2;
+        DAS_CUDA_CHECK(cudaMemset(pb.ticket, 0, sizeof(int32_t)));
+    }
+    p->peers = pb;
+    drop_graphs(p);
+    return DAS_OK;
+}
+
+extern "C" int das_ipc_alloc(int64_t bytes, void** dev_ptr, unsigned char handle[64]) {
+    using namespace das;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    DAS_REQUIRE(bytes > 0 && dev_ptr && handle, DAS_ERR_ARG, "das_ipc_alloc: bad argument");
+    void* q = nullptr;
+    DAS_CUDA_CHECK(cudaMalloc(&q, static_cast<size_t>(bytes)));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, q);
+    if (e != cudaSuccess) { cudaFree(q); set_error("cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); return DAS_ERR_CUDA; }
+    DAS_CUDA_CHECK(cudaMemset(q, 0, static_cast<size_t>(bytes)));
+    std::memcpy(handle, &h, 64);
+    *dev_ptr = q;
+    return DAS_OK;
+}
+extern "C" int das_ipc_open(const unsigned char handle[64], void** dev_ptr) {
+    using namespace das;
+    DAS_REQUIRE(handle && dev_ptr, DAS_ERR_ARG, "das_ipc_open: null pointer");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    DAS_CUDA_CHECK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return DAS_OK;
+}
+extern "C" int das_ipc_close(void* dev_ptr) {
+    using namespace das;
+    if (dev_ptr) DAS_CUDA_CHECK(cudaIpcCloseMemHandle(dev_ptr));
+    return DAS_OK;
+}
+extern "C" int das_ipc_free(void* dev_ptr) {
+    using namespace das;
+    if (dev_ptr) DAS_CUDA_CHECK(cudaFree(dev_ptr));
+    return DAS_OK;
+}
+
 extern "C" int das_plan_set_refine_mode(das_plan* p, int32_t mode) {
     using namespace das;
     DAS_REQUIRE(p, DAS_ERR_ARG, "null plan");
-    DAS_REQUIRE(mode >= 0 && mode <= 40, DAS_ERR_ARG, "refine mode %d", mode);   // 3..9: timing experiments (split bits = mode - 2)
+    DAS_REQUIRE(mode >= 0 && mode <= 2, DAS_ERR_ARG, "refine mode %d (0 = fp32 SIMT, 1 = tcgen05 3xTF32, 2 = tcgen05 TF32)", mode);
     DAS_REQUIRE(p->launches == 0, DAS_ERR_ARG, "das_plan_set_refine_mode must be called before the first run");
     DAS_REQUIRE(mode == 0 || p->tc_panels, DAS_ERR_UNSUPPORTED, "tensor-core refinement needs refine=1, feat_channels=256, num_heads=4");
     p->refine_mode = mode;
@@ -457,7 +548,10 @@ static int set_row_cache(das_plan* p, bool on) {
     using namespace das;
     on = on && p->cfg.refine && p->refine_mode != 0 && p->tc_panels;
     if (on && !p->rc.table) {
-        const long long records = static_cast<long long>(p->B) * p->CT * p->cfg.num_joints * (32 + 4);
+        // distinct rows are bounded both by the row records (32 sampled + 4 target-corner rows per item) and by the
+        // number of cells there are; the table holds twice that many entries
+        const long long records = std::min<long long>(static_cast<long long>(p->B) * p->CT * p->cfg.num_joints * (32 + 4),
+                                                      static_cast<long long>(p->B) * p->hw_sum);
         int bits = 10;
         while (bits < 26 && (1ll << bits) < 2 * records) ++bits;
         long long cap = std::min<long long>(records, 262144);
@@ -472,12 +566,30 @@ static int set_row_cache(das_plan* p, bool on) {
     }
     if (on != p->rc_active) {
         p->rc_active = on;
-        if (p->exec) { cudaGraphExecDestroy(p->exec); p->exec = nullptr; }
-        if (p->exec_prof) { cudaGraphExecDestroy(p->exec_prof); p->exec_prof = nullptr; }
+        drop_graphs(p);
     }
     return DAS_OK;
 }
 extern "C" int64_t das_plan_d2h_bytes(const das_plan* p) { return p ? p->d2h_bytes : 0; }
+
+// Row-cache occupancy after the last host-mode run: stats[0] = distinct feature rows copied into the device row buffer,
+// stats[1] = candidates above score_thr (each fetched its F(p) row once).  Synchronises with the device.
+extern "C" int das_plan_row_cache_stats(das_plan* p, int32_t stats[2]) {
+    using namespace das;
+    DAS_REQUIRE(p && stats, DAS_ERR_ARG, "das_plan_row_cache_stats: null pointer");
+    stats[0] = stats[1] = 0;
+    if (p->rc.table) {
+        const size_t n = static_cast<size_t>(1) << p->rc.table_bits;
+        const unsigned char* counter = static_cast<const unsigned char*>(p->rc.table) + n * 12;
+        int32_t c = -1;
+        DAS_CUDA_CHECK(cudaMemcpy(&c, counter, sizeof(c), cudaMemcpyDeviceToHost));
+        stats[0] = std::min<int32_t>(c + 1, p->rc.max_rows);
+    }
+    int32_t v = 0;
+    DAS_CUDA_CHECK(cudaMemcpy(&v, p->work_counter + 1, sizeof(v), cudaMemcpyDeviceToHost));
+    stats[1] = v;
+    return DAS_OK;
+}
 
 extern "C" int das_plan_run_host(das_plan* p, const das_levels* levels, const float* scale_xy, const double* cam,
                                  das_buffers host_out, void* stream) {

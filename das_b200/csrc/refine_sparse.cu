@@ -140,8 +140,9 @@ refine_sparse_kernel(const RefineParams p) {
                     bool won = false;
                     if (p.rc.keys && ok) {
                         if (lane == 0) {
-                            won = row_cache_insert(p.rc, reinterpret_cast<unsigned long long>(rowp), hh, slot, false);
-                            if (!won) slot = row_cache_wait(p.rc, hh);
+                            const int ins = row_cache_insert(p.rc, reinterpret_cast<unsigned long long>(rowp), hh, slot, false);
+                            won = ins > 0;
+                            if (ins == 0) slot = row_cache_wait(p.rc, hh);      // bounded; -2 = read the row at home
                         }
                         won = __shfl_sync(FULL, won, 0);
                         slot = __shfl_sync(FULL, slot, 0);

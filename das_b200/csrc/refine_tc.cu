@@ -423,9 +423,10 @@ row_cache_kernel(float* row_records, const int32_t* valid_list, const int32_t* n
         int slot = -1;
         bool won = false;
         uint32_t h = 0;
-        if (ptr) won = row_cache_insert(rc, ptr, h, slot);
+        int ins = -1;
+        if (ptr) { ins = row_cache_insert(rc, ptr, h, slot); won = ins > 0; }
         __syncwarp();
-        if (ptr && !won) slot = row_cache_wait(rc, h);
+        if (ptr && ins == 0) slot = row_cache_wait(rc, h);       // bounded; a negative slot leaves the record pointing at the host row
         unsigned todo = __ballot_sync(0xffffffffu, won && slot >= 0);
         while (todo) {
             const int src = __ffs(todo) - 1;

@@ -31,27 +31,34 @@ inline RowCacheView row_cache_view(const das_row_cache* rc) {
     return v;
 }
 
-// Insert `ptr` (never 0).  Returns true if this thread created the entry: then `slot` is its row-buffer slot (or -2
-// when the buffer is full) and is already published.  Otherwise the entry exists at `h`; its slot may still be -1
-// for a while (row_cache_wait).  With publish = true the row DATA of a slot is only guaranteed complete after the
-// inserting kernel has finished.
+constexpr int kRowCacheMaxProbes = 512;      // open-addressing probe limit: beyond it the table counts as full
+constexpr int kRowCacheMaxPolls = 1 << 16;   // bounded wait for another thread's copy (~tens of ms), then fall back
+
+// Insert `ptr` (never 0).  Returns 1 if this thread created the entry: then `slot` is its row-buffer slot (or -2
+// when the buffer is full) and is already published.  Returns 0 if the entry exists at `h`; its slot may still be -1
+// for a while (row_cache_wait).  Returns -1 if no free table entry was found within kRowCacheMaxProbes probes (table
+// full): nothing was inserted, slot = -2, and the caller keeps reading the row from where it lives (always correct --
+// the cache only ever holds copies).  With publish = true the row DATA of a slot is only guaranteed complete after
+// the inserting kernel has finished.
 // publish = false: the caller fills the row first and then calls row_cache_publish, so that a thread that finds the
 // entry (row_cache_wait) may read the row's DATA in the same kernel; a full buffer (-2) is always published at once.
-__device__ __forceinline__ bool row_cache_insert(const RowCacheView& rc, unsigned long long ptr, uint32_t& h, int& slot,
-                                                 bool publish = true) {
+__device__ __forceinline__ int row_cache_insert(const RowCacheView& rc, unsigned long long ptr, uint32_t& h, int& slot,
+                                                bool publish = true) {
     constexpr unsigned long long EMPTY = ~0ull;
     h = static_cast<uint32_t>(((ptr >> 10) * 0x9E3779B97F4A7C15ull) >> 40) & rc.mask;   // rows are >= 512 B apart
-    while (true) {
+    for (int probe = 0; probe < kRowCacheMaxProbes; ++probe) {
         const unsigned long long old = atomicCAS(rc.keys + h, EMPTY, ptr);
         if (old == EMPTY) {
             const int sl = atomicAdd(rc.counter, 1) + 1;
             slot = sl < rc.cap ? sl : -2;
             if (publish || slot < 0) atomicExch(rc.slots + h, slot);
-            return true;
+            return 1;
         }
-        if (old == ptr) { slot = -1; return false; }
+        if (old == ptr) { slot = -1; return 0; }
         h = (h + 1) & rc.mask;
     }
+    slot = -2;
+    return -1;
 }
 
 __device__ __forceinline__ void row_cache_publish(const RowCacheView& rc, uint32_t h, int slot) {
@@ -59,11 +66,17 @@ __device__ __forceinline__ void row_cache_publish(const RowCacheView& rc, uint32
     atomicExch(rc.slots + h, slot);
 }
 
+// Wait for the inserting thread to publish the slot of entry `h`.  Bounded: a publisher that is not resident (or is
+// itself waiting) must never hang the grid, so after kRowCacheMaxPolls polls the waiter gives up and returns -2 = "read
+// the row from its home address", which is always correct.
 __device__ __forceinline__ int row_cache_wait(const RowCacheView& rc, uint32_t h) {
     volatile int32_t* sl = rc.slots + h;
-    int v;
-    while ((v = *sl) == -1) {}
-    return v;
+    for (int poll = 0; poll < kRowCacheMaxPolls; ++poll) {
+        const int v = *sl;
+        if (v != -1) return v;
+        __nanosleep(64);
+    }
+    return -2;
 }
 
 }  // namespace das

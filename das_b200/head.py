@@ -153,6 +153,8 @@ class DecodePlan:
             out_world=_as_tensor(bufs.out_world, (B, P, J, 3), "<f8", dev),
         )
         self._keep = []          # tensors whose storage the plan currently points at
+        self._out_keep = None    # caller-owned output block (kept alive while the plan points at it)
+        self._run = self.lib.das_plan_run
 
     def __del__(self):
         try:
@@ -263,11 +265,61 @@ class DecodePlan:
             _lib.check(self.lib.das_plan_set_metas(self._plan, C.c_void_p(sxy.ctypes.data), C.c_void_p(cam.ctypes.data),
                                                    _stream_ptr(self.device)), "das_plan_set_metas")
 
+    # ---- outputs: where the packed result block lives ------------------------------------------------------------
+    def _refresh_views(self):
+        bufs = Buffers()
+        ct, p = C.c_int32(), C.c_int32()
+        _lib.check(self.lib.das_plan_buffers(self._plan, C.byref(bufs), C.byref(ct), C.byref(p)), "das_plan_buffers")
+        B, P, J, dev = self.batch, self.out_slots, self.cfg.num_joints, self.device
+        self.t.update(out_count=_as_tensor(bufs.out_count, (B,), "<i4", dev), out_score=_as_tensor(bufs.out_score, (B, P), "<f4", dev),
+                      out_slot=_as_tensor(bufs.out_slot, (B, P), "<i4", dev), out_pose=_as_tensor(bufs.out_pose, (B, P, J, 3), "<f4", dev),
+                      out_center=_as_tensor(bufs.out_center, (B, P, 3), "<f4", dev), out_cam=_as_tensor(bufs.out_cam, (B, P, J, 3), "<f8", dev),
+                      out_world=_as_tensor(bufs.out_world, (B, P, J, 3), "<f8", dev))
+
+    @property
+    def block_stride(self) -> int:
+        """Bytes one plan occupies in a caller-owned buffer: the packed outputs plus the 256-byte sequence trailer."""
+        return int(self.output_block().numel()) + 256
+
+    def set_output_block(self, block: Optional[torch.Tensor]):
+        """Make the plan write its results into `block` (uint8 CUDA tensor of >= block_stride bytes, 256-B aligned) --
+        typically a slice of one staging / gathered buffer shared by several plans, so that collecting results needs no
+        device-to-device copy.  None returns to the plan's own allocation."""
+        with torch.cuda.device(self.device):
+            if block is None:
+                _lib.check(self.lib.das_plan_set_output_block(self._plan, None, 0), "das_plan_set_output_block")
+            else:
+                assert block.dtype == torch.uint8 and block.is_cuda and block.is_contiguous()
+                _lib.check(self.lib.das_plan_set_output_block(self._plan, C.c_void_p(block.data_ptr()), block.numel()),
+                           "das_plan_set_output_block")
+        self._out_keep = block
+        self._refresh_views()
+
+    def set_output_ptr(self, ptr: int, nbytes: int, keep=None):
+        """set_output_block for raw device memory (e.g. from das_ipc_alloc)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.das_plan_set_output_block(self._plan, C.c_void_p(int(ptr)), int(nbytes)), "das_plan_set_output_block")
+        self._out_keep = keep
+        self._refresh_views()
+
+    def set_peer_blocks(self, peer_ptrs: Sequence[int]):
+        """Fused result all-gather: the NMS / back-projection kernel also stores every result value at the same offset of
+        each address in `peer_ptrs` (this rank's slot in every peer's gathered buffer, mapped with das_ipc_open), over
+        NVLink.  An empty list switches it off."""
+        arr = (C.c_void_p * max(len(peer_ptrs), 1))(*[int(q) for q in peer_ptrs])
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.das_plan_set_peer_blocks(self._plan, len(peer_ptrs), arr), "das_plan_set_peer_blocks")
+
     # ---- run -----------------------------------------------------------------------------------
-    def run(self, use_graph: bool = True, stage_events: bool = False):
-        """Enqueue one decode on the current stream: eager launches, a CUDA-graph replay, or a replay
-        with event nodes at the stage boundaries (then stage_ms() after a synchronize)."""
+    def run(self, use_graph: bool = True, stage_events: bool = False, stream: Optional[int] = None):
+        """Enqueue one decode on the current stream (or on the raw cudaStream_t `stream`): eager launches, a CUDA-graph
+        replay, or a replay with event nodes at the stage boundaries (then stage_ms() after a synchronize)."""
         mode = 2 if stage_events else int(bool(use_graph))
+        if stream is not None:             # lean path for tight loops: no torch stream / device context lookups
+            st = self._run(self._plan, C.c_void_p(stream), mode)
+            if st != 0:
+                _lib.check(st, "das_plan_run")
+            return
         with torch.cuda.device(self.device):
             _lib.check(self.lib.das_plan_run(self._plan, _stream_ptr(self.device), mode), "das_plan_run")
 
@@ -314,6 +366,14 @@ class DecodePlan:
         mode = (2 if row_cache else 1) if zero_copy else 0
         _lib.check(self.lib.das_plan_set_host_mode(self._plan, mode), "das_plan_set_host_mode")
 
+    def row_cache_stats(self):
+        """(distinct feature rows fetched into the device row cache, candidates above score_thr) of the last host-mode
+        run; synchronises with the device."""
+        arr = (C.c_int32 * 2)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.das_plan_row_cache_stats(self._plan, arr), "das_plan_row_cache_stats")
+        return int(arr[0]), int(arr[1])
+
     @property
     def h2d_explicit_bytes(self) -> int:
         return int(self.lib.das_plan_h2d_explicit_bytes(self._plan))
@@ -355,7 +415,7 @@ class DASHeadB200:
 
     def __init__(self, num_classes=1, in_channels=256, *, num_joints=15, strides=(8, 16, 32, 64, 128),
                  depth_factor=1, z_norm=1, root_idx=None, recursive_update=None, test_cfg=None,
-                 train_cfg=None, peak_kernel=0, device="cuda", **unused):
+                 train_cfg=None, peak_kernel=0, device="cuda", dataset_depth_factor=1.0, **unused):
         assert num_classes == 1, "the DAS head has one class (configs/_base_/models/das.py:26)"
         ru = dict(num_heads=4, feat_channels=256, num_layers=1, dim=3)
         ru.update(recursive_update or {})
@@ -373,6 +433,7 @@ class DASHeadB200:
         self.train_cfg = train_cfg
         self.peak_kernel = peak_kernel
         self.device = device
+        self.dataset_depth_factor = float(dataset_depth_factor)     # cmupanoptic_mono_dataset.py:399 (dataset-side, default 1)
         self.group_reg_dims = [2, 1, 3 * self.num_joints, 3 * self.num_joints]
         self.training = False
         self._plans: Dict[tuple, DecodePlan] = {}
@@ -395,7 +456,8 @@ class DASHeadB200:
                            test_cfg=cfg, num_heads=self.recursive_update["num_heads"],
                            feat_channels=self.recursive_update["feat_channels"],
                            num_layers=self.recursive_update["num_layers"], refine=refine,
-                           peak_kernel=self.peak_kernel, device=self.device)
+                           peak_kernel=self.peak_kernel, device=self.device,
+                           dataset_depth_factor=self.dataset_depth_factor)
             if refine:
                 assert self._layers is not None, "call load_refine_weights() before a refining decode"
                 p.set_weights(self._layers)
@@ -403,20 +465,42 @@ class DASHeadB200:
         return p
 
     @staticmethod
-    def _split_rest(rest, cfg):
-        """(img_metas[, cfg[, rescale]]) as the reference takes them, or (refine_feats, img_metas) for the extended call."""
-        if len(rest) == 1:
-            return None, rest[0], cfg
-        if len(rest) == 2 and isinstance(rest[1], (list, tuple)) and (len(rest[1]) == 0 or isinstance(rest[1][0], dict)):
-            return rest[0], rest[1], cfg
-        if len(rest) >= 2:                        # positional cfg / rescale like the reference allows
-            return None, rest[0], rest[1] if cfg is None else cfg
-        raise TypeError("get_poses() missing img_metas")
+    def _is_metas(x) -> bool:
+        """img_metas is a list of per-image dicts (das_head.py:653-659); an empty list counts as one (empty batch)."""
+        return isinstance(x, (list, tuple)) and all(isinstance(m, dict) for m in x)
 
-    def decode_to_device(self, cls_scores, pose_preds, centernesses, *rest, cfg=None, rescale=None) -> DecodePlan:
+    @classmethod
+    def _split_rest(cls, rest, cfg, img_metas=None):
+        """Resolve the positional tail of get_poses by CONTENT:
+          reference form   (img_metas[, cfg[, rescale]])                  -- das_head.py:653-659
+          extended form    (refine_feats, img_metas[, cfg[, rescale]])    -- refine_feats[level] = list of feature maps
+        and the keyword form get_poses(..., img_metas=..., [refine_feats positional]).  Returns (refine_feats, img_metas, cfg)."""
+        rest = tuple(rest)
+        if img_metas is not None:                      # keyword img_metas: what is left can only be refine_feats
+            if len(rest) > 1:
+                raise TypeError("get_poses(): img_metas was passed by keyword; at most refine_feats may be positional")
+            return (rest[0] if rest else None), img_metas, cfg
+        if not rest:
+            raise TypeError("get_poses() missing img_metas")
+        second_is_metas = len(rest) >= 2 and cls._is_metas(rest[1])
+        # an empty rest[0] followed by a non-empty list of dicts can only be (refine_feats of zero levels, img_metas)
+        if cls._is_metas(rest[0]) and not (second_is_metas and len(rest[0]) == 0 and len(rest[1]) > 0):
+            tail, feats, metas = rest[1:], None, rest[0]
+        elif second_is_metas:
+            tail, feats, metas = rest[2:], rest[0], rest[1]
+        else:
+            raise TypeError("get_poses(): expected (img_metas[, cfg[, rescale]]) or (refine_feats, img_metas[, cfg[, rescale]]); "
+                            "img_metas must be a list of dicts")
+        if len(tail) > 2:
+            raise TypeError("get_poses(): too many positional arguments")
+        if tail and tail[0] is not None and cfg is None:
+            cfg = tail[0]                                # positional cfg like the reference allows
+        return feats, metas, cfg
+
+    def decode_to_device(self, cls_scores, pose_preds, centernesses, *rest, img_metas=None, cfg=None, rescale=None) -> DecodePlan:
         """get_poses without the device->host read: enqueues the decode on the current stream and returns the plan
         whose `output_block()` / `views_of_block()` hold the padded pose lists on the device (same arguments)."""
-        refine_feats, img_metas, cfg = self._split_rest(rest, cfg)
+        refine_feats, img_metas, cfg = self._split_rest(rest, cfg, img_metas)
         assert len(cls_scores) == len(pose_preds) == len(centernesses)
         cfg = self.test_cfg if cfg is None else dict(cfg)
         num_levels = len(cls_scores)
@@ -437,15 +521,18 @@ class DASHeadB200:
         plan.run()
         return plan
 
-    def get_poses(self, cls_scores, pose_preds, centernesses, *rest, cfg=None, rescale=None):
+    def get_poses(self, cls_scores, pose_preds, centernesses, *rest, img_metas=None, cfg=None, rescale=None):
         """Reference call: get_poses(cls_scores, pose_preds, centernesses, img_metas, cfg=None, rescale=None)
-        with pose_preds already refined + eval-tailed (das_head.py:264-267 outputs).
+        (das_head.py:653-659; img_metas / cfg / rescale positional or by keyword) with pose_preds already refined +
+        eval-tailed (das_head.py:264-267 outputs).
         Extended call: get_poses(cls_scores, raw_pose_preds, centernesses, refine_feats, img_metas, ...)
         where refine_feats[level] is the list of per-layer feature maps; refinement then runs on the GPU.
-        Returns the reference's list of per-image dicts (das_head.py:680-687) plus 'poses_cam' / 'poses_world'."""
-        img_metas = self._split_rest(rest, cfg)[1]
-        plan = self.decode_to_device(cls_scores, pose_preds, centernesses, *rest, cfg=cfg, rescale=rescale)
-        return plan.results(img_metas)
+        Returns the reference's list of per-image dicts (das_head.py:680-687) plus 'poses_cam' / 'poses_world'
+        (valid for the shipped dataset flags norm_depth=True, abs_dz=True: cmupanoptic_mono_dataset.py:391-401;
+        `dataset_depth_factor` is that file's :399 factor)."""
+        metas = self._split_rest(rest, cfg, img_metas)[1]
+        plan = self.decode_to_device(cls_scores, pose_preds, centernesses, *rest, img_metas=img_metas, cfg=cfg, rescale=rescale)
+        return plan.results(metas)
 
     def simple_test_decode(self, outs, img_metas, rescale=False):
         """What DAS.simple_test does after the head forward (detectors/das.py:74-79)."""

@@ -50,10 +50,12 @@ def _gen(seed: int, device) -> torch.Generator:
     return g
 
 
-def make_layers(cfg: HeadConfig, seed: int = 7, device="cpu") -> List[dict]:
+def make_layers(cfg: HeadConfig, seed: int = 7, device="cpu", so_std: float = 0.01) -> List[dict]:
     """1x1 projection weights of every refinement layer, named after the reference
     modules (recursive_update.py:171-180): so = sampling_offset [J*nh*2, C],
-    sc = sampling_conf [3J, C], uw = update_weight [3J, C], uv = update_offset_value [3J, C]."""
+    sc = sampling_conf [3J, C], uw = update_weight [3J, C], uv = update_offset_value [3J, C].
+    so_std: std of the sampling-offset weights; 0.01 is the reference's init (recursive_update.py:174-175, sampled
+    offsets of ~0.2 px), the "spread" bench workload uses 0.3 (offsets of ~5 px, like a trained model's)."""
     g = _gen(seed, device)
     J, nh, C = cfg.num_joints, cfg.num_heads, cfg.feat_channels
     bnd = 1.0 / math.sqrt(C)
@@ -64,7 +66,7 @@ def make_layers(cfg: HeadConfig, seed: int = 7, device="cpu") -> List[dict]:
 
         def b(o):
             return (torch.rand(o, generator=g, device=device) * 2 - 1) * bnd
-        layers.append(dict(so_w=w(J * nh * 2, 0.01), so_b=b(J * nh * 2),
+        layers.append(dict(so_w=w(J * nh * 2, so_std), so_b=b(J * nh * 2),
                            sc_w=w(3 * J, 0.02), sc_b=b(3 * J),
                            uw_w=w(3 * J, 0.02), uw_b=b(3 * J),
                            uv_w=w(3 * J, 0.02), uv_b=b(3 * J)))
@@ -80,7 +82,7 @@ def _smooth(x: torch.Tensor, k: int = 9) -> torch.Tensor:
 
 def make_level(cfg: HeadConfig, batch: int, h: int, w: int, stride: int, seed: int, device="cpu",
                peaks: int = 16, smooth: int = 9, scales=(1.0, 1.0, 1.0, 1.0), channels_last: bool = True,
-               with_feats: bool = True, coherent: int = 0) -> dict:
+               with_feats: bool = True, coherent: int = 0, uv_scale: float = 4.0) -> dict:
     g = _gen(seed, device)
     J, C = cfg.num_joints, cfg.feat_channels
 
@@ -110,8 +112,8 @@ def make_level(cfg: HeadConfig, batch: int, h: int, w: int, stride: int, seed: i
     if smooth > 1:
         pose[:, 2:3] = F.avg_pool2d(pose[:, 2:3], smooth, 1, smooth // 2, count_include_pad=False)
     uvd = _smooth(randn(batch, 3 * J, h, w), smooth)
-    uvd[:, 0::3] *= 4.0
-    uvd[:, 1::3] *= 4.0
+    uvd[:, 0::3] *= uv_scale
+    uvd[:, 1::3] *= uv_scale
     if coherent > 0:
         # person-like fields: every cell of a coherent x coherent block points at the same joints (u = target - x),
         # so neighbouring candidates decode to near-identical poses and OKS-NMS has something to suppress
@@ -138,13 +140,148 @@ def make_level(cfg: HeadConfig, batch: int, h: int, w: int, stride: int, seed: i
     return lvl
 
 
-def make_levels(cfg: HeadConfig, batch: int, h: int, w: int, seed: int, device="cpu", **kw) -> List[dict]:
-    """One dict per stride in ``cfg.strides``; level l has size ceil(h / 2^l) x ceil(w / 2^l)."""
+def make_levels(cfg: HeadConfig, batch: int, h: int, w: int, seed: int, device="cpu", margin_for=None, **kw) -> List[dict]:
+    """One dict per stride in ``cfg.strides``; level l has size ceil(h / 2^l) x ceil(w / 2^l).
+
+    ``margin_for`` = dict(nms_pre=..., score_thr=..., peak_kernel=...) reject-samples the centerness logits until
+    every decision boundary of that decode has a rank margin of at least MIN_MARGIN_ULPS."""
     out = []
     for l, s in enumerate(cfg.strides):
         hl, wl = -(-h // (1 << l)), -(-w // (1 << l))
         out.append(make_level(cfg, batch, hl, wl, s, seed + 101 * l, device, **kw))
+    if margin_for is not None:
+        enforce_rank_margins(out, seed=seed + 7919, **margin_for)
     return out
+
+
+# ---- rank margins (SURVEY.md 8(d): "reject-sample to guarantee rank margins >= 16 ulp at every boundary <= K+1
+# and for |score - score_thr|") ------------------------------------------------------------------------------
+MIN_MARGIN_ULPS = 16
+
+
+def _ulps(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """|a - b| in float32 ulps (non-negative finite floats order like their bit patterns)."""
+    return (a.contiguous().view(torch.int32).to(torch.int64) - b.contiguous().view(torch.int32).to(torch.int64)).abs()
+
+
+def _level_candidates(lv: dict, nms_pre: int, peak_kernel: int):
+    """(ranked score [B,R], cell index [B,R], n_cand) of one level: the first n_cand columns are the cells the decode
+    hands on (das_head.py:716-723), column n_cand (if present) is the best cell that is left out."""
+    sc = (lv["cls"].sigmoid() * lv["ctr"].sigmoid())
+    b, _, h, w = sc.shape
+    rank = sc
+    if peak_kernel and peak_kernel > 1 and nms_pre > 0 and h * w > nms_pre:
+        pooled = F.max_pool2d(sc, peak_kernel, 1, peak_kernel // 2)
+        rank = torch.where(sc == pooled, sc, torch.zeros_like(sc))
+    rank = rank.flatten(1)
+    hw = h * w
+    if nms_pre > 0 and hw > nms_pre:
+        v, i = rank.topk(min(nms_pre + 1, hw), dim=1)
+        return v, i, nms_pre
+    v, i = rank.sort(dim=1, descending=True)
+    return v, i, hw
+
+
+def _margin_violations(levels: List[dict], nms_pre: int, score_thr: float, peak_kernel: int, min_ulps: int):
+    """Smallest ulp gap at any boundary that decides the decode's output, plus per level the (image, cell) pairs whose
+    score sits too close to such a boundary.  Boundaries (das_head.py:716-723, 763-769, pose_nms.py:97):
+      * adjacent ranks among a level's candidates and the first cell left out, whenever the better one survives
+        score_thr (order inside a level, and which cell makes the cut),
+      * every candidate and the first cell left out against score_thr,
+      * adjacent scores of the surviving candidates of ALL levels together (OKS-NMS visits them by score),
+      * peak mode: every cell that could rank among the candidates against its best 3x3 neighbour."""
+    worst = 1 << 40
+    bad = []
+    per_level = []
+    thr = float(score_thr)
+    for lv in levels:
+        v, i, n = _level_candidates(lv, nms_pre, peak_kernel)
+        per_level.append((v, i, n))
+        mask = torch.zeros_like(v, dtype=torch.bool)
+        if v.shape[1] > 1:
+            gap = _ulps(v[:, :-1], v[:, 1:])
+            rel = v[:, :-1] > thr if thr > 0 else torch.ones_like(gap, dtype=torch.bool)
+            rel = rel & (v[:, :-1] > 0)
+            if rel.any():
+                worst = min(worst, int(gap[rel].min()))
+            close = rel & (gap < min_ulps)
+            mask[:, 1:] |= close
+        if thr > 0:
+            g = _ulps(v, torch.full_like(v, thr))
+            worst = min(worst, int(g.min()))
+            mask |= g < min_ulps
+        bad.append((len(bad), mask, i))
+    # cross-level order of the survivors (only matters when several levels feed one NMS)
+    if len(levels) > 1:
+        vs = torch.cat([v[:, :n] for v, _, n in per_level], dim=1)
+        where = torch.cat([torch.full((n,), l, dtype=torch.int64) for l, (_, _, n) in enumerate(per_level)]).to(vs.device)
+        col = torch.cat([torch.arange(n) for _, _, n in per_level]).to(vs.device)
+        sv, si = vs.sort(dim=1, descending=True)
+        gap = _ulps(sv[:, :-1], sv[:, 1:])
+        rel = (sv[:, :-1] > thr) if thr > 0 else torch.ones_like(gap, dtype=torch.bool)
+        if rel.any():
+            worst = min(worst, int(gap[rel].min()))
+        close = rel & (gap < min_ulps)
+        if close.any():
+            bi, pi = close.nonzero(as_tuple=True)
+            lower = si[bi, pi + 1]
+            for l in range(len(levels)):
+                sel = where[lower] == l
+                if sel.any():
+                    bad[l][1][bi[sel], col[lower[sel]]] = True
+    if peak_kernel and peak_kernel > 1:
+        for l, lv in enumerate(levels):
+            v, i, n = per_level[l]
+            sc = (lv["cls"].sigmoid() * lv["ctr"].sigmoid())
+            b, _, h, w = sc.shape
+            if not (nms_pre > 0 and h * w > nms_pre):
+                continue
+            pad = F.pad(sc, (1, 1, 1, 1), value=0.0)
+            nb = torch.stack([pad[:, :, dy:dy + h, dx:dx + w] for dy in range(3) for dx in range(3) if (dy, dx) != (1, 1)]).amax(0)
+            cut = v[:, min(n, v.shape[1] - 1)].view(b, 1, 1, 1)
+            rel = (sc >= cut) & (sc > 0)
+            gap = _ulps(sc, nb)
+            if rel.any():
+                worst = min(worst, int(gap[rel].min()))
+            close = (rel & (gap < min_ulps)).flatten(1)
+            if close.any():
+                bi, ci = close.nonzero(as_tuple=True)
+                extra_mask = torch.zeros((b, h * w), dtype=torch.bool, device=sc.device)
+                extra_mask[bi, ci] = True
+                bad.append((l, extra_mask, torch.arange(h * w, device=sc.device).expand(b, -1)))
+    return worst, bad
+
+
+def rank_margin_ulps(levels: List[dict], nms_pre: int, score_thr: float = 0.0, peak_kernel: int = 0) -> int:
+    """Smallest float32-ulp gap at any boundary that decides which candidates the decode outputs and in which order
+    (see _margin_violations).  The CPU reference's own sigmoid is only ~2 ulp accurate, so bit-exact index parity is
+    only defined when this is comfortably above that; the parity tests assert >= MIN_MARGIN_ULPS."""
+    return _margin_violations(levels, int(nms_pre), float(score_thr or 0.0), int(peak_kernel or 0), MIN_MARGIN_ULPS)[0]
+
+
+def enforce_rank_margins(levels: List[dict], nms_pre: int = -1, score_thr: float = 0.0, peak_kernel: int = 0,
+                         seed: int = 0, min_ulps: int = 4 * MIN_MARGIN_ULPS, max_iter: int = 200) -> int:
+    """Reject-sampling step of the generator: re-draw the centerness logit of every cell whose score sits within
+    `min_ulps` of a decision boundary until none is left (in place; deterministic for a given seed).  The default
+    leaves 4x the margin the tests require.  Returns the number of re-drawn cells."""
+    dev = levels[0]["ctr"].device
+    g = _gen(seed, dev)
+    redrawn = 0
+    for _ in range(max_iter):
+        worst, bad = _margin_violations(levels, int(nms_pre), float(score_thr or 0.0), int(peak_kernel or 0), min_ulps)
+        n_bad = 0
+        for l, mask, idx in bad:
+            if not mask.any():
+                continue
+            bi, ci = mask.nonzero(as_tuple=True)
+            cells = idx[bi, ci]
+            flat = levels[l]["ctr"].view(levels[l]["ctr"].shape[0], -1)
+            flat[bi, cells] = torch.randn(len(bi), generator=g, device=dev) + 1.0
+            n_bad += len(bi)
+        redrawn += n_bad
+        if n_bad == 0:
+            return redrawn
+    raise RuntimeError(f"enforce_rank_margins: still {n_bad} cells within {min_ulps} ulp of a boundary after {max_iter} rounds")
 
 
 def make_metas(batch: int, h: int, w: int, stride: int = 8, seed: int = 3, identity_rt: bool = False) -> List[dict]:

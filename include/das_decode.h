@@ -36,6 +36,7 @@ extern "C" {
 #define DAS_MAX_JOINTS 32
 #define DAS_MAX_NMS_PRE 2048  /* per-level top-k capacity (reference configs use 1000) */
 #define DAS_CAM_DOUBLES 18    /* K[0,:3], K[1,:3], R row-major 3x3, t[3] */
+#define DAS_MAX_PEERS 15      /* other GPUs of one NVSwitch box that receive a copy of a rank's result block */
 #define DAS_NUM_STAGES 5      /* score_topk | dense layers | refine phases 1-2 (tensor-core mode) | refine + assemble | nms+backproject */
 
 typedef enum das_status {
@@ -102,7 +103,24 @@ typedef struct das_buffers {
     double*  out_world;    /* [B,P,J,3] world space  (vis_3d.py x3)                               */
 } das_buffers;
 
+/* Peer copies of a rank's packed output block (the one collective of the path).  delta[q] is the BYTE
+ * distance from the rank's local output block to its copy inside peer q's gathered buffer (a peer-mapped device
+ * address: cudaIpcOpenMemHandle / cudaDeviceEnablePeerAccess); das_nms_backproject_peers stores every result value
+ * locally AND at +delta[q] for q < n, over NVLink.  seq / ticket (both inside / beside the LOCAL block, device int32,
+ * or NULL): the last CTA increments *seq locally and on every peer after a system-scope fence, so a consumer on a
+ * peer that observes seq == s may read step s. */
+typedef struct das_peer_blocks {
+    int32_t n;
+    int32_t reserved_;
+    int64_t delta[DAS_MAX_PEERS];
+    int32_t* seq;
+    int32_t* ticket;
+} das_peer_blocks;
+
 const char* das_version(void);
+/* sizeof of the structs that cross the ABI by value or pointer: {das_levels, das_decode_cfg, das_buffers, das_row_cache}.
+ * A binding checks these against its own mirrors at load time (a stale library must fail loudly, not corrupt memory). */
+void das_abi_struct_sizes(int32_t out[4]);
 const char* das_last_error(void);
 
 /* slot bookkeeping (host-side pure functions) */
@@ -198,6 +216,12 @@ int das_nms_backproject(const das_decode_cfg* cfg, int32_t batch, int32_t cand_s
                         const float* cand_score, const float* cand_pose, const float* cand_center,
                         const double* cam, das_buffers out, void* stream);
 
+/* Same, with the result all-gather fused in: every output value is also stored into each peer's copy of this rank's
+ * block (see das_peer_blocks). peers == NULL or peers->n == 0: identical to das_nms_backproject. */
+int das_nms_backproject_peers(const das_decode_cfg* cfg, int32_t batch, int32_t cand_slots,
+                              const float* cand_score, const float* cand_pose, const float* cand_center,
+                              const double* cam, das_buffers out, const das_peer_blocks* peers, void* stream);
+
 /* Repack the four 1x1 convolutions of one RecursiveUpdateLayer (nn.Conv2d weight [O,C] + bias [O],
  * recursive_update.py:171-180) into the joint-major layout the kernels read:
  * dst[j][17][C] rows = {sampling_offset 2*nh, update_weight 3, update_offset_value 3, sampling_conf 3}
@@ -232,6 +256,22 @@ int das_plan_output_block(const das_plan* plan, void** ptr, int64_t* bytes);
  * num_heads = 4), 2 = tensor cores, single TF32 pass (looser accuracy). Call before the first run. */
 int das_plan_set_refine_mode(das_plan* plan, int32_t mode);
 int das_plan_buffers(const das_plan* plan, das_buffers* out, int32_t* cand_slots, int32_t* out_slots);
+/* Caller-owned output block: the plan writes its out_* buffers into `block` (device memory, 256-B aligned, at least
+ * das_plan_output_block() bytes + 256 for the sequence word) instead of its own allocation -- e.g. a slice of one
+ * contiguous staging / gathered buffer shared by several plans, so collecting results needs no copy.  Any captured
+ * graph is dropped and re-captured by the next run; das_plan_buffers / das_plan_output_block report the new pointers. */
+int das_plan_set_output_block(das_plan* plan, void* block, int64_t bytes);
+/* Fused result all-gather over NVLink: peer_blocks[q] = address (mapped into THIS process) of this rank's slot inside
+ * peer q's gathered buffer, same layout as the local block.  n_peers == 0 switches it off.  With it on, the local
+ * block carries a sequence word right behind the packed outputs (offset das_plan_output_block() bytes, int32). */
+int das_plan_set_peer_blocks(das_plan* plan, int32_t n_peers, void* const* peer_blocks);
+/* Device memory that other processes on the box can map (cudaIpc*): das_ipc_alloc on the owner, the 64-byte handle is
+ * sent to the peers through any host channel, das_ipc_open on each peer (enables peer access), das_ipc_close there,
+ * das_ipc_free on the owner. */
+int das_ipc_alloc(int64_t bytes, void** dev_ptr, unsigned char handle[64]);
+int das_ipc_open(const unsigned char handle[64], void** dev_ptr);
+int das_ipc_close(void* dev_ptr);
+int das_ipc_free(void* dev_ptr);
 int64_t das_plan_kernel_launches(const das_plan* plan);   /* kernels enqueued by das_plan_run so far */
 
 /* Host-buffer entry (the end-to-end call): copies every input from HOST memory (pinned for full
@@ -248,6 +288,9 @@ int64_t das_plan_h2d_bytes(const das_plan* plan);
 int das_plan_set_host_mode(das_plan* plan, int32_t mode);
 int64_t das_plan_h2d_explicit_bytes(const das_plan* plan);   /* bytes explicitly copied by the last run_host */
 int64_t das_plan_d2h_bytes(const das_plan* plan);
+/* after a host_mode-2 run: stats[0] = distinct feature rows the row cache fetched over PCIe, stats[1] = candidates above
+ * score_thr (one F(p) row each).  Synchronises with the device; for measurement, not for the hot path. */
+int das_plan_row_cache_stats(das_plan* plan, int32_t stats[2]);
 
 /* ---- diagnostics ------------------------------------------------------------------------------- */
 /* Self-test of the tcgen05/TMEM building blocks: D[128,N] = A[128,K] * B[N,K]^T (row-major fp32 device

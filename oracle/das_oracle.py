@@ -184,11 +184,13 @@ def oks_to_head(g, d, a_g, a_d):
     return out
 
 
-def oks_nms(scores, kpts, areas, thr, stable: bool = False):
+def oks_nms(scores, kpts, areas, thr, stable: bool = False, trace: dict | None = None):
     """Greedy OKS suppression; returns kept indices in pick order.
 
     ``stable=False`` reproduces the reference ordering (``argsort()[::-1]``);
     ``stable=True`` is the tie rule of this repo: equal scores -> lower index first.
+    ``trace`` (test bookkeeping, not in the reference): receives 'oks_margin' = the smallest |oks - thr| of any
+    suppression decision taken, so a test can tell a robust decision from a coin flip.
     """
     if len(scores) == 0:
         return np.zeros(0, dtype=np.int64)
@@ -201,13 +203,17 @@ def oks_nms(scores, kpts, areas, thr, stable: bool = False):
         i = order[0]
         keep.append(i)
         ovr = oks_to_head(kpts[i], kpts[order[1:]], areas[i], areas[order[1:]])
+        if trace is not None and len(ovr):
+            trace["oks_margin"] = min(trace.get("oks_margin", np.inf), float(np.abs(ovr.astype(np.float64) - thr).min()))
         order = order[np.where(ovr <= thr)[0] + 1]
     return np.array(keep)
 
 
-def soft_oks_nms(scores, kpts, areas, thr, max_dets, stable: bool = False):
+def soft_oks_nms(scores, kpts, areas, thr, max_dets, stable: bool = False, trace: dict | None = None):
     """Gaussian soft OKS-NMS (pose_nms.py:129-194): nothing is removed; after every pick the remaining
-    scores are multiplied by exp(-oks^2 / thr) (float32) and the best one is taken next."""
+    scores are multiplied by exp(-oks^2 / thr) (float32) and the best one is taken next.
+    ``trace`` receives 'soft_gap_ulps' = the smallest float32-ulp gap between the best and the second-best rescored
+    candidate at any pick (how robust the pick order is)."""
     if len(scores) == 0:
         return np.zeros(0, dtype=np.int64)
     order = np.argsort(-scores.astype(np.float64), kind="stable") if stable else scores.argsort()[::-1]
@@ -220,6 +226,9 @@ def soft_oks_nms(scores, kpts, areas, thr, max_dets, stable: bool = False):
         cur = cur[1:] * np.exp(-ovr ** 2 / thr)
         tmp = np.argsort(-cur.astype(np.float64), kind="stable") if stable else cur.argsort()[::-1]
         order, cur = order[tmp], cur[tmp]
+        if trace is not None and len(cur) > 1 and len(keep) + 1 < max_dets:
+            a = np.ascontiguousarray(cur[:2], dtype=np.float32).view(np.int32).astype(np.int64)
+            trace["soft_gap_ulps"] = min(trace.get("soft_gap_ulps", 1 << 40), int(abs(a[0] - a[1])))
         keep.append(i)
     return np.array(keep)
 
@@ -285,22 +294,24 @@ def decode_image(cls_l, pose_l, ctr_l, strides, scale_factor, cfg, num_joints,
         ok = scores > thr
         scores, poses, centres, lvls, idxs = scores[ok], poses[ok], centres[ok], lvls[ok], idxs[ok]
     nms_post = cfg.get("nms_post", -1)
-    oks_trace = None
+    trace = {}
     if nms_post > 0 and len(scores) > 0:
         hi = poses[..., :2].max(1)[0]
         lo = poses[..., :2].min(1)[0]
         areas = (hi - lo).prod(-1).cpu().numpy()
         kp = torch.cat([poses[..., :2], torch.ones_like(poses[..., :1])], -1).reshape(len(poses), -1).cpu().numpy()
         if cfg.get("nms_type", "hard") == "hard":
-            keep = oks_nms(scores.cpu().numpy(), kp, areas, cfg.get("nms_thr", 0.9), stable=stable).tolist()
+            keep = oks_nms(scores.cpu().numpy(), kp, areas, cfg.get("nms_thr", 0.9), stable=stable, trace=trace).tolist()
             keep = keep[:cfg.get("nms_post", 100)]
         else:                                           # das_head.py:789-790
             keep = soft_oks_nms(scores.cpu().numpy(), kp, areas, cfg.get("nms_thr", 0.9), cfg.get("nms_post", 100),
-                                stable=stable).tolist()
+                                stable=stable, trace=trace).tolist()
         scores, poses, centres, lvls, idxs = scores[keep], poses[keep], centres[keep], lvls[keep], idxs[keep]
     out = dict(scores=scores, poses=poses, vis=torch.ones(poses.shape[:2], device=poses.device), centers=centres,
                level=lvls, index=idxs)
     out.update(cand)
+    out["oks_margin"] = trace.get("oks_margin", float("inf"))          # test bookkeeping (see oks_nms)
+    out["soft_gap_ulps"] = trace.get("soft_gap_ulps", 1 << 40)
     return out
 
 

@@ -65,7 +65,9 @@ def checksum(levels):
 def build_case(name):
     cfg, b, h, w, seed, peaks, scales, tc = CASES[name][:8]
     extra = CASES[name][8] if len(CASES[name]) > 8 else {}
-    levels = synth.make_levels(cfg, b, h, w, seed=seed, peaks=peaks, scales=scales, **extra)
+    # reject-sampled so that every rank / score_thr boundary of THIS decode has a safe margin
+    margin_for = dict(nms_pre=tc.get("nms_pre", -1), score_thr=tc.get("score_thr", 0.0))
+    levels = synth.make_levels(cfg, b, h, w, seed=seed, peaks=peaks, scales=scales, margin_for=margin_for, **extra)
     layers = synth.make_layers(cfg, seed=seed + 1)
     metas = synth.make_metas(b, h, w, stride=cfg.strides[0], seed=seed + 2)
     return cfg, levels, layers, metas, tc
@@ -93,7 +95,14 @@ def main():
         ours, our_pp = O.decode_full(levels, layers, metas, cfg.as_dict(), tc)
         for a, b in zip(our_pp, ref_pp):
             assert torch.equal(a, b), f"{name}: refined pose_pred differs from the reference"
-        blob = dict(checksum=checksum(levels), n_images=np.array(len(ref)))
+        margin = synth.rank_margin_ulps(levels, tc.get("nms_pre", -1), tc.get("score_thr", 0.0))
+        oks_margin = min(o["oks_margin"] for o in ours)
+        assert margin >= synth.MIN_MARGIN_ULPS, f"{name}: rank margin {margin} ulp"
+        assert oks_margin >= 1e-6, f"{name}: an OKS decision sits {oks_margin:.2e} from nms_thr"
+        if tc.get("nms_type", "hard") != "hard":
+            assert min(o["soft_gap_ulps"] for o in ours) >= 64, f"{name}: soft-NMS pick order is fragile"
+        blob = dict(checksum=checksum(levels), n_images=np.array(len(ref)), rank_margin_ulps=np.array(margin),
+                    oks_margin=np.array(min(oks_margin, 1e30)))
         for i, (o, r) in enumerate(zip(ours, ref)):
             assert torch.equal(o["poses"], r["poses"]), f"{name}[{i}] poses"
             assert torch.equal(o["centers"], r["centers"]), f"{name}[{i}] centers"

@@ -6,13 +6,20 @@ pulls their source out of ``/root/reference`` with ``ast`` at run time and ``exe
 golden vectors under ``tests/golden/`` come from the reference's own code, not from our
 restatement.  Nothing is copied into this repository.
 
-``/root/reference`` does not exist on the GPU box: this module is only used by
-``oracle/make_golden.py`` and by CPU tests that skip when the tree is absent.
+``/root/reference`` does not exist on the GPU box.  ``oracle/make_ref.py`` (run by ``__graft_entry__.build()`` in the
+build container) therefore writes the extracted function sources to ``oracle/_ref/reference_functions.json`` --
+git-ignored, so never part of this repository's history, but shipped to the GPU box by ``gpurun`` like a built
+``.so`` -- and this module falls back to that bundle when the tree is absent.  Used by ``oracle/make_golden.py``, the
+CPU tests, and ``bench.py``'s CPU-baseline / ``--impl reference`` legs (``kind: "reference"``).
+
+Containment: only NAMED function definitions are ever exec'd (no module-level code of the reference runs), and the
+source files are pinned by sha256.
 """
 from __future__ import annotations
 
 import ast
-import importlib.util
+import hashlib
+import json
 import os
 
 import numpy as np
@@ -20,50 +27,113 @@ import torch
 import torch.nn.functional as F
 
 REF = os.environ.get("DAS_REFERENCE_ROOT", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+BUNDLE = os.path.join(HERE, "_ref", "reference_functions.json")
+
+# The only reference code this module ever executes: NAMED function definitions out of these files, nothing at module
+# level.  The files are pinned by hash, so a changed (or substituted) tree is refused instead of executed.
+FILES = {
+    "das_head": ("mmdet3d/models/pose_heads/das_head.py", "7598909ed7fd694af7122afaf03897cf218a6ff32b22bbe630075807c7db913c"),
+    "anchor_free": ("mmdet3d/models/pose_heads/anchor_free_mono3d_pose_head.py", "fb88297a040adee5fd635ce72a656f209f42cbf6b1a80f7b525123c5af98d449"),
+    "recursive_update": ("mmdet3d/models/pose_heads/recursive_update.py", "51a1bcef5c49697c4e0e949343d19d0a16281cbd60bacbd579f9b2816643c451"),
+    "pose_nms": ("mmdet3d/core/post_processing/pose_nms.py", "b0b409b1da2b2af7d5ed9bbe21d463d03906af8004fab0ccb7947517da770306"),
+    "vis_3d": ("mytools/vis_3d.py", "fbca19f0c680c7b34d5da660b66c5f0dd11786f0affb22a18b82769f85a92367"),
+}
+WANTED = {
+    # file key: (class name or None, function names)
+    "anchor_free": ("AnchorFreeMono3DPoseHead", ["get_points", "_get_points_single"]),
+    "das_head": ("DASHead", ["get_poses", "_get_poses_single", "_get_points_single"]),
+    "recursive_update": (None, ["offset_sample", "offset_sample_core"]),
+    "pose_nms": (None, ["oks_iou", "oks_nms", "_rescore", "soft_oks_nms"]),
+    "vis_3d": (None, ["pixel2world"]),
+}
+
+
+def tree_available() -> bool:
+    return os.path.isfile(os.path.join(REF, FILES["das_head"][0]))
+
+
+def bundle_available() -> bool:
+    return os.path.isfile(BUNDLE)
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REF, "mmdet3d/models/pose_heads/das_head.py"))
+    """The reference's own functions can be run: from the live tree (build container) or from the bundle that
+    oracle/make_ref.py extracted from it (oracle/_ref/, git-ignored, travels to the GPU box with gpurun)."""
+    return tree_available() or bundle_available()
 
 
-def _load_by_path(rel, name):
-    if not hasattr(np, "float"):
-        np.float = float              # pose_nms.py:72 uses the alias removed in NumPy 1.24
-    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    return mod
+def _read_pinned(key: str) -> str:
+    rel, want = FILES[key]
+    data = open(os.path.join(REF, rel), "rb").read()
+    got = hashlib.sha256(data).hexdigest()
+    if got != want and os.environ.get("DAS_REFERENCE_UNPINNED") != "1":
+        raise RuntimeError(f"{rel}: sha256 {got[:12]}.. differs from the pinned reference file; refusing to execute it "
+                           f"(set DAS_REFERENCE_UNPINNED=1 to override)")
+    return data.decode()
 
 
-def _class_methods(rel, cls, names):
-    tree = ast.parse(open(os.path.join(REF, rel)).read())
+def extract_sources() -> dict:
+    """{'<file key>.<function>': source} of every wanted function, via ast (decorators stripped) -- from the live tree."""
     out = {}
-    for node in tree.body:
-        if isinstance(node, ast.ClassDef) and node.name == cls:
-            for fn in node.body:
-                if isinstance(fn, ast.FunctionDef) and fn.name in names:
-                    fn.decorator_list = []
-                    out[fn.name] = fn
+    for key, (cls, names) in WANTED.items():
+        tree = ast.parse(_read_pinned(key))
+        body = tree.body
+        if cls is not None:
+            body = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls).body
+        for fn in body:
+            if isinstance(fn, ast.FunctionDef) and fn.name in names:
+                fn.decorator_list = []
+                out[f"{key}.{fn.name}"] = ast.unparse(fn)
+        missing = [n for n in names if f"{key}.{n}" not in out]
+        assert not missing, f"{FILES[key][0]}: functions {missing} not found"
     return out
 
 
-def _module_functions(rel, names):
-    tree = ast.parse(open(os.path.join(REF, rel)).read())
-    return {n.name: n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names}
+_sources = None
+
+
+def sources() -> dict:
+    global _sources
+    if _sources is None:
+        if tree_available():
+            _sources = extract_sources()
+        elif bundle_available():
+            blob = json.load(open(BUNDLE))
+            assert blob.get("pins") == {k: v[1] for k, v in FILES.items()}, "oracle/_ref bundle was made from other reference files"
+            _sources = blob["functions"]
+        else:
+            raise RuntimeError("neither the reference tree nor oracle/_ref/reference_functions.json is present")
+    return _sources
+
+
+def _exec_functions(key: str, ns: dict, rewrite=None) -> dict:
+    """exec the wanted functions of one reference file into `ns` (function definitions only)."""
+    for name in WANTED[key][1]:
+        src = sources()[f"{key}.{name}"]
+        exec(rewrite(src) if rewrite else src, ns)
+    return ns
 
 
 _cache = {}
 
 
+class _Namespace:
+    def __init__(self, ns):
+        self.__dict__.update(ns)
+
+
 def pose_nms():
     if "nms" not in _cache:
-        _cache["nms"] = _load_by_path("mmdet3d/core/post_processing/pose_nms.py", "ref_pose_nms")
+        if not hasattr(np, "float"):
+            np.float = float              # pose_nms.py:72 uses the alias removed in NumPy 1.24
+        _cache["nms"] = _Namespace(_exec_functions("pose_nms", dict(np=np)))
     return _cache["nms"]
 
 
 def vis_3d():
     if "vis" not in _cache:
-        _cache["vis"] = _load_by_path("mytools/vis_3d.py", "ref_vis_3d")
+        _cache["vis"] = _Namespace(_exec_functions("vis_3d", dict(np=np)))
     return _cache["vis"]
 
 
@@ -75,18 +145,16 @@ def head(num_joints, strides, test_cfg):
     class Base:
         pass
 
-    for k, fn in _class_methods("mmdet3d/models/pose_heads/anchor_free_mono3d_pose_head.py",
-                                "AnchorFreeMono3DPoseHead", ["get_points", "_get_points_single"]).items():
-        exec(ast.unparse(fn), ns)
+    _exec_functions("anchor_free", ns)
+    for k in WANTED["anchor_free"][1]:
         setattr(Base, k, ns[k])
 
     class Head(Base):
         pass
 
     ns["Head"] = Head
-    for k, fn in _class_methods("mmdet3d/models/pose_heads/das_head.py", "DASHead",
-                                ["get_poses", "_get_poses_single", "_get_points_single"]).items():
-        exec(ast.unparse(fn).replace("super()", "super(Head, self)"), ns)
+    _exec_functions("das_head", ns, rewrite=lambda src: src.replace("super()", "super(Head, self)"))
+    for k in WANTED["das_head"][1]:
         setattr(Head, k, ns[k])
     h = Head()
     h.training = False
@@ -100,11 +168,7 @@ def head(num_joints, strides, test_cfg):
 
 def offset_sample_fn():
     if "os" not in _cache:
-        ns = dict(torch=torch, F=F)
-        for k, fn in _module_functions("mmdet3d/models/pose_heads/recursive_update.py",
-                                       ["offset_sample", "offset_sample_core"]).items():
-            exec(ast.unparse(fn), ns)
-        _cache["os"] = ns["offset_sample"]
+        _cache["os"] = _exec_functions("recursive_update", dict(torch=torch, F=F))["offset_sample"]
     return _cache["os"]
 
 

@@ -90,3 +90,75 @@ def test_two_rank_shard_gather_equals_unsharded():
             np.testing.assert_allclose(rank_views["out_score"][i, :n], np.asarray(full[b]["scores_list"], np.float32), rtol=1e-6)
             b += 1
     assert b == B
+
+
+class _FakePlan:
+    """Host stand-in for DecodePlan in the collection logic: same block layout / views / result construction."""
+
+    def __init__(self, batch, P, J):
+        self.batch, self.out_slots, self.J = batch, P, J
+
+    def views_of_block(self, block):
+        return H.block_views(block, self.batch, self.out_slots, self.J)
+
+    def results(self, metas, src):
+        return H.DecodePlan.results(self, metas, src=src)
+
+
+def _worker_uneven(rank, world, port, q, total):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    levels = synth.make_levels(CFG, total, HH, WW, seed=91, peaks=6)
+    layers = synth.make_layers(CFG, seed=92)
+    metas = synth.make_metas(total, HH, WW, seed=93)
+    lo, hi = ddist.shard_bounds(total, world, rank)
+    per = ddist.padded_shard_size(total, world)
+    idx = ddist.pad_shard(list(range(lo, hi)), per)              # the short rank repeats its last image
+    shard = [dict(lv, cls=lv["cls"][idx], ctr=lv["ctr"][idx], pose_raw=lv["pose_raw"][idx],
+                  feats=[f[idx] for f in lv["feats"]]) for lv in levels]
+    res, _ = O.decode_full(shard, layers, [metas[i] for i in idx], CFG.as_dict(), TC)
+    block = _pack(res, per, TC["nms_post"], CFG.num_joints)
+    plan = _FakePlan(per, TC["nms_post"], CFG.num_joints)
+    all_metas = [[metas[i] for i in range(*ddist.shard_bounds(total, world, r))] for r in range(world)]
+    merged = ddist.collect_results(plan, block, [metas[i] for i in idx], world, rank, total, all_metas=all_metas,
+                                   n_real=hi - lo, order="contiguous")
+    # blocks of different size must raise on every rank instead of hanging the collective
+    raised = False
+    try:
+        ddist.gather_blocks(block[: block.numel() - 256 * rank], world)
+    except ValueError:
+        raised = True
+    if rank == 0:
+        q.put((raised, [(r["image_paths"], r["scores"], r["poses"].numpy()) for r in merged]))
+    else:
+        assert raised and merged is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_with_a_batch_that_does_not_divide():
+    """B % world != 0 (the last partial batch of a dataset): the short rank pads its plan to ceil(B / world) images, one
+    all-gather moves equally sized blocks, the padding rows are dropped (unequal blocks hung the collective)."""
+    total = 5
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_uneven, args=(r, 2, port, q, total)) for r in range(2)]
+    for p in procs:
+        p.start()
+    raised, merged = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert raised and len(merged) == total
+    levels = synth.make_levels(CFG, total, HH, WW, seed=91, peaks=6)
+    full, _ = O.decode_full(levels, synth.make_layers(CFG, seed=92), synth.make_metas(total, HH, WW, seed=93), CFG.as_dict(), TC)
+    for b, ((paths, scores, poses), o) in enumerate(zip(merged, full)):
+        assert paths == o["image_paths"] == [f"synthetic_{b:05d}.jpg"]
+        np.testing.assert_allclose(np.asarray(scores, np.float32), np.asarray(o["scores_list"], np.float32), rtol=1e-6)
+        np.testing.assert_allclose(poses, o["poses"].numpy(), rtol=1e-4, atol=1e-3)

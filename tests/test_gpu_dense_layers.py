@@ -18,19 +18,21 @@ pytestmark = pytest.mark.gpu
 def test_multi_layer_refinement_matches_oracle(layers, J, root, mode):
     cfg = synth.HeadConfig(num_joints=J, root_idx=root, depth_factor=1.0, z_norm=50.0, num_layers=layers)
     tc = dict(nms_pre=20, nms_post=20, nms_thr=0.9, score_thr=0.0)
-    case = util.make_case(cfg, 2, 28, 36, seed=600 + layers, scales=(1.05, 0.95, 1.1, 0.9))
+    case = util.make_case(cfg, 2, 28, 36, seed=600 + layers, scales=(1.05, 0.95, 1.1, 0.9), tc=tc)
     ref, _ = util.run_oracle(case, tc)
+    util.assert_margins(case, tc, ref)
     plan, got = util.run_gpu(case, tc, refine=True, refine_mode=mode)
-    compare(plan, got, ref, util.rank_margin_ulps(case["levels"], 20))
+    compare(plan, got, ref)
 
 
 def test_multi_layer_pyramid():
     cfg = synth.HeadConfig(num_joints=15, root_idx=2, depth_factor=20.0, z_norm=50.0, num_layers=2, strides=(8, 16, 32))
     tc = dict(nms_pre=50, nms_post=30, nms_thr=0.9, score_thr=0.03)
-    case = util.make_case(cfg, 2, 32, 48, seed=700, peaks=20)
+    case = util.make_case(cfg, 2, 32, 48, seed=700, peaks=20, tc=tc)
     ref, _ = util.run_oracle(case, tc)
+    util.assert_margins(case, tc, ref)
     plan, got = util.run_gpu(case, tc, refine=True)
-    compare(plan, got, ref, util.rank_margin_ulps(case["levels"], 50, 0.03))
+    compare(plan, got, ref)
 
 
 def test_golden_mupots17_three_layers():
@@ -38,8 +40,10 @@ def test_golden_mupots17_three_layers():
     gold = np.load(os.path.join(GOLDEN, name + ".npz"))
     cfg, levels, layers, metas, tc = G.build_case(name)
     case = dict(cfg=cfg, levels=levels, layers=layers, metas=metas, batch=levels[0]["cls"].shape[0])
+    assert util.assert_margins(levels, tc) == int(gold["rank_margin_ulps"]) and float(gold["oks_margin"]) >= util.MIN_OKS_MARGIN
     plan, got = util.run_gpu(case, tc, refine=True)
     ci = plan.t["cand_index"].cpu()
+    assert len(got) == int(gold["n_images"])
     for i, g in enumerate(got):
         lv, idx = util.slot_to_level_index(plan, g["slots"].cpu(), ci[i])
         assert idx == gold[f"index_{i}"].tolist()

@@ -2,9 +2,11 @@
 against the golden vectors of the reference's own code, and through size-independent properties at
 the full BASELINE size.
 
-Bars: person order / selected cells bit-exact when every rank boundary has a
-margin >= 16 ulp (the CPU reference's own fp32 sigmoid is only accurate to ~2 ulp, SURVEY.md section 7);
-scores within 8 ulp; 3D joint coordinates within 1e-4 relative to their magnitude (floor 1 unit).
+Bars: person order / selected cells BIT-EXACT; scores within 8 ulp; 3D joint coordinates
+within 1e-4 relative to their magnitude (floor 1 unit).  Every case first ASSERTS that it is decidable -- rank
+margins >= 16 ulp over the candidates that survive score_thr (the CPU reference's own fp32 sigmoid is only accurate
+to ~2 ulp) and every OKS decision >= 1e-6 from nms_thr; the generator reject-samples to
+guarantee it (synth.enforce_rank_margins) -- so no comparison is ever skipped.
 """
 import dataclasses
 import os
@@ -26,19 +28,17 @@ TOL = 1e-4
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def compare(plan, got, ref, margin, strict_order=True):
+def compare(plan, got, ref):
+    """Person order and source cells bit-exact, values within the bars.  Callers assert the case's margins first
+    (util.assert_margins), so there is no tolerance on the order and nothing is skipped."""
     ci = plan.t["cand_index"].cpu()
+    assert len(got) == len(ref)
     for b, (g, o) in enumerate(zip(got, ref)):
         lv, idx = util.slot_to_level_index(plan, g["slots"].cpu(), ci[b])
         ref_pairs = list(zip(o["level"].tolist(), o["index"].tolist()))
-        if margin >= 16 and strict_order:
-            assert list(zip(lv, idx)) == ref_pairs, f"image {b}: person order differs (margin {margin} ulp)"
-        else:
-            assert sorted(zip(lv, idx)) == sorted(ref_pairs) or margin < 16, f"image {b}: selected set differs"
-            if list(zip(lv, idx)) != ref_pairs:
-                continue
+        assert list(zip(lv, idx)) == ref_pairs, f"image {b}: person order / source cells differ"
         if not idx:
-            assert g["poses"].shape[0] == 0
+            assert g["poses"].shape[0] == 0 and g["scores"] == []
             continue
         assert int(util.ulp_gap(torch.tensor(g["scores"]), o["scores"]).max()) <= 8
         assert util.rel_err(g["poses"].cpu().numpy(), o["poses"].numpy()) < TOL
@@ -68,25 +68,24 @@ CASES = [
 
 @pytest.mark.parametrize("case_id,cfg,B,H,W,tc,kw", CASES, ids=[c[0] for c in CASES])
 def test_full_path_matches_oracle(case_id, cfg, B, H, W, tc, kw):
-    case = util.make_case(cfg, B, H, W, seed=1234, **kw)
+    case = util.make_case(cfg, B, H, W, seed=1234, tc=tc, **kw)
     ref, _ = util.run_oracle(case, tc)
+    util.assert_margins(case, tc, ref)
     plan, got = util.run_gpu(case, tc, refine=True)
-    margin = util.rank_margin_ulps(case["levels"], tc.get("nms_pre", -1), tc.get("score_thr", 0.0))
-    compare(plan, got, ref, margin)
+    compare(plan, got, ref)
 
 
 @pytest.mark.parametrize("case_id,cfg,B,H,W,tc,kw", CASES[:5], ids=[c[0] for c in CASES[:5]])
 def test_reference_contract_decode_only(case_id, cfg, B, H, W, tc, kw):
     """get_poses with already-refined pose maps (the reference signature): the decode arithmetic is the same
     fp32 op sequence, so poses must be BIT-equal to the oracle's."""
-    case = util.make_case(cfg, B, H, W, seed=99, **kw)
+    case = util.make_case(cfg, B, H, W, seed=99, tc=tc, **kw)
     ref, pose_preds = util.run_oracle(case, tc)
+    util.assert_margins(case, tc, ref)
     plan, got = util.run_gpu(case, tc, refine=False, pose_override=pose_preds)
-    margin = util.rank_margin_ulps(case["levels"], tc.get("nms_pre", -1), tc.get("score_thr", 0.0))
-    compare(plan, got, ref, margin)
-    if margin >= 16:
-        for g, o in zip(got, ref):
-            assert torch.equal(g["poses"].cpu(), o["poses"]) and torch.equal(g["centers"].cpu(), o["centers"])
+    compare(plan, got, ref)
+    for g, o in zip(got, ref):
+        assert torch.equal(g["poses"].cpu(), o["poses"]) and torch.equal(g["centers"].cpu(), o["centers"])
 
 
 @pytest.mark.parametrize("name", sorted(G.CASES))
@@ -97,15 +96,16 @@ def test_golden_vectors_of_the_reference(name):
     cfg, levels, layers, metas, tc = G.build_case(name)
     np.testing.assert_allclose(G.checksum(levels), gold["checksum"], rtol=1e-9, atol=1e-6)
     case = dict(cfg=cfg, levels=levels, layers=layers, metas=metas, batch=levels[0]["cls"].shape[0])
+    # the golden case is decidable (margins were asserted and stored when it was generated; re-checked here)
+    assert util.assert_margins(levels, tc) == int(gold["rank_margin_ulps"]) and float(gold["oks_margin"]) >= util.MIN_OKS_MARGIN
     plan, got = util.run_gpu(case, tc, refine=True)
-    margin = util.rank_margin_ulps(levels, tc.get("nms_pre", -1), tc.get("score_thr", 0.0))
     ci = plan.t["cand_index"].cpu()
+    assert len(got) == int(gold["n_images"])
     for i, g in enumerate(got):
         lv, idx = util.slot_to_level_index(plan, g["slots"].cpu(), ci[i])
-        if margin >= 16:
-            assert idx == gold[f"index_{i}"].tolist() and lv == gold[f"level_{i}"].tolist()
-        elif idx != gold[f"index_{i}"].tolist():
-            continue
+        assert idx == gold[f"index_{i}"].tolist() and lv == gold[f"level_{i}"].tolist()
+        if idx:
+            assert int(util.ulp_gap(torch.tensor(g["scores"], dtype=torch.float32), torch.tensor(gold[f"scores_{i}"])).max()) <= 8
         assert util.rel_err(g["poses"].cpu().numpy(), gold[f"poses_{i}"]) < TOL
         assert util.rel_err(g["poses_cam"].cpu().numpy(), gold[f"cam_{i}"]) < TOL
         assert util.rel_err(g["poses_world"].cpu().numpy(), gold[f"world_{i}"]) < TOL
@@ -114,10 +114,11 @@ def test_golden_vectors_of_the_reference(name):
 def test_peak_mask_mode_matches_oracle_variant():
     tc = dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)
     for (h, w) in ((48, 64), (130, 210)):
-        case = util.make_case(P, 2, h, w, seed=5)
+        case = util.make_case(P, 2, h, w, seed=5, tc=tc, peak_kernel=3)
         ref, _ = util.run_oracle(case, tc, peak_kernel=3)
+        util.assert_margins(case, tc, ref, peak_kernel=3)
         plan, got = util.run_gpu(case, tc, refine=True, peak_kernel=3)
-        compare(plan, got, ref, margin=10 ** 6)
+        compare(plan, got, ref)
         # a 3x3 bump contributes exactly one candidate under the peak mask
         for g in got:
             assert len(set(g["slots"].tolist())) == len(g["scores"])
@@ -136,7 +137,7 @@ def test_ties_break_towards_lower_index():
     ci = plan.t["cand_index"].cpu()
     assert ci[0, :7].tolist() == [5 * 20 + 7, 0, 1, 2, 3, 4, 5]
     assert ci[1, :7].tolist() == [0, 1, 2, 3, 4, 5, 6]
-    compare(plan, got, ref, margin=10 ** 6)
+    compare(plan, got, ref)          # exact ties by construction: the order is the tie rule's, nothing to excuse
 
 
 def test_large_k_exact_select_with_many_ties():
@@ -168,28 +169,30 @@ def test_pass_through_level_keeps_raster_order():
     ref, _ = util.run_oracle(case, tc)
     plan, got = util.run_gpu(case, tc, refine=True)
     assert plan.t["cand_index"].cpu()[0].tolist() == list(range(54))
-    compare(plan, got, ref, margin=10 ** 6)
+    compare(plan, got, ref)          # no nms_post: output order = raster order, independent of the scores
 
 
 def test_targets_outside_the_map_sample_zero():
     """Huge offsets push every sampling location out of the map: grid_sample's zero padding."""
     tc = dict(nms_pre=8, nms_post=8, nms_thr=0.9, score_thr=0.0)
-    case = util.make_case(P, 2, 20, 28, seed=13)
+    case = util.make_case(P, 2, 20, 28, seed=13, tc=tc)
     J = P.num_joints
     for lv in case["levels"]:
         lv["pose_raw"][:, 3:3 + 3 * J:3] += 500.0
         lv["pose_raw"][1, 4:3 + 3 * J:3] -= 37.25      # and some joints only partially outside
     ref, _ = util.run_oracle(case, tc)
+    util.assert_margins(case, tc, ref)
     plan, got = util.run_gpu(case, tc, refine=True)
-    compare(plan, got, ref, margin=util.rank_margin_ulps(case["levels"], 8))
+    compare(plan, got, ref)
 
 
 def test_white_noise_fields_within_reference_noise_floor():
     """Unsmoothed pose fields amplify fp32 coordinate round-off; the fp64 run of the same algorithm arbitrates:
     the GPU must be as close to it as the fp32 reference is, within 3x + 1e-5."""
     tc = dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)
-    case = util.make_case(P, 2, 32, 48, seed=21, smooth=1)
+    case = util.make_case(P, 2, 32, 48, seed=21, smooth=1, tc=tc)
     ref32, _ = util.run_oracle(case, tc)
+    util.assert_margins(case, tc, ref32)
     case64 = dict(case)
     case64["levels"] = [dict(lv, cls=lv["cls"], ctr=lv["ctr"], pose_raw=lv["pose_raw"].double(),
                              feats=[f.double() for f in lv["feats"]]) for lv in case["levels"]]
@@ -199,9 +202,11 @@ def test_white_noise_fields_within_reference_noise_floor():
     ref64 = O.get_poses([lv["cls"] for lv in case["levels"]], [p.float() for p in pp64],
                         [lv["ctr"] for lv in case["levels"]], case["metas"], tc, [8], 15)
     plan, got = util.run_gpu(case, tc, refine=True)
-    for g, a, e in zip(got, ref32, ref64):
-        if a["index"].tolist() != e["index"].tolist():
-            continue
+    ci = plan.t["cand_index"].cpu()
+    for b, (g, a, e) in enumerate(zip(got, ref32, ref64)):
+        # scores (hence the candidates) do not depend on the pose arithmetic, and random poses never overlap in OKS
+        assert a["index"].tolist() == e["index"].tolist()
+        assert util.slot_to_level_index(plan, g["slots"].cpu(), ci[b])[1] == a["index"].tolist()
         err_ref = util.rel_err(a["poses"].numpy(), e["poses"].numpy())
         err_gpu = util.rel_err(g["poses"].cpu().numpy(), e["poses"].numpy())
         assert err_gpu <= 3 * err_ref + 1e-5, (err_gpu, err_ref)
@@ -323,56 +328,54 @@ def test_drop_in_head_api():
         head.get_poses([dl[0]["cls"]], [], [dl[0]["ctr"]], case["metas"])
 
 
-def test_full_size_properties_config2():
-    """BASELINE config #2 (B=64, 128x208, K=10) generated on the device; properties the domain offers."""
+def test_full_size_config2_all_images_and_properties():
+    """BASELINE config #2 at full size (B=64, J=15, 128x208, K=10, L=1), generated on the device: EVERY image against the
+    CPU oracle (run on host copies in chunks), plus the size-independent properties the domain offers."""
     tc = dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)
     B, H, W = 64, 128, 208
-    dev = torch.device("cuda")
-    levels = synth.make_levels(P, B, H, W, seed=1234, device=dev)
-    layers = synth.make_layers(P, seed=1235, device=dev)
-    metas = synth.make_metas(B, H, W)
-    case = dict(cfg=P, levels=levels, layers=layers, metas=metas, batch=B)
-    plan = util.make_plan(case, tc)
-    lv = levels[0]
-    plan.bind([dict(cls=lv["cls"], ctr=lv["ctr"], pose=lv["pose_raw"], feats=lv["feats"], scales=lv["scales"])])
-    plan.set_metas(metas)
-    plan.run()
-    torch.cuda.synchronize()
+    case, plan, got, ref = util.run_full_size(P, B, H, W, tc, seed=1234, peaks=16, chunk=8)
+    util.assert_margins(case, tc, ref)
+    compare(plan, got, ref)
     t = {k: v.clone() for k, v in plan.t.items()}
-    # selected cells are exactly torch.topk's on the same device scores (set equality; ordering by score)
+    lv = case["levels"][0]
+    # selected cells are exactly torch.topk's on the same device scores, in the same order
     score = (lv["cls"].sigmoid() * lv["ctr"].sigmoid()).flatten(1)
     top_v, top_i = score.topk(10, dim=1)
-    assert torch.equal(torch.sort(t["cand_index"].long(), 1)[0], torch.sort(top_i, 1)[0])
+    assert torch.equal(t["cand_index"].long(), top_i)
     assert torch.all(t["cand_score"][:, :-1] >= t["cand_score"][:, 1:])
     assert int(util.ulp_gap(t["cand_score"].cpu(), top_v.cpu()).max()) <= 8
     # counts, ordering and finiteness of the outputs
     cnt = t["out_count"]
     assert int(cnt.min()) >= 1 and int(cnt.max()) <= 10
-    for b in range(0, B, 7):
+    for b in range(B):
         n = int(cnt[b])
         s = t["out_score"][b, :n]
         assert torch.all(s[:-1] >= s[1:])
         assert torch.isfinite(t["out_pose"][b, :n]).all() and torch.isfinite(t["out_cam"][b, :n]).all()
         assert torch.all(t["out_score"][b, n:] == 0)
-    # batch independence: image 5 decoded alone gives the same rows (images are independent, das_head.py:666)
+    # batch independence: image 5 decoded alone gives the same bits (images are independent, das_head.py:666)
     one = dict(cfg=P, levels=[dict(lv, cls=lv["cls"][5:6], ctr=lv["ctr"][5:6], pose_raw=lv["pose_raw"][5:6],
-                                   feats=[f[5:6] for f in lv["feats"]])], layers=layers, metas=metas[5:6], batch=1)
-    p1 = util.make_plan(one, tc)
-    l1 = one["levels"][0]
-    p1.bind([dict(cls=l1["cls"], ctr=l1["ctr"], pose=l1["pose_raw"], feats=l1["feats"], scales=l1["scales"])])
-    p1.set_metas(metas[5:6])
-    p1.run()
-    torch.cuda.synchronize()
+                                   feats=[f[5:6] for f in lv["feats"]])], layers=case["layers"], metas=case["metas"][5:6], batch=1)
+    p1, _ = util.run_gpu(one, tc, refine=True)
     assert torch.equal(p1.t["out_pose"][0], t["out_pose"][5]) and torch.equal(p1.t["out_cam"][0], t["out_cam"][5])
-    # spot parity against the CPU oracle for two images of the full-size batch
-    sub = [dict(lv, cls=lv["cls"][b:b + 1].cpu(), ctr=lv["ctr"][b:b + 1].cpu(), pose_raw=lv["pose_raw"][b:b + 1].cpu(),
-                feats=[f[b:b + 1].cpu() for f in lv["feats"]]) for b in (0, 63)]
-    lay_cpu = synth.layers_to(layers, "cpu")
-    for b, s in zip((0, 63), sub):
-        ref, _ = O.decode_full([s], lay_cpu, metas[b:b + 1], P.as_dict(), tc)
-        n = int(cnt[b])
-        if t["cand_index"][b, t["out_slot"][b, :n].long()].tolist() == ref[0]["index"].tolist():
-            assert util.rel_err(t["out_cam"][b, :n].cpu().numpy(), ref[0]["poses_cam"]) < TOL
+
+
+def test_full_size_config3_mupots_three_layers():
+    """BASELINE config #3 at its real map size: J=17 (COCO sigma table in OKS), L=3 (two dense layers + the sparse one),
+    K=20, 128x208; a 4-image batch, every image against the oracle."""
+    tc = dict(nms_pre=20, nms_post=20, nms_thr=0.9, score_thr=0.0)
+    case, plan, got, ref = util.run_full_size(synth.MUPOTS17, 4, 128, 208, tc, seed=1239, peaks=30, chunk=2)
+    util.assert_margins(case, tc, ref)
+    compare(plan, got, ref)
+
+
+def test_full_size_config4_crowded():
+    """BASELINE config #4: 256x416 map, K=64 people per image; a 3-image batch, every image against the oracle."""
+    tc = dict(nms_pre=64, nms_post=64, nms_thr=0.9, score_thr=0.0)
+    case, plan, got, ref = util.run_full_size(P, 3, 256, 416, tc, seed=1240, peaks=96, chunk=1)
+    util.assert_margins(case, tc, ref)
+    compare(plan, got, ref)
+    assert all(len(g["scores"]) == 64 for g in got)
 
 
 @pytest.mark.parametrize("mode,tol", [(1, TOL), (2, 5e-2)])
@@ -380,35 +383,37 @@ def test_tensor_core_refinement_modes(mode, tol):
     """tcgen05 path (das_refine_heads + das_refine_tc): 3xTF32 meets the fp32 bar, single-pass TF32 is looser."""
     tc = dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)
     for (B, H, W, seed, kw) in ((3, 40, 56, 71, {}), (2, 64, 96, 72, dict(scales=(1.1, 0.9, 1.05, 0.95)))):
-        case = util.make_case(P, B, H, W, seed=seed, **kw)
+        case = util.make_case(P, B, H, W, seed=seed, tc=tc, **kw)
         ref, _ = util.run_oracle(case, tc)
+        util.assert_margins(case, tc, ref)
         plan, got = util.run_gpu(case, tc, refine=True, refine_mode=mode)
         plan0, got0 = util.run_gpu(case, tc, refine=True, refine_mode=0)
         for g, g0, o in zip(got, got0, ref):
-            assert g["scores"] == g0["scores"]
-            if g["slots"].tolist() == g0["slots"].tolist():
-                assert util.rel_err(g["poses"].cpu().numpy(), o["poses"].numpy()) < tol
-                assert util.rel_err(g["poses_cam"].cpu().numpy(), o["poses_cam"]) < tol
+            assert g["scores"] == g0["scores"] and g["slots"].tolist() == g0["slots"].tolist()
+            assert util.rel_err(g["poses"].cpu().numpy(), o["poses"].numpy()) < tol
+            assert util.rel_err(g["poses_cam"].cpu().numpy(), o["poses_cam"]) < tol
 
 
 def test_tensor_core_refinement_with_threshold_and_pyramid():
     cfg = dataclasses.replace(P, strides=(8, 16, 32))
     tc = dict(nms_pre=60, nms_post=30, nms_thr=0.9, score_thr=0.05)
-    case = util.make_case(cfg, 2, 48, 64, seed=73, peaks=20)
+    case = util.make_case(cfg, 2, 48, 64, seed=73, peaks=20, tc=tc)
     ref, _ = util.run_oracle(case, tc)
+    util.assert_margins(case, tc, ref)
     plan, got = util.run_gpu(case, tc, refine=True, refine_mode=1)
-    compare(plan, got, ref, util.rank_margin_ulps(case["levels"], 60, 0.05))
+    compare(plan, got, ref)
 
 
 def test_soft_oks_nms_matches_oracle():
     """test_cfg.nms_type != 'hard' -> soft_oks_nms (pose_nms.py:129-194): rescoring changes the order, nothing is dropped."""
     tc = dict(nms_pre=30, nms_post=12, nms_thr=0.9, score_thr=0.0, nms_type="soft")
-    case = util.make_case(P, 3, 32, 48, seed=81, peaks=12, coherent=8)
+    case = util.make_case(P, 3, 32, 48, seed=81, peaks=12, coherent=8, tc=tc)
     ref, _ = util.run_oracle(case, tc)
+    util.assert_margins(case, tc, ref)
     plan, got = util.run_gpu(case, tc, refine=True)
     hard, _ = util.run_oracle(case, dict(tc, nms_type="hard"))
     assert any(a["index"].tolist() != b["index"].tolist() for a, b in zip(ref, hard)), "case does not exercise the rescoring"
-    compare(plan, got, ref, util.rank_margin_ulps(case["levels"], 30))
+    compare(plan, got, ref)
     for g in got:
         assert len(g["scores"]) == 12
 
@@ -426,3 +431,47 @@ def test_fp16_head_outputs_are_upcast_at_the_boundary():
                        [half(lv["ctr"]).float() for lv in dl], [[half(f).float() for f in lv["feats"]] for lv in dl], case["metas"])
     for x, y in zip(a, b):
         assert x["scores"] == y["scores"] and torch.equal(x["poses"], y["poses"])
+
+
+def test_caller_owned_output_block_and_fused_peer_stores():
+    """das_plan_set_output_block: two plans write straight into slices of ONE staging buffer (no copy when results are
+    collected); das_plan_set_peer_blocks: the NMS kernel also stores every result value into each peer's copy of the
+    block -- here a second buffer on the same device stands in for a peer GPU -- and bumps the sequence word there."""
+    tc = dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)
+    case = util.make_case(P, 3, 24, 40, seed=61, tc=tc)
+    plan, got = util.run_gpu(case, tc, refine=True)
+    want = plan.output_block().clone()
+    nb, stride = want.numel(), plan.block_stride
+    staging = torch.zeros((2, stride), dtype=torch.uint8, device="cuda")
+    peer = torch.full((2, stride), 0xAB, dtype=torch.uint8, device="cuda")
+    plans = []
+    for k in range(2):
+        p = util.make_plan(case, tc)
+        dl = synth.levels_to(case["levels"], "cuda")
+        p.bind([dict(cls=lv["cls"], ctr=lv["ctr"], pose=lv["pose_raw"], feats=lv["feats"], scales=lv["scales"]) for lv in dl])
+        p.set_metas(case["metas"])
+        p.set_output_block(staging[k])
+        if k == 1:
+            peer[1, nb:].zero_()
+            p.set_peer_blocks([peer[1].data_ptr()])
+        plans.append(p)
+    for rep in range(3):                       # eager, capture, replay
+        for p in plans:
+            p.run()
+    torch.cuda.synchronize()
+    for k in range(2):
+        assert torch.equal(staging[k, :nb], want), k
+        assert plans[k].output_block().data_ptr() == staging[k].data_ptr()
+        assert torch.equal(plans[k].t["out_pose"], plan.t["out_pose"])
+    assert torch.equal(peer[1, :nb], want)                       # the "peer" received the same block ...
+    assert int(peer[1, nb:nb + 4].view(torch.int32)) == 3        # ... and three sequence bumps
+    assert int(staging[1, nb:nb + 4].view(torch.int32)) == 3
+    assert torch.all(peer[0] == 0xAB)                            # nothing else was touched
+    res = plans[1].results(case["metas"])
+    for g, h in zip(got, res):
+        assert g["scores"] == h["scores"] and torch.equal(g["poses_cam"], h["poses_cam"])
+    # back to the plan's own block
+    plans[0].set_output_block(None)
+    plans[0].run()
+    torch.cuda.synchronize()
+    assert torch.equal(plans[0].output_block(), want) and plans[0].output_block().data_ptr() != staging[0].data_ptr()

@@ -100,7 +100,9 @@ def test_bench_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "decoded_images_per_sec" and d["unit"] == "images/s"
     assert d["value"] > 0 and d["higher_is_better"] is True and d["steps"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # the reference's own extracted functions when the tree or the oracle/_ref bundle is present, else the port
+    from oracle import ref_extract as R
+    assert d["cpu_baseline"]["kind"] == ("reference" if R.available() else "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     # a non-zero rank of a torchrun launch exits without output
     env["RANK"] = "1"
@@ -110,8 +112,9 @@ def test_bench_reference_arm_prints_one_json_line():
 
 
 def test_get_poses_argument_forms():
-    """The three call forms get_poses accepts: the reference's (img_metas[, cfg[, rescale]]) and the extended
-    (refine_feats, img_metas) one (das_head.py:653-659; detectors/das.py:78 splats the head outputs)."""
+    """The call forms get_poses accepts, resolved by content: the reference's (img_metas[, cfg[, rescale]]), positional or
+    by keyword (das_head.py:653-659; detectors/das.py:78 splats the head outputs), and the extended
+    (refine_feats, img_metas[, cfg[, rescale]]) one."""
     from das_b200.head import DASHeadB200
     metas = [dict(scale_factor=np.ones(4, np.float32), filename="a.jpg")]
     feats = [[object()]]
@@ -122,8 +125,17 @@ def test_get_poses_argument_forms():
     assert sr((metas, None, True), dict(nms_pre=7)) == (None, metas, dict(nms_pre=7))
     assert sr((feats, metas), None) == (feats, metas, None)                            # extended call
     assert sr((feats, []), None) == (feats, [], None)                                  # empty batch
+    assert sr((feats, metas, dict(nms_pre=5)), None) == (feats, metas, dict(nms_pre=5))          # extended + positional cfg
+    assert sr((feats, metas, dict(nms_pre=5), True), None) == (feats, metas, dict(nms_pre=5))    # ... and rescale
+    assert sr((feats, metas, None, False), dict(nms_pre=9)) == (feats, metas, dict(nms_pre=9))
+    assert sr(([], dict(nms_pre=5)), None) == (None, [], dict(nms_pre=5))               # reference form, empty batch
+    assert sr((), None, img_metas=metas) == (None, metas, None)                        # img_metas= by keyword
+    assert sr((feats,), dict(nms_pre=3), img_metas=metas) == (feats, metas, dict(nms_pre=3))
+    for bad in ((), (feats,), (feats, 3), (metas, None, None, None), (object(), object())):
+        with pytest.raises(TypeError):
+            sr(bad, None)
     with pytest.raises(TypeError):
-        sr((), None)
+        sr((feats, metas), None, img_metas=metas)
 
 
 def test_pack_metas_fast_and_general_paths_agree():

@@ -10,17 +10,21 @@ from das_b200.head import DecodePlan
 from oracle import das_oracle as O
 
 
+MIN_OKS_MARGIN = 1e-6      # |oks - nms_thr| of every suppression decision
+MIN_SOFT_GAP_ULPS = 64     # soft NMS: best vs second-best rescored candidate at every pick
+
+
 def make_case(cfg: synth.HeadConfig, batch, h, w, seed=1234, peaks=16, scales=(1.0, 1.0, 1.0, 1.0), smooth=9,
-              identity_rt=False, coherent=0):
+              identity_rt=False, coherent=0, tc=None, peak_kernel=0, device="cpu"):
+    """Seeded synthetic case.  With `tc` (the test_cfg the case will be decoded with) the generator reject-samples
+    until every rank / threshold boundary of that decode has a safe margin (synth.enforce_rank_margins)."""
+    margin_for = None if tc is None else dict(nms_pre=tc.get("nms_pre", -1), score_thr=tc.get("score_thr", 0.0),
+                                              peak_kernel=peak_kernel)
     levels = synth.make_levels(cfg, batch, h, w, seed=seed, peaks=peaks, scales=scales, smooth=smooth,
-                               coherent=coherent)
+                               coherent=coherent, margin_for=margin_for, device=device)
     layers = synth.make_layers(cfg, seed=seed + 1)
     metas = synth.make_metas(batch, h, w, stride=cfg.strides[0], seed=seed + 2, identity_rt=identity_rt)
     return dict(cfg=cfg, levels=levels, layers=layers, metas=metas, batch=batch)
-
-
-def score_maps(levels):
-    return [(lv["cls"].sigmoid() * lv["ctr"].sigmoid()).flatten(1) for lv in levels]
 
 
 def ulp_gap(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
@@ -30,21 +34,26 @@ def ulp_gap(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return (ia - ib).abs()
 
 
-def rank_margin_ulps(levels, nms_pre, score_thr=0.0):
-    """Smallest ulp gap at any decision boundary of the ranking: adjacent scores among the first
-    nms_pre+1 ranks of every (image, level), and every score against score_thr."""
-    worst = 1 << 40
-    for sm in score_maps(levels):
-        hw = sm.shape[1]
-        if nms_pre > 0 and hw > nms_pre:
-            top = sm.topk(min(nms_pre + 1, hw), dim=1)[0]
-        else:
-            top = sm.sort(dim=1, descending=True)[0]
-        if top.shape[1] > 1:
-            worst = min(worst, int(ulp_gap(top[:, :-1], top[:, 1:]).min()))
-        if score_thr > 0:
-            worst = min(worst, int(ulp_gap(top, torch.full_like(top, score_thr)).min()))
-    return worst
+def rank_margin_ulps(levels, nms_pre, score_thr=0.0, peak_kernel=0):
+    """Smallest ulp gap at any boundary that decides the decode's output: adjacent ranks among the candidates that
+    survive score_thr (per level incl. the first cell left out, and across levels for the NMS order) and every
+    candidate against score_thr (synth.rank_margin_ulps)."""
+    return synth.rank_margin_ulps(levels, nms_pre, score_thr, peak_kernel)
+
+
+def assert_margins(case_or_levels, tc, ref=None, peak_kernel=0):
+    """Every parity case must be decidable: rank margins >= 16 ulp and, when the oracle result is given, every OKS
+    suppression decision at least MIN_OKS_MARGIN away from nms_thr.  Without this a mismatch could be excused as a
+    near-tie -- and a vacuous pass could hide behind one."""
+    levels = case_or_levels["levels"] if isinstance(case_or_levels, dict) else case_or_levels
+    m = rank_margin_ulps(levels, tc.get("nms_pre", -1), tc.get("score_thr", 0.0), peak_kernel)
+    assert m >= synth.MIN_MARGIN_ULPS, f"case has a rank margin of only {m} ulp: regenerate it with margin_for"
+    if ref is not None:
+        for b, o in enumerate(ref):
+            assert o["oks_margin"] >= MIN_OKS_MARGIN, f"image {b}: an OKS decision sits {o['oks_margin']:.2e} from nms_thr"
+            if tc.get("nms_type", "hard") != "hard":
+                assert o["soft_gap_ulps"] >= MIN_SOFT_GAP_ULPS, f"image {b}: soft-NMS pick decided by {o['soft_gap_ulps']} ulp"
+    return m
 
 
 def run_oracle(case, test_cfg, stable=False, peak_kernel=0):
@@ -80,6 +89,22 @@ def run_gpu(case, test_cfg, refine=True, peak_kernel=0, pose_override=None, use_
     plan.run(use_graph=use_graph)
     torch.cuda.synchronize()
     return plan, plan.results(case["metas"])
+
+
+def run_full_size(cfg, batch, h, w, test_cfg, seed, peaks, chunk=8, refine_mode=None):
+    """A BASELINE-sized case generated on the device (the host generator would take minutes), decoded through the C-ABI,
+    and the oracle run on host copies of the same bits, `chunk` images at a time (its dense refinement materialises
+    ~0.2 GB of temporaries per image).  Returns (case, plan, gpu results, oracle results)."""
+    case = make_case(cfg, batch, h, w, seed=seed, peaks=peaks, tc=test_cfg, device="cuda")
+    plan, got = run_gpu(case, test_cfg, refine=True, refine_mode=refine_mode)
+    ref = []
+    for b0 in range(0, batch, chunk):
+        b1 = min(batch, b0 + chunk)
+        sub = [dict(lv, cls=lv["cls"][b0:b1].cpu(), ctr=lv["ctr"][b0:b1].cpu(), pose_raw=lv["pose_raw"][b0:b1].cpu(),
+                    feats=[f[b0:b1].cpu() for f in lv["feats"]]) for lv in case["levels"]]
+        r, _ = O.decode_full(sub, case["layers"], case["metas"][b0:b1], cfg.as_dict(), test_cfg)
+        ref += r
+    return case, plan, got, ref
 
 
 def slot_to_level_index(plan, slots_b, cand_index_b):
