@@ -337,7 +337,8 @@ class Runner:
                        for lv in self.keep[i % n_sets]])
             plan.set_metas(self.metas)
             self.plans.append(plan)
-        self.n_streams = max(1, min(args.streams, n_sets))
+        # dense layers (num_layers > 1) fill the GPU by themselves: concurrent batches only thrash L2, so they run on one stream
+        self.n_streams = 1 if head.num_layers > 1 else max(1, min(args.streams, n_sets))
         self.streams = ([torch.cuda.Stream(device=dev) for _ in range(self.n_streams)] if self.n_streams > 1
                         else [torch.cuda.current_stream(dev)])
         self.stream_ptrs = [st.cuda_stream for st in self.streams]

@@ -59,6 +59,12 @@ class PeerBlocks(C.Structure):
                 ("seq", C.c_void_p), ("ticket", C.c_void_p)]
 
 
+class RefineScratch(C.Structure):
+    _fields_ = [("unique_rows", C.c_void_p), ("unique_out", C.c_void_p), ("row_records", C.c_void_p),
+                ("item_records", C.c_void_p), ("valid_list", C.c_void_p), ("counters", C.c_void_p),
+                ("row_cap", C.c_int32), ("reserved_", C.c_int32)]
+
+
 class RowCache(C.Structure):
     _fields_ = [("table", C.c_void_p), ("rows", C.c_void_p), ("cand_rows", C.c_void_p),
                 ("table_bits", C.c_int32), ("max_rows", C.c_int32)]
@@ -77,11 +83,12 @@ SIGNATURES = {
     "das_gather_refine_assemble": (C.c_int, [_VP, C.POINTER(Levels), C.POINTER(DecodeCfg), _VP, _VP, _VP, _VP, _VP,
                                              C.c_int32, _VP, _VP, _VP, _VP]),
     "das_refine_heads": (C.c_int, [_VP, C.POINTER(Levels), C.POINTER(DecodeCfg), _VP, _VP, _VP, _VP, _VP, C.c_int32,
-                                   _VP, _VP, _VP, _VP, _VP, C.POINTER(RowCache), _VP]),
-    "das_refine_tc": (C.c_int, [_VP, C.POINTER(Levels), C.POINTER(DecodeCfg), _VP, _VP, C.c_int32, _VP, _VP, _VP, _VP, _VP,
+                                   C.POINTER(RefineScratch), _VP, C.POINTER(RowCache), _VP]),
+    "das_refine_tc": (C.c_int, [_VP, C.POINTER(Levels), C.POINTER(DecodeCfg), _VP, _VP, C.c_int32, C.POINTER(RefineScratch),
                                 C.c_int32, _VP]),
+    "das_refine_finish": (C.c_int, [C.POINTER(Levels), C.POINTER(DecodeCfg), C.c_int32, C.POINTER(RefineScratch), _VP, _VP]),
     "das_pack_tc_panels": (C.c_int, [C.POINTER(DecodeCfg), _VP, _VP, _VP]),
-    "das_refine_row_cache": (C.c_int, [C.POINTER(DecodeCfg), _VP, _VP, _VP, C.POINTER(RowCache), _VP]),
+    "das_refine_row_cache": (C.c_int, [C.POINTER(DecodeCfg), C.POINTER(RefineScratch), C.POINTER(RowCache), _VP]),
     "das_row_cache_table_bytes": (C.c_int64, [C.c_int32]),
     "das_row_cache_clear": (C.c_int, [C.POINTER(RowCache), _VP]),
     "das_refine_cand_rows": (C.c_int, [_VP, C.POINTER(Levels), C.POINTER(DecodeCfg), _VP, _VP, C.c_int32,
@@ -155,9 +162,9 @@ def load():
         fn = getattr(lib, name)          # AttributeError here = header and library disagree
         fn.restype = res
         fn.argtypes = args
-    sizes = (C.c_int32 * 4)()
+    sizes = (C.c_int32 * 6)()
     lib.das_abi_struct_sizes(sizes)
-    mine = [C.sizeof(Levels), C.sizeof(DecodeCfg), C.sizeof(Buffers), C.sizeof(RowCache)]
+    mine = [C.sizeof(Levels), C.sizeof(DecodeCfg), C.sizeof(Buffers), C.sizeof(RowCache), C.sizeof(RefineScratch), C.sizeof(PeerBlocks)]
     if list(sizes) != mine:
         raise DasError(f"ABI mismatch: library struct sizes {list(sizes)} != ctypes mirrors {mine}; rebuild with "
                        "python -m das_b200.build --force")

@@ -12,6 +12,8 @@
 // the same cell tile at the same time, so the 128-KB feature tile is fetched from HBM once and re-read from L2.
 #include <algorithm>
 
+#include <cuda.h>
+
 #include "refine_common.cuh"
 #include "tc_common.cuh"
 
@@ -26,34 +28,42 @@ constexpr int DT_NOUT = 2 * DT_NH + 9;           // 17
 constexpr int DT_PANEL_KB = 2 * DT_N * 128;      // bytes per k-block: 64 hi rows then 64 lo rows
 constexpr int DT_PANEL = DT_KB * DT_PANEL_KB;    // 128 KB
 constexpr int DT_EG = 2;                         // epilogue groups / accumulator buffers
-constexpr int DT_PG = 3;                         // producer groups
-constexpr int DT_STAGES = 2;                     // smem stages per producer group
+constexpr int DT_PG = 2;                         // producer groups (k-block g goes to group g % 2)
+constexpr int DT_STAGES = 6;                     // TMA ring of A k-block tiles: 5 k-blocks (~2300 MMA cycles) of look-ahead
 constexpr int DT_SLOTS = 4;                      // TMEM A slots (64 columns: 32 hi + 32 lo)
 constexpr int DT_A_BYTES = 128 * 128;
 constexpr int DT_FIRST_PRODUCER = 4 * DT_EG;     // warp 8
 constexpr int DT_MMA_WARP = DT_FIRST_PRODUCER + 4 * DT_PG;   // warp 20
-constexpr int DT_THREADS = 32 * (DT_MMA_WARP + 1);
+constexpr int DT_TMA_WARP = DT_MMA_WARP + 1;     // warp 21: one elected lane issues the TMA loads
+constexpr int DT_THREADS = 32 * (DT_TMA_WARP + 1);
 constexpr int DT_D_COL = 0;                      // accumulators: 2 x 128 columns
 constexpr int DT_A_COL = 2 * DT_N * DT_EG;       // 256: A ring 4 x 64 columns
-constexpr int DT_SMEM = 1024 + DT_PG * DT_STAGES * DT_A_BYTES + DT_PANEL;
+constexpr int DT_SMEM = 1024 + DT_STAGES * DT_A_BYTES + DT_PANEL;
 
 struct DenseTcParams {
     const das_levels* lv;
     const float* wpack;            // [J][17][C] + biases
     const unsigned char* panels;   // [Q][DT_PANEL]
     const float* uvd_in;           // nullptr -> scaled raw uvd from lv.pose; else joint-major [B][J][HW][4]
-    float* proj;                   // two joint-major planes: S [B][J][HW][8], then OC [B][J][HW][8] = {O 3, conf 3, -, -}
+    float* proj;                   // four joint-major planes, see DensePlanes (refine_common.cuh)
+    int* progress;                 // [G] tiles issued by the Q CTAs that share tile sequence m (zeroed before the launch)
     int level, layer, J, root, B, Q;
 };
 
-__global__ void __launch_bounds__(DT_THREADS, 1)
-dense_project_tc_kernel(const DenseTcParams p) {
+constexpr int DT_LOCKSTEP_TILES = 2;             // the Q CTAs that read the same feature tiles stay within this many tiles
+
+// The feature map of a level as a 2-D tensor {C = 256 floats, B*H*W cells}: one TMA box = 32 channels x 128 cells
+// (a k-block of a 128-cell tile), 128-byte swizzle = the K-major operand layout of tc_common.cuh.
+__global__ void __maxnreg__(112)               // 576 threads x 112 registers = 63 K: one CTA per SM anyway (208 KB of shared memory)
+dense_project_tc_kernel(const DenseTcParams p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    unsigned char* sA = base;                                      // [group][stage] k-block tiles (128-B swizzle)
-    unsigned char* sB = sA + DT_PG * DT_STAGES * DT_A_BYTES;       // resident panel of this CTA's joint group
+    unsigned char* sA = base;                                      // [stage] k-block tiles (128-B swizzle), filled by TMA
+    unsigned char* sB = sA + DT_STAGES * DT_A_BYTES;               // resident panel of this CTA's joint group
+    __shared__ uint64_t st_full[DT_STAGES], st_empty[DT_STAGES];   // TMA -> producers, producers -> TMA
     __shared__ uint64_t a_full[DT_SLOTS], a_empty[DT_SLOTS], acc_full[DT_EG], acc_free[DT_EG];
     __shared__ uint32_t tmem_base;
+    __shared__ float s_bias[DT_JG * DT_NOUT];                      // biases of this CTA's joint group
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const das_level_desc& d = p.lv->lv[p.level];
@@ -67,9 +77,13 @@ dense_project_tc_kernel(const DenseTcParams p) {
     const int my_tiles = (n_tiles - m + G - 1) / G;          // tiles m, m+G, ...
     if (my_tiles <= 0) return;
     const int total_kb = my_tiles * DT_KB;
-    const float* __restrict__ F = d.feats[p.layer];
 
+    if (tid < DT_JG * DT_NOUT) {
+        const int j = q * DT_JG + tid / DT_NOUT;
+        s_bias[tid] = j < J ? p.wpack[static_cast<size_t>(J) * DT_NOUT * DT_C + j * DT_NOUT + tid % DT_NOUT] : 0.f;
+    }
     if (tid == 0) {
+        for (int s = 0; s < DT_STAGES; ++s) { tc::mbar_init(&st_full[s], 1); tc::mbar_init(&st_empty[s], 4); }
         for (int s = 0; s < DT_SLOTS; ++s) { tc::mbar_init(&a_full[s], 4); tc::mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < DT_EG; ++s) { tc::mbar_init(&acc_full[s], 1); tc::mbar_init(&acc_free[s], 4); }
         tc::mbar_fence_init();
@@ -80,8 +94,34 @@ dense_project_tc_kernel(const DenseTcParams p) {
     tc::tc_fence_after();
     const uint32_t tmem0 = tmem_base;
     const uint32_t sB_u = tc::smem_u32(sB);
+    const uint32_t sA_u = tc::smem_u32(sA);
 
-    if (warp == DT_MMA_WARP) {
+    if (warp == DT_TMA_WARP) {
+        // ===== TMA issuer: streams the k-blocks of this CTA's tiles through the ring, DT_STAGES - 1 ahead ============
+        if (lane == 0) {
+            tc::tma_prefetch_desc(&tmap);
+            volatile int* prog = p.progress + m;
+            for (int g = 0; g < total_kb; ++g) {
+                const int s = g % DT_STAGES;
+                if (g >= DT_STAGES) tc::mbar_wait(&st_empty[s], ((g / DT_STAGES) - 1) & 1);   // the 4 warps that read it are done
+                const int i = g / DT_KB, kb = g - i * DT_KB;
+                if (kb == 0) {
+                    // Loose lock-step of the Q CTAs (one per joint group) that walk the same tiles: nobody starts tile i
+                    // before everybody has issued tile i - DT_LOCKSTEP_TILES, so a feature tile is fetched from HBM by
+                    // the first CTA and found in L2 by the other Q - 1 (unsynchronised they drift apart by more than
+                    // the L2 holds: ncu showed 40 % L2 hits and 2.8x the map's bytes from DRAM).  All CTAs of the grid
+                    // are co-resident (grid <= SM count, one CTA per SM), so the wait cannot deadlock.
+                    if (i > 0) atomicAdd(p.progress + m, 1);                                   // tile i - 1 fully issued
+                    const int need = Q * (i - DT_LOCKSTEP_TILES);
+                    while (*prog < need) __nanosleep(32);
+                }
+                const long long cell0 = (static_cast<long long>(m) + static_cast<long long>(i) * G) * 128;
+                tc::mbar_arrive_expect_tx(&st_full[s], DT_A_BYTES);
+                // rows beyond the map (last tile) are zero-filled by the TMA unit and still count towards the byte total
+                tc::tma_load_2d(sA_u + s * DT_A_BYTES, &tmap, &st_full[s], kb * 32, static_cast<int>(cell0), tc::kEvictNormal);
+            }
+        }
+    } else if (warp == DT_MMA_WARP) {
         // ===== MMA issuer warp: loads this joint group's panel once, then one burst per k-block =====================
         {
             const unsigned char* src = p.panels + static_cast<size_t>(q) * DT_PANEL;
@@ -108,40 +148,21 @@ dense_project_tc_kernel(const DenseTcParams p) {
             }
         }
     } else if (warp >= DT_FIRST_PRODUCER) {
-        // ===== producer groups: contiguous 128-cell k-block -> smem (cp.async) -> own row -> hi/lo -> TMEM ===========
+        // ===== producer groups: own row of the TMA-staged k-block -> hi/lo split in registers -> TMEM ===============
         const int pg = (warp - DT_FIRST_PRODUCER) >> 2;
         const int qw = warp & 3;
         const int gt = (qw << 5) | lane;
-        const uint32_t sG_u = tc::smem_u32(sA) + pg * DT_STAGES * DT_A_BYTES;
-        unsigned char* sG = sA + pg * DT_STAGES * DT_A_BYTES;
-        const int bar_id = 1 + pg;
-        const int my_n = (total_kb - pg + DT_PG - 1) / DT_PG;
-        auto gather = [&](int n) {
-            const int g = pg + n * DT_PG;
-            const int i = g / DT_KB, kb = g - i * DT_KB, st = n % DT_STAGES;
-            const long long cell0 = static_cast<long long>(m + static_cast<long long>(i) * G) * 128;
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int row = (gt >> 3) + 16 * it, ch = gt & 7;
-                const bool ok = cell0 + row < cells;
-                tc::cp_async16(sG_u + st * DT_A_BYTES + tc::swz128(row, ch), F + (ok ? (cell0 + row) : 0) * DT_C + kb * 32 + ch * 4, ok);
-            }
-        };
-        for (int n = 0; n < DT_STAGES - 1; ++n) { if (n < my_n) gather(n); tc::cp_async_commit(); }
-        for (int n = 0; n < my_n; ++n) {
-            const int g = pg + n * DT_PG;
-            const int slot = g % DT_SLOTS, st = n % DT_STAGES;
-            tc::cp_async_wait<DT_STAGES - 2>();
-            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        for (int g = pg; g < total_kb; g += DT_PG) {
+            const int slot = g % DT_SLOTS, s = g % DT_STAGES;
+            tc::mbar_wait(&st_full[s], (g / DT_STAGES) & 1);
             float hi[32];
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) {
-                const float4 a = *reinterpret_cast<const float4*>(sG + st * DT_A_BYTES + tc::swz128(gt, ch));
+                const float4 a = *reinterpret_cast<const float4*>(sA + s * DT_A_BYTES + tc::swz128(gt, ch));
                 hi[4 * ch] = a.x; hi[4 * ch + 1] = a.y; hi[4 * ch + 2] = a.z; hi[4 * ch + 3] = a.w;
             }
-            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-            if (n + DT_STAGES - 1 < my_n) gather(n + DT_STAGES - 1);
-            tc::cp_async_commit();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&st_empty[s]);          // this warp's 32 rows are in registers
             if (g >= DT_SLOTS) tc::mbar_wait(&a_empty[slot], ((g / DT_SLOTS) - 1) & 1);
             tc::tc_fence_after();
             const uint32_t taddr = tmem0 + (static_cast<uint32_t>(qw * 32) << 16) + DT_A_COL + slot * 64;
@@ -154,67 +175,89 @@ dense_project_tc_kernel(const DenseTcParams p) {
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&a_full[slot]);
         }
-        tc::cp_async_wait<0>();
     } else {
-        // ===== epilogue groups: thread = cell; bias, gate, blend with the previous offset, 64-B records ==============
+        // ===== epilogue groups: thread = cell; bias, gate, blend with the previous offset -> the four planes =============
         const int e = warp >> 2;
         const int qw = warp & 3;
         const int row = (qw << 5) | lane;
-        const float* __restrict__ Bias = p.wpack + static_cast<size_t>(J) * DT_NOUT * DT_C;
+        const int nj = min(DT_JG, J - q * DT_JG);                  // joints of this group (uniform across the CTA)
+        const DensePlanes pl = dense_planes(p.proj, p.B, J, HW);
+        // the previous offsets of a cell for the group's joints, RAW (the Scale factors are applied at use): loaded one
+        // own tile ahead, so the global-load latency hides behind two tiles of MMAs instead of stalling the drain
+        auto load_prev = [&](int i, float (&pv)[DT_JG][3]) {
+            const long long cell = (static_cast<long long>(m) + static_cast<long long>(i) * G) * 128 + row;
+#pragma unroll
+            for (int jj = 0; jj < DT_JG; ++jj) pv[jj][0] = pv[jj][1] = pv[jj][2] = 0.f;
+            if (i >= my_tiles || cell >= cells) return;
+            const int b = static_cast<int>(cell / HW);
+            const int pix = static_cast<int>(cell - static_cast<long long>(b) * HW);
+#pragma unroll
+            for (int jj = 0; jj < DT_JG; ++jj) {
+                if (jj >= nj) break;
+                const int j = q * DT_JG + jj;
+                if (p.uvd_in) {
+                    const float4 qv = __ldg(reinterpret_cast<const float4*>(p.uvd_in) + (static_cast<size_t>(b) * J + j) * HW + pix);
+                    pv[jj][0] = qv.x; pv[jj][1] = qv.y; pv[jj][2] = qv.z;
+                } else {
+                    const float* qv = d.pose + (static_cast<size_t>(b) * (3 + 6 * J) + 3 + 3 * j) * HW + pix;
+                    pv[jj][0] = __ldg(qv);
+                    pv[jj][1] = __ldg(qv + HW);
+                    pv[jj][2] = (j == p.root) ? 0.f : __ldg(qv + 2 * static_cast<size_t>(HW));
+                }
+            }
+        };
+        const float sc_uv = p.uvd_in ? 1.0f : d.scale_uv, sc_d = p.uvd_in ? 1.0f : d.scale_d;
+        float prev[DT_JG][3], nxt[DT_JG][3];
+        load_prev(e, prev);
         for (int i = e; i < my_tiles; i += DT_EG) {
             const long long cell = (static_cast<long long>(m) + static_cast<long long>(i) * G) * 128 + row;
             const bool live = cell < cells;
             const int b = live ? static_cast<int>(cell / HW) : 0;
             const int pix = live ? static_cast<int>(cell - static_cast<long long>(b) * HW) : 0;
+            load_prev(i + DT_EG, nxt);
             tc::mbar_wait(&acc_full[e], (i / DT_EG) & 1);
             tc::tc_fence_after();
             const uint32_t tbase = tmem0 + (static_cast<uint32_t>(qw * 32) << 16) + DT_D_COL + e * (2 * DT_N);
-#pragma unroll 1
-            for (int jj = 0; jj < DT_JG; ++jj) {
-                const int j = q * DT_JG + jj;
-                if (j >= J) break;                                // uniform across the CTA
-                float v[32], w2[32];
-                {
-                    float t0[16], t1[16], t2[16], t3[16];
-                    tc::tmem_ld16(tbase + jj * DT_NOUT, t0);
-                    tc::tmem_ld16(tbase + jj * DT_NOUT + 16, t1);
-                    tc::tmem_ld16(tbase + DT_N + jj * DT_NOUT, t2);
-                    tc::tmem_ld16(tbase + DT_N + jj * DT_NOUT + 16, t3);
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) { v[k] = t0[k]; v[16 + k] = t1[k]; w2[k] = t2[k]; w2[16 + k] = t3[k]; }
+            for (int jj = 0; jj < DT_JG; ++jj) {
+                if (jj >= nj) break;                               // uniform across the CTA
+                const int j = q * DT_JG + jj;
+                // outputs 0..15 (+ their lo-pass partners in the second half of the accumulator), then output 16
+                float t0[16], t2[16], t1[16], t3[16];
+                tc::tmem_ld16_nowait(tbase + jj * DT_NOUT, t0);
+                tc::tmem_ld16_nowait(tbase + DT_N + jj * DT_NOUT, t2);
+                tc::tmem_ld16_nowait(tbase + jj * DT_NOUT + 16, t1);
+                tc::tmem_ld16_nowait(tbase + DT_N + jj * DT_NOUT + 16, t3);
+                tc::tmem_ld_wait();
+                if (jj == nj - 1) {                                // accumulator drained: hand it back before the stores
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&acc_free[e]);
                 }
                 if (!live) continue;
-                const float* bj = Bias + j * DT_NOUT;
+                const float* bj = s_bias + jj * DT_NOUT;
                 float o[DT_NOUT];
 #pragma unroll
-                for (int k = 0; k < DT_NOUT; ++k) o[k] = (v[k] + w2[k]) + __ldg(bj + k);
-                float prev[3];
-                if (p.uvd_in) {
-                    const float4 qv = __ldg(reinterpret_cast<const float4*>(p.uvd_in) + (static_cast<size_t>(b) * J + j) * HW + pix);
-                    prev[0] = qv.x; prev[1] = qv.y; prev[2] = qv.z;
-                } else {
-                    const float* qv = d.pose + (static_cast<size_t>(b) * (3 + 6 * J) + 3 + 3 * j) * HW + pix;
-                    prev[0] = __ldg(qv) * d.scale_uv;
-                    prev[1] = __ldg(qv + HW) * d.scale_uv;
-                    prev[2] = (j == p.root) ? 0.f : __ldg(qv + 2 * static_cast<size_t>(HW)) * d.scale_d;
-                }
+                for (int k = 0; k < 16; ++k) o[k] = (t0[k] + t2[k]) + bj[k];
+                o[16] = (t1[0] + t3[0]) + bj[16];
+                // layer 0 reads the raw predictor output: das_head.py:243-249 Scale factors here (exact: one multiply each)
+                const float pv0 = prev[jj][0] * sc_uv, pv1 = prev[jj][1] * sc_uv, pv2 = prev[jj][2] * sc_d;
+                const float pvk[3] = {pv0, pv1, pv2};
                 float blend[3];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const float gate = sigmoid_acc(o[2 * DT_NH + k]);
-                    blend[k] = __fadd_rn(__fmul_rn(1.0f - gate, prev[k]), __fmul_rn(gate, o[2 * DT_NH + 3 + k]));
+                    blend[k] = __fadd_rn(__fmul_rn(1.0f - gate, pvk[k]), __fmul_rn(gate, o[2 * DT_NH + 3 + k]));
                 }
-                const size_t rec = ((static_cast<size_t>(b) * J + j) * HW + pix) * 2;            // float4 index into a plane
-                float4* outS = reinterpret_cast<float4*>(p.proj) + rec;
-                float4* outOC = reinterpret_cast<float4*>(p.proj) + static_cast<size_t>(p.B) * J * HW * 2 + rec;
-                outS[0] = make_float4(o[0], o[1], o[2], o[3]);
-                outS[1] = make_float4(o[4], o[5], o[6], o[7]);
-                outOC[0] = make_float4(blend[0], blend[1], blend[2], o[2 * DT_NH + 6]);          // blended offset | conf.x
-                outOC[1] = make_float4(o[2 * DT_NH + 7], o[2 * DT_NH + 8], 0.f, 0.f);            // conf.y, conf.z
+                const size_t cellj = (static_cast<size_t>(b) * J + j) * HW + pix;
+                // 16-byte plane entries: the 32 threads of a warp (consecutive cells) fill whole 128-byte lines
+                pl.s0[cellj] = make_float4(o[0], o[1], o[2], o[3]);
+                pl.s1[cellj] = make_float4(o[4], o[5], o[6], o[7]);
+                pl.oa[cellj] = make_float4(blend[0], blend[1], blend[2], o[2 * DT_NH + 6]);           // blended offset | conf.u
+                pl.cb[cellj] = make_float2(o[2 * DT_NH + 7], o[2 * DT_NH + 8]);                       // conf.v, conf.d
             }
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&acc_free[e]);
+#pragma unroll
+            for (int jj = 0; jj < DT_JG; ++jj) { prev[jj][0] = nxt[jj][0]; prev[jj][1] = nxt[jj][1]; prev[jj][2] = nxt[jj][2]; }
         }
     }
     tc::tc_fence_before();
@@ -280,8 +323,41 @@ extern "C" int das_dense_project_tc(const das_levels* d_levels, const das_levels
     if (attr_done.need()) {
         DAS_CUDA_CHECK(cudaFuncSetAttribute(dense_project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
     }
+    // TMA descriptor of this level's feature map: {256 channels, B*H*W cells}, box = 32 channels x 128 cells, 128-B swizzle
+    const float* feat = h_levels->lv[level].feats[layer];
+    DAS_REQUIRE(feat && (reinterpret_cast<uintptr_t>(feat) & 15) == 0, DAS_ERR_ARG, "das_dense_project_tc: feature map is null or not 16-byte aligned");
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        DAS_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        DAS_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, DAS_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t cells = static_cast<cuuint64_t>(h_levels->batch) * h_levels->lv[level].H * h_levels->lv[level].W;
+    const cuuint64_t gdim[2] = {DT_C, cells};
+    const cuuint64_t gstride[1] = {DT_C * sizeof(float)};
+    const cuuint32_t box[2] = {32, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    CUtensorMap tmap;
+    const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(feat), gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DAS_REQUIRE(cr == CUDA_SUCCESS, DAS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(cr));
     const int grid = (kSMs / p.Q) * p.Q;
-    dense_project_tc_kernel<<<grid, DT_THREADS, DT_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+    {
+        // lock-step counters live in the unused tail of the projection scratch (16 floats are allocated per (cell, joint),
+        // the four planes use 14)
+        const size_t n = static_cast<size_t>(p.B) * p.J * h_levels->lv[level].H * h_levels->lv[level].W;
+        DAS_REQUIRE(n * 8 >= static_cast<size_t>(kSMs) * sizeof(int), DAS_ERR_ARG, "das_dense_project_tc: map too small for the tensor-core path");
+        const DensePlanes pl = dense_planes(proj, p.B, p.J, h_levels->lv[level].H * h_levels->lv[level].W);
+        p.progress = reinterpret_cast<int*>(pl.cb + n);
+        DAS_CUDA_CHECK(cudaMemsetAsync(p.progress, 0, kSMs * sizeof(int), static_cast<cudaStream_t>(stream)));
+    }
+    dense_project_tc_kernel<<<grid, DT_THREADS, DT_SMEM, static_cast<cudaStream_t>(stream)>>>(p, tmap);
     DAS_CUDA_CHECK(cudaGetLastError());
     return DAS_OK;
 }

@@ -33,14 +33,22 @@ struct NmsParams {
     das_peer_blocks peers;     // n == 0: local stores only
 };
 
-// Every output value goes to the local block and, when peers are configured, to the same offset of every peer's copy
-// of this rank's block (NVLink P2P stores, fire-and-forget): the result all-gather is fused into the kernel that
-// produces the results ("only the final small pose lists are gathered over NVLink").
-template <typename T>
-__device__ __forceinline__ void store_all(const das_peer_blocks& pe, T* local, T v) {
-    *local = v;
-    for (int q = 0; q < pe.n; ++q)
-        *reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(local) + pe.delta[q]) = v;
+// Fused result all-gather: once an image's part of the packed output block is complete, its CTA copies it to the same
+// offsets of every peer's copy of this rank's block -- NVLink P2P stores to IPC-mapped memory, 16 bytes wide where the
+// chunk allows it, fire-and-forget ("only the final small pose lists are gathered over NVLink").
+template <int NT>
+__device__ __forceinline__ void copy_chunk_to_peers(const das_peer_blocks& pe, const void* local, int words) {
+    const uint32_t* src = static_cast<const uint32_t*>(local);
+    const int head = min(words, static_cast<int>(((16u - (reinterpret_cast<uintptr_t>(src) & 15u)) & 15u) >> 2));
+    const int nvec = (words - head) >> 2;
+    const int tail0 = head + (nvec << 2);
+    for (int q = 0; q < pe.n; ++q) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(const_cast<uint32_t*>(src)) + pe.delta[q]);
+        for (int i = threadIdx.x; i < nvec; i += NT)
+            reinterpret_cast<uint4*>(dst + head)[i] = __ldcg(reinterpret_cast<const uint4*>(src + head) + i);
+        for (int i = threadIdx.x; i < head; i += NT) dst[i] = __ldcg(src + i);
+        for (int i = tail0 + threadIdx.x; i < words; i += NT) dst[i] = __ldcg(src + i);
+    }
 }
 
 __device__ __forceinline__ double oks_var(int j, int J) {
@@ -323,7 +331,7 @@ nms_backproject_kernel(const NmsParams p) {
     // ---- outputs -----------------------------------------------------------------------------------
     const das_buffers& o = p.out;
     const das_peer_blocks& pe = p.peers;
-    if (tid == 0) store_all(pe, o.out_count + b, kept);
+    if (tid == 0) o.out_count[b] = kept;
     const double* __restrict__ cam = p.cam + static_cast<size_t>(b) * DAS_CAM_DOUBLES;
     const double K00 = cam[0], K01 = cam[1], K02 = cam[2], K10 = cam[3], K11 = cam[4], K12 = cam[5];
     const double* R = cam + 6;
@@ -339,9 +347,9 @@ nms_backproject_kernel(const NmsParams p) {
     for (int k = tid; k < P; k += NT) {
         const bool live = k < kept;
         const int c = live ? kept_list[k] : 0;
-        store_all(pe, o.out_score + static_cast<size_t>(b) * P + k, live ? score[c] : 0.f);
-        store_all(pe, o.out_slot + static_cast<size_t>(b) * P + k, live ? c : -1);
-        for (int d = 0; d < 3; ++d) store_all(pe, o.out_center + (static_cast<size_t>(b) * P + k) * 3 + d, live ? center[c * 3 + d] : 0.f);
+        *(o.out_score + static_cast<size_t>(b) * P + k) = (live ? score[c] : 0.f);
+        *(o.out_slot + static_cast<size_t>(b) * P + k) = (live ? c : -1);
+        for (int d = 0; d < 3; ++d) *(o.out_center + (static_cast<size_t>(b) * P + k) * 3 + d) = (live ? center[c * 3 + d] : 0.f);
     }
     for (int e = tid; e < P * J; e += NT) {
         const int k = e / J, j = e - k * J;
@@ -350,7 +358,7 @@ nms_backproject_kernel(const NmsParams p) {
             const int c = kept_list[k];
             const float* pc = pose + static_cast<size_t>(c) * J * 3;
             const float fx = pc[3 * j], fy = pc[3 * j + 1], fz = pc[3 * j + 2];
-            store_all(pe, o.out_pose + ob, fx); store_all(pe, o.out_pose + ob + 1, fy); store_all(pe, o.out_pose + ob + 2, fz);
+            *(o.out_pose + ob) = (fx); *(o.out_pose + ob + 1) = (fy); *(o.out_pose + ob + 2) = (fz);
             const double zr = static_cast<double>(pc[3 * p.root + 2]);
             double Z = zr * nd + (static_cast<double>(fz) - zr);
             Z *= p.ddf;
@@ -358,27 +366,40 @@ nms_backproject_kernel(const NmsParams p) {
             const double a = (K11 * X0 - K01 * X1) / detK;
             const double bb = (-K10 * X0 + K00 * X1) / detK;
             const double cx = a * Z, cy = bb * Z, cz = Z;
-            store_all(pe, o.out_cam + ob, cx); store_all(pe, o.out_cam + ob + 1, cy); store_all(pe, o.out_cam + ob + 2, cz);
+            *(o.out_cam + ob) = (cx); *(o.out_cam + ob + 1) = (cy); *(o.out_cam + ob + 2) = (cz);
             const double dx = cx - T[0], dy = cy - T[1], dz = cz - T[2];
-            store_all(pe, o.out_world + ob, (c00 * dx + c01 * dy + c02 * dz) / detR);
-            store_all(pe, o.out_world + ob + 1, (c10 * dx + c11 * dy + c12 * dz) / detR);
-            store_all(pe, o.out_world + ob + 2, (c20 * dx + c21 * dy + c22 * dz) / detR);
+            *(o.out_world + ob) = ((c00 * dx + c01 * dy + c02 * dz) / detR);
+            *(o.out_world + ob + 1) = ((c10 * dx + c11 * dy + c12 * dz) / detR);
+            *(o.out_world + ob + 2) = ((c20 * dx + c21 * dy + c22 * dz) / detR);
         } else {
-            for (int d = 0; d < 3; ++d) { store_all(pe, o.out_pose + ob + d, 0.f); store_all(pe, o.out_cam + ob + d, 0.0); store_all(pe, o.out_world + ob + d, 0.0); }
+            for (int d = 0; d < 3; ++d) { *(o.out_pose + ob + d) = (0.f); *(o.out_cam + ob + d) = (0.0); *(o.out_world + ob + d) = (0.0); }
         }
     }
-    if (pe.n > 0 && pe.seq) {
-        // publish: the last CTA to finish bumps the block's sequence number on every peer, after every CTA's stores have
-        // been made visible system-wide -- a consumer on the peer that sees seq == s may read step s's results
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0) {
-            const int ticket = atomicAdd(pe.ticket, 1);
-            if (ticket == static_cast<int>(gridDim.x) - 1) {
-                *pe.ticket = 0;
-                const int sq = *pe.seq + 1;
-                __threadfence_system();
-                store_all(pe, pe.seq, sq);
+    if (pe.n > 0) {
+        __syncthreads();          // this image's slice of the local block is complete
+        const size_t bP = static_cast<size_t>(b) * P;
+        copy_chunk_to_peers<NT>(pe, o.out_count + b, 1);
+        copy_chunk_to_peers<NT>(pe, o.out_score + bP, P);
+        copy_chunk_to_peers<NT>(pe, o.out_slot + bP, P);
+        copy_chunk_to_peers<NT>(pe, o.out_center + bP * 3, 3 * P);
+        copy_chunk_to_peers<NT>(pe, o.out_pose + bP * J * 3, 3 * P * J);
+        copy_chunk_to_peers<NT>(pe, o.out_cam + bP * J * 3, 6 * P * J);
+        copy_chunk_to_peers<NT>(pe, o.out_world + bP * J * 3, 6 * P * J);
+        if (pe.seq) {
+            // publish: the last CTA to finish bumps the block's sequence number on every peer, after every CTA's stores
+            // have been made visible system-wide -- a consumer on the peer that sees seq == s may read step s's results
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0) {
+                const int ticket = atomicAdd(pe.ticket, 1);
+                if (ticket == static_cast<int>(gridDim.x) - 1) {
+                    *pe.ticket = 0;
+                    const int sq = *pe.seq + 1;
+                    *pe.seq = sq;
+                    __threadfence_system();
+                    for (int q = 0; q < pe.n; ++q)
+                        *reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(pe.seq) + pe.delta[q]) = sq;
+                }
             }
         }
     }

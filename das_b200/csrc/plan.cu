@@ -39,9 +39,7 @@ struct das_plan {
     // tensor-core refinement (C = 256, nh = 4)
     int refine_mode = 0;              // 0 SIMT, 1 tcgen05 3xTF32, 2 tcgen05 single TF32
     unsigned char* tc_panels = nullptr;
-    float* item_heads = nullptr;      // row records [B*CT*J][32][8]
-    float* item_asm = nullptr;        // item records [B*CT*J][8]
-    int32_t* valid_list = nullptr;
+    das_refine_scratch rs{};          // distinct-row lists, row / item records, valid list, counters (= work_counter)
     unsigned char* dense_panels[DAS_MAX_LAYERS] = {};   // tensor-core panels of the dense layers (0..L-2)
     // dense layers (num_layers > 1): ping-pong joint-major [B][J][HW][4] maps per level + projection scratch [B][J][HW][16]
     float* uvd_map[2][DAS_MAX_LEVELS] = {};
@@ -73,8 +71,9 @@ struct das_plan {
 
 extern "C" const char* das_version(void) { return "das-b200 0.1 (sm_100a)"; }
 extern "C" const char* das_last_error(void) { return das::g_err; }
-extern "C" void das_abi_struct_sizes(int32_t out[4]) {
+extern "C" void das_abi_struct_sizes(int32_t out[6]) {
     out[0] = sizeof(das_levels); out[1] = sizeof(das_decode_cfg); out[2] = sizeof(das_buffers); out[3] = sizeof(das_row_cache);
+    out[4] = sizeof(das_refine_scratch); out[5] = sizeof(das_peer_blocks);
 }
 
 extern "C" int32_t das_level_slots(int32_t H, int32_t W, int32_t nms_pre) { return das::level_slots(H * W, nms_pre); }
@@ -138,6 +137,11 @@ extern "C" int das_plan_create(const das_decode_cfg* cfg, const das_levels* shap
         return DAS_ERR_CAPACITY;
     }
     const size_t B = p->B, CT = p->CT, P = p->P, J = cfg->num_joints;
+    if (static_cast<long long>(p->B) * p->CT * 32 >= (1ll << 31)) {
+        set_error("batch * candidate slots = %lld is beyond the row-record capacity", static_cast<long long>(p->B) * p->CT);
+        delete p;
+        return DAS_ERR_CAPACITY;
+    }
     int s = DAS_OK;
     auto A = [&](int r) { if (s == DAS_OK) s = r; };
     A(dev_alloc(&p->d_levels, 1));
@@ -165,7 +169,7 @@ extern "C" int das_plan_create(const das_decode_cfg* cfg, const das_levels* shap
         }
     }
     A(dev_alloc(&p->scratch, B * static_cast<size_t>(p->hw_sum)));
-    A(dev_alloc(&p->work_counter, 4));
+    A(dev_alloc(&p->work_counter, 4 + DAS_MAX_JOINTS));
     A(dev_alloc(&p->d_scale_xy, B * 2));
     A(dev_alloc(&p->d_cam, B * DAS_CAM_DOUBLES));
     if (cfg->refine) {
@@ -175,9 +179,13 @@ extern "C" int das_plan_create(const das_decode_cfg* cfg, const das_levels* shap
             // das_plan_set_refine_mode(plan, 0) selects the fp32 SIMT kernel
             p->refine_mode = 1;
             A(dev_alloc(&p->tc_panels, static_cast<size_t>(das_tc_panel_bytes(cfg))));
-            A(dev_alloc(&p->item_heads, B * CT * J * 32 * 8));
-            A(dev_alloc(&p->item_asm, B * CT * J * 8));
-            A(dev_alloc(&p->valid_list, B * CT));
+            p->rs.row_cap = static_cast<int32_t>(B * CT * 32);
+            A(dev_alloc(&p->rs.unique_rows, J * B * CT * 32 * 8));
+            A(dev_alloc(&p->rs.unique_out, J * B * CT * 32 * 8));
+            A(dev_alloc(&p->rs.row_records, B * CT * J * 32 * 4));
+            A(dev_alloc(&p->rs.item_records, B * CT * J * 8));
+            A(dev_alloc(&p->rs.valid_list, B * CT));
+            p->rs.counters = p->work_counter;
         }
         if (cfg->num_layers > 1) {
             size_t max_hw = 0;
@@ -233,7 +241,8 @@ extern "C" void das_plan_destroy(das_plan* p) {
     for (cudaEvent_t e : p->ev) if (e) cudaEventDestroy(e);
     void* ptrs[] = {p->d_levels, p->buf.cand_score, p->buf.cand_index, p->buf.cand_pose, p->buf.cand_center,
                     p->own_block, p->scratch, p->work_counter, p->d_scale_xy, p->d_cam,
-                    p->proj, p->d_prev_ptrs, p->tc_panels, p->item_heads, p->item_asm, p->valid_list};
+                    p->proj, p->d_prev_ptrs, p->tc_panels, p->rs.unique_rows, p->rs.unique_out, p->rs.row_records,
+                    p->rs.item_records, p->rs.valid_list};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->rc.table) cudaFree(p->rc.table);
     if (p->rc.rows) cudaFree(p->rc.rows);
@@ -339,16 +348,15 @@ static int enqueue(das_plan* p, cudaStream_t st, int* n_launch, bool events) {
             ++n;
         }
         DAS_TRY(das_refine_heads(p->d_levels, &p->bound, &c, w, prev, p->d_scale_xy, p->buf.cand_score, p->buf.cand_index, p->CT,
-                                 p->item_heads, p->item_asm, p->buf.cand_center, p->valid_list, p->work_counter,
-                                 p->rc_active ? &p->rc : nullptr, st));
+                                 &p->rs, p->buf.cand_center, p->rc_active ? &p->rc : nullptr, st));
         DAS_TRY(mark(3));
         if (p->rc_active) {
-            DAS_TRY(das_refine_row_cache(&c, p->item_heads, p->valid_list, p->work_counter + 1, &p->rc, st));
+            DAS_TRY(das_refine_row_cache(&c, &p->rs, &p->rc, st));
             ++n;
         }
-        DAS_TRY(das_refine_tc(p->d_levels, &p->bound, &c, w, p->tc_panels, p->CT, p->item_heads, p->item_asm, p->valid_list,
-                              p->work_counter + 1, p->buf.cand_pose,
-                              p->refine_mode == 1 ? 1 : 0, st));
+        DAS_TRY(das_refine_tc(p->d_levels, &p->bound, &c, w, p->tc_panels, p->CT, &p->rs, p->refine_mode == 1 ? 1 : 0, st));
+        DAS_TRY(das_refine_finish(&p->bound, &c, p->CT, &p->rs, p->buf.cand_pose, st));
+        ++n;
         n += 2;
     } else {
         DAS_TRY(das_gather_refine_assemble(p->d_levels, &p->bound, &c, c.refine ? p->wpack[c.num_layers - 1] : nullptr, prev,

@@ -78,6 +78,26 @@ __device__ __forceinline__ float reduce4_permuted(const float (&a)[4]) {
     return c;
 }
 
+// Projection scratch of a dense layer: four joint-major planes [B][J][HW] inside one allocation of 16 floats per
+// (cell, joint).  Entries are 16 (8) bytes so that a warp of 32 consecutive cells reads whole 128-byte lines per tap.
+//   s0 = {S head0.x, head0.y, head1.x, head1.y}   s1 = {S head2.x, head2.y, head3.x, head3.y}   (sampling offsets)
+//   oa = {blended O.u, O.v, O.d, conf.u}          cb = {conf.v, conf.d}
+struct DensePlanes {
+    float4* s0;
+    float4* s1;
+    float4* oa;
+    float2* cb;
+};
+__host__ __device__ __forceinline__ DensePlanes dense_planes(float* proj, int B, int J, int HW) {
+    const size_t n = static_cast<size_t>(B) * J * HW;
+    DensePlanes pl;
+    pl.s0 = reinterpret_cast<float4*>(proj);
+    pl.s1 = pl.s0 + n;
+    pl.oa = pl.s1 + n;
+    pl.cb = reinterpret_cast<float2*>(pl.oa + n);
+    return pl;
+}
+
 // Index-space sample coordinate of `cell + 0.5 + off` after the reference's normalise ->
 // grid_sample un-normalise chain (recursive_update.py:52-54, ATen align_corners=False).
 __device__ __forceinline__ float sample_coord(int cell, float off, float size) {

@@ -21,7 +21,7 @@ struct DenseParams {
     const float* wpack;
     const float* uvd_in;   // nullptr -> scaled raw uvd from lv.pose (layer 0); else joint-major [B][J][HW][4]
     float* uvd_out;        // joint-major [B][J][HW][4] (u, v, d, -)
-    float* proj;           // two joint-major planes: S [B][J][HW][8], then OC [B][J][HW][8] = {O 3, conf 3, -, -}
+    float* proj;           // four joint-major planes, see DensePlanes (refine_common.cuh)
     int level, layer, J, root, B;
 };
 
@@ -65,13 +65,15 @@ dense_project_kernel(const DenseParams p) {
                 res[o] = reduce8_permuted(acc) + __ldg(Bj + o);
             }
             if (!live) continue;
-            const size_t rec = ((static_cast<size_t>(b) * J + j) * HW + pix) * 8;
-            float* outS = p.proj + rec;
-            float* outOC = p.proj + static_cast<size_t>(p.B) * J * HW * 8 + rec;
+            const DensePlanes pl = dense_planes(p.proj, p.B, J, HW);
+            const size_t cellj = (static_cast<size_t>(b) * J + j) * HW + pix;
             // the quad of lanes owning this cell shares the stores: lane q writes S[2q], S[2q+1] and dim q
+            {
+                float* outS = reinterpret_cast<float*>(q < 2 ? pl.s0 + cellj : pl.s1 + cellj) + 2 * (q & 1);
 #pragma unroll
-            for (int o = 0; o < 2 * NH; ++o)
-                if ((o >> 1) == q) outS[o] = res[o];
+                for (int o = 0; o < 2 * NH; ++o)
+                    if ((o >> 1) == q) outS[o & 1] = res[o];
+            }
             if (q < 3) {
                 const float rg = q == 0 ? res[O_GATE] : (q == 1 ? res[O_GATE + 1] : res[O_GATE + 2]);
                 const float rn = q == 0 ? res[O_VAL] : (q == 1 ? res[O_VAL + 1] : res[O_VAL + 2]);
@@ -82,35 +84,36 @@ dense_project_kernel(const DenseParams p) {
                 else prev = __ldg(d.pose + (static_cast<size_t>(b) * (3 + 6 * J) + 3 + 3 * j + q) * HW + pix) *
                             (q < 2 ? d.scale_uv : d.scale_d);
                 const float gate = sigmoid_acc(rg);
-                outOC[q] = __fadd_rn(__fmul_rn(1.0f - gate, prev), __fmul_rn(gate, rn));  // blended offset
-                outOC[3 + q] = rc;                                                       // confidence logits
+                reinterpret_cast<float*>(pl.oa + cellj)[q] = __fadd_rn(__fmul_rn(1.0f - gate, prev), __fmul_rn(gate, rn));  // blended offset
+                if (q == 0) reinterpret_cast<float*>(pl.oa + cellj)[3] = rc;             // confidence logits: x next to O, y / z apart
+                else reinterpret_cast<float*>(pl.cb + cellj)[q - 1] = rc;
             }
         }
     }
 }
 
 template <int NH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 dense_sample_kernel(const DenseParams p) {
-    static_assert(NH == 4, "record layout below is for 2*NH = 8 sampling offsets");
-    // two planes of 32-B records (4 cells per 128-B line): S = the 8 sampling offsets, OC = {O.x,O.y,O.z,cf.x,cf.y,cf.z,-,-}
+    static_assert(NH == 4, "plane layout below is for 2*NH = 8 sampling offsets");
+    // Four joint-major planes (refine_common.cuh: DensePlanes) of 16-byte (8-byte) entries: a warp = 32 consecutive cells of
+    // one joint, whose bilinear taps are (nearly) consecutive entries, so a 128-bit load per lane fills whole 128-byte
+    // lines -- with the earlier 32-byte records every L1 wavefront carried half a line (ncu: l1tex 88 % busy, 2.5 ms).
     const das_level_desc& d = p.lv->lv[p.level];
     const int H = d.H, W = d.W, HW = H * W, J = p.J;
     const float fW = static_cast<float>(W), fH = static_cast<float>(H);
     const long long total = static_cast<long long>(p.B) * HW * J;
+    const DensePlanes pl = dense_planes(p.proj, p.B, J, HW);
     for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
          t += static_cast<long long>(gridDim.x) * blockDim.x) {
-        // joint-major thread order: a warp covers 32 consecutive cells of ONE joint, whose records are contiguous and
-        // whose bilinear taps overlap -> coalesced record loads, L1 hits on the taps
         const int pix = static_cast<int>(t % HW);
         const long long bj = t / HW;                 // b * J + j
-        const int j = static_cast<int>(bj % J);
         const int y = pix / W, x = pix - y * W;
-        const float4* __restrict__ pS = reinterpret_cast<const float4*>(p.proj + static_cast<size_t>(bj) * HW * 8);
-        const float4* __restrict__ pOC = reinterpret_cast<const float4*>(p.proj + (static_cast<size_t>(p.B) * J + bj) * HW * 8);
-        (void)j;
-        const F8 sp = ldg_f8(pS + 2 * pix);
-        const float4 s0 = sp.lo, s1 = sp.hi, om = __ldg(pOC + 2 * pix);
+        const float4* __restrict__ pS0 = pl.s0 + static_cast<size_t>(bj) * HW;
+        const float4* __restrict__ pS1 = pl.s1 + static_cast<size_t>(bj) * HW;
+        const float4* __restrict__ pOA = pl.oa + static_cast<size_t>(bj) * HW;
+        const float2* __restrict__ pCB = pl.cb + static_cast<size_t>(bj) * HW;
+        const float4 s0 = __ldg(pS0 + pix), s1 = __ldg(pS1 + pix), om = __ldg(pOA + pix);
         const float ox = om.x, oy = om.y;
         float hx[2 * NH], hy[2 * NH];
         {
@@ -122,13 +125,12 @@ dense_sample_kernel(const DenseParams p) {
             for (int k = 0; k < 4; ++k) {
                 if (!corner_ok(ct, k, W, H)) continue;
                 const float wk = corner_wgt(ct, k);
-                const float4* c = pS + 2 * corner_pix(ct, k, W);
-                const F8 a = ldg_f8(c);
-                const float4 a0 = a.lo, a1 = a.hi;
-                s[0] = __fadd_rn(s[0], __fmul_rn(a0.x, wk)); s[1] = __fadd_rn(s[1], __fmul_rn(a0.y, wk));
-                s[2] = __fadd_rn(s[2], __fmul_rn(a0.z, wk)); s[3] = __fadd_rn(s[3], __fmul_rn(a0.w, wk));
-                s[4] = __fadd_rn(s[4], __fmul_rn(a1.x, wk)); s[5] = __fadd_rn(s[5], __fmul_rn(a1.y, wk));
-                s[6] = __fadd_rn(s[6], __fmul_rn(a1.z, wk)); s[7] = __fadd_rn(s[7], __fmul_rn(a1.w, wk));
+                const int cp = corner_pix(ct, k, W);
+                const float4 a0 = __ldg(pS0 + cp), a1 = __ldg(pS1 + cp);
+                s[0] = fmaf(a0.x, wk, s[0]); s[1] = fmaf(a0.y, wk, s[1]);
+                s[2] = fmaf(a0.z, wk, s[2]); s[3] = fmaf(a0.w, wk, s[3]);
+                s[4] = fmaf(a1.x, wk, s[4]); s[5] = fmaf(a1.y, wk, s[5]);
+                s[6] = fmaf(a1.z, wk, s[6]); s[7] = fmaf(a1.w, wk, s[7]);
             }
             const float sm[2 * NH] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
@@ -148,13 +150,11 @@ dense_sample_kernel(const DenseParams p) {
             for (int k = 0; k < 4; ++k) {
                 if (!corner_ok(ch, k, W, H)) continue;
                 const float wk = corner_wgt(ch, k);
-                const float4* c = pOC + 2 * corner_pix(ch, k, W);
-                const F8 rec = ldg_f8(c);                          // {O.x,O.y,O.z,cf.x} {cf.y,cf.z,-,-}
-                const float4 oo = rec.lo, cc = rec.hi;
-                cf[0] = __fadd_rn(cf[0], __fmul_rn(oo.w, wk)); cf[1] = __fadd_rn(cf[1], __fmul_rn(cc.x, wk));
-                cf[2] = __fadd_rn(cf[2], __fmul_rn(cc.y, wk));
-                v[0] = __fadd_rn(v[0], __fmul_rn(oo.x, wk)); v[1] = __fadd_rn(v[1], __fmul_rn(oo.y, wk));
-                v[2] = __fadd_rn(v[2], __fmul_rn(oo.z, wk));
+                const int cp = corner_pix(ch, k, W);
+                const float4 oo = __ldg(pOA + cp);                 // {O.x, O.y, O.z, cf.x}
+                const float2 cc = __ldg(pCB + cp);                 // {cf.y, cf.z}
+                v[0] = fmaf(oo.x, wk, v[0]); v[1] = fmaf(oo.y, wk, v[1]); v[2] = fmaf(oo.z, wk, v[2]);
+                cf[0] = fmaf(oo.w, wk, cf[0]); cf[1] = fmaf(cc.x, wk, cf[1]); cf[2] = fmaf(cc.y, wk, cf[2]);
             }
             hv[h][0] = v[0] + hx[h];
             hv[h][1] = v[1] + hy[h];
@@ -170,9 +170,10 @@ dense_sample_kernel(const DenseParams p) {
             float ex[2 * NH], se = 0.f;
 #pragma unroll
             for (int h = 0; h < 2 * NH; ++h) { ex[h] = expf(hc[h][e] - m); se += ex[h]; }
+            const float inv = __frcp_rn(se);
             float o = 0.f;
 #pragma unroll
-            for (int h = 0; h < 2 * NH; ++h) o += hv[h][e] * (ex[h] / se);
+            for (int h = 0; h < 2 * NH; ++h) o = fmaf(hv[h][e], ex[h] * inv, o);
             res[e] = o;
         }
         reinterpret_cast<float4*>(p.uvd_out)[static_cast<size_t>(bj) * HW + pix] = make_float4(res[0], res[1], res[2], 0.f);

@@ -19,6 +19,7 @@
 // finished with a transposing butterfly so 8 rows cost 9 shuffles per output instead of 40; rows are loaded
 // in a lane-permuted order so that butterfly needs no selects, and FMAs are packed fma.rn.f32x2.
 #include <algorithm>
+#include <cstdlib>
 
 #include "refine_common.cuh"
 #include "row_cache.cuh"
@@ -36,10 +37,12 @@ struct RefineParams {
     const int32_t* cand_index;
     float* cand_pose;
     float* cand_center;
-    int* work_counter;             // [0] work queue head, [1] number of valid candidates (heads-only mode)
-    float* item_heads;             // heads-only mode: row records [B*CT*J][32 rows][8 floats] (see TcRowRec in refine_tc.cu)
+    int* work_counter;             // [0] work queue head, [1] number of valid candidates, [4 + j] distinct rows of joint j (heads-only mode)
+    float* urow;                   // heads-only mode: distinct feature rows per joint [J][row_cap][8] = {ptr lo, ptr hi, prev u, v, d, -, -, -}
+    float* lrow;                   // heads-only mode: row records [B*CT*J][32 rows][4] = {distinct-row index (int bits; -1 = zero padding), bilinear weight, head offset x, y}
     float* item_asm;               // heads-only mode: per-item assembly record [B*CT*J][8] = {Px, Py, zq, sx, sy, stride, -, -}
     int32_t* valid_list;           // heads-only mode: candidate slots (b*CT+slot) that pass score_thr
+    int row_cap;                   // capacity of one joint's distinct-row list (B*CT*32)
     int CT, J, root, nms_pre, layer;
     float depth_factor, z_norm, score_thr;
     int n_items;
@@ -200,15 +203,32 @@ refine_sparse_kernel(const RefineParams p) {
                 for (int i = 1; i < 2 * NH; ++i) { hxv = (h == i) ? hx[i] : hxv; hyv = (h == i) ? hy[i] : hyv; }
                 const Corner c = make_corner(sample_coord(x, hxv, fW), sample_coord(y, hyv, fH), W, H);
                 const bool ok = corner_ok(c, ck2, W, H);
-                const int pix = ok ? corner_pix(c, ck2, W) : 0;
-                const float* ptr = ok ? F + static_cast<size_t>(pix) * C : nullptr;
+                const int pix = ok ? corner_pix(c, ck2, W) : -1;
                 const float wk = ok ? corner_wgt(c, ck2) : 0.f;
-                float pv0 = 0.f, pv1 = 0.f, pv2 = 0.f;
-                if (ok) { pv0 = prev_at(pix, 0); pv1 = prev_at(pix, 1); pv2 = prev_at(pix, 2); }
-                const unsigned long long pb = reinterpret_cast<unsigned long long>(ptr);
-                float4* dst = reinterpret_cast<float4*>(p.item_heads + (static_cast<size_t>(item) * 32 + lane) * 8);
-                dst[0] = make_float4(__uint_as_float(static_cast<unsigned>(pb)), __uint_as_float(static_cast<unsigned>(pb >> 32)), wk, pv0);
-                dst[1] = make_float4(pv1, pv2, hxv, hyv);
+                // The gate / value / confidence projections and the blended offset depend on (cell, joint) only, and the
+                // 8 heads x 4 corners of an item mostly land on a handful of cells: keep ONE entry per distinct cell in the
+                // joint's row list (what the tensor-core kernel multiplies) and let the 32 row records point at it.
+                const unsigned same = __match_any_sync(FULL, pix);
+                const int leader = __ffs(same) - 1;
+                const bool is_leader = ok && lane == leader;
+                const unsigned lead_mask = __ballot_sync(FULL, is_leader);
+                const int n_u = __popc(lead_mask);
+                int base = 0;
+                if (lane == 0 && n_u) base = atomicAdd(p.work_counter + 4 + j, n_u);
+                base = __shfl_sync(FULL, base, 0);
+                const int my_u = __popc(lead_mask & ((1u << lane) - 1u));
+                const int u_of_leader = __shfl_sync(FULL, my_u, leader);
+                const int gidx = ok ? base + u_of_leader : -1;
+                if (is_leader) {
+                    const float* ptr = F + static_cast<size_t>(pix) * C;
+                    const float pv0 = prev_at(pix, 0), pv1 = prev_at(pix, 1), pv2 = prev_at(pix, 2);
+                    const unsigned long long pb = reinterpret_cast<unsigned long long>(ptr);
+                    float4* dst = reinterpret_cast<float4*>(p.urow + (static_cast<size_t>(j) * p.row_cap + base + my_u) * 8);
+                    dst[0] = make_float4(__uint_as_float(static_cast<unsigned>(pb)), __uint_as_float(static_cast<unsigned>(pb >> 32)), pv0, pv1);
+                    dst[1] = make_float4(pv2, 0.f, 0.f, 0.f);
+                }
+                reinterpret_cast<float4*>(p.lrow)[static_cast<size_t>(item) * 32 + lane] =
+                    make_float4(__int_as_float(gidx), wk, hxv, hyv);
             }
             if (lane == 0) {
                 // eval-tail / assembly inputs of this item (das_head.py:254-262, 725-743), and the centre for joint 0
@@ -464,26 +484,30 @@ extern "C" int das_gather_refine_assemble(const das_levels* d_levels, const das_
     return DAS_OK;
 }
 
-// Phases 1-2 of the sparse refinement only (feeds das_refine_tc): per (candidate, joint) item it writes the 32 row
-// records of the sampling phase (row_records [item][32][8 floats]: feature-row pointer, bilinear weight, previous
-// offset, head offset), the item's assembly record (item_records [item][8]) and, for joint 0, the centre and the
-// candidate's entry in valid_list; counters[0] is the work-queue head, counters[1] receives the number of valid
-// candidates.
+// Phases 1-2 of the sparse refinement only (feeds das_refine_tc / das_refine_finish): per (candidate, joint) item it
+// appends the item's DISTINCT sampled cells to that joint's row list (scratch->unique_rows), writes the 32 row records
+// that point into it (scratch->row_records), the item's assembly record (scratch->item_records) and, for joint 0, the
+// centre and the candidate's entry in valid_list.  counters: [0] work-queue head, [1] number of valid candidates,
+// [4 + j] distinct rows of joint j.
 extern "C" int das_refine_heads(const das_levels* d_levels, const das_levels* h_levels, const das_decode_cfg* cfg,
                                 const float* weights, const float* const* prev_uvd, const float* scale_xy,
                                 const float* cand_score, const int32_t* cand_index, int32_t cand_slots,
-                                float* row_records, float* item_records, float* cand_center,
-                                int32_t* valid_list, int32_t* counters, const das_row_cache* rc, void* stream) {
+                                const das_refine_scratch* scratch, float* cand_center, const das_row_cache* rc, void* stream) {
     using namespace das;
-    DAS_REQUIRE(d_levels && h_levels && cfg && weights && scale_xy && cand_score && cand_index && row_records && item_records &&
-                cand_center && valid_list && counters, DAS_ERR_ARG, "das_refine_heads: null pointer");
+    DAS_REQUIRE(d_levels && h_levels && cfg && weights && scale_xy && cand_score && cand_index && scratch && cand_center,
+                DAS_ERR_ARG, "das_refine_heads: null pointer");
+    DAS_REQUIRE(scratch->unique_rows && scratch->row_records && scratch->item_records && scratch->valid_list && scratch->counters,
+                DAS_ERR_ARG, "das_refine_heads: null scratch buffer");
     DAS_REQUIRE(cfg->feat_channels == 256 && cfg->num_heads == 4, DAS_ERR_UNSUPPORTED,
                 "das_refine_heads is built for feat_channels=256, num_heads=4");
     DAS_REQUIRE(cfg->num_joints >= 1 && cfg->num_joints <= DAS_MAX_JOINTS, DAS_ERR_CAPACITY, "num_joints=%d", cfg->num_joints);
+    const long long want_cap = static_cast<long long>(h_levels->batch) * cand_slots * 32;
+    DAS_REQUIRE(scratch->row_cap >= want_cap, DAS_ERR_ARG, "das_refine_heads: row_cap=%d < batch*cand_slots*32=%lld", scratch->row_cap, want_cap);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     RefineParams p{};
     p.lv = d_levels; p.wpack = weights; p.prev_uvd = prev_uvd; p.cand_score = cand_score; p.cand_index = cand_index;
-    p.work_counter = counters; p.item_heads = row_records; p.item_asm = item_records; p.valid_list = valid_list;
+    p.work_counter = scratch->counters; p.urow = scratch->unique_rows; p.lrow = scratch->row_records;
+    p.item_asm = scratch->item_records; p.valid_list = scratch->valid_list; p.row_cap = scratch->row_cap;
     p.scale_xy = scale_xy; p.cand_center = cand_center;
     p.CT = cand_slots; p.J = cfg->num_joints; p.root = cfg->root_idx; p.nms_pre = cfg->nms_pre; p.layer = cfg->num_layers - 1;
     p.depth_factor = cfg->depth_factor; p.z_norm = cfg->z_norm; p.score_thr = cfg->score_thr;
@@ -491,9 +515,15 @@ extern "C" int das_refine_heads(const das_levels* d_levels, const das_levels* h_
     DAS_REQUIRE(items < (1ll << 31), DAS_ERR_CAPACITY, "too many work items");
     p.n_items = static_cast<int>(items);
     p.rc = row_cache_view(rc);
-    DAS_CUDA_CHECK(cudaMemsetAsync(counters, 0, 2 * sizeof(int32_t), st));
-    if (p.rc.keys) refine_sparse_kernel<8, 4, 4, true, true><<<kSMs * 4, RS_WARPS * 32, 0, st>>>(p);
-    else refine_sparse_kernel<8, 4, 4, true><<<kSMs * 4, RS_WARPS * 32, 0, st>>>(p);
+    // [0] queue head, [1] n_valid, [4..4+J) per-joint distinct-row counts; [2] (the peer-store ticket) is left alone
+    DAS_CUDA_CHECK(cudaMemsetAsync(scratch->counters, 0, 2 * sizeof(int32_t), st));
+    DAS_CUDA_CHECK(cudaMemsetAsync(scratch->counters + 4, 0, DAS_MAX_JOINTS * sizeof(int32_t), st));
+    // 3 CTAs per SM (85 registers): with the de-duplication bookkeeping the 64-register variant spills, and the kernel is
+    // bound by its dependent DRAM round trips, not by occupancy (profiles/r01_ncu_summary.md)
+    static const int minb = std::getenv("DAS_HEADS_MINB") ? std::atoi(std::getenv("DAS_HEADS_MINB")) : 3;
+    if (p.rc.keys) refine_sparse_kernel<8, 4, 3, true, true><<<kSMs * 3, RS_WARPS * 32, 0, st>>>(p);
+    else if (minb == 4) refine_sparse_kernel<8, 4, 4, true><<<kSMs * 4, RS_WARPS * 32, 0, st>>>(p);
+    else refine_sparse_kernel<8, 4, 3, true><<<kSMs * 3, RS_WARPS * 32, 0, st>>>(p);
     DAS_CUDA_CHECK(cudaGetLastError());
     return DAS_OK;
 }

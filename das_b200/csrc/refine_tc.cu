@@ -26,6 +26,8 @@
 //                     with the previous offset, bilinear weight / zero padding, corner sum (2 shuffles), softmax
 //                     over the 8 heads (3 shuffles), eval tail, assembly; they also prepare the row pointers and
 //                     per-row state 6 tiles ahead and prefetch those rows into L2
+#include <algorithm>
+
 #include "refine_common.cuh"
 #include "row_cache.cuh"
 #include "tc_common.cuh"
@@ -47,38 +49,46 @@ struct TcParams {
     const das_levels* lv;
     const float* wpack;              // biases live behind the [J][17][C] weights
     const unsigned char* bpanel;     // [J][2][TC_B_BYTES] swizzled hi / lo panels
-    const float* item_heads;         // row records [B*CT*J][32][8 floats] written by das_refine_heads
+    const float* urow;               // distinct feature rows per joint [J][row_cap][8] = {ptr lo, ptr hi, prev u, v, d, -, -, -}
+    float* ures;                     // per distinct row [J][row_cap][8] = {O u, v, d, conf u, v, d, -, -} (written by the GEMM epilogue)
+    const float* lrow;               // row records [B*CT*J][32][4] = {distinct-row index, bilinear weight, head offset x, y}
     const float* item_asm;           // assembly records [B*CT*J][8] = {Px, Py, zq, sx, sy, stride, -, -}
     const int32_t* valid_list;       // candidates that survive score_thr, any order
     const int32_t* n_valid;
+    const int32_t* joint_count;      // [J] distinct rows of every joint
     float* cand_pose;
-    int CT, J, root, split;
+    int CT, J, root, split, row_cap;
     float depth_factor, z_norm;
     long long* dbg;                  // optional [gridDim.x][16] cycle counters (profiling builds of the host code)
 };
 
 struct RowState {                    // what thread t keeps about row t of a tile until its epilogue
-    const float* ptr;                // feature row, nullptr = outside the map / padding row
-    float wk, prev0, prev1, prev2, hxv, hyv;
-    int cs;
-    bool item_ok;
+    const float* ptr;                // feature row, nullptr = padding row of a joint's last tile
+    float prev0, prev1, prev2;
+    int r;                           // index of the row in its joint's list
 };
 
-// Row t of tile `tile`: (item = t >> 5, head = (t >> 2) & 7, corner = t & 3).  The phase-1/2 kernel (das_refine_heads)
-// has already resolved every row to a 32-byte record; setting a row up is two dependent loads.
-__device__ __forceinline__ RowState setup_row(const TcParams& p, int tile, int n_groups, int n_valid, int tid) {
+// tile index -> (joint, 128-row chunk of that joint's distinct-row list); pref[j] = first tile of joint j, pref[J] = total
+__device__ __forceinline__ void tile_joint(const int* pref, int J, int tile, int& j, int& chunk) {
+    j = 0;
+    while (j + 1 < J && pref[j + 1] <= tile) ++j;
+    chunk = tile - pref[j];
+}
+
+// Row t of tile (j, chunk) = entry chunk*128 + t of joint j's distinct-row list.  The phase-1/2 kernel (das_refine_heads)
+// has already resolved every distinct sampled cell to a 32-byte record; setting a row up is two loads.
+__device__ __forceinline__ RowState setup_row(const TcParams& p, const int* pref, int tile, int tid) {
     RowState r;
-    const int j = tile / n_groups, g = tile - j * n_groups;
-    const int vi = g * 4 + (tid >> 5);
-    r.item_ok = vi < n_valid;
-    r.cs = r.item_ok ? __ldg(p.valid_list + vi) : 0;
-    r.ptr = nullptr; r.wk = 0.f; r.prev0 = r.prev1 = r.prev2 = 0.f; r.hxv = r.hyv = 0.f;
-    if (!r.item_ok) return r;
-    const float4* rec = reinterpret_cast<const float4*>(p.item_heads) + ((static_cast<size_t>(r.cs) * p.J + j) * 32 + (tid & 31)) * 2;
+    int j, chunk;
+    tile_joint(pref, p.J, tile, j, chunk);
+    r.r = chunk * 128 + tid;
+    r.ptr = nullptr; r.prev0 = r.prev1 = r.prev2 = 0.f;
+    if (r.r >= __ldg(p.joint_count + j)) return r;
+    const float4* rec = reinterpret_cast<const float4*>(p.urow) + (static_cast<size_t>(j) * p.row_cap + r.r) * 2;
     const float4 a = __ldg(rec), c = __ldg(rec + 1);
     r.ptr = reinterpret_cast<const float*>(static_cast<unsigned long long>(__float_as_uint(a.x)) |
                                            (static_cast<unsigned long long>(__float_as_uint(a.y)) << 32));
-    r.wk = a.z; r.prev0 = a.w; r.prev1 = c.x; r.prev2 = c.y; r.hxv = c.z; r.hyv = c.w;
+    r.prev0 = a.z; r.prev1 = a.w; r.prev2 = c.x;
     if (r.ptr) {
         // the producers gather this row a few tiles from now: pull its 8 lines into L2 already, so that a k-block's
         // arrival is bounded by L2 latency instead of by its slowest DRAM miss
@@ -88,60 +98,24 @@ __device__ __forceinline__ RowState setup_row(const TcParams& p, int tile, int n
     return r;
 }
 
-// Row epilogue shared by both tensor-core kernels: v[0..8] = this row's {gate 3, value 3, conf 3} projections.
-// Lanes of a warp = the 32 rows of one item (head = lane >> 2, corner = lane & 3).
-__device__ __forceinline__ void tc_epilogue(const TcParams& p, const RowState& cur, const float (&v)[16], int j, int lane) {
-    const int J = p.J;
-    const float* Bj = p.wpack + static_cast<size_t>(J) * TC_NOUT * TC_C + j * TC_NOUT + TC_OGATE;
-    float val[3], cf[3];
-    {
-        const float pv[3] = {cur.prev0, cur.prev1, cur.prev2};
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float gte = sigmoid_acc(v[k] + __ldg(Bj + k));
-            const float n = v[3 + k] + __ldg(Bj + 3 + k);
-            const float o = __fadd_rn(__fmul_rn(1.0f - gte, pv[k]), __fmul_rn(gte, n));
-            const bool ok = cur.ptr != nullptr;
-            val[k] = ok ? o * cur.wk : 0.f;
-            cf[k] = ok ? (v[6 + k] + __ldg(Bj + 6 + k)) * cur.wk : 0.f;
-        }
-    }
-    float out[3];
+// Row epilogue of the tensor-core kernel: v[0..8] = this distinct row's {gate 3, value 3, conf 3} projections ->
+// bias, sigmoid gate, blend with the previous offset at that cell (recursive_update.py:193-195) and the confidence
+// logits; one 32-byte result per distinct (cell, joint), shared by every head / corner that sampled the cell.
+__device__ __forceinline__ void tc_epilogue(const TcParams& p, const RowState& cur, const float (&v)[16], int j) {
+    if (!cur.ptr) return;
+    const float* Bj = p.wpack + static_cast<size_t>(p.J) * TC_NOUT * TC_C + j * TC_NOUT + TC_OGATE;
+    const float pv[3] = {cur.prev0, cur.prev1, cur.prev2};
+    float o[3], cf[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        // bilinear sum over the 4 corners (lane bits 0,1)
-        val[k] += __shfl_xor_sync(FULL, val[k], 1);
-        cf[k] += __shfl_xor_sync(FULL, cf[k], 1);
-        val[k] += __shfl_xor_sync(FULL, val[k], 2);
-        cf[k] += __shfl_xor_sync(FULL, cf[k], 2);
-        const float hv = val[k] + (k == 0 ? cur.hxv : (k == 1 ? cur.hyv : 0.f));   // + diff
-        // softmax over the 8 heads (lane bits 2,3,4); every corner lane carries the same head value
-        float m = cf[k];
-        m = fmaxf(m, __shfl_xor_sync(FULL, m, 4));
-        m = fmaxf(m, __shfl_xor_sync(FULL, m, 8));
-        m = fmaxf(m, __shfl_xor_sync(FULL, m, 16));
-        const float e = expf(cf[k] - m);
-        float se = e;
-        se += __shfl_xor_sync(FULL, se, 4);
-        se += __shfl_xor_sync(FULL, se, 8);
-        se += __shfl_xor_sync(FULL, se, 16);
-        float o = hv * (e / se);
-        o += __shfl_xor_sync(FULL, o, 4);
-        o += __shfl_xor_sync(FULL, o, 8);
-        o += __shfl_xor_sync(FULL, o, 16);
-        out[k] = o;
+        const float gte = sigmoid_acc(v[k] + __ldg(Bj + k));
+        const float n = v[3 + k] + __ldg(Bj + 3 + k);
+        o[k] = __fadd_rn(__fmul_rn(1.0f - gte, pv[k]), __fmul_rn(gte, n));
+        cf[k] = v[6 + k] + __ldg(Bj + 6 + k);
     }
-    if (cur.item_ok && lane < 3) {
-        // eval tail + assembly (das_head.py:254-262, 725-743) from the item's record {Px, Py, zq, sx, sy, stride}
-        const float4* ar = reinterpret_cast<const float4*>(p.item_asm) + (static_cast<size_t>(cur.cs) * J + j) * 2;
-        const float4 a0 = __ldg(ar), a1 = __ldg(ar + 1);
-        const float o = lane == 0 ? out[0] : (lane == 1 ? out[1] : out[2]);
-        float r;
-        if (lane == 0) r = __fdiv_rn(__fadd_rn(__fmul_rn(o, a1.y), a0.x), a0.w);
-        else if (lane == 1) r = __fdiv_rn(__fadd_rn(__fmul_rn(o, a1.y), a0.y), a1.x);
-        else r = __fadd_rn((j == p.root) ? 0.0f : __fmul_rn(o, p.z_norm), a0.z);
-        p.cand_pose[(static_cast<size_t>(cur.cs) * J + j) * 3 + lane] = r;
-    }
+    float4* dst = reinterpret_cast<float4*>(p.ures) + (static_cast<size_t>(j) * p.row_cap + cur.r) * 2;
+    dst[0] = make_float4(o[0], o[1], o[2], cf[0]);
+    dst[1] = make_float4(cf[1], cf[2], 0.f, 0.f);
 }
 
 constexpr int T2_PGROUPS = 3;                   // producer groups (4 warps each)
@@ -173,9 +147,14 @@ refine_tc2_kernel(const TcParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long kernel_t0 = (PROF ? clock64() : 0ll);
     const int J = p.J;
-    const int n_valid = __ldg(p.n_valid);
-    const int n_groups = (n_valid + 3) >> 2;
-    const int n_tiles = J * n_groups;
+    __shared__ int s_pref[DAS_MAX_JOINTS + 1];      // first tile of every joint (tiles = 128-row chunks of its distinct-row list)
+    if (tid == 0) {
+        int acc = 0;
+        for (int j = 0; j < J; ++j) { s_pref[j] = acc; acc += (__ldg(p.joint_count + j) + 127) >> 7; }
+        s_pref[J] = acc;
+    }
+    __syncthreads();
+    const int n_tiles = s_pref[J];
     const int t0 = static_cast<int>(static_cast<long long>(n_tiles) * blockIdx.x / gridDim.x);
     const int t1 = static_cast<int>(static_cast<long long>(n_tiles) * (blockIdx.x + 1) / gridDim.x);
     if (t0 >= t1) return;
@@ -204,7 +183,8 @@ refine_tc2_kernel(const TcParams p) {
         for (int i = 0; i < my_tiles; ++i) {
             const uint32_t dcol = tmem0 + T2_D_COL + (i % T2_EG) * 32;
             const long long tb0 = (PROF ? clock64() : 0ll);
-            const int j = (t0 + i) / n_groups;
+            int j, chunk_unused;
+            tile_joint(s_pref, J, t0 + i, j, chunk_unused);
             if (j != cur_j) {
                 // new joint: every earlier MMA must have finished reading the old panels
                 if (g > 0) tc::mbar_wait(&a_empty[(g - 1) % T2_SLOTS], ((g - 1) / T2_SLOTS) & 1);
@@ -310,13 +290,13 @@ refine_tc2_kernel(const TcParams p) {
         // this group's tiles are e, e+EG, e+2EG, ...; their row state is prepared two of them (= 2*EG tiles) ahead
         RowState cur{}, nx1{};
         if (e < my_tiles) {
-            cur = setup_row(p, t0 + e, n_groups, n_valid, rt);
+            cur = setup_row(p, s_pref, t0 + e, rt);
             s_rowptr[e][rt] = cur.ptr;
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&rows_ready[e]);
         }
         if (e + T2_EG < my_tiles) {
-            nx1 = setup_row(p, t0 + e + T2_EG, n_groups, n_valid, rt);
+            nx1 = setup_row(p, s_pref, t0 + e + T2_EG, rt);
             s_rowptr[e + T2_EG][rt] = nx1.ptr;
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&rows_ready[e + T2_EG]);
@@ -324,7 +304,8 @@ refine_tc2_kernel(const TcParams p) {
 #pragma unroll 1
         for (int i = e; i < my_tiles; i += T2_EG) {
             const int tile = t0 + i;
-            const int j = tile / n_groups;
+            int j, chunk_unused;
+            tile_joint(s_pref, J, tile, j, chunk_unused);
             const long long e0 = (PROF ? clock64() : 0ll);
             tc::mbar_wait(&acc_full[e], (i / T2_EG) & 1);
             tc::tc_fence_after();
@@ -343,12 +324,12 @@ refine_tc2_kernel(const TcParams p) {
             // tile i+2EG reuses tile i's pointer buffer: every gather of tile i was issued before its MMAs completed
             RowState nx2{};
             if (i + T2_RB < my_tiles) {
-                nx2 = setup_row(p, tile + T2_RB, n_groups, n_valid, rt);
+                nx2 = setup_row(p, s_pref, tile + T2_RB, rt);
                 s_rowptr[i % T2_RB][rt] = nx2.ptr;
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&rows_ready[i % T2_RB]);
             }
-            tc_epilogue(p, cur, v, j, lane);
+            tc_epilogue(p, cur, v, j);
             cur = nx1;
             nx1 = nx2;
             if (PROF && p.dbg && tid == 0) { long long* o = p.dbg + blockIdx.x * 16; o[9] += e1 - e0; o[10] += (PROF ? clock64() : 0ll) - e1; }
@@ -410,16 +391,17 @@ namespace das {
 // device-resident row buffer, and every record is re-pointed at the copy.  Rows the heads kernel already left in the
 // cache are found, not fetched again.  A full buffer just leaves the remaining records pointing at the host.
 __global__ void __launch_bounds__(256)
-row_cache_kernel(float* row_records, const int32_t* valid_list, const int32_t* n_valid, int J, const RowCacheView rc) {
+row_cache_kernel(float* urow, const int32_t* joint_count, int row_cap, const RowCacheView rc) {
+    // grid: x = warps over a joint's distinct-row list (32 records per warp step), y = joint
     const int lane = threadIdx.x & 31;
-    const int n_items = *n_valid * J;
-    for (int it = blockIdx.x * 8 + (threadIdx.x >> 5); it < n_items; it += gridDim.x * 8) {
-        const int cs = __ldg(valid_list + it / J);
-        const int j = it % J;
-        float4* rec = reinterpret_cast<float4*>(row_records) + ((static_cast<size_t>(cs) * J + j) * 32 + lane) * 2;
+    const int j = blockIdx.y;
+    const int n = __ldg(joint_count + j);
+    for (int r0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 32; r0 < n; r0 += gridDim.x * 8 * 32) {
+        const int r = r0 + lane;
+        float4* rec = reinterpret_cast<float4*>(urow) + (static_cast<size_t>(j) * row_cap + min(r, n - 1)) * 2;
         float4 a = *rec;
-        const unsigned long long ptr = static_cast<unsigned long long>(__float_as_uint(a.x)) |
-                                       (static_cast<unsigned long long>(__float_as_uint(a.y)) << 32);
+        const unsigned long long ptr = r < n ? (static_cast<unsigned long long>(__float_as_uint(a.x)) |
+                                                (static_cast<unsigned long long>(__float_as_uint(a.y)) << 32)) : 0ull;
         int slot = -1;
         bool won = false;
         uint32_t h = 0;
@@ -439,11 +421,73 @@ row_cache_kernel(float* row_records, const int32_t* valid_list, const int32_t* n
             d4[0] = v0;
             d4[1] = v1;
         }
-        if (slot >= 0) {
+        if (ptr && slot >= 0) {
             const unsigned long long np = reinterpret_cast<unsigned long long>(rc.rows + static_cast<size_t>(slot) * TC_C);
             a.x = __uint_as_float(static_cast<uint32_t>(np));
             a.y = __uint_as_float(static_cast<uint32_t>(np >> 32));
             *rec = a;
+        }
+    }
+}
+
+// Last step of the sparse refinement: one warp per (candidate, joint) item, lane = (head = lane >> 2, corner = lane & 3).
+// Every lane fetches the {O, conf} result of the distinct cell its row record points at, applies its bilinear weight
+// (zero padding outside the map), the 4 corners are summed, the head offset added (recursive_update.py:72-75, 28),
+// softmax over the 2*nh heads per dim (:29-31), eval tail and joint assembly (das_head.py:254-262, 725-743).
+__global__ void __launch_bounds__(256)
+refine_finish_kernel(const TcParams p) {
+    const int lane = threadIdx.x & 31;
+    const int J = p.J;
+    const int n_items = __ldg(p.n_valid) * J;
+    for (int it = blockIdx.x * 8 + (threadIdx.x >> 5); it < n_items; it += gridDim.x * 8) {
+        const int cs = __ldg(p.valid_list + it / J);
+        const int j = it - (it / J) * J;
+        const size_t item = static_cast<size_t>(cs) * J + j;
+        const float4 rec = __ldg(reinterpret_cast<const float4*>(p.lrow) + item * 32 + lane);
+        const int gidx = __float_as_int(rec.x);
+        const float wk = rec.y, hxv = rec.z, hyv = rec.w;
+        float val[3] = {0.f, 0.f, 0.f}, cf[3] = {0.f, 0.f, 0.f};
+        if (gidx >= 0) {
+            const float4* res = reinterpret_cast<const float4*>(p.ures) + (static_cast<size_t>(j) * p.row_cap + gidx) * 2;
+            const float4 a = __ldcg(res), c = __ldcg(res + 1);
+            val[0] = a.x * wk; val[1] = a.y * wk; val[2] = a.z * wk;
+            cf[0] = a.w * wk; cf[1] = c.x * wk; cf[2] = c.y * wk;
+        }
+        float out[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            // bilinear sum over the 4 corners (lane bits 0,1)
+            val[k] += __shfl_xor_sync(FULL, val[k], 1);
+            cf[k] += __shfl_xor_sync(FULL, cf[k], 1);
+            val[k] += __shfl_xor_sync(FULL, val[k], 2);
+            cf[k] += __shfl_xor_sync(FULL, cf[k], 2);
+            const float hv = val[k] + (k == 0 ? hxv : (k == 1 ? hyv : 0.f));   // + diff
+            // softmax over the 8 heads (lane bits 2,3,4); every corner lane carries the same head value
+            float m = cf[k];
+            m = fmaxf(m, __shfl_xor_sync(FULL, m, 4));
+            m = fmaxf(m, __shfl_xor_sync(FULL, m, 8));
+            m = fmaxf(m, __shfl_xor_sync(FULL, m, 16));
+            const float e = expf(cf[k] - m);
+            float se = e;
+            se += __shfl_xor_sync(FULL, se, 4);
+            se += __shfl_xor_sync(FULL, se, 8);
+            se += __shfl_xor_sync(FULL, se, 16);
+            float o = hv * (e / se);
+            o += __shfl_xor_sync(FULL, o, 4);
+            o += __shfl_xor_sync(FULL, o, 8);
+            o += __shfl_xor_sync(FULL, o, 16);
+            out[k] = o;
+        }
+        if (lane < 3) {
+            // eval tail + assembly (das_head.py:254-262, 725-743) from the item's record {Px, Py, zq, sx, sy, stride}
+            const float4* ar = reinterpret_cast<const float4*>(p.item_asm) + item * 2;
+            const float4 a0 = __ldg(ar), a1 = __ldg(ar + 1);
+            const float o = lane == 0 ? out[0] : (lane == 1 ? out[1] : out[2]);
+            float r;
+            if (lane == 0) r = __fdiv_rn(__fadd_rn(__fmul_rn(o, a1.y), a0.x), a0.w);
+            else if (lane == 1) r = __fdiv_rn(__fadd_rn(__fmul_rn(o, a1.y), a0.y), a1.x);
+            else r = __fadd_rn((j == p.root) ? 0.0f : __fmul_rn(o, p.z_norm), a0.z);
+            p.cand_pose[item * 3 + lane] = r;
         }
     }
 }
@@ -470,33 +514,48 @@ extern "C" int das_row_cache_clear(const das_row_cache* rc, void* stream) {
     return DAS_OK;
 }
 
-extern "C" int das_refine_row_cache(const das_decode_cfg* cfg, float* row_records, const int32_t* valid_list,
-                                    const int32_t* n_valid, const das_row_cache* rc, void* stream) {
+static int check_scratch(const das_refine_scratch* sc, const char* who) {
     using namespace das;
-    DAS_REQUIRE(cfg && row_records && valid_list && n_valid, DAS_ERR_ARG, "das_refine_row_cache: null pointer");
+    DAS_REQUIRE(sc && sc->unique_rows && sc->unique_out && sc->row_records && sc->item_records && sc->valid_list && sc->counters &&
+                sc->row_cap >= 1, DAS_ERR_ARG, "%s: null / empty scratch", who);
+    return DAS_OK;
+}
+
+extern "C" int das_refine_row_cache(const das_decode_cfg* cfg, const das_refine_scratch* scratch, const das_row_cache* rc, void* stream) {
+    using namespace das;
+    DAS_REQUIRE(cfg, DAS_ERR_ARG, "das_refine_row_cache: null pointer");
+    DAS_TRY(check_scratch(scratch, "das_refine_row_cache"));
     DAS_TRY(check_row_cache(rc, "das_refine_row_cache"));
     DAS_REQUIRE(cfg->feat_channels == TC_C, DAS_ERR_UNSUPPORTED, "the row cache is built for feat_channels=256");
-    row_cache_kernel<<<kSMs * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(row_records, valid_list, n_valid, cfg->num_joints,
-                                                                            row_cache_view(rc));
+    const dim3 grid(std::min(kSMs * 2, (scratch->row_cap + 255) / 256), cfg->num_joints);
+    row_cache_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(scratch->unique_rows, scratch->counters + 4, scratch->row_cap,
+                                                                         row_cache_view(rc));
     DAS_CUDA_CHECK(cudaGetLastError());
     return DAS_OK;
 }
 
+static das::TcParams tc_params(const das_levels* d_levels, const das_decode_cfg* cfg, const float* weights, const void* panels,
+                               int32_t cand_slots, const das_refine_scratch* sc, float* cand_pose, int32_t split) {
+    das::TcParams p{};
+    p.lv = d_levels; p.wpack = weights; p.bpanel = static_cast<const unsigned char*>(panels);
+    p.urow = sc->unique_rows; p.ures = sc->unique_out; p.lrow = sc->row_records; p.item_asm = sc->item_records;
+    p.valid_list = sc->valid_list; p.n_valid = sc->counters + 1; p.joint_count = sc->counters + 4;
+    p.cand_pose = cand_pose;
+    p.CT = cand_slots; p.J = cfg->num_joints; p.root = cfg->root_idx; p.row_cap = sc->row_cap;
+    p.split = split; p.depth_factor = cfg->depth_factor; p.z_norm = cfg->z_norm;
+    return p;
+}
+
 extern "C" int das_refine_tc(const das_levels* d_levels, const das_levels* h_levels, const das_decode_cfg* cfg,
                              const float* weights, const void* panels, int32_t cand_slots,
-                             const float* row_records, const float* item_records, const int32_t* valid_list,
-                             const int32_t* n_valid, float* cand_pose, int32_t split, void* stream) {
+                             const das_refine_scratch* scratch, int32_t split, void* stream) {
     using namespace das;
-    DAS_REQUIRE(d_levels && h_levels && cfg && weights && panels && row_records && item_records && valid_list && n_valid &&
-                cand_pose, DAS_ERR_ARG, "das_refine_tc: null pointer");
+    DAS_REQUIRE(d_levels && h_levels && cfg && weights && panels, DAS_ERR_ARG, "das_refine_tc: null pointer");
+    DAS_TRY(check_scratch(scratch, "das_refine_tc"));
     DAS_REQUIRE(cfg->feat_channels == TC_C && cfg->num_heads == TC_NH, DAS_ERR_UNSUPPORTED,
                 "tensor-core refinement is built for feat_channels=256, num_heads=4");
-    TcParams p{};
-    p.lv = d_levels; p.wpack = weights; p.bpanel = static_cast<const unsigned char*>(panels);
-    p.item_heads = row_records; p.item_asm = item_records; p.valid_list = valid_list; p.n_valid = n_valid;
-    p.cand_pose = cand_pose;
-    p.CT = cand_slots; p.J = cfg->num_joints; p.root = cfg->root_idx;
-    p.split = split; p.depth_factor = cfg->depth_factor; p.z_norm = cfg->z_norm;
+    DAS_REQUIRE(cfg->num_joints >= 1 && cfg->num_joints <= DAS_MAX_JOINTS, DAS_ERR_CAPACITY, "num_joints=%d", cfg->num_joints);
+    TcParams p = tc_params(d_levels, cfg, weights, panels, cand_slots, scratch, nullptr, split);
     p.dbg = g_tc_dbg;
     static DeviceOnce attr2_done;
     if (attr2_done.need()) {
@@ -505,6 +564,20 @@ extern "C" int das_refine_tc(const das_levels* d_levels, const das_levels* h_lev
     }
     if (p.dbg) refine_tc2_kernel<true><<<kSMs, T2_THREADS, T2_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
     else refine_tc2_kernel<false><<<kSMs, T2_THREADS, T2_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+    DAS_CUDA_CHECK(cudaGetLastError());
+    return DAS_OK;
+}
+
+extern "C" int das_refine_finish(const das_levels* h_levels, const das_decode_cfg* cfg, int32_t cand_slots,
+                                 const das_refine_scratch* scratch, float* cand_pose, void* stream) {
+    using namespace das;
+    DAS_REQUIRE(h_levels && cfg && cand_pose, DAS_ERR_ARG, "das_refine_finish: null pointer");
+    DAS_TRY(check_scratch(scratch, "das_refine_finish"));
+    DAS_REQUIRE(cfg->num_heads == TC_NH, DAS_ERR_UNSUPPORTED, "das_refine_finish is built for num_heads=4");
+    TcParams p = tc_params(nullptr, cfg, nullptr, nullptr, cand_slots, scratch, cand_pose, 0);
+    const long long items = static_cast<long long>(h_levels->batch) * cand_slots * cfg->num_joints;
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((items + 7) / 8, 8LL * kSMs)));
+    refine_finish_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
     DAS_CUDA_CHECK(cudaGetLastError());
     return DAS_OK;
 }

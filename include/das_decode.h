@@ -37,7 +37,7 @@ extern "C" {
 #define DAS_MAX_NMS_PRE 2048  /* per-level top-k capacity (reference configs use 1000) */
 #define DAS_CAM_DOUBLES 18    /* K[0,:3], K[1,:3], R row-major 3x3, t[3] */
 #define DAS_MAX_PEERS 15      /* other GPUs of one NVSwitch box that receive a copy of a rank's result block */
-#define DAS_NUM_STAGES 5      /* score_topk | dense layers | refine phases 1-2 (tensor-core mode) | refine + assemble | nms+backproject */
+#define DAS_NUM_STAGES 5      /* score_topk | dense layers | refine phases 1-2 (tensor-core mode) | refine GEMM + finish / SIMT refine | nms+backproject */
 
 typedef enum das_status {
     DAS_OK = 0,
@@ -118,9 +118,10 @@ typedef struct das_peer_blocks {
 } das_peer_blocks;
 
 const char* das_version(void);
-/* sizeof of the structs that cross the ABI by value or pointer: {das_levels, das_decode_cfg, das_buffers, das_row_cache}.
- * A binding checks these against its own mirrors at load time (a stale library must fail loudly, not corrupt memory). */
-void das_abi_struct_sizes(int32_t out[4]);
+/* sizeof of the structs that cross the ABI by value or pointer: {das_levels, das_decode_cfg, das_buffers, das_row_cache,
+ * das_refine_scratch, das_peer_blocks}.  A binding checks these against its own mirrors at load time (a stale library
+ * must fail loudly, not corrupt memory). */
+void das_abi_struct_sizes(int32_t out[6]);
 const char* das_last_error(void);
 
 /* slot bookkeeping (host-side pure functions) */
@@ -156,24 +157,40 @@ typedef struct das_row_cache {
     int32_t max_rows;
 } das_row_cache;
 
-/* Tensor-core variant of stage 3+4 (feat_channels = 256, num_heads = 4), two launches:
- *   das_refine_heads  phases 1-2 per (candidate, joint) item: the 32 row records of the sampling phase
- *                     (row_records [B*CT*J][32][8 floats]: feature-row pointer, bilinear weight, previous offset,
- *                     head offset), the item's assembly record (item_records [B*CT*J][8]), the centre (joint 0),
- *                     surviving candidates -> valid_list, counters[1] = their number (counters: 2 int32)
- *   das_refine_tc     the 32 sampled rows per item as a gathered tcgen05 GEMM (split=1: 3xTF32, fp32-level
- *                     accuracy; split=0: one TF32 pass) + gate/blend/softmax epilogue, eval tail, assembly.
+/* Scratch of the tensor-core sparse refinement (device memory, caller- or plan-owned).  row_cap >= B*CT*32. */
+typedef struct das_refine_scratch {
+    float* unique_rows;    /* [J][row_cap][8]   distinct sampled cells of every joint: {feature-row pointer (2 words), previous
+                                                offset u, v, d at that cell, -, -, -}                                          */
+    float* unique_out;     /* [J][row_cap][8]   per distinct cell: {blended O u, v, d, confidence u, v, d, -, -}                */
+    float* row_records;    /* [B*CT*J][32][4]   per (item, head, corner): {index into the joint's distinct-row list (int32 bits,
+                                                -1 = outside the map), bilinear weight, head offset x, y}                      */
+    float* item_records;   /* [B*CT*J][8]       assembly record {Px, Py, zq, sx, sy, stride, -, -}                             */
+    int32_t* valid_list;   /* [B*CT]            candidates above score_thr (b*CT + slot)                                        */
+    int32_t* counters;     /* [4 + DAS_MAX_JOINTS] [0] work queue, [1] number of valid candidates, [2] reserved (peer-store
+                                                ticket of the plan), [4+j] distinct rows of joint j                            */
+    int32_t row_cap;
+    int32_t reserved_;
+} das_refine_scratch;
+
+/* Tensor-core variant of stage 3+4 (feat_channels = 256, num_heads = 4), three launches:
+ *   das_refine_heads   phases 1-2 per (candidate, joint) item: the sampling position of each of the 32 (head, corner) rows;
+ *                      the item's DISTINCT sampled cells are appended to the joint's row list (the gate / value / confidence
+ *                      projections depend on (cell, joint) only, and the 8 heads x 4 corners mostly land on a handful of
+ *                      cells), the 32 row records point into it; assembly record; the centre (joint 0); valid_list
+ *   das_refine_tc      the distinct rows of every joint as a gathered tcgen05 GEMM in 128-row tiles (split=1: 3xTF32,
+ *                      fp32-level accuracy; split=0: one TF32 pass) + bias / gate / blend epilogue -> unique_out
+ *   das_refine_finish  per item: bilinear weights, corner sums, softmax over the 2*nh heads, eval tail, assembly -> cand_pose
  * panels: das_pack_tc_panels() image of the last layer's packed weights (das_tc_panel_bytes() bytes). */
 int das_refine_heads(const das_levels* d_levels, const das_levels* h_levels, const das_decode_cfg* cfg,
                      const float* weights, const float* const* prev_uvd, const float* scale_xy,
                      const float* cand_score, const int32_t* cand_index, int32_t cand_slots,
-                     float* row_records, float* item_records, float* cand_center,
-                     int32_t* valid_list, int32_t* counters, const das_row_cache* rc /* NULL = off */,
+                     const das_refine_scratch* scratch, float* cand_center, const das_row_cache* rc /* NULL = off */,
                      void* stream);
 int das_refine_tc(const das_levels* d_levels, const das_levels* h_levels, const das_decode_cfg* cfg,
                   const float* weights, const void* panels, int32_t cand_slots,
-                  const float* row_records, const float* item_records, const int32_t* valid_list,
-                  const int32_t* n_valid, float* cand_pose, int32_t split, void* stream);
+                  const das_refine_scratch* scratch, int32_t split, void* stream);
+int das_refine_finish(const das_levels* h_levels, const das_decode_cfg* cfg, int32_t cand_slots,
+                      const das_refine_scratch* scratch, float* cand_pose, void* stream);
 int das_pack_tc_panels(const das_decode_cfg* cfg, const float* packed_weights, void* panels, void* stream);
 /* Row cache for the host zero-copy mode (feature maps read in place from pinned HOST memory).  On device memory L2
  * absorbs the ~10x re-use of feature rows between heads / joints / candidates; reads of host memory are not
@@ -181,8 +198,8 @@ int das_pack_tc_panels(const das_decode_cfg* cfg, const float* packed_weights, v
  *   das_row_cache_clear    empties the table (before das_refine_cand_rows / das_refine_heads of a batch)
  *   das_refine_cand_rows   copies F(p) of every candidate above score_thr into rc->cand_rows (read by all J joints)
  *   das_refine_heads(rc)   reads F(p) from rc->cand_rows and leaves the target-corner rows it fetched in the cache
- *   das_refine_row_cache   between das_refine_heads and das_refine_tc: copies every still-missing DISTINCT row the row
- *                          records point at into rc->rows and re-points the records at the copies.
+ *   das_refine_row_cache   between das_refine_heads and das_refine_tc: copies every still-missing row of the joints'
+ *                          distinct-row lists into rc->rows and re-points the list entries at the copies.
  * A full row buffer leaves the remaining records pointing at the host.  2^table_bits should be at least twice the
  * number of row records (B*CT*J*32). */
 int64_t das_row_cache_table_bytes(int32_t table_bits);
@@ -190,8 +207,7 @@ int das_row_cache_clear(const das_row_cache* rc, void* stream);
 int das_refine_cand_rows(const das_levels* d_levels, const das_levels* h_levels, const das_decode_cfg* cfg,
                          const float* cand_score, const int32_t* cand_index, int32_t cand_slots,
                          const das_row_cache* rc, void* stream);
-int das_refine_row_cache(const das_decode_cfg* cfg, float* row_records, const int32_t* valid_list,
-                         const int32_t* n_valid, const das_row_cache* rc, void* stream);
+int das_refine_row_cache(const das_decode_cfg* cfg, const das_refine_scratch* scratch, const das_row_cache* rc, void* stream);
 int64_t das_tc_panel_bytes(const das_decode_cfg* cfg);
 /* profiling aid: per-CTA cycle counters of das_refine_tc's warp roles ([148][16] int64 device buffer; NULL = off) */
 int das_tc_set_debug_buffer(long long* dev_buf);

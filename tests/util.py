@@ -91,19 +91,40 @@ def run_gpu(case, test_cfg, refine=True, peak_kernel=0, pose_override=None, use_
     return plan, plan.results(case["metas"])
 
 
-def run_full_size(cfg, batch, h, w, test_cfg, seed, peaks, chunk=8, refine_mode=None):
+def run_oracle64(levels, layers, metas, cfg, test_cfg):
+    """fp64 ARBITER: the same algorithm with the pose / feature maps and weights in float64 (scores stay fp32, so the
+    candidates are the same).  It says how far the fp32 reference itself is from the exact answer -- its noise floor."""
+    hc = cfg.as_dict()
+    lv64 = [dict(lv, pose_raw=lv["pose_raw"].double(), feats=[f.double() for f in lv["feats"]]) for lv in levels]
+    lay64 = [{k: v.double() for k, v in l.items()} for l in layers]
+    pp64 = [O.head_eval_tail(lv["pose_raw"], lv["feats"], lay64, lv["scales"], num_joints=hc["num_joints"],
+                             num_heads=hc["num_heads"], root_idx=hc["root_idx"], depth_factor=hc["depth_factor"],
+                             z_norm=hc["z_norm"], stride=lv["stride"]) for lv in lv64]
+    res = O.get_poses([lv["cls"] for lv in levels], [p.float() for p in pp64], [lv["ctr"] for lv in levels], metas, test_cfg,
+                      [lv["stride"] for lv in levels], hc["num_joints"])
+    for r, meta in zip(res, metas):
+        cam = meta["cam"]
+        r["poses_cam"], r["poses_world"] = O.backproject(r["poses"].numpy(), cam["K"], cam["R"], cam["t"], hc["root_idx"])
+    return res
+
+
+def run_full_size(cfg, batch, h, w, test_cfg, seed, peaks, chunk=8, refine_mode=None, arbiter=False):
     """A BASELINE-sized case generated on the device (the host generator would take minutes), decoded through the C-ABI,
     and the oracle run on host copies of the same bits, `chunk` images at a time (its dense refinement materialises
     ~0.2 GB of temporaries per image).  Returns (case, plan, gpu results, oracle results)."""
     case = make_case(cfg, batch, h, w, seed=seed, peaks=peaks, tc=test_cfg, device="cuda")
     plan, got = run_gpu(case, test_cfg, refine=True, refine_mode=refine_mode)
-    ref = []
+    ref, ref64 = [], []
     for b0 in range(0, batch, chunk):
         b1 = min(batch, b0 + chunk)
         sub = [dict(lv, cls=lv["cls"][b0:b1].cpu(), ctr=lv["ctr"][b0:b1].cpu(), pose_raw=lv["pose_raw"][b0:b1].cpu(),
                     feats=[f[b0:b1].cpu() for f in lv["feats"]]) for lv in case["levels"]]
         r, _ = O.decode_full(sub, case["layers"], case["metas"][b0:b1], cfg.as_dict(), test_cfg)
         ref += r
+        if arbiter:
+            ref64 += run_oracle64(sub, case["layers"], case["metas"][b0:b1], cfg, test_cfg)
+    if arbiter:
+        return case, plan, got, ref, ref64
     return case, plan, got, ref
 
 
