@@ -54,7 +54,7 @@ constexpr int DT_LOCKSTEP_TILES = 2;             // the Q CTAs that read the sam
 
 // The feature map of a level as a 2-D tensor {C = 256 floats, B*H*W cells}: one TMA box = 32 channels x 128 cells
 // (a k-block of a 128-cell tile), 128-byte swizzle = the K-major operand layout of tc_common.cuh.
-__global__ void __maxnreg__(112)               // 576 threads x 112 registers = 63 K: one CTA per SM anyway (208 KB of shared memory)
+__global__ void __maxnreg__(88)                // 704 threads x 88 registers = 62 K of the 64 K: one CTA per SM anyway (224 KB of shared memory)
 dense_project_tc_kernel(const DenseTcParams p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -101,6 +101,7 @@ dense_project_tc_kernel(const DenseTcParams p, const __grid_constant__ CUtensorM
         if (lane == 0) {
             tc::tma_prefetch_desc(&tmap);
             volatile int* prog = p.progress + m;
+            bool lockstep = true;
             for (int g = 0; g < total_kb; ++g) {
                 const int s = g % DT_STAGES;
                 if (g >= DT_STAGES) tc::mbar_wait(&st_empty[s], ((g / DT_STAGES) - 1) & 1);   // the 4 warps that read it are done
@@ -113,7 +114,12 @@ dense_project_tc_kernel(const DenseTcParams p, const __grid_constant__ CUtensorM
                     // are co-resident (grid <= SM count, one CTA per SM), so the wait cannot deadlock.
                     if (i > 0) atomicAdd(p.progress + m, 1);                                   // tile i - 1 fully issued
                     const int need = Q * (i - DT_LOCKSTEP_TILES);
-                    while (*prog < need) __nanosleep(32);
+                    // bounded: if a sibling CTA is not resident (two such grids sharing the SMs from different
+                    // streams), give the lock-step up after ~2 ms instead of waiting for a CTA that cannot start
+                    for (int spin = 0; lockstep && *prog < need; ++spin) {
+                        __nanosleep(64);
+                        if (spin > (1 << 15)) lockstep = false;
+                    }
                 }
                 const long long cell0 = (static_cast<long long>(m) + static_cast<long long>(i) * G) * 128;
                 tc::mbar_arrive_expect_tx(&st_full[s], DT_A_BYTES);
