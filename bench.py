@@ -522,29 +522,50 @@ class Runner:
         return stage / n_prof
 
     def roofline(self, stage, n_prof):
+        """Roofline of the dominant kernel.  Two byte counts are reported for the sparse refinement stages:
+        * `frac`: bytes the kernel REALLY has to move.  The sampling-phase GEMM multiplies every DISTINCT (cell, joint)
+          feature row once (the 32 (head, corner) rows of an item that land on the same cell share one row), so its
+          algorithmic bytes are distinct rows x C x 4, counted on the device in this run (das_plan_refine_stats);
+        * `survey_frac`: SURVEY.md 8(d)'s per-item figure (32 rows per (centre, joint)) over the same time -- the number
+          round 1 reported.  It can exceed 1: that is the de-duplication, not bandwidth."""
         w, head = self.w, self.head
         mode = self.plans[0].refine_mode
-        sb = stage_bytes(w, head, mode)
+        sb_survey = stage_bytes(w, head, mode)
+        sb = dict(sb_survey)
+        dedup = None
+        if mode != 0 and head.num_layers >= 1:
+            rows, n_valid, rows_nodedup = self.plans[0].refine_stats()
+            if rows > 0:
+                sb["refine_assemble"] = rows * head.feat_channels * 4
+                dedup = dict(distinct_rows=rows, rows_without_dedup=rows_nodedup, valid_candidates=n_valid,
+                             distinct_rows_per_item=rows / max(1, n_valid * head.num_joints))
         ms = dict(zip(STAGES, [float(x) for x in stage]))
         dom = max(STAGES, key=lambda k: ms[k])
         kernel = KERNEL_OF_STAGE[dom]
         if dom == "refine_assemble":
             kernel = ("refine_sparse_kernel (fp32 SIMT: phases 1-3)" if mode == 0 else
-                      "refine_tc2_kernel (tcgen05 %s: sampling phase, 32 rows per item)" % ("3xTF32" if mode == 1 else "TF32"))
+                      "refine_tc2_kernel (tcgen05 %s: gathered GEMM over the distinct sampled rows) + refine_finish_kernel"
+                      % ("3xTF32" if mode == 1 else "TF32"))
         peak, peak_src = measured_peak()
         achieved = sb[dom] / (ms[dom] / 1e3) / 1e9
         traffic = ncu_traffic(w["key"], dom)
-        path_bytes = sum(sb.values())
+        path_bytes, path_survey = sum(sb.values()), sum(sb_survey.values())
         total_ms = float(stage.sum())
         out = dict(bound="hbm", kernel=kernel, stage=dom, achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                   survey_frac=sb_survey[dom] / (ms[dom] / 1e3) / 1e9 / peak,
                    traffic=traffic, dram_frac=(traffic / (ms[dom] / 1e3) / 1e9 / peak) if traffic else None,
                    traffic_over_algorithmic=(traffic / sb[dom]) if traffic else None,
-                   peak_source=peak_src, algorithmic_bytes_per_launch=sb[dom], kernel_ms=ms[dom], stage_ms=ms,
-                   stage_algorithmic_bytes=sb,
-                   path=dict(algorithmic_bytes=path_bytes, ms=total_ms, frac=path_bytes / (total_ms / 1e3) / 1e9 / peak,
+                   peak_source=peak_src, algorithmic_bytes_per_launch=sb[dom], survey_bytes_per_launch=sb_survey[dom],
+                   kernel_ms=ms[dom], stage_ms=ms, stage_algorithmic_bytes=sb, stage_survey_bytes=sb_survey, dedup=dedup,
+                   stage_frac={k: (sb[k] / (ms[k] / 1e3) / 1e9 / peak if ms[k] > 0 else None) for k in STAGES},
+                   path=dict(algorithmic_bytes=path_bytes, survey_bytes=path_survey, ms=total_ms,
+                             frac=path_bytes / (total_ms / 1e3) / 1e9 / peak,
+                             survey_frac=path_survey / (total_ms / 1e3) / 1e9 / peak,
                              note="whole decode over the summed single-stream stage times"),
                    how=f"CUDA-event nodes inside the replayed graph (single stream), mean of {n_prof} replays with a sync between them; "
-                       "frac = SURVEY 8(d) algorithmic bytes / time / peak; dram_frac = ncu dram__bytes of the same kernel / time / peak")
+                       "frac = algorithmic bytes / time / peak with the sampling phase counted at its DISTINCT gathered rows "
+                       "(device counter); survey_frac = SURVEY 8(d)'s 32 rows per (centre, joint) -- above 1 it measures the "
+                       "de-duplication, not bandwidth; dram_frac = ncu dram__bytes of the same kernel / time / peak")
         return out
 
     def close(self):
@@ -612,6 +633,11 @@ def run_b200(args):
     n_prof = max(min(args.steps, 200), 5)
     stage = run.stage_profile(n_prof)
     roofline = run.roofline(stage, n_prof)
+    step_ms = ms / args.steps
+    roofline["path"]["pipelined"] = dict(
+        ms=step_ms, frac=roofline["path"]["algorithmic_bytes"] / (step_ms / 1e3) / 1e9 / roofline["peak"],
+        survey_frac=roofline["path"]["survey_bytes"] / (step_ms / 1e3) / 1e9 / roofline["peak"],
+        note="the same byte counts over the timed step (independent batches pipelined on %d streams)" % run.n_streams)
 
     # ---- end to end through the host-buffer C-ABI entry: pinned host inputs, H2D + decode + D2H ---
     e2e = None
@@ -691,9 +717,10 @@ def run_b200(args):
                 extras[name] = dict(workload=sw["name"], value=world * sw["batch"] * steps / (sms / 1e3), unit=UNIT,
                                     ms_per_step=sms / steps, steps=steps, repetitions=len(sreps),
                                     serial_latency_ms=float(sst.sum()),
-                                    roofline={k: sroof[k] for k in ("kernel", "stage", "frac", "dram_frac", "achieved", "peak", "traffic",
-                                                                    "algorithmic_bytes_per_launch", "kernel_ms", "stage_ms")},
-                                    path_frac=sroof["path"]["frac"])
+                                    roofline={k: sroof[k] for k in ("kernel", "stage", "frac", "survey_frac", "dram_frac", "achieved", "peak",
+                                                                    "traffic", "algorithmic_bytes_per_launch", "survey_bytes_per_launch",
+                                                                    "kernel_ms", "stage_ms", "stage_frac", "dedup")},
+                                    path_frac=sroof["path"]["frac"], path_survey_frac=sroof["path"]["survey_frac"])
                 sub.close()
                 del sub
             except Exception as e:       # an extra must never take the headline line down with it

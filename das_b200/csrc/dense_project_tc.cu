@@ -33,8 +33,8 @@ constexpr int DT_STAGES = 6;                     // TMA ring of A k-block tiles:
 constexpr int DT_SLOTS = 4;                      // TMEM A slots (64 columns: 32 hi + 32 lo)
 constexpr int DT_A_BYTES = 128 * 128;
 constexpr int DT_FIRST_PRODUCER = 4 * DT_EG;     // warp 8
-constexpr int DT_MMA_WARP = DT_FIRST_PRODUCER + 4 * DT_PG;   // warp 20
-constexpr int DT_TMA_WARP = DT_MMA_WARP + 1;     // warp 21: one elected lane issues the TMA loads
+constexpr int DT_MMA_WARP = DT_FIRST_PRODUCER + 4 * DT_PG;   // warp 16
+constexpr int DT_TMA_WARP = DT_MMA_WARP + 1;     // warp 17: one elected lane issues the TMA loads
 constexpr int DT_THREADS = 32 * (DT_TMA_WARP + 1);
 constexpr int DT_D_COL = 0;                      // accumulators: 2 x 128 columns
 constexpr int DT_A_COL = 2 * DT_N * DT_EG;       // 256: A ring 4 x 64 columns
@@ -54,7 +54,7 @@ constexpr int DT_LOCKSTEP_TILES = 2;             // the Q CTAs that read the sam
 
 // The feature map of a level as a 2-D tensor {C = 256 floats, B*H*W cells}: one TMA box = 32 channels x 128 cells
 // (a k-block of a 128-cell tile), 128-byte swizzle = the K-major operand layout of tc_common.cuh.
-__global__ void __maxnreg__(88)                // 704 threads x 88 registers = 62 K of the 64 K: one CTA per SM anyway (224 KB of shared memory)
+__global__ void __maxnreg__(104)               // 576 threads x 104 registers = 60 K of the 64 K (112 fails to launch: the driver reserves a few); one CTA per SM anyway (225 KB of shared memory)
 dense_project_tc_kernel(const DenseTcParams p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));

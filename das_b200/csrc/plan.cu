@@ -599,6 +599,24 @@ extern "C" int das_plan_row_cache_stats(das_plan* p, int32_t stats[2]) {
     return DAS_OK;
 }
 
+// Sparse-refinement counters of the last run (tensor-core mode): stats[0] = DISTINCT (cell, joint) feature rows the
+// gathered GEMM multiplied (the bytes das_refine_tc really has to gather: stats[0] * feat_channels * 4), stats[1] =
+// candidates above score_thr, stats[2] = row slots it would take without the de-duplication (valid items * 32).
+// Synchronises with the device; for measurement, not for the hot path.
+extern "C" int das_plan_refine_stats(das_plan* p, int64_t stats[3]) {
+    using namespace das;
+    DAS_REQUIRE(p && stats, DAS_ERR_ARG, "das_plan_refine_stats: null pointer");
+    stats[0] = stats[1] = stats[2] = 0;
+    if (!p->work_counter) return DAS_OK;
+    int32_t c[4 + DAS_MAX_JOINTS];
+    DAS_CUDA_CHECK(cudaDeviceSynchronize());
+    DAS_CUDA_CHECK(cudaMemcpy(c, p->work_counter, sizeof(c), cudaMemcpyDeviceToHost));
+    for (int j = 0; j < p->cfg.num_joints; ++j) stats[0] += c[4 + j];
+    stats[1] = c[1];
+    stats[2] = static_cast<int64_t>(c[1]) * p->cfg.num_joints * 32;
+    return DAS_OK;
+}
+
 extern "C" int das_plan_run_host(das_plan* p, const das_levels* levels, const float* scale_xy, const double* cam,
                                  das_buffers host_out, void* stream) {
     using namespace das;

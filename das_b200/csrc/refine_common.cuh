@@ -106,6 +106,21 @@ __device__ __forceinline__ float sample_coord(int cell, float off, float size) {
     return __fadd_rn(__fmul_rn(__fadd_rn(g, 1.0f), size * 0.5f), -0.5f);
 }
 
+// a / size with the reciprocal precomputed (rsize = __frcp_rn(size)): q0 = a * rsize, one exact-remainder step, one
+// correction -- Markstein's sequence, which returns the correctly rounded quotient (checked against IEEE division for every
+// map size up to 600 and 240 k numerators each, tools/check_div.py), so the coordinate chain stays bit-identical to
+// sample_coord() at 3 instructions per division instead of the ~10 of __fdiv_rn.
+__device__ __forceinline__ float div_by(float a, float size, float rsize) {
+    const float q0 = __fmul_rn(a, rsize);
+    const float r = __fmaf_rn(-q0, size, a);
+    return __fmaf_rn(r, rsize, q0);
+}
+__device__ __forceinline__ float sample_coord(int cell, float off, float size, float rsize) {
+    const float loc = div_by(__fadd_rn(static_cast<float>(cell) + 0.5f, off), size, rsize);
+    const float g = __fadd_rn(__fmul_rn(2.0f, loc), -1.0f);
+    return __fadd_rn(__fmul_rn(__fadd_rn(g, 1.0f), size * 0.5f), -0.5f);
+}
+
 struct Corner {
     int x0, y0;        // north-west corner (clamped to a safe int range)
     float w, n;        // distance to the west / north side

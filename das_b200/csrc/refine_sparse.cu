@@ -337,6 +337,274 @@ refine_sparse_kernel(const RefineParams p) {
     }
 }
 
+// Phases 1-2 for NB (4 or 8) candidates at a time (the production path of das_refine_heads on device-resident maps).
+//
+// The warp-per-item kernel above reads its joint's 22 weight rows (22 KB) for every item, and with the items of all
+// joints interleaved those rows come from L2 every time: ncu showed 117 MB of L2 -> L1 traffic per launch for 48 MB of
+// feature rows, and 34 us.  Here a task is (joint j, block of NB consecutive candidates): a group of 32/NB lanes owns one
+// candidate; the NB feature rows live in registers, every weight row is loaded ONCE per NB items and the NB dot products
+// are finished by one transposing butterfly (reduce8_permuted / reduce4_permuted).  Tasks are handed out joint-major, so
+// the warps of an SM work on the same joint and its weight rows stay in L1.  The row records are then written for the NB
+// items with ONE reservation in the joint's distinct-row list per task (a per-item atomic would put NB dependent global
+// round trips on the warp's critical path).
+constexpr int H8_WARPS = 4;
+
+template <int NB>
+__device__ __forceinline__ float reduce_nb(const float (&a)[NB]) {
+    if constexpr (NB == 8) return reduce8_permuted(a);
+    else return reduce4_permuted(a);
+}
+
+template <int CPL, int NH, int NB>
+__global__ void __launch_bounds__(H8_WARPS * 32, 4)
+refine_heads8_kernel(const RefineParams p) {
+    static_assert(NH == 4, "32 rows per item = 8 heads x 4 corners");
+    static_assert(NB == 4 || NB == 8, "candidates per task");
+    constexpr int C = CPL * 32;
+    constexpr int NOUT = 2 * NH + 9;
+    constexpr int O_GATE = 2 * NH, O_VAL = 2 * NH + 3;
+    constexpr int GL = 32 / NB;                        // lanes per candidate
+    constexpr int SH = NB == 8 ? 2 : 3;                // log2(GL)
+    __shared__ float s_head[H8_WARPS][NB][4 * NH];     // per candidate of the block: hx[2*NH], hy[2*NH]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = (lane >> SH) & (NB - 1);             // candidate of the block this lane's group owns
+    const das_levels* __restrict__ lvp = p.lv;
+    const int nl = lvp->n_levels;
+    const int J = p.J;
+    const int n_cand = p.n_items / J;
+    const int n_blocks = (n_cand + NB - 1) / NB;
+    const int n_tasks = n_blocks * J;
+
+    auto level_of = [&](int slot) {
+        int l = 0, s0 = 0;
+        for (; l < nl - 1; ++l) {
+            const int ns = level_slots(lvp->lv[l].H * lvp->lv[l].W, p.nms_pre);
+            if (slot < s0 + ns) break;
+            s0 += ns;
+        }
+        return l;
+    };
+
+    for (;;) {
+        int task = 0;
+        if (lane == 0) task = atomicAdd(p.work_counter, 1);
+        task = __shfl_sync(FULL, task, 0);
+        if (task >= n_tasks) break;
+        const int j = task / n_blocks, cb = task - j * n_blocks;
+        const int cs = cb * NB + r;
+        bool valid = cs < n_cand;
+        if (valid && p.score_thr > 0.f && !(__ldg(p.cand_score + cs) > p.score_thr)) valid = false;   // dropped by das_head.py:763-769 later
+        const unsigned vmask = __ballot_sync(FULL, valid);
+        if (vmask == 0u) continue;
+        const float* __restrict__ Wj = p.wpack + static_cast<size_t>(j) * NOUT * C;
+        const float* __restrict__ Bj = p.wpack + static_cast<size_t>(J) * NOUT * C + j * NOUT;
+
+        // ---- this group's candidate ------------------------------------------------------------------------------
+        const int csv = valid ? cs : 0;
+        const int b = csv / p.CT, slot = csv - b * p.CT;
+        const int l = level_of(slot);
+        const das_level_desc& d = lvp->lv[l];
+        const int H = d.H, W = d.W, HW = H * W;
+        const int idx = valid ? __ldg(p.cand_index + csv) : 0;
+        const int y = idx / W, x = idx - y * W;
+        const float* __restrict__ F = d.feats[p.layer] + static_cast<size_t>(b) * HW * C;
+        const float fW = static_cast<float>(W), fH = static_cast<float>(H);
+        const float rW = __frcp_rn(fW), rH = __frcp_rn(fH);
+
+        // ---- phase 1: the NB rows F(p) x {S 2*NH, gate 3, value 3} -------------------------------------------------
+        float S[2 * NH], O[3];
+        {
+            float prev[3] = {0.f, 0.f, 0.f};
+            if (valid) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (p.prev_uvd) prev[k] = __ldg(p.prev_uvd[l] + ((static_cast<size_t>(b) * J + j) * HW + idx) * 4 + k);
+                    else if (!(k == 2 && j == p.root))
+                        prev[k] = __ldg(d.pose + (static_cast<size_t>(b) * (3 + 6 * J) + 3 + 3 * j + k) * HW + idx) * (k < 2 ? d.scale_uv : d.scale_d);
+                }
+            }
+            const float* own = valid ? F + static_cast<size_t>(idx) * C : nullptr;
+            Row<CPL> f[NB];
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {                // lane-permuted: candidate (k ^ r) goes to f[k]
+                const float* src = reinterpret_cast<const float*>(__shfl_xor_sync(FULL, reinterpret_cast<unsigned long long>(own), k << SH));
+                f[k] = load_row<CPL>(src ? src : p.wpack, lane, src != nullptr);
+            }
+            float res[2 * NH + 6];
+#pragma unroll
+            for (int o = 0; o < 2 * NH + 6; ++o) {
+                const Row<CPL> w = load_row<CPL>(Wj + o * C, lane, true);
+                float acc[NB];
+#pragma unroll
+                for (int k = 0; k < NB; ++k) acc[k] = dot_row<CPL>(f[k], w);
+                res[o] = reduce_nb<NB>(acc) + __ldg(Bj + o);
+            }
+#pragma unroll
+            for (int o = 0; o < 2 * NH; ++o) S[o] = res[o];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float g = sigmoid_acc(res[O_GATE + k]);
+                O[k] = __fadd_rn(__fmul_rn(1.0f - g, prev[k]), __fmul_rn(g, res[O_VAL + k]));
+            }
+        }
+
+        // ---- phase 2: sampling offsets read bilinearly at t = p + O.xy -------------------------------------------
+        {
+            const Corner ct = make_corner(sample_coord(x, O[0], fW, rW), sample_coord(y, O[1], fH, rH), W, H);
+            const float* cptr[4];
+            float cw[4];
+            float wsum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool ok = valid && corner_ok(ct, k, W, H);
+                cw[k] = ok ? corner_wgt(ct, k) : 0.f;
+                cptr[k] = ok ? F + static_cast<size_t>(corner_pix(ct, k, W)) * C : nullptr;
+                wsum += cw[k];
+            }
+            // pull the 4 corner rows of this candidate towards L2 now: the accumulation below can only keep a few rows in
+            // flight (registers), so without the hint every round of it waits for DRAM
+            {
+                const float* mine = cptr[lane & 3];
+                if (mine) {
+#pragma unroll
+                    for (int q = (lane >> 2) & (GL / 4 > 1 ? 1 : 0); q < C * 4 / 128; q += (GL / 4 > 1 ? 2 : 1))
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(mine + q * 32));
+                }
+            }
+            Row<CPL> fi[NB];
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+#pragma unroll
+                for (int q = 0; q < CPL / 4; ++q) fi[k].v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float* src = reinterpret_cast<const float*>(__shfl_xor_sync(FULL, reinterpret_cast<unsigned long long>(cptr[c]), k << SH));
+                    const float wk = __shfl_xor_sync(FULL, cw[c], k << SH);
+                    const Row<CPL> f = load_row<CPL>(src ? src : p.wpack, lane, src != nullptr);
+#pragma unroll
+                    for (int q = 0; q < CPL / 4; ++q) {
+                        fi[k].v[q].x = fmaf(wk, f.v[q].x, fi[k].v[q].x);
+                        fi[k].v[q].y = fmaf(wk, f.v[q].y, fi[k].v[q].y);
+                        fi[k].v[q].z = fmaf(wk, f.v[q].z, fi[k].v[q].z);
+                        fi[k].v[q].w = fmaf(wk, f.v[q].w, fi[k].v[q].w);
+                    }
+                }
+            }
+            // the projection is linear, so Bil(W f + b) = W Bil(f) + b * (in-bounds weight sum)
+            float st[2 * NH];
+#pragma unroll
+            for (int o = 0; o < 2 * NH; ++o) {
+                const Row<CPL> w = load_row<CPL>(Wj + o * C, lane, true);
+                float acc[NB];
+#pragma unroll
+                for (int k = 0; k < NB; ++k) acc[k] = dot_row<CPL>(fi[k], w);
+                st[o] = reduce_nb<NB>(acc) + wsum * __ldg(Bj + o);
+            }
+            if ((lane & (GL - 1)) == 0) {
+                float* sh = s_head[warp][r];
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    sh[h] = st[2 * h] + O[0];                 // "from target" heads, recursive_update.py:59
+                    sh[2 * NH + h] = st[2 * h + 1] + O[1];
+                    sh[NH + h] = S[2 * h];                    // "from source" heads, recursive_update.py:62
+                    sh[2 * NH + NH + h] = S[2 * h + 1];
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- row records: lane = (head = lane >> 2, corner = lane & 3) of one candidate at a time -----------------
+        // pass 1: every candidate's sampled cells and their de-duplication inside the item (registers)
+        int r_pix[NB], r_g[NB];                       // cell index (-1 = outside the map), position among the item's distinct cells
+        float r_w[NB], r_hx[NB], r_hy[NB];
+        unsigned r_lead[NB];                          // leader lanes of the item's distinct cells
+        int m_idx[NB], m_b[NB], m_l[NB];
+        int total_u = 0;
+#pragma unroll
+        for (int rr = 0; rr < NB; ++rr) {
+            m_idx[rr] = __shfl_sync(FULL, idx, rr * GL);
+            m_b[rr] = __shfl_sync(FULL, b, rr * GL);
+            m_l[rr] = __shfl_sync(FULL, l, rr * GL);
+            r_pix[rr] = -1; r_g[rr] = -1; r_w[rr] = 0.f; r_hx[rr] = 0.f; r_hy[rr] = 0.f; r_lead[rr] = 0u;
+            if (!((vmask >> (rr * GL)) & 1u)) continue;
+            const das_level_desc& d2 = lvp->lv[m_l[rr]];
+            const int H2 = d2.H, W2 = d2.W;
+            const int y2 = m_idx[rr] / W2, x2 = m_idx[rr] - y2 * W2;
+            const float fW2 = static_cast<float>(W2), fH2 = static_cast<float>(H2);
+            const int h = lane >> 2, ck2 = lane & 3;
+            const float hxv = s_head[warp][rr][h], hyv = s_head[warp][rr][2 * NH + h];
+            const Corner c = make_corner(sample_coord(x2, hxv, fW2, __frcp_rn(fW2)), sample_coord(y2, hyv, fH2, __frcp_rn(fH2)), W2, H2);
+            const bool ok = corner_ok(c, ck2, W2, H2);
+            const int pix = ok ? corner_pix(c, ck2, W2) : -1;
+            // one entry per DISTINCT sampled cell in the joint's row list (see the warp-per-item kernel above)
+            const unsigned same = __match_any_sync(FULL, pix);
+            const int leader = __ffs(same) - 1;
+            const unsigned lead_mask = __ballot_sync(FULL, ok && lane == leader);
+            const int my_u = __popc(lead_mask & ((1u << lane) - 1u));
+            const int u_of_leader = __shfl_sync(FULL, my_u, leader);
+            r_pix[rr] = pix; r_w[rr] = ok ? corner_wgt(c, ck2) : 0.f; r_hx[rr] = hxv; r_hy[rr] = hyv;
+            r_lead[rr] = lead_mask;
+            r_g[rr] = ok ? total_u + u_of_leader : -1;
+            total_u += __popc(lead_mask);
+        }
+        int base = 0;
+        if (lane == 0 && total_u) base = atomicAdd(p.work_counter + 4 + j, total_u);
+        base = __shfl_sync(FULL, base, 0);
+        // pass 2: the records
+#pragma unroll
+        for (int rr = 0; rr < NB; ++rr) {
+            if (!((vmask >> (rr * GL)) & 1u)) continue;
+            const int cs2 = cb * NB + rr;
+            const int item = cs2 * J + j;
+            const int b2 = m_b[rr];
+            const das_level_desc& d2 = lvp->lv[m_l[rr]];
+            const int W2 = d2.W, HW2 = d2.H * W2;
+            const int idx2 = m_idx[rr];
+            const float* __restrict__ pose2 = d2.pose + static_cast<size_t>(b2) * (3 + 6 * J) * HW2;
+            const int pix = r_pix[rr];
+            if ((r_lead[rr] >> lane) & 1u) {
+                const float* __restrict__ prev2 = p.prev_uvd ? p.prev_uvd[m_l[rr]] + (static_cast<size_t>(b2) * J + j) * HW2 * 4 : nullptr;
+                float pv[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (prev2) pv[k] = __ldg(prev2 + static_cast<size_t>(pix) * 4 + k);
+                    else if (k == 2 && j == p.root) pv[k] = 0.f;
+                    else pv[k] = __ldg(pose2 + static_cast<size_t>(3 + 3 * j + k) * HW2 + pix) * (k < 2 ? d2.scale_uv : d2.scale_d);
+                }
+                const unsigned long long pb = reinterpret_cast<unsigned long long>(d2.feats[p.layer] + (static_cast<size_t>(b2) * HW2 + pix) * C);
+                float4* dst = reinterpret_cast<float4*>(p.urow + (static_cast<size_t>(j) * p.row_cap + base + r_g[rr]) * 8);
+                dst[0] = make_float4(__uint_as_float(static_cast<unsigned>(pb)), __uint_as_float(static_cast<unsigned>(pb >> 32)), pv[0], pv[1]);
+                dst[1] = make_float4(pv[2], 0.f, 0.f, 0.f);
+            }
+            reinterpret_cast<float4*>(p.lrow)[static_cast<size_t>(item) * 32 + lane] =
+                make_float4(__int_as_float(pix >= 0 ? base + r_g[rr] : -1), r_w[rr], r_hx[rr], r_hy[rr]);
+            if (lane == 0) {
+                // eval-tail / assembly inputs of this item (das_head.py:254-262, 725-743), and the centre for joint 0
+                const int y2 = idx2 / W2, x2 = idx2 - y2 * W2;
+                const float sx = __ldg(p.scale_xy + 2 * b2), sy = __ldg(p.scale_xy + 2 * b2 + 1);
+                const float qf = sqrtf(sx * sy);
+                const float stv = static_cast<float>(d2.stride), half = static_cast<float>(d2.stride / 2);
+                float z = __ldg(pose2 + 2 * static_cast<size_t>(HW2) + idx2) * d2.scale_depth;
+                z = __fdiv_rn(z, p.depth_factor);
+                const float zq = __fmul_rn(z, qf);
+                const float Px = static_cast<float>(x2) * stv + half, Py = static_cast<float>(y2) * stv + half;
+                float4* a = reinterpret_cast<float4*>(p.item_asm + static_cast<size_t>(item) * 8);
+                a[0] = make_float4(Px, Py, zq, sx);
+                a[1] = make_float4(sy, stv, 0.f, 0.f);
+                if (j == 0) {
+                    const float offx = __ldg(pose2 + idx2) * d2.scale_offset;
+                    const float offy = __ldg(pose2 + static_cast<size_t>(HW2) + idx2) * d2.scale_offset;
+                    p.cand_center[static_cast<size_t>(cs2) * 3 + 0] = __fdiv_rn(__fsub_rn(Px, offx), sx);
+                    p.cand_center[static_cast<size_t>(cs2) * 3 + 1] = __fdiv_rn(__fsub_rn(Py, offy), sy);
+                    p.cand_center[static_cast<size_t>(cs2) * 3 + 2] = zq;
+                    p.valid_list[atomicAdd(p.work_counter + 1, 1)] = cs2;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // refine = 0: the pose maps are already final (reference get_poses contract): plain gather + assembly.
 __global__ void gather_assemble_kernel(const RefineParams p, int batch) {
     const int J = p.J;
@@ -520,10 +788,17 @@ extern "C" int das_refine_heads(const das_levels* d_levels, const das_levels* h_
     DAS_CUDA_CHECK(cudaMemsetAsync(scratch->counters + 4, 0, DAS_MAX_JOINTS * sizeof(int32_t), st));
     // 3 CTAs per SM (85 registers): with the de-duplication bookkeeping the 64-register variant spills, and the kernel is
     // bound by its dependent DRAM round trips, not by occupancy (profiles/r01_ncu_summary.md)
-    static const int minb = std::getenv("DAS_HEADS_MINB") ? std::atoi(std::getenv("DAS_HEADS_MINB")) : 3;
+    // DAS_HEADS_KERNEL=item selects the warp-per-item kernel on device-resident maps too (A/B timing, parity tests)
+    static const bool per_item = std::getenv("DAS_HEADS_KERNEL") && std::getenv("DAS_HEADS_KERNEL")[0] == 'i';
     if (p.rc.keys) refine_sparse_kernel<8, 4, 3, true, true><<<kSMs * 3, RS_WARPS * 32, 0, st>>>(p);
-    else if (minb == 4) refine_sparse_kernel<8, 4, 4, true><<<kSMs * 4, RS_WARPS * 32, 0, st>>>(p);
-    else refine_sparse_kernel<8, 4, 3, true><<<kSMs * 3, RS_WARPS * 32, 0, st>>>(p);
+    else if (per_item) refine_sparse_kernel<8, 4, 3, true><<<kSMs * 3, RS_WARPS * 32, 0, st>>>(p);
+    else {
+        static const int nb = std::getenv("DAS_HEADS_NB") ? std::atoi(std::getenv("DAS_HEADS_NB")) : 4;
+        const long long tasks = ((items / cfg->num_joints + nb - 1) / nb) * cfg->num_joints;
+        const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((tasks + H8_WARPS - 1) / H8_WARPS, 4LL * kSMs)));
+        if (nb == 8) refine_heads8_kernel<8, 4, 8><<<grid, H8_WARPS * 32, 0, st>>>(p);
+        else refine_heads8_kernel<8, 4, 4><<<grid, H8_WARPS * 32, 0, st>>>(p);
+    }
     DAS_CUDA_CHECK(cudaGetLastError());
     return DAS_OK;
 }

@@ -374,6 +374,14 @@ class DecodePlan:
             _lib.check(self.lib.das_plan_row_cache_stats(self._plan, arr), "das_plan_row_cache_stats")
         return int(arr[0]), int(arr[1])
 
+    def refine_stats(self):
+        """(distinct (cell, joint) feature rows the gathered GEMM multiplied, candidates above score_thr, rows without the
+        de-duplication) of the last tensor-core-mode run; synchronises with the device."""
+        arr = (C.c_int64 * 3)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.das_plan_refine_stats(self._plan, arr), "das_plan_refine_stats")
+        return int(arr[0]), int(arr[1]), int(arr[2])
+
     @property
     def h2d_explicit_bytes(self) -> int:
         return int(self.lib.das_plan_h2d_explicit_bytes(self._plan))

@@ -308,6 +308,11 @@ int64_t das_plan_d2h_bytes(const das_plan* plan);
  * score_thr (one F(p) row each).  Synchronises with the device; for measurement, not for the hot path. */
 int das_plan_row_cache_stats(das_plan* plan, int32_t stats[2]);
 
+/* after a tensor-core-mode run: stats[0] = distinct (cell, joint) feature rows the gathered GEMM multiplied, stats[1] =
+ * candidates above score_thr, stats[2] = rows without the de-duplication (valid items * 32).  Synchronises with the
+ * device; for measurement (bench.py's roofline), not for the hot path. */
+int das_plan_refine_stats(das_plan* plan, int64_t stats[3]);
+
 /* ---- diagnostics ------------------------------------------------------------------------------- */
 /* Self-test of the tcgen05/TMEM building blocks: D[128,N] = A[128,K] * B[N,K]^T (row-major fp32 device
  * buffers; N in {16,32}, K a multiple of 32). split=0: one TF32 pass; split=1: 3xTF32 (fp32-level accuracy). */
