@@ -29,7 +29,11 @@ class LevelDesc(C.Structure):
 
 
 class Levels(C.Structure):
-    _fields_ = [("n_levels", C.c_int32), ("batch", C.c_int32), ("lv", LevelDesc * MAX_LEVELS)]
+    _fields_ = [("n_levels", C.c_int32), ("batch", C.c_int32), ("in_dtype", C.c_int32), ("reserved_", C.c_int32),
+                ("lv", LevelDesc * MAX_LEVELS)]
+
+
+DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2      # das_levels.in_dtype (include/das_decode.h: DAS_DTYPE_*)
 
 
 class DecodeCfg(C.Structure):

@@ -1,6 +1,8 @@
 // Shared helpers for the DAS decode kernels (sm_100a).
 #pragma once
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -70,6 +72,20 @@ __device__ __forceinline__ int block_sum_1024(int v, int* red /* >= 33 ints smem
     t = __reduce_add_sync(0xffffffffu, t);
     return t;
 }
+
+// A head-output map (cls / ctr / pose) in the element type the caller bound (das_levels.in_dtype): map(i) = element i as
+// fp32.  The branch is uniform; fp16 / bf16 values convert exactly, so every result equals the up-cast path bit for bit.
+struct InMap {
+    const void* p;
+    int dt;
+    __device__ __forceinline__ InMap(const float* base, int dtype) : p(base), dt(dtype) {}
+    __device__ __forceinline__ float operator()(size_t i) const {
+        if (dt == DAS_DTYPE_F16) return __half2float(__ldg(reinterpret_cast<const __half*>(p) + i));
+        if (dt == DAS_DTYPE_BF16) return __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(p) + i));
+        return __ldg(reinterpret_cast<const float*>(p) + i);
+    }
+};
+__host__ __device__ __forceinline__ int dtype_bytes(int dt) { return dt == DAS_DTYPE_F32 ? 4 : 2; }
 
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 

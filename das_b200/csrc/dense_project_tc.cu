@@ -54,7 +54,7 @@ constexpr int DT_LOCKSTEP_TILES = 2;             // the Q CTAs that read the sam
 
 // The feature map of a level as a 2-D tensor {C = 256 floats, B*H*W cells}: one TMA box = 32 channels x 128 cells
 // (a k-block of a 128-cell tile), 128-byte swizzle = the K-major operand layout of tc_common.cuh.
-__global__ void __maxnreg__(104)               // 576 threads x 104 registers = 60 K of the 64 K (112 fails to launch: the driver reserves a few); one CTA per SM anyway (225 KB of shared memory)
+__global__ void __maxnreg__(96)                // 18 warps are allocated as 20 (granularity 4): 20 x 32 x 96 = 60 K of the 64 K registers (104 and 112 fail to launch); one CTA per SM anyway (225 KB of shared memory)
 dense_project_tc_kernel(const DenseTcParams p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -205,10 +205,11 @@ dense_project_tc_kernel(const DenseTcParams p, const __grid_constant__ CUtensorM
                     const float4 qv = __ldg(reinterpret_cast<const float4*>(p.uvd_in) + (static_cast<size_t>(b) * J + j) * HW + pix);
                     pv[jj][0] = qv.x; pv[jj][1] = qv.y; pv[jj][2] = qv.z;
                 } else {
-                    const float* qv = d.pose + (static_cast<size_t>(b) * (3 + 6 * J) + 3 + 3 * j) * HW + pix;
-                    pv[jj][0] = __ldg(qv);
-                    pv[jj][1] = __ldg(qv + HW);
-                    pv[jj][2] = (j == p.root) ? 0.f : __ldg(qv + 2 * static_cast<size_t>(HW));
+                    const InMap pose(d.pose, p.lv->in_dtype);
+                    const size_t qv = (static_cast<size_t>(b) * (3 + 6 * J) + 3 + 3 * j) * HW + pix;
+                    pv[jj][0] = pose(qv);
+                    pv[jj][1] = pose(qv + HW);
+                    pv[jj][2] = (j == p.root) ? 0.f : pose(qv + 2 * static_cast<size_t>(HW));
                 }
             }
         };

@@ -285,10 +285,14 @@ extern "C" int das_plan_bind(das_plan* p, const das_levels* levels, void* stream
     DAS_REQUIRE(levels->n_levels == p->shape.n_levels && levels->batch == p->shape.batch, DAS_ERR_ARG,
                 "bind: n_levels/batch (%d/%d) differ from the plan (%d/%d)", levels->n_levels, levels->batch,
                 p->shape.n_levels, p->shape.batch);
+    DAS_REQUIRE(levels->in_dtype == DAS_DTYPE_F32 || levels->in_dtype == DAS_DTYPE_F16 || levels->in_dtype == DAS_DTYPE_BF16, DAS_ERR_ARG,
+                "bind: in_dtype=%d (DAS_DTYPE_F32 / F16 / BF16)", levels->in_dtype);
     for (int l = 0; l < levels->n_levels; ++l) {
         const das_level_desc& d = levels->lv[l];
         DAS_REQUIRE(d.H == p->shape.lv[l].H && d.W == p->shape.lv[l].W && d.stride == p->shape.lv[l].stride, DAS_ERR_ARG,
                     "bind: level %d shape differs from the plan", l);
+        DAS_REQUIRE((reinterpret_cast<uintptr_t>(d.cls) | reinterpret_cast<uintptr_t>(d.ctr) | reinterpret_cast<uintptr_t>(d.pose)) %
+                    das::dtype_bytes(levels->in_dtype) == 0, DAS_ERR_ARG, "bind: level %d map is not aligned to its element type", l);
         DAS_REQUIRE(d.cls && d.ctr && d.pose, DAS_ERR_ARG, "bind: level %d has a null map", l);
         if (p->cfg.refine)
             for (int k = 0; k < p->cfg.num_layers; ++k) {
@@ -665,6 +669,8 @@ extern "C" int das_plan_run_host(das_plan* p, const das_levels* levels, const fl
     }
     DAS_TRY(set_row_cache(p, zero_copy && p->host_mode == 2));
     das_levels run = p->staging;
+    run.in_dtype = levels->in_dtype;
+    const size_t es = static_cast<size_t>(dtype_bytes(levels->in_dtype));     // element size of cls / ctr / pose
     int64_t copied = 0;
     for (int l = 0; l < p->shape.n_levels; ++l) {
         const das_level_desc& h = levels->lv[l];
@@ -673,16 +679,16 @@ extern "C" int das_plan_run_host(das_plan* p, const das_levels* levels, const fl
         DAS_REQUIRE(h.cls && h.ctr && h.pose, DAS_ERR_ARG, "run_host: level %d has a null map", l);
         const size_t hw = static_cast<size_t>(h.H) * h.W;
         d.scale_offset = h.scale_offset; d.scale_depth = h.scale_depth; d.scale_uv = h.scale_uv; d.scale_d = h.scale_d;
-        DAS_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(d.cls), h.cls, B * hw * 4, cudaMemcpyHostToDevice, st));
-        DAS_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(d.ctr), h.ctr, B * hw * 4, cudaMemcpyHostToDevice, st));
-        copied += static_cast<int64_t>(B * hw * 8);
+        DAS_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(d.cls), h.cls, B * hw * es, cudaMemcpyHostToDevice, st));
+        DAS_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(d.ctr), h.ctr, B * hw * es, cudaMemcpyHostToDevice, st));
+        copied += static_cast<int64_t>(B * hw * 2 * es);
         das_level_desc& sd = p->staging.lv[l];      // bulk staging, allocated lazily
         if (zero_copy && pose_sparse) {
             d.pose = dev_alias[l][0];
         } else {
             if (!sd.pose) { float* c = nullptr; DAS_TRY(dev_alloc(&c, B * hw * (3 + 6 * J))); sd.pose = c; }
-            DAS_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(sd.pose), h.pose, B * hw * (3 + 6 * J) * 4, cudaMemcpyHostToDevice, st));
-            copied += static_cast<int64_t>(B * hw * (3 + 6 * J) * 4);
+            DAS_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(sd.pose), h.pose, B * hw * (3 + 6 * J) * es, cudaMemcpyHostToDevice, st));
+            copied += static_cast<int64_t>(B * hw * (3 + 6 * J) * es);
             d.pose = sd.pose;
         }
         for (int k = 0; k < L; ++k) {

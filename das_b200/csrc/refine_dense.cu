@@ -82,7 +82,7 @@ dense_project_kernel(const DenseParams p) {
                 float prev;
                 if (p.uvd_in) prev = __ldg(p.uvd_in + ((static_cast<size_t>(b) * J + j) * HW + pix) * 4 + q);
                 else if (q == 2 && j == p.root) prev = 0.f;
-                else prev = __ldg(d.pose + (static_cast<size_t>(b) * (3 + 6 * J) + 3 + 3 * j + q) * HW + pix) *
+                else prev = InMap(d.pose, p.lv->in_dtype)((static_cast<size_t>(b) * (3 + 6 * J) + 3 + 3 * j + q) * HW + pix) *
                             (q < 2 ? d.scale_uv : d.scale_d);
                 const float gate = sigmoid_acc(rg);
                 reinterpret_cast<float*>(pl.oa + cellj)[q] = __fadd_rn(__fmul_rn(1.0f - gate, prev), __fmul_rn(gate, rn));  // blended offset

@@ -82,7 +82,8 @@ refine_sparse_kernel(const RefineParams p) {
         const int idx = __ldg(p.cand_index + cs);
         const int y = idx / W, x = idx - y * W;
         const float* __restrict__ F = d.feats[p.layer] + static_cast<size_t>(b) * HW * C;
-        const float* __restrict__ pose = d.pose + static_cast<size_t>(b) * (3 + 6 * J) * HW;
+        const InMap pose(d.pose, lvp->in_dtype);
+        const size_t pb = static_cast<size_t>(b) * (3 + 6 * J) * HW;     // first element of image b in the pose map
         const float* __restrict__ prev = p.prev_uvd ? p.prev_uvd[l] : nullptr;
         if (prev) prev += (static_cast<size_t>(b) * J + j) * HW * 4;
         const float* __restrict__ Wj = p.wpack + static_cast<size_t>(j) * NOUT * C;
@@ -93,7 +94,7 @@ refine_sparse_kernel(const RefineParams p) {
         auto prev_at = [&](int pix, int k) -> float {
             if (prev) return __ldg(prev + static_cast<size_t>(pix) * 4 + k);
             if (k == 2 && j == p.root) return 0.0f;
-            const float raw = __ldg(pose + static_cast<size_t>(3 + 3 * j + k) * HW + pix);
+            const float raw = pose(pb + static_cast<size_t>(3 + 3 * j + k) * HW + pix);
             return raw * (k < 2 ? d.scale_uv : d.scale_d);
         };
 
@@ -235,7 +236,7 @@ refine_sparse_kernel(const RefineParams p) {
                 const float sx = __ldg(p.scale_xy + 2 * b), sy = __ldg(p.scale_xy + 2 * b + 1);
                 const float qf = sqrtf(sx * sy);
                 const float st = static_cast<float>(d.stride), half = static_cast<float>(d.stride / 2);
-                float z = __ldg(pose + 2 * static_cast<size_t>(HW) + idx) * d.scale_depth;
+                float z = pose(pb + 2 * static_cast<size_t>(HW) + idx) * d.scale_depth;
                 z = __fdiv_rn(z, p.depth_factor);
                 const float zq = __fmul_rn(z, qf);
                 const float Px = static_cast<float>(x) * st + half, Py = static_cast<float>(y) * st + half;
@@ -243,8 +244,8 @@ refine_sparse_kernel(const RefineParams p) {
                 a[0] = make_float4(Px, Py, zq, sx);
                 a[1] = make_float4(sy, st, 0.f, 0.f);
                 if (j == 0) {
-                    const float offx = __ldg(pose + idx) * d.scale_offset;
-                    const float offy = __ldg(pose + static_cast<size_t>(HW) + idx) * d.scale_offset;
+                    const float offx = pose(pb + idx) * d.scale_offset;
+                    const float offy = pose(pb + static_cast<size_t>(HW) + idx) * d.scale_offset;
                     p.cand_center[static_cast<size_t>(cs) * 3 + 0] = __fdiv_rn(__fsub_rn(Px, offx), sx);
                     p.cand_center[static_cast<size_t>(cs) * 3 + 1] = __fdiv_rn(__fsub_rn(Py, offy), sy);
                     p.cand_center[static_cast<size_t>(cs) * 3 + 2] = zq;
@@ -315,7 +316,7 @@ refine_sparse_kernel(const RefineParams p) {
             const float qf = sqrtf(sx * sy);
             const float st = static_cast<float>(d.stride);
             const float half = static_cast<float>(d.stride / 2);
-            float z = __ldg(pose + 2 * static_cast<size_t>(HW) + idx) * d.scale_depth;
+            float z = pose(pb + 2 * static_cast<size_t>(HW) + idx) * d.scale_depth;
             z = __fdiv_rn(z, p.depth_factor);
             const float zq = __fmul_rn(z, qf);
             float v;
@@ -327,7 +328,7 @@ refine_sparse_kernel(const RefineParams p) {
                 float c;
                 if (lane == 2) c = zq;
                 else {
-                    const float off = __ldg(pose + static_cast<size_t>(lane) * HW + idx) * d.scale_offset;
+                    const float off = pose(pb + static_cast<size_t>(lane) * HW + idx) * d.scale_offset;
                     const float P = static_cast<float>(lane == 0 ? x : y) * st + half;
                     c = __fdiv_rn(__fsub_rn(P, off), lane == 0 ? sx : sy);
                 }
@@ -356,7 +357,7 @@ __device__ __forceinline__ float reduce_nb(const float (&a)[NB]) {
 }
 
 template <int CPL, int NH, int NB>
-__global__ void __launch_bounds__(H8_WARPS * 32, 4)
+__global__ void __launch_bounds__(H8_WARPS * 32, NB == 4 ? 5 : 4)     // NB = 4: 96 registers, 20 warps per SM (2 960 task slots: BASELINE config #2 has 2 400 tasks -> one wave)
 refine_heads8_kernel(const RefineParams p) {
     static_assert(NH == 4, "32 rows per item = 8 heads x 4 corners");
     static_assert(NB == 4 || NB == 8, "candidates per task");
@@ -385,11 +386,8 @@ refine_heads8_kernel(const RefineParams p) {
         return l;
     };
 
-    for (;;) {
-        int task = 0;
-        if (lane == 0) task = atomicAdd(p.work_counter, 1);
-        task = __shfl_sync(FULL, task, 0);
-        if (task >= n_tasks) break;
+    // static round-robin hand-out (a ticket counter would put one more global round trip in front of every task)
+    for (int task = blockIdx.x * H8_WARPS + warp; task < n_tasks; task += gridDim.x * H8_WARPS) {
         const int j = task / n_blocks, cb = task - j * n_blocks;
         const int cs = cb * NB + r;
         bool valid = cs < n_cand;
@@ -420,7 +418,7 @@ refine_heads8_kernel(const RefineParams p) {
                 for (int k = 0; k < 3; ++k) {
                     if (p.prev_uvd) prev[k] = __ldg(p.prev_uvd[l] + ((static_cast<size_t>(b) * J + j) * HW + idx) * 4 + k);
                     else if (!(k == 2 && j == p.root))
-                        prev[k] = __ldg(d.pose + (static_cast<size_t>(b) * (3 + 6 * J) + 3 + 3 * j + k) * HW + idx) * (k < 2 ? d.scale_uv : d.scale_d);
+                        prev[k] = InMap(d.pose, lvp->in_dtype)((static_cast<size_t>(b) * (3 + 6 * J) + 3 + 3 * j + k) * HW + idx) * (k < 2 ? d.scale_uv : d.scale_d);
                 }
             }
             const float* own = valid ? F + static_cast<size_t>(idx) * C : nullptr;
@@ -560,7 +558,8 @@ refine_heads8_kernel(const RefineParams p) {
             const das_level_desc& d2 = lvp->lv[m_l[rr]];
             const int W2 = d2.W, HW2 = d2.H * W2;
             const int idx2 = m_idx[rr];
-            const float* __restrict__ pose2 = d2.pose + static_cast<size_t>(b2) * (3 + 6 * J) * HW2;
+            const InMap pose2(d2.pose, lvp->in_dtype);
+            const size_t pb2 = static_cast<size_t>(b2) * (3 + 6 * J) * HW2;
             const int pix = r_pix[rr];
             if ((r_lead[rr] >> lane) & 1u) {
                 const float* __restrict__ prev2 = p.prev_uvd ? p.prev_uvd[m_l[rr]] + (static_cast<size_t>(b2) * J + j) * HW2 * 4 : nullptr;
@@ -569,7 +568,7 @@ refine_heads8_kernel(const RefineParams p) {
                 for (int k = 0; k < 3; ++k) {
                     if (prev2) pv[k] = __ldg(prev2 + static_cast<size_t>(pix) * 4 + k);
                     else if (k == 2 && j == p.root) pv[k] = 0.f;
-                    else pv[k] = __ldg(pose2 + static_cast<size_t>(3 + 3 * j + k) * HW2 + pix) * (k < 2 ? d2.scale_uv : d2.scale_d);
+                    else pv[k] = pose2(pb2 + static_cast<size_t>(3 + 3 * j + k) * HW2 + pix) * (k < 2 ? d2.scale_uv : d2.scale_d);
                 }
                 const unsigned long long pb = reinterpret_cast<unsigned long long>(d2.feats[p.layer] + (static_cast<size_t>(b2) * HW2 + pix) * C);
                 float4* dst = reinterpret_cast<float4*>(p.urow + (static_cast<size_t>(j) * p.row_cap + base + r_g[rr]) * 8);
@@ -584,7 +583,7 @@ refine_heads8_kernel(const RefineParams p) {
                 const float sx = __ldg(p.scale_xy + 2 * b2), sy = __ldg(p.scale_xy + 2 * b2 + 1);
                 const float qf = sqrtf(sx * sy);
                 const float stv = static_cast<float>(d2.stride), half = static_cast<float>(d2.stride / 2);
-                float z = __ldg(pose2 + 2 * static_cast<size_t>(HW2) + idx2) * d2.scale_depth;
+                float z = pose2(pb2 + 2 * static_cast<size_t>(HW2) + idx2) * d2.scale_depth;
                 z = __fdiv_rn(z, p.depth_factor);
                 const float zq = __fmul_rn(z, qf);
                 const float Px = static_cast<float>(x2) * stv + half, Py = static_cast<float>(y2) * stv + half;
@@ -592,8 +591,8 @@ refine_heads8_kernel(const RefineParams p) {
                 a[0] = make_float4(Px, Py, zq, sx);
                 a[1] = make_float4(sy, stv, 0.f, 0.f);
                 if (j == 0) {
-                    const float offx = __ldg(pose2 + idx2) * d2.scale_offset;
-                    const float offy = __ldg(pose2 + static_cast<size_t>(HW2) + idx2) * d2.scale_offset;
+                    const float offx = pose2(pb2 + idx2) * d2.scale_offset;
+                    const float offy = pose2(pb2 + static_cast<size_t>(HW2) + idx2) * d2.scale_offset;
                     p.cand_center[static_cast<size_t>(cs2) * 3 + 0] = __fdiv_rn(__fsub_rn(Px, offx), sx);
                     p.cand_center[static_cast<size_t>(cs2) * 3 + 1] = __fdiv_rn(__fsub_rn(Py, offy), sy);
                     p.cand_center[static_cast<size_t>(cs2) * 3 + 2] = zq;
@@ -626,14 +625,15 @@ __global__ void gather_assemble_kernel(const RefineParams p, int batch) {
         const int W = d.W, HW = d.H * d.W;
         const int idx = __ldg(p.cand_index + cs);
         const int y = idx / W, x = idx - y * W;
-        const float* __restrict__ pose = d.pose + static_cast<size_t>(b) * (3 + 6 * J) * HW;
+        const InMap pose(d.pose, lvp->in_dtype);
+        const size_t pb = static_cast<size_t>(b) * (3 + 6 * J) * HW;
         const float sx = __ldg(p.scale_xy + 2 * b), sy = __ldg(p.scale_xy + 2 * b + 1);
         const float qf = sqrtf(sx * sy);
         const float st = static_cast<float>(d.stride), half = static_cast<float>(d.stride / 2);
-        const float zq = __fmul_rn(__ldg(pose + 2 * static_cast<size_t>(HW) + idx), qf);
+        const float zq = __fmul_rn(pose(pb + 2 * static_cast<size_t>(HW) + idx), qf);
         if (e < 3 * J) {
             const int k = e % 3;
-            const float raw = __ldg(pose + static_cast<size_t>(3 + e) * HW + idx);
+            const float raw = pose(pb + static_cast<size_t>(3 + e) * HW + idx);
             float v;
             if (k == 0) v = __fdiv_rn(__fadd_rn(raw, static_cast<float>(x) * st + half), sx);
             else if (k == 1) v = __fdiv_rn(__fadd_rn(raw, static_cast<float>(y) * st + half), sy);
@@ -644,7 +644,7 @@ __global__ void gather_assemble_kernel(const RefineParams p, int batch) {
             float c;
             if (k == 2) c = zq;
             else {
-                const float off = __ldg(pose + static_cast<size_t>(k) * HW + idx);
+                const float off = pose(pb + static_cast<size_t>(k) * HW + idx);
                 const float P = static_cast<float>(k == 0 ? x : y) * st + half;
                 c = __fdiv_rn(__fsub_rn(P, off), k == 0 ? sx : sy);
             }
@@ -795,7 +795,7 @@ extern "C" int das_refine_heads(const das_levels* d_levels, const das_levels* h_
     else {
         static const int nb = std::getenv("DAS_HEADS_NB") ? std::atoi(std::getenv("DAS_HEADS_NB")) : 4;
         const long long tasks = ((items / cfg->num_joints + nb - 1) / nb) * cfg->num_joints;
-        const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((tasks + H8_WARPS - 1) / H8_WARPS, 4LL * kSMs)));
+        const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((tasks + H8_WARPS - 1) / H8_WARPS, (nb == 8 ? 4LL : 5LL) * kSMs)));
         if (nb == 8) refine_heads8_kernel<8, 4, 8><<<grid, H8_WARPS * 32, 0, st>>>(p);
         else refine_heads8_kernel<8, 4, 4><<<grid, H8_WARPS * 32, 0, st>>>(p);
     }

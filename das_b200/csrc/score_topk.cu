@@ -26,6 +26,41 @@ constexpr int TK_LIST_CAP = 4096;   // >= 2 * DAS_MAX_NMS_PRE
 constexpr int TK_FAST_K = 128;
 constexpr int TK_TILE_FLOATS = 16384;  // peak-mode row strip (64 KB)
 
+// Element loads of a logit plane in its bound dtype (das_levels.in_dtype): one element, or 4 consecutive ones as one
+// 128-bit (fp32) / 64-bit (fp16, bf16) read.  STREAM: bypass L1 (planes that are swept once).
+template <typename T> __device__ __forceinline__ float ld1(const T* p, size_t i);
+template <> __device__ __forceinline__ float ld1<float>(const float* p, size_t i) { return __ldg(p + i); }
+template <> __device__ __forceinline__ float ld1<__half>(const __half* p, size_t i) { return __half2float(__ldg(p + i)); }
+template <> __device__ __forceinline__ float ld1<__nv_bfloat16>(const __nv_bfloat16* p, size_t i) { return __bfloat162float(__ldg(p + i)); }
+
+template <typename T, bool STREAM> __device__ __forceinline__ float4 ld4(const T* p, int q);
+template <> __device__ __forceinline__ float4 ld4<float, false>(const float* p, int q) { return ldg_f4(p + 4 * q); }
+template <> __device__ __forceinline__ float4 ld4<float, true>(const float* p, int q) { return ldg_f4_stream(p + 4 * q); }
+__device__ __forceinline__ uint2 ldg_u2(const void* p, int q, bool stream) {
+    uint2 r;
+    if (stream) asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(reinterpret_cast<const uint2*>(p) + q));
+    else r = __ldg(reinterpret_cast<const uint2*>(p) + q);
+    return r;
+}
+template <> __device__ __forceinline__ float4 ld4<__half, false>(const __half* p, int q) {
+    const uint2 r = ldg_u2(p, q, false);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <> __device__ __forceinline__ float4 ld4<__half, true>(const __half* p, int q) {
+    const uint2 r = ldg_u2(p, q, true);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <> __device__ __forceinline__ float4 ld4<__nv_bfloat16, false>(const __nv_bfloat16* p, int q) {
+    const uint2 r = ldg_u2(p, q, false);      // bf16 -> fp32 is a 16-bit shift
+    return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xFFFF0000u), __uint_as_float(r.y << 16), __uint_as_float(r.y & 0xFFFF0000u));
+}
+template <> __device__ __forceinline__ float4 ld4<__nv_bfloat16, true>(const __nv_bfloat16* p, int q) {
+    const uint2 r = ldg_u2(p, q, true);
+    return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xFFFF0000u), __uint_as_float(r.y << 16), __uint_as_float(r.y & 0xFFFF0000u));
+}
+
 __device__ __forceinline__ uint64_t compose(uint32_t key, uint32_t idx) {
     return (static_cast<uint64_t>(key) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - idx);
 }
@@ -46,10 +81,10 @@ __device__ void bitonic_desc(uint64_t* a, int n2) {
     }
 }
 
-__global__ void __launch_bounds__(TK_THREADS, 1)
-score_topk_kernel(const das_levels* __restrict__ lvp, int nms_pre, int peak,
-                  float* __restrict__ cand_score, int32_t* __restrict__ cand_index, int cand_slots,
-                  uint32_t* __restrict__ scratch, int scratch_per_image) {
+template <typename T>
+__device__ __forceinline__ void score_topk_body(const das_levels* __restrict__ lvp, int nms_pre, int peak,
+                                                float* __restrict__ cand_score, int32_t* __restrict__ cand_index, int cand_slots,
+                                                uint32_t* __restrict__ scratch, int scratch_per_image) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* list = reinterpret_cast<uint64_t*>(smem_raw);                       // TK_LIST_CAP
     float* tile = reinterpret_cast<float*>(smem_raw + TK_LIST_CAP * sizeof(uint64_t));  // peak mode only
@@ -67,15 +102,16 @@ score_topk_kernel(const das_levels* __restrict__ lvp, int nms_pre, int peak,
         sc0 += hw;
     }
     const int K = level_slots(HW, nms_pre);
-    const float* __restrict__ cls = lvp->lv[l].cls + static_cast<size_t>(b) * HW;
-    const float* __restrict__ ctr = lvp->lv[l].ctr + static_cast<size_t>(b) * HW;
+    const T* __restrict__ cls = reinterpret_cast<const T*>(lvp->lv[l].cls) + static_cast<size_t>(b) * HW;
+    const T* __restrict__ ctr = reinterpret_cast<const T*>(lvp->lv[l].ctr) + static_cast<size_t>(b) * HW;
+    constexpr uintptr_t VMASK = 4 * sizeof(T) - 1;     // alignment of a 4-element vector load
     float* oscore = cand_score + static_cast<size_t>(b) * cand_slots + slot0;
     int32_t* oidx = cand_index + static_cast<size_t>(b) * cand_slots + slot0;
     const int tid = threadIdx.x;
 
     if (K == HW) {  // pass-through: raster order, no ranking (das_head.py:717 false branch)
         for (int i = tid; i < HW; i += TK_THREADS) {
-            oscore[i] = sigmoid_acc(cls[i]) * sigmoid_acc(ctr[i]);
+            oscore[i] = sigmoid_acc(ld1<T>(cls, i)) * sigmoid_acc(ld1<T>(ctr, i));
             oidx[i] = i;
         }
         return;
@@ -91,13 +127,13 @@ score_topk_kernel(const das_levels* __restrict__ lvp, int nms_pre, int peak,
         // known, only cells with cls >= logit(tau) can matter: the exp/div work and the centerness reads shrink from
         // every cell to a few dozen.  tau = K-th largest of the exact scores of each thread's best-cls cell (1024
         // distinct cells => a valid lower bound).
-        const bool vec = ((HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(cls) & 15) == 0);
+        const bool vec = ((HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(cls) & VMASK) == 0);
         float bc = -INFINITY;
         int bi = -1;
         if (vec) {
             const int n4 = HW >> 2;
             for (int q = tid; q < n4; q += TK_THREADS) {
-                const float4 a = ldg_f4(cls + 4 * q);          // stays in L1 for the second sweep
+                const float4 a = ld4<T, false>(cls, q);        // stays in L1 for the second sweep
                 if (a.x > bc) { bc = a.x; bi = 4 * q; }
                 if (a.y > bc) { bc = a.y; bi = 4 * q + 1; }
                 if (a.z > bc) { bc = a.z; bi = 4 * q + 2; }
@@ -105,7 +141,7 @@ score_topk_kernel(const das_levels* __restrict__ lvp, int nms_pre, int peak,
             }
         } else {
             for (int i = tid; i < HW; i += TK_THREADS) {
-                const float a = __ldg(cls + i);
+                const float a = ld1<T>(cls, i);
                 if (a > bc) { bc = a; bi = i; }
             }
         }
@@ -122,7 +158,7 @@ score_topk_kernel(const das_levels* __restrict__ lvp, int nms_pre, int peak,
                 const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
                 if (ob > wb || (ob == wb && oi >= 0 && (wi < 0 || oi < wi))) { wb = ob; wi = oi; }
             }
-            if (lane == 0) red[warp] = (wi >= 0) ? static_cast<int>(__float_as_uint(sigmoid_acc(wb) * sigmoid_acc(__ldg(ctr + wi)))) : 0;
+            if (lane == 0) red[warp] = (wi >= 0) ? static_cast<int>(__float_as_uint(sigmoid_acc(wb) * sigmoid_acc(ld1<T>(ctr, wi)))) : 0;
             __syncthreads();
             if (warp == 0) {
                 uint32_t v = static_cast<uint32_t>(red[lane]);
@@ -142,7 +178,7 @@ score_topk_kernel(const das_levels* __restrict__ lvp, int nms_pre, int peak,
             tau = static_cast<uint32_t>(red[32]);
         } else {
             uint32_t mykey = 0;
-            if (bi >= 0) mykey = __float_as_uint(sigmoid_acc(bc) * sigmoid_acc(__ldg(ctr + bi)));
+            if (bi >= 0) mykey = __float_as_uint(sigmoid_acc(bc) * sigmoid_acc(ld1<T>(ctr, bi)));
             for (int bit = 30; bit >= 0; --bit) {
                 const uint32_t trial = tau | (1u << bit);
                 if (__syncthreads_count(mykey >= trial) >= K) tau = trial;
@@ -153,7 +189,7 @@ score_topk_kernel(const das_levels* __restrict__ lvp, int nms_pre, int peak,
             const float a_thr = fminf(logf(tf / (1.0f - tf)) - 0.01f, 13.0f);   // conservative logit(tau)
             auto consider = [&](float a, int i) {
                 if (a >= a_thr) {
-                    const uint32_t k = __float_as_uint(sigmoid_acc(a) * sigmoid_acc(__ldg(ctr + i)));
+                    const uint32_t k = __float_as_uint(sigmoid_acc(a) * sigmoid_acc(ld1<T>(ctr, i)));
                     if (k >= tau) {
                         const int pos = atomicAdd(&list_n, 1);
                         if (pos < TK_LIST_CAP) list[pos] = compose(k, i);
@@ -163,11 +199,11 @@ score_topk_kernel(const das_levels* __restrict__ lvp, int nms_pre, int peak,
             if (vec) {
                 const int n4 = HW >> 2;
                 for (int q = tid; q < n4; q += TK_THREADS) {
-                    const float4 a = ldg_f4(cls + 4 * q);
+                    const float4 a = ld4<T, false>(cls, q);
                     consider(a.x, 4 * q); consider(a.y, 4 * q + 1); consider(a.z, 4 * q + 2); consider(a.w, 4 * q + 3);
                 }
             } else {
-                for (int i = tid; i < HW; i += TK_THREADS) consider(__ldg(cls + i), i);
+                for (int i = tid; i < HW; i += TK_THREADS) consider(ld1<T>(cls, i), i);
             }
             __syncthreads();
             done = (list_n <= TK_LIST_CAP && list_n >= K);   // block-uniform
@@ -178,14 +214,14 @@ score_topk_kernel(const das_levels* __restrict__ lvp, int nms_pre, int peak,
         // ---- A: rank keys -> scratch, per-thread maximum ---------------------------------------------
         uint64_t best = 0;
         if (!peak) {
-            const bool vec = ((HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(cls) & 15) == 0) &&
-                             ((reinterpret_cast<uintptr_t>(ctr) & 15) == 0) &&
+            const bool vec = ((HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(cls) & VMASK) == 0) &&
+                             ((reinterpret_cast<uintptr_t>(ctr) & VMASK) == 0) &&
                              ((reinterpret_cast<uintptr_t>(keys) & 15) == 0);
             if (vec) {
                 const int n4 = HW >> 2;
                 for (int q = tid; q < n4; q += TK_THREADS) {
-                    const float4 a = ldg_f4_stream(cls + 4 * q);
-                    const float4 c = ldg_f4_stream(ctr + 4 * q);
+                    const float4 a = ld4<T, true>(cls, q);
+                    const float4 c = ld4<T, true>(ctr, q);
                     uint4 k;
                     k.x = __float_as_uint(sigmoid_acc(a.x) * sigmoid_acc(c.x));
                     k.y = __float_as_uint(sigmoid_acc(a.y) * sigmoid_acc(c.y));
@@ -201,7 +237,7 @@ score_topk_kernel(const das_levels* __restrict__ lvp, int nms_pre, int peak,
                 }
             } else {
                 for (int i = tid; i < HW; i += TK_THREADS) {
-                    const uint32_t k = __float_as_uint(sigmoid_acc(__ldg(cls + i)) * sigmoid_acc(__ldg(ctr + i)));
+                    const uint32_t k = __float_as_uint(sigmoid_acc(ld1<T>(cls, i)) * sigmoid_acc(ld1<T>(ctr, i)));
                     keys[i] = k;
                     const uint64_t c = compose(k, i);
                     best = c > best ? c : best;
@@ -217,7 +253,7 @@ score_topk_kernel(const das_levels* __restrict__ lvp, int nms_pre, int peak,
                     const int ry = e / W, x = e - ry * W;
                     const int y = r0 - 1 + ry;
                     float s = 0.0f;  // scores are >= 0, so 0 stands in for "outside the map" (max-pool pads -inf)
-                    if (y >= 0 && y < H) s = sigmoid_acc(__ldg(cls + y * W + x)) * sigmoid_acc(__ldg(ctr + y * W + x));
+                    if (y >= 0 && y < H) s = sigmoid_acc(ld1<T>(cls, y * W + x)) * sigmoid_acc(ld1<T>(ctr, y * W + x));
                     tile[e] = s;
                 }
                 __syncthreads();
@@ -308,7 +344,7 @@ score_topk_kernel(const das_levels* __restrict__ lvp, int nms_pre, int peak,
             if (rnk < K) {
                 const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(c & 0xFFFFFFFFull);
                 float sc = __uint_as_float(static_cast<uint32_t>(c >> 32));
-                if (peak) sc = sigmoid_acc(__ldg(cls + idx)) * sigmoid_acc(__ldg(ctr + idx));
+                if (peak) sc = sigmoid_acc(ld1<T>(cls, idx)) * sigmoid_acc(ld1<T>(ctr, idx));
                 oscore[rnk] = sc;
                 oidx[rnk] = static_cast<int32_t>(idx);
             }
@@ -324,10 +360,22 @@ score_topk_kernel(const das_levels* __restrict__ lvp, int nms_pre, int peak,
         const uint64_t c = list[rnk];
         const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(c & 0xFFFFFFFFull);
         float s = __uint_as_float(static_cast<uint32_t>(c >> 32));
-        if (peak) s = sigmoid_acc(__ldg(cls + idx)) * sigmoid_acc(__ldg(ctr + idx));  // masked cells rank as 0
+        if (peak) s = sigmoid_acc(ld1<T>(cls, idx)) * sigmoid_acc(ld1<T>(ctr, idx));  // masked cells rank as 0
         oscore[rnk] = s;
         oidx[rnk] = static_cast<int32_t>(idx);
     }
+}
+
+// The element type of the logit planes is a property of the bound inputs (das_levels.in_dtype, read on the device), so
+// re-binding fp16 maps to a captured graph needs no re-capture.
+__global__ void __launch_bounds__(TK_THREADS, 1)
+score_topk_kernel(const das_levels* __restrict__ lvp, int nms_pre, int peak,
+                  float* __restrict__ cand_score, int32_t* __restrict__ cand_index, int cand_slots,
+                  uint32_t* __restrict__ scratch, int scratch_per_image) {
+    const int dt = lvp->in_dtype;
+    if (dt == DAS_DTYPE_F16) score_topk_body<__half>(lvp, nms_pre, peak, cand_score, cand_index, cand_slots, scratch, scratch_per_image);
+    else if (dt == DAS_DTYPE_BF16) score_topk_body<__nv_bfloat16>(lvp, nms_pre, peak, cand_score, cand_index, cand_slots, scratch, scratch_per_image);
+    else score_topk_body<float>(lvp, nms_pre, peak, cand_score, cand_index, cand_slots, scratch, scratch_per_image);
 }
 
 }  // namespace das

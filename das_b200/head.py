@@ -57,10 +57,24 @@ def _check_f32(t: torch.Tensor, what: str):
         raise RuntimeError(f"{what}: the decode path only runs on CUDA tensors")
 
 
+_IN_DTYPES = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16, torch.bfloat16: _lib.DTYPE_BF16}
+
+
 def _to_f32(t: torch.Tensor) -> torch.Tensor:
-    """fp16 / bf16 head outputs (the reference's fp16 mode, das_head.py:180,218 + exp_panoptic.py:222) are up-cast at
-    the boundary exactly like mmcv's force_fp32 does before get_poses; the kernels compute in fp32."""
+    """Refinement feature maps are fp32 at the C ABI (inside the reference's force_fp32 region they are fp32 too)."""
     return t if t.dtype == torch.float32 else t.float()
+
+
+def _head_maps(cls_l, ctr_l, pose_l):
+    """The three head-output maps of every level in ONE common element type the kernels read natively: fp32, or -- the
+    reference's shipped fp16 mode (das_head.py:180,218 out_fp16=True, exp_panoptic.py:222) -- fp16 / bf16 as they are
+    (half the scan and gather bytes; the arithmetic is fp32 either way, so results equal the up-cast path bit for bit).
+    Mixed or other dtypes are up-cast to fp32."""
+    dts = {t.dtype for t in list(cls_l) + list(ctr_l) + list(pose_l)}
+    if len(dts) == 1 and next(iter(dts)) in _IN_DTYPES:
+        return cls_l, ctr_l, pose_l
+    f = lambda ts: [t.float() for t in ts]
+    return f(cls_l), f(ctr_l), f(pose_l)
 
 
 _BLOCK_SPEC = (("out_count", torch.int32, 0), ("out_score", torch.float32, 1), ("out_slot", torch.int32, 1),
@@ -198,8 +212,14 @@ class DecodePlan:
             assert tuple(ctr.shape) == (self.batch, 1, h, w)
             assert tuple(pose.shape) == (self.batch, 3 + 6 * J, h, w), tuple(pose.shape)
             for name, t in (("cls", cls), ("ctr", ctr), ("pose", pose)):
-                if not host:
-                    _check_f32(t, name)
+                if t.dtype not in _IN_DTYPES:
+                    raise TypeError(f"{name}: expected float32 / float16 / bfloat16 at the C ABI, got {t.dtype}")
+                if not host and not t.is_cuda:
+                    raise RuntimeError(f"{name}: the decode path only runs on CUDA tensors")
+                if l == 0 and name == "cls":
+                    lv.in_dtype = _IN_DTYPES[t.dtype]
+                elif _IN_DTYPES[t.dtype] != lv.in_dtype:
+                    raise TypeError(f"{name} of level {l} is {t.dtype}: cls / ctr / pose of every level must share one dtype")
             cls, ctr, pose = cls.contiguous(), ctr.contiguous(), pose.contiguous()
             keep += [cls, ctr, pose]
             lv.lv[l].cls, lv.lv[l].ctr, lv.lv[l].pose = cls.data_ptr(), ctr.data_ptr(), pose.data_ptr()
@@ -517,10 +537,11 @@ class DASHeadB200:
         refine = refine_feats is not None
         plan = self._plan(batch, sizes, cfg, refine)
         levels = []
+        cls_l, ctr_l, pose_l = _head_maps([t.detach() for t in cls_scores], [t.detach() for t in centernesses],
+                                          [t.detach() for t in pose_preds])
         for l in range(num_levels):
             assert cls_scores[l].shape[-2:] == pose_preds[l].shape[-2:]
-            d = dict(cls=_to_f32(cls_scores[l].detach()), ctr=_to_f32(centernesses[l].detach()),
-                     pose=_to_f32(pose_preds[l].detach()), scales=self.scales[l])
+            d = dict(cls=cls_l[l], ctr=ctr_l[l], pose=pose_l[l], scales=self.scales[l])
             if refine:
                 d["feats"] = [_to_f32(f.detach()) for f in refine_feats[l]]
             levels.append(d)

@@ -47,7 +47,15 @@ typedef enum das_status {
     DAS_ERR_UNSUPPORTED = -4   /* feature not built (e.g. channel count other than 128/256/512) */
 } das_status;
 
-/* One pyramid level.  All pointers are device pointers owned by the caller. */
+/* Element type of the head-output maps cls / ctr / pose (das_levels.in_dtype).  The reference's shipped fp16 mode
+ * (das_head.py:180,218 out_fp16=True, exp_panoptic.py:222) hands get_poses fp16 tensors; the kernels read them in
+ * place (half the scan / gather bytes) and compute in fp32 -- bit-identical to up-casting the maps first. */
+#define DAS_DTYPE_F32 0
+#define DAS_DTYPE_F16 1
+#define DAS_DTYPE_BF16 2
+
+/* One pyramid level.  All pointers are device pointers owned by the caller.  cls / ctr / pose point at elements of
+ * das_levels.in_dtype (declared const float* for the common fp32 case; cast for fp16 / bf16). */
 typedef struct das_level_desc {
     const float* cls;                    /* [B,1,H,W] centre-heat-map logits (cls_score)          */
     const float* ctr;                    /* [B,1,H,W] centerness logits                           */
@@ -61,6 +69,8 @@ typedef struct das_level_desc {
 typedef struct das_levels {
     int32_t n_levels;
     int32_t batch;
+    int32_t in_dtype;                    /* DAS_DTYPE_* of cls / ctr / pose of every level (feats are always fp32) */
+    int32_t reserved_;
     das_level_desc lv[DAS_MAX_LEVELS];
 } das_levels;
 

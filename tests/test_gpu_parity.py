@@ -428,19 +428,56 @@ def test_soft_oks_nms_matches_oracle():
         assert len(g["scores"]) == 12
 
 
-def test_fp16_head_outputs_are_upcast_at_the_boundary():
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("refine", [True, False])
+def test_fp16_head_outputs_are_read_natively(dtype, refine):
+    """The reference's shipped fp16 mode (das_head.py:180,218 out_fp16=True, exp_panoptic.py:222) hands get_poses fp16
+    maps.  The kernels read fp16 / bf16 cls, ctr and pose maps in place (das_levels.in_dtype) and compute in fp32: the
+    result must equal the up-cast path bit for bit -- same people, same order, same coordinates."""
     tc = dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)
     case = util.make_case(P, 2, 24, 40, seed=91)
     dl = synth.levels_to(case["levels"], "cuda")
     head = DASHeadB200(num_joints=15, strides=[8], depth_factor=20, z_norm=50, root_idx=2, test_cfg=tc)
     head.load_refine_weights(synth.layers_to(case["layers"], "cuda"))
-    half = lambda t: t.half()
-    a = head.get_poses([half(lv["cls"]) for lv in dl], [half(lv["pose_raw"]) for lv in dl], [half(lv["ctr"]) for lv in dl],
-                       [[half(f) for f in lv["feats"]] for lv in dl], case["metas"])
-    b = head.get_poses([half(lv["cls"]).float() for lv in dl], [half(lv["pose_raw"]).float() for lv in dl],
-                       [half(lv["ctr"]).float() for lv in dl], [[half(f).float() for f in lv["feats"]] for lv in dl], case["metas"])
+    low = lambda t: t.to(dtype)
+    feats = [[f for f in lv["feats"]] for lv in dl]
+    args_low = [[low(lv["cls"]) for lv in dl], [low(lv["pose_raw"]) for lv in dl], [low(lv["ctr"]) for lv in dl]]
+    args_up = [[t.float() for t in a] for a in args_low]
+    if refine:
+        a = head.get_poses(*args_low, feats, case["metas"])
+        b = head.get_poses(*args_up, feats, case["metas"])
+    else:
+        a = head.get_poses(*args_low, case["metas"])
+        b = head.get_poses(*args_up, case["metas"])
+    assert sum(len(x["scores"]) for x in a) > 0
     for x, y in zip(a, b):
-        assert x["scores"] == y["scores"] and torch.equal(x["poses"], y["poses"])
+        assert x["scores"] == y["scores"] and torch.equal(x["poses"], y["poses"]) and torch.equal(x["centers"], y["centers"])
+        assert torch.equal(x["poses_cam"], y["poses_cam"])
+
+
+@pytest.mark.parametrize("variant", ["pyramid_pass_through", "k200_radix", "peak_mask", "odd_unaligned"])
+def test_fp16_native_scan_paths(variant):
+    """Every selection path of score_topk (bounded fast path, scratch keys + radix for K > 128, pass-through levels,
+    3x3 peak mask, scalar loads for odd map sizes) on fp16 logit planes == the same planes up-cast to fp32."""
+    kw = dict(pyramid_pass_through=dict(h=32, w=48, levels=4, tc=dict(nms_pre=60, nms_post=20, nms_thr=0.9, score_thr=0.0), peak=0),
+              k200_radix=dict(h=40, w=56, levels=1, tc=dict(nms_pre=200, nms_post=50, nms_thr=0.9, score_thr=0.0), peak=0),
+              peak_mask=dict(h=32, w=48, levels=1, tc=dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0), peak=3),
+              odd_unaligned=dict(h=23, w=37, levels=1, tc=dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0), peak=0))[variant]
+    tc = kw["tc"]
+    strides = [8 * 2 ** l for l in range(kw["levels"])]
+    case = util.make_case(dataclasses.replace(P, strides=tuple(strides)), 2, kw["h"], kw["w"], seed=93)
+    dl = synth.levels_to(case["levels"], "cuda")
+    assert len(dl) == kw["levels"]
+    outs = []
+    for up in (False, True):
+        head = DASHeadB200(num_joints=15, strides=strides, depth_factor=20, z_norm=50, root_idx=2, test_cfg=tc,
+                           peak_kernel=kw["peak"])
+        conv = (lambda t: t.half().float()) if up else (lambda t: t.half())
+        outs.append(head.get_poses([conv(lv["cls"]) for lv in dl], [conv(lv["pose_raw"]) for lv in dl], [conv(lv["ctr"]) for lv in dl],
+                                   case["metas"]))
+    assert sum(len(x["scores"]) for x in outs[0]) > 0
+    for x, y in zip(*outs):
+        assert x["scores"] == y["scores"] and torch.equal(x["poses"], y["poses"]) and torch.equal(x["centers"], y["centers"])
 
 
 def test_caller_owned_output_block_and_fused_peer_stores():
