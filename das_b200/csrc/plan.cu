@@ -278,6 +278,8 @@ extern "C" int das_plan_set_weights(das_plan* p, int32_t layer, const float* so_
 
 static int set_row_cache(das_plan* p, bool on);
 
+static void drop_graphs(das_plan* p);
+
 extern "C" int das_plan_bind(das_plan* p, const das_levels* levels, void* stream) {
     using namespace das;
     DAS_REQUIRE(p && levels, DAS_ERR_ARG, "das_plan_bind: null pointer");
@@ -300,6 +302,7 @@ extern "C" int das_plan_bind(das_plan* p, const das_levels* levels, void* stream
                 DAS_REQUIRE((reinterpret_cast<uintptr_t>(d.feats[k]) & 15) == 0, DAS_ERR_ARG, "feature maps must be 16-byte aligned");
             }
     }
+    if (levels->in_dtype != p->bound.in_dtype) drop_graphs(p);   // score_topk is instantiated per element type: re-capture
     p->bound = *levels;
     // pageable host -> device copy of 0.5 KB: stream-ordered, returns after staging
     DAS_CUDA_CHECK(cudaMemcpyAsync(p->d_levels, &p->bound, sizeof(das_levels), cudaMemcpyHostToDevice,

@@ -27,6 +27,7 @@
 //                     over the 8 heads (3 shuffles), eval tail, assembly; they also prepare the row pointers and
 //                     per-row state 6 tiles ahead and prefetch those rows into L2
 #include <algorithm>
+#include <cstdlib>
 
 #include "refine_common.cuh"
 #include "row_cache.cuh"
@@ -57,7 +58,7 @@ struct TcParams {
     const int32_t* n_valid;
     const int32_t* joint_count;      // [J] distinct rows of every joint
     float* cand_pose;
-    int CT, J, root, split, row_cap;
+    int CT, J, root, split, row_cap, gather_cg;
     float depth_factor, z_norm;
     long long* dbg;                  // optional [gridDim.x][16] cycle counters (profiling builds of the host code)
 };
@@ -129,7 +130,7 @@ constexpr int T2_THREADS = 32 * (T2_MMA_WARP + 1);
 constexpr int T2_TMEM_COLS = 512;
 constexpr int T2_D_COL = 0;                     // accumulators: T2_EG x 32 columns
 constexpr int T2_A_COL = 32 * T2_EG;            // A ring: 4 slots x 64 columns
-constexpr int T2_SMEM = 1024 + T2_PGROUPS * T2_STAGES * TC_A_BYTES + 2 * TC_B_BYTES;
+constexpr int T2_SMEM = 1024 + T2_PGROUPS * T2_STAGES * TC_A_BYTES + 2 * 2 * TC_B_BYTES;   // A rings + two joint panels (current, prefetched)
 
 // PROF: per-role cycle counters into p.dbg (tools/tc_role_cycles.py); the production instantiation carries none.
 template <bool PROF>
@@ -140,7 +141,7 @@ refine_tc2_kernel(const TcParams p) {
     unsigned char* sA = base;                                              // [group][stage] k-block tiles
     unsigned char* sB = sA + T2_PGROUPS * T2_STAGES * TC_A_BYTES;          // per k-block: 16 hi rows then 16 lo rows
     __shared__ uint64_t a_full[T2_SLOTS], a_empty[T2_SLOTS];               // producers -> MMA, MMA -> producers
-    __shared__ uint64_t acc_full[T2_EG], acc_free[T2_EG], rows_ready[T2_RB];
+    __shared__ uint64_t acc_full[T2_EG], acc_free[T2_EG], rows_ready[T2_RB], b_full[2];
     __shared__ uint32_t tmem_base;
     __shared__ const float* s_rowptr[T2_RB][128];   // row pointers are produced T2_RB tiles ahead of their epilogue
 
@@ -165,6 +166,7 @@ refine_tc2_kernel(const TcParams p) {
         for (int s = 0; s < T2_SLOTS; ++s) { tc::mbar_init(&a_full[s], 4); tc::mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < T2_EG; ++s) { tc::mbar_init(&acc_full[s], 1); tc::mbar_init(&acc_free[s], TC_EPI_WARPS); }
         for (int s = 0; s < T2_RB; ++s) tc::mbar_init(&rows_ready[s], TC_EPI_WARPS);
+        tc::mbar_init(&b_full[0], 1); tc::mbar_init(&b_full[1], 1);
         tc::mbar_fence_init();
     }
     if (warp == 0) tc::tmem_alloc(&tmem_base, T2_TMEM_COLS);
@@ -178,22 +180,48 @@ refine_tc2_kernel(const TcParams p) {
         // ===== MMA issuer warp (also owns the B panels) ================================================================
         constexpr uint32_t idesc32 = tc::instr_desc_tf32(128, 2 * TC_N);   // A_hi x [B_hi ; B_lo]  -> D[:, 0:32]
         constexpr uint32_t idesc16 = tc::instr_desc_tf32(128, TC_N);       // A_lo x  B_hi          -> D[:, 0:16]
-        int g = 0, cur_j = -1;
+        int g = 0, cur_j = -1, cur_buf = 0;
         long long m_w = 0, m_i = 0, m_b = 0, m_f = 0;
+        // Two panel buffers, filled by bulk copies (one instruction per 32-KB panel, no LSU traffic next to the producers'
+        // gathers): the first joint's panel and -- a CTA's contiguous tile range spans at most two joints unless the lists
+        // are tiny -- the second joint's are requested up front, so neither the start nor the switch inside the range
+        // waits for 64 rounds of cp.async (the synchronous reload took 29 % of the kernel: tools/tc_role_cycles.py).
+        int buf_joint[2] = {-1, -1};
+        uint32_t buf_phase[2] = {0u, 0u};
+        auto load_panel = [&](int j, int buf) {
+            if (lane == 0) {
+                tc::mbar_arrive_expect_tx(&b_full[buf], 2 * TC_B_BYTES);
+                tc::bulk_load(sB_u + buf * 2 * TC_B_BYTES, p.bpanel + static_cast<size_t>(j) * 2 * TC_B_BYTES, 2 * TC_B_BYTES, &b_full[buf]);
+            }
+            buf_joint[buf] = j;
+        };
+        {
+            int j0, j1, chunk_unused;
+            tile_joint(s_pref, J, t0, j0, chunk_unused);
+            load_panel(j0, 0);
+            tile_joint(s_pref, J, t1 - 1, j1, chunk_unused);
+            if (j1 != j0) {
+                int jn = j0 + 1;
+                while (jn < j1 && s_pref[jn + 1] == s_pref[jn]) ++jn;     // next joint that owns a tile
+                load_panel(jn, 1);
+            }
+        }
         for (int i = 0; i < my_tiles; ++i) {
             const uint32_t dcol = tmem0 + T2_D_COL + (i % T2_EG) * 32;
             const long long tb0 = (PROF ? clock64() : 0ll);
             int j, chunk_unused;
             tile_joint(s_pref, J, t0 + i, j, chunk_unused);
             if (j != cur_j) {
-                // new joint: every earlier MMA must have finished reading the old panels
-                if (g > 0) tc::mbar_wait(&a_empty[(g - 1) % T2_SLOTS], ((g - 1) / T2_SLOTS) & 1);
-                const unsigned char* src = p.bpanel + static_cast<size_t>(j) * 2 * TC_B_BYTES;
-                for (int c = lane; c < 2 * TC_B_BYTES / 16; c += 32) tc::cp_async16(sB_u + c * 16, src + c * 16, true);
-                tc::cp_async_commit();
-                tc::cp_async_wait<0>();
-                tc::fence_proxy_async();
-                __syncwarp();
+                if (buf_joint[0] == j || buf_joint[1] == j) {
+                    cur_buf = buf_joint[0] == j ? 0 : 1;
+                } else {
+                    // third joint of a range (tiny lists only): every earlier MMA must have finished reading the panels
+                    if (g > 0) tc::mbar_wait(&a_empty[(g - 1) % T2_SLOTS], ((g - 1) / T2_SLOTS) & 1);
+                    cur_buf ^= 1;
+                    load_panel(j, cur_buf);
+                }
+                tc::mbar_wait(&b_full[cur_buf], buf_phase[cur_buf]);
+                buf_phase[cur_buf] ^= 1u;
                 cur_j = j;
             }
             const long long tb1 = (PROF ? clock64() : 0ll);
@@ -208,7 +236,7 @@ refine_tc2_kernel(const TcParams p) {
                 const long long c1 = (PROF ? clock64() : 0ll);
                 m_w += c1 - c0;
                 const uint32_t a_hi = tmem0 + T2_A_COL + slot * 64, a_lo = a_hi + 32;
-                const uint32_t b_pk = sB_u + kb * TC_BK_BYTES;
+                const uint32_t b_pk = sB_u + cur_buf * 2 * TC_B_BYTES + kb * TC_BK_BYTES;
                 if (p.split & 1) {
                     tc::umma_kblock_3xtf32_ts(dcol, a_hi, a_lo, tc::smem_desc_sw128(b_pk), idesc32, idesc16, kb != 0);
                 } else {
@@ -240,7 +268,8 @@ refine_tc2_kernel(const TcParams p) {
             for (int it = 0; it < 8; ++it) {
                 const int row = (gt >> 3) + 16 * it, ch = gt & 7;
                 const float* src = s_rowptr[i % T2_RB][row];
-                tc::cp_async16_ca(sG_u + st * TC_A_BYTES + tc::swz128(row, ch), src ? src + kb * 32 + ch * 4 : p.wpack, src != nullptr);
+                if (p.gather_cg) tc::cp_async16(sG_u + st * TC_A_BYTES + tc::swz128(row, ch), src ? src + kb * 32 + ch * 4 : p.wpack, src != nullptr);
+                else tc::cp_async16_ca(sG_u + st * TC_A_BYTES + tc::swz128(row, ch), src ? src + kb * 32 + ch * 4 : p.wpack, src != nullptr);
             }
         };
         for (int n = 0; n < T2_STAGES - 1; ++n) { if (n < my_n) gather(n); tc::cp_async_commit(); }
@@ -557,6 +586,8 @@ extern "C" int das_refine_tc(const das_levels* d_levels, const das_levels* h_lev
     DAS_REQUIRE(cfg->num_joints >= 1 && cfg->num_joints <= DAS_MAX_JOINTS, DAS_ERR_CAPACITY, "num_joints=%d", cfg->num_joints);
     TcParams p = tc_params(d_levels, cfg, weights, panels, cand_slots, scratch, nullptr, split);
     p.dbg = g_tc_dbg;
+    static const int gather_cg = std::getenv("DAS_TC_GATHER_CG") ? std::atoi(std::getenv("DAS_TC_GATHER_CG")) : 1;   // .cg: no L1 allocation (the rows are distinct)
+    p.gather_cg = gather_cg;
     static DeviceOnce attr2_done;
     if (attr2_done.need()) {
         DAS_CUDA_CHECK(cudaFuncSetAttribute(refine_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));

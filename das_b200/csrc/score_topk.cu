@@ -366,16 +366,14 @@ __device__ __forceinline__ void score_topk_body(const das_levels* __restrict__ l
     }
 }
 
-// The element type of the logit planes is a property of the bound inputs (das_levels.in_dtype, read on the device), so
-// re-binding fp16 maps to a captured graph needs no re-capture.
+// One instantiation per element type of the logit planes (das_levels.in_dtype); the launcher picks it from the HOST copy
+// of the level table, so a plan whose inputs change type re-captures its graph (das_plan_bind).
+template <typename T>
 __global__ void __launch_bounds__(TK_THREADS, 1)
 score_topk_kernel(const das_levels* __restrict__ lvp, int nms_pre, int peak,
                   float* __restrict__ cand_score, int32_t* __restrict__ cand_index, int cand_slots,
                   uint32_t* __restrict__ scratch, int scratch_per_image) {
-    const int dt = lvp->in_dtype;
-    if (dt == DAS_DTYPE_F16) score_topk_body<__half>(lvp, nms_pre, peak, cand_score, cand_index, cand_slots, scratch, scratch_per_image);
-    else if (dt == DAS_DTYPE_BF16) score_topk_body<__nv_bfloat16>(lvp, nms_pre, peak, cand_score, cand_index, cand_slots, scratch, scratch_per_image);
-    else score_topk_body<float>(lvp, nms_pre, peak, cand_score, cand_index, cand_slots, scratch, scratch_per_image);
+    score_topk_body<T>(lvp, nms_pre, peak, cand_score, cand_index, cand_slots, scratch, scratch_per_image);
 }
 
 }  // namespace das
@@ -403,12 +401,27 @@ extern "C" int das_score_topk(const das_levels* d_levels, const das_levels* h_le
     const size_t smem = TK_LIST_CAP * sizeof(uint64_t) + (peak ? TK_TILE_FLOATS * sizeof(float) : 0);
     static DeviceOnce attr_done;
     if (attr_done.need()) {
-        DAS_CUDA_CHECK(cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(TK_LIST_CAP * sizeof(uint64_t) + TK_TILE_FLOATS * sizeof(float))));
+        const int max_smem = static_cast<int>(TK_LIST_CAP * sizeof(uint64_t) + TK_TILE_FLOATS * sizeof(float));
+        DAS_CUDA_CHECK(cudaFuncSetAttribute(score_topk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        DAS_CUDA_CHECK(cudaFuncSetAttribute(score_topk_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        DAS_CUDA_CHECK(cudaFuncSetAttribute(score_topk_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     }
     const int grid = h_levels->batch * h_levels->n_levels;
-    score_topk_kernel<<<grid, TK_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
-        d_levels, nms_pre, peak, cand_score, cand_index, cand_slots, scratch, per_image);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (h_levels->in_dtype) {
+        case DAS_DTYPE_F32:
+            score_topk_kernel<float><<<grid, TK_THREADS, smem, st>>>(d_levels, nms_pre, peak, cand_score, cand_index, cand_slots, scratch, per_image);
+            break;
+        case DAS_DTYPE_F16:
+            score_topk_kernel<__half><<<grid, TK_THREADS, smem, st>>>(d_levels, nms_pre, peak, cand_score, cand_index, cand_slots, scratch, per_image);
+            break;
+        case DAS_DTYPE_BF16:
+            score_topk_kernel<__nv_bfloat16><<<grid, TK_THREADS, smem, st>>>(d_levels, nms_pre, peak, cand_score, cand_index, cand_slots, scratch, per_image);
+            break;
+        default:
+            set_error("das_score_topk: in_dtype=%d", h_levels->in_dtype);
+            return DAS_ERR_ARG;
+    }
     DAS_CUDA_CHECK(cudaGetLastError());
     return DAS_OK;
 }

@@ -70,6 +70,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap,
         ::"r"(smem_dst), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
         : "memory");
 }
+// 1-D bulk copy global -> shared (cp.async.bulk): one instruction moves `bytes` (multiple of 16, 16-B aligned on both
+// sides) without touching the LSU; completion is signalled on the mbarrier like a tensor load.
+__device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_dst), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) { asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory"); }
 
 // ---- TMEM ----------------------------------------------------------------------------------------------
