@@ -76,6 +76,31 @@ def emit(obj):
         os.write(_JSON_FD, line)
 
 
+def pin_rank_to_cores(local_rank, world):
+    """One rank per GPU: give every rank its own slice of the host cores nearest to ITS GPU (NVML's CPU affinity of the
+    device = its NUMA node / root complex), so that 8 ranks do not migrate across each other and the pinned host buffers
+    a rank allocates afterwards come from that node (first-touch).  Returns a short description for the JSON line."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        near = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local_rank])
+                                                  if os.environ.get("CUDA_VISIBLE_DEVICES") else local_rank)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            near = [c for c in allowed if (words[c // 64] >> (c % 64)) & 1]
+        except Exception:
+            near = None
+        pool = near if near else allowed
+        per = max(1, len(pool) // max(1, world))
+        mine = pool[(local_rank % max(1, len(pool) // per)) * per:][:per] or pool
+        os.sched_setaffinity(0, set(mine))
+        return dict(cores=[mine[0], mine[-1]], n=len(mine), near_gpu=bool(near))
+    except Exception as e:       # affinity is an optimisation, never a reason to fail
+        return dict(error=repr(e)[:100])
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -298,7 +323,7 @@ def stage_bytes(w, head, mode):
 
 KERNEL_OF_STAGE = {
     "score_topk": "score_topk_kernel", "dense_layers": "dense_project_tc_kernel + dense_sample_kernel (layers 1..L-1)",
-    "refine_phase12": "refine_sparse_kernel<heads only> (phases 1-2)", "refine_assemble": None,
+    "refine_phase12": "refine_heads8_kernel (phases 1-2, 4 candidates per warp; warp-per-item kernel for small decodes)", "refine_assemble": None,
     "nms_backproject": "nms_backproject_kernel"}
 
 
@@ -521,6 +546,27 @@ class Runner:
             stage += np.array(p.stage_ms())
         return stage / n_prof
 
+    def serial_replay(self, n=200):
+        """One decode at a time: graph replays back to back on ONE stream over the rotating input sets, with programmatic
+        dependent launch along the kernel chain (das_plan_set_pdl(1), the latency mode).  ms per decode."""
+        plans = self.plans[:self.n_sets]
+        for p in plans:
+            p.set_pdl(1)
+        try:
+            for i in range(2 * len(plans)):
+                plans[i % len(plans)].run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(n):
+                plans[i % len(plans)].run()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+        finally:
+            for p in plans:
+                p.set_pdl(-1)
+
     def roofline(self, stage, n_prof):
         """Roofline of the dominant kernel.  Two byte counts are reported for the sparse refinement stages:
         * `frac`: bytes the kernel REALLY has to move.  The sampling-phase GEMM multiplies every DISTINCT (cell, joint)
@@ -604,6 +650,7 @@ def run_b200(args):
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the decode path has no CPU fallback")
+    pinning = pin_rank_to_cores(local_rank, world) if world > 1 else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -634,6 +681,12 @@ def run_b200(args):
     stage = run.stage_profile(n_prof)
     roofline = run.roofline(stage, n_prof)
     step_ms = ms / args.steps
+    ser_ms = run.serial_replay(200 if w["key"] != "mupots" else 10)
+    roofline["path"]["serial_replay"] = dict(
+        ms=ser_ms, frac=roofline["path"]["algorithmic_bytes"] / (ser_ms / 1e3) / 1e9 / roofline["peak"],
+        survey_frac=roofline["path"]["survey_bytes"] / (ser_ms / 1e3) / 1e9 / roofline["peak"],
+        note="one decode at a time: graph replays back to back on ONE stream, programmatic dependent launch on "
+             "(the stage times above carry event nodes between the kernels, which rules PDL out)")
     roofline["path"]["pipelined"] = dict(
         ms=step_ms, frac=roofline["path"]["algorithmic_bytes"] / (step_ms / 1e3) / 1e9 / roofline["peak"],
         survey_frac=roofline["path"]["survey_bytes"] / (step_ms / 1e3) / 1e9 / roofline["peak"],
@@ -712,11 +765,12 @@ def run_b200(args):
                 steps = {"single": 400, "panoptic_spread": 200, "crowded": 100, "mupots": 12}[name]
                 sms, sreps, _, _ = sub.timed(steps, 3, 0.15)
                 sst = sub.stage_profile(5 if name == "mupots" else 20)
+                sser = sub.serial_replay(10 if name == "mupots" else 100)
                 sroof = sub.roofline(sst, 5 if name == "mupots" else 20)
                 sw = sub.w
                 extras[name] = dict(workload=sw["name"], value=world * sw["batch"] * steps / (sms / 1e3), unit=UNIT,
                                     ms_per_step=sms / steps, steps=steps, repetitions=len(sreps),
-                                    serial_latency_ms=float(sst.sum()),
+                                    serial_latency_ms=float(sst.sum()), serial_replay_ms=sser,
                                     roofline={k: sroof[k] for k in ("kernel", "stage", "frac", "survey_frac", "dram_frac", "achieved", "peak",
                                                                     "traffic", "algorithmic_bytes_per_launch", "survey_bytes_per_launch",
                                                                     "kernel_ms", "stage_ms", "stage_frac", "dedup")},
@@ -756,6 +810,8 @@ def run_b200(args):
         }
         if collect_check is not None:
             out["config"]["collect_check"] = collect_check
+        if pinning is not None:
+            out["config"]["host_cores_rank0"] = pinning
         if extras:
             out["extra_workloads"] = extras
         if e2e is not None:

@@ -29,6 +29,35 @@ struct DeviceOnce {
 
 void set_error(const char* fmt, ...);
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------------
+// The kernels of one decode form a chain on one stream.  Launched with the programmatic-stream-serialization attribute,
+// kernel n+1 may be scheduled (and run the part of its prologue that touches no predecessor data: barrier / TMEM set-up,
+// weight-panel loads) as soon as every CTA of kernel n has called pdl_trigger(); pdl_wait() then blocks until kernel n has
+// COMPLETED and its writes are visible -- so correctness only needs pdl_wait() before the first dependent access.  Both
+// are no-ops in a kernel launched without the attribute (the stand-alone stage launchers of the C ABI).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// What das_plan's enqueue tells the stage launchers it calls (thread-local; default = stand-alone behaviour).
+struct ChainCtx {
+    bool pdl = false;                 // launch with the PDL attribute (the previous node on the stream is a kernel of this chain)
+    int32_t* zero_counters = nullptr; // das_score_topk: refine counters to clear ([0], [1], [4 .. 4+DAS_MAX_JOINTS)) for the chain
+    bool counters_cleared = false;    // das_refine_heads: the counters were cleared by das_score_topk of this chain -> no memset nodes
+};
+ChainCtx& chain_ctx();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #define DAS_CUDA_CHECK(expr)                                                              \
     do {                                                                                  \
         cudaError_t _e = (expr);                                                          \

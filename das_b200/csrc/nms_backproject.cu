@@ -135,6 +135,7 @@ nms_backproject_kernel(const NmsParams p) {
     int* kept_list = order;   // reused after ranking: kept_list[k] = candidate slot of output row k
 
     if (tid == 0) { s_n = 0; s_kept = 0; }
+    pdl_wait();          // candidates' poses come from the refinement kernels in front of this one (last kernel of the chain: no trigger)
     __syncthreads();
 
     // ---- validity (das_head.py:763-769) + stable compaction in slot order ---------------------------
@@ -445,8 +446,8 @@ extern "C" int das_nms_backproject_peers(const das_decode_cfg* cfg, int32_t batc
                                             NM_MAX_CAND * 8 + NM_MAX_CAND * 13 + 32));
     }
     // few candidates (the usual case): 8 warps keep the ~20 block barriers of this latency-bound kernel cheap
-    if (cand_slots <= 32) nms_backproject_kernel<256><<<batch, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
-    else nms_backproject_kernel<NM_THREADS><<<batch, NM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    if (cand_slots <= 32) DAS_CUDA_CHECK(launch_chain(nms_backproject_kernel<256>, dim3(batch), dim3(256), smem, static_cast<cudaStream_t>(stream), chain_ctx().pdl, p));
+    else DAS_CUDA_CHECK(launch_chain(nms_backproject_kernel<NM_THREADS>, dim3(batch), dim3(NM_THREADS), smem, static_cast<cudaStream_t>(stream), chain_ctx().pdl, p));
     DAS_CUDA_CHECK(cudaGetLastError());
     return DAS_OK;
 }

@@ -56,6 +56,8 @@ refine_sparse_kernel(const RefineParams p) {
     constexpr int NOUT = 2 * NH + 9;
     constexpr int O_GATE = 2 * NH, O_VAL = 2 * NH + 3, O_CONF = 2 * NH + 6;
     const int lane = threadIdx.x & 31;
+    pdl_wait();          // candidates (and, for L > 1, the dense layers' maps) come from the kernels in front of this one
+    pdl_trigger();
     const das_levels* __restrict__ lvp = p.lv;
     const int nl = lvp->n_levels;
     const int J = p.J;
@@ -368,6 +370,8 @@ refine_heads8_kernel(const RefineParams p) {
     constexpr int SH = NB == 8 ? 2 : 3;                // log2(GL)
     __shared__ float s_head[H8_WARPS][NB][4 * NH];     // per candidate of the block: hx[2*NH], hy[2*NH]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_wait();          // candidates (and, for L > 1, the dense layers' maps) come from the kernels in front of this one
+    pdl_trigger();
     const int r = (lane >> SH) & (NB - 1);             // candidate of the block this lane's group owns
     const das_levels* __restrict__ lvp = p.lv;
     const int nl = lvp->n_levels;
@@ -783,21 +787,27 @@ extern "C" int das_refine_heads(const das_levels* d_levels, const das_levels* h_
     DAS_REQUIRE(items < (1ll << 31), DAS_ERR_CAPACITY, "too many work items");
     p.n_items = static_cast<int>(items);
     p.rc = row_cache_view(rc);
-    // [0] queue head, [1] n_valid, [4..4+J) per-joint distinct-row counts; [2] (the peer-store ticket) is left alone
-    DAS_CUDA_CHECK(cudaMemsetAsync(scratch->counters, 0, 2 * sizeof(int32_t), st));
-    DAS_CUDA_CHECK(cudaMemsetAsync(scratch->counters + 4, 0, DAS_MAX_JOINTS * sizeof(int32_t), st));
-    // 3 CTAs per SM (85 registers): with the de-duplication bookkeeping the 64-register variant spills, and the kernel is
-    // bound by its dependent DRAM round trips, not by occupancy (profiles/r01_ncu_summary.md)
-    // DAS_HEADS_KERNEL=item selects the warp-per-item kernel on device-resident maps too (A/B timing, parity tests)
-    static const bool per_item = std::getenv("DAS_HEADS_KERNEL") && std::getenv("DAS_HEADS_KERNEL")[0] == 'i';
-    if (p.rc.keys) refine_sparse_kernel<8, 4, 3, true, true><<<kSMs * 3, RS_WARPS * 32, 0, st>>>(p);
-    else if (per_item) refine_sparse_kernel<8, 4, 3, true><<<kSMs * 3, RS_WARPS * 32, 0, st>>>(p);
-    else {
+    // [0] queue head, [1] n_valid, [4..4+J) per-joint distinct-row counts; [2] (the peer-store ticket) is left alone.
+    // Inside das_plan's chain das_score_topk has already cleared them (no memset nodes between the kernels).
+    const ChainCtx& cx = chain_ctx();
+    if (!cx.counters_cleared) {
+        DAS_CUDA_CHECK(cudaMemsetAsync(scratch->counters, 0, 2 * sizeof(int32_t), st));
+        DAS_CUDA_CHECK(cudaMemsetAsync(scratch->counters + 4, 0, DAS_MAX_JOINTS * sizeof(int32_t), st));
+    }
+    // DAS_HEADS_KERNEL=item / =batch forces one of the two kernels (A/B timing, parity tests)
+    static const char* force = std::getenv("DAS_HEADS_KERNEL");
+    // fewer items than warp slots (one image, a few centres): one warp per item finishes sooner than 4 items per warp
+    const bool per_item = force ? force[0] == 'i' : items <= 24LL * kSMs;
+    if (p.rc.keys) {
+        DAS_CUDA_CHECK(launch_chain(refine_sparse_kernel<8, 4, 3, true, true>, dim3(kSMs * 3), dim3(RS_WARPS * 32), 0, st, cx.pdl, p));
+    } else if (per_item) {
+        DAS_CUDA_CHECK(launch_chain(refine_sparse_kernel<8, 4, 3, true, false>, dim3(kSMs * 3), dim3(RS_WARPS * 32), 0, st, cx.pdl, p));
+    } else {
         static const int nb = std::getenv("DAS_HEADS_NB") ? std::atoi(std::getenv("DAS_HEADS_NB")) : 4;
         const long long tasks = ((items / cfg->num_joints + nb - 1) / nb) * cfg->num_joints;
         const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((tasks + H8_WARPS - 1) / H8_WARPS, (nb == 8 ? 4LL : 5LL) * kSMs)));
-        if (nb == 8) refine_heads8_kernel<8, 4, 8><<<grid, H8_WARPS * 32, 0, st>>>(p);
-        else refine_heads8_kernel<8, 4, 4><<<grid, H8_WARPS * 32, 0, st>>>(p);
+        if (nb == 8) DAS_CUDA_CHECK(launch_chain(refine_heads8_kernel<8, 4, 8>, dim3(grid), dim3(H8_WARPS * 32), 0, st, cx.pdl, p));
+        else DAS_CUDA_CHECK(launch_chain(refine_heads8_kernel<8, 4, 4>, dim3(grid), dim3(H8_WARPS * 32), 0, st, cx.pdl, p));
     }
     DAS_CUDA_CHECK(cudaGetLastError());
     return DAS_OK;

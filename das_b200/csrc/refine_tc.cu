@@ -147,6 +147,8 @@ refine_tc2_kernel(const TcParams p) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long kernel_t0 = (PROF ? clock64() : 0ll);
+    pdl_wait();          // the row lists and their counters come from das_refine_heads
+    pdl_trigger();
     const int J = p.J;
     __shared__ int s_pref[DAS_MAX_JOINTS + 1];      // first tile of every joint (tiles = 128-row chunks of its distinct-row list)
     if (tid == 0) {
@@ -466,6 +468,8 @@ row_cache_kernel(float* urow, const int32_t* joint_count, int row_cap, const Row
 __global__ void __launch_bounds__(256)
 refine_finish_kernel(const TcParams p) {
     const int lane = threadIdx.x & 31;
+    pdl_wait();          // unique_out comes from das_refine_tc
+    pdl_trigger();
     const int J = p.J;
     const int n_items = __ldg(p.n_valid) * J;
     for (int it = blockIdx.x * 8 + (threadIdx.x >> 5); it < n_items; it += gridDim.x * 8) {
@@ -593,8 +597,8 @@ extern "C" int das_refine_tc(const das_levels* d_levels, const das_levels* h_lev
         DAS_CUDA_CHECK(cudaFuncSetAttribute(refine_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
         DAS_CUDA_CHECK(cudaFuncSetAttribute(refine_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
     }
-    if (p.dbg) refine_tc2_kernel<true><<<kSMs, T2_THREADS, T2_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
-    else refine_tc2_kernel<false><<<kSMs, T2_THREADS, T2_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+    if (p.dbg) DAS_CUDA_CHECK(launch_chain(refine_tc2_kernel<true>, dim3(kSMs), dim3(T2_THREADS), T2_SMEM, static_cast<cudaStream_t>(stream), chain_ctx().pdl, p));
+    else DAS_CUDA_CHECK(launch_chain(refine_tc2_kernel<false>, dim3(kSMs), dim3(T2_THREADS), T2_SMEM, static_cast<cudaStream_t>(stream), chain_ctx().pdl, p));
     DAS_CUDA_CHECK(cudaGetLastError());
     return DAS_OK;
 }
@@ -608,7 +612,7 @@ extern "C" int das_refine_finish(const das_levels* h_levels, const das_decode_cf
     TcParams p = tc_params(nullptr, cfg, nullptr, nullptr, cand_slots, scratch, cand_pose, 0);
     const long long items = static_cast<long long>(h_levels->batch) * cand_slots * cfg->num_joints;
     const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((items + 7) / 8, 8LL * kSMs)));
-    refine_finish_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    DAS_CUDA_CHECK(launch_chain(refine_finish_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), chain_ctx().pdl, p));
     DAS_CUDA_CHECK(cudaGetLastError());
     return DAS_OK;
 }

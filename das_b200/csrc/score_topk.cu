@@ -84,8 +84,14 @@ __device__ void bitonic_desc(uint64_t* a, int n2) {
 template <typename T>
 __device__ __forceinline__ void score_topk_body(const das_levels* __restrict__ lvp, int nms_pre, int peak,
                                                 float* __restrict__ cand_score, int32_t* __restrict__ cand_index, int cand_slots,
-                                                uint32_t* __restrict__ scratch, int scratch_per_image) {
+                                                uint32_t* __restrict__ scratch, int scratch_per_image, int32_t* __restrict__ zero_counters) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_trigger();       // first kernel of the chain: the phase 1-2 kernel may be scheduled now; it waits for this grid to complete
+    if (zero_counters && blockIdx.x == 0 && threadIdx.x < 2 + DAS_MAX_JOINTS) {
+        // the refinement's work-queue / valid / per-joint row counters of this decode ([2] = peer-store ticket: left alone);
+        // every kernel of the previous decode that read them has completed (stream order)
+        zero_counters[threadIdx.x < 2 ? threadIdx.x : threadIdx.x + 2] = 0;
+    }
     uint64_t* list = reinterpret_cast<uint64_t*>(smem_raw);                       // TK_LIST_CAP
     float* tile = reinterpret_cast<float*>(smem_raw + TK_LIST_CAP * sizeof(uint64_t));  // peak mode only
     __shared__ int red[33];
@@ -372,8 +378,8 @@ template <typename T>
 __global__ void __launch_bounds__(TK_THREADS, 1)
 score_topk_kernel(const das_levels* __restrict__ lvp, int nms_pre, int peak,
                   float* __restrict__ cand_score, int32_t* __restrict__ cand_index, int cand_slots,
-                  uint32_t* __restrict__ scratch, int scratch_per_image) {
-    score_topk_body<T>(lvp, nms_pre, peak, cand_score, cand_index, cand_slots, scratch, scratch_per_image);
+                  uint32_t* __restrict__ scratch, int scratch_per_image, int32_t* __restrict__ zero_counters) {
+    score_topk_body<T>(lvp, nms_pre, peak, cand_score, cand_index, cand_slots, scratch, scratch_per_image, zero_counters);
 }
 
 }  // namespace das
@@ -408,15 +414,16 @@ extern "C" int das_score_topk(const das_levels* d_levels, const das_levels* h_le
     }
     const int grid = h_levels->batch * h_levels->n_levels;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int32_t* zc = chain_ctx().zero_counters;     // inside das_plan's chain: clear the refinement counters here (no memset nodes)
     switch (h_levels->in_dtype) {
         case DAS_DTYPE_F32:
-            score_topk_kernel<float><<<grid, TK_THREADS, smem, st>>>(d_levels, nms_pre, peak, cand_score, cand_index, cand_slots, scratch, per_image);
+            score_topk_kernel<float><<<grid, TK_THREADS, smem, st>>>(d_levels, nms_pre, peak, cand_score, cand_index, cand_slots, scratch, per_image, zc);
             break;
         case DAS_DTYPE_F16:
-            score_topk_kernel<__half><<<grid, TK_THREADS, smem, st>>>(d_levels, nms_pre, peak, cand_score, cand_index, cand_slots, scratch, per_image);
+            score_topk_kernel<__half><<<grid, TK_THREADS, smem, st>>>(d_levels, nms_pre, peak, cand_score, cand_index, cand_slots, scratch, per_image, zc);
             break;
         case DAS_DTYPE_BF16:
-            score_topk_kernel<__nv_bfloat16><<<grid, TK_THREADS, smem, st>>>(d_levels, nms_pre, peak, cand_score, cand_index, cand_slots, scratch, per_image);
+            score_topk_kernel<__nv_bfloat16><<<grid, TK_THREADS, smem, st>>>(d_levels, nms_pre, peak, cand_score, cand_index, cand_slots, scratch, per_image, zc);
             break;
         default:
             set_error("das_score_topk: in_dtype=%d", h_levels->in_dtype);

@@ -394,6 +394,11 @@ class DecodePlan:
             _lib.check(self.lib.das_plan_row_cache_stats(self._plan, arr), "das_plan_row_cache_stats")
         return int(arr[0]), int(arr[1])
 
+    def set_pdl(self, mode: int):
+        """Programmatic dependent launch along the kernel chain: 1 on (latency mode, one decode at a time), 0 off (throughput
+        mode, several decodes in flight on different streams), -1 auto (default: on for decodes too small to fill the GPU)."""
+        _lib.check(self.lib.das_plan_set_pdl(self._plan, int(mode)), "das_plan_set_pdl")
+
     def refine_stats(self):
         """(distinct (cell, joint) feature rows the gathered GEMM multiplied, candidates above score_thr, rows without the
         de-duplication) of the last tensor-core-mode run; synchronises with the device."""

@@ -281,6 +281,11 @@ int das_plan_output_block(const das_plan* plan, void** ptr, int64_t* bytes);
 /* refinement implementation: 0 = fp32 SIMT, 1 = tensor cores 3xTF32 (default when feat_channels = 256 and
  * num_heads = 4), 2 = tensor cores, single TF32 pass (looser accuracy). Call before the first run. */
 int das_plan_set_refine_mode(das_plan* plan, int32_t mode);
+/* Programmatic dependent launch along the decode's kernel chain: 1 = every kernel may be scheduled while its predecessor
+ * still runs and waits on the SM for it (hides launch gaps and ramps: the latency mode, for one decode at a time),
+ * 0 = plain stream order (the throughput mode, for several independent decodes in flight on different streams: waiting
+ * CTAs would take SM resources from them), -1 = auto (default): on when batch * candidate slots * joints <= 24 * 148. */
+int das_plan_set_pdl(das_plan* plan, int32_t mode);
 int das_plan_buffers(const das_plan* plan, das_buffers* out, int32_t* cand_slots, int32_t* out_slots);
 /* Caller-owned output block: the plan writes its out_* buffers into `block` (device memory, 256-B aligned, at least
  * das_plan_output_block() bytes + 256 for the sequence word) instead of its own allocation -- e.g. a slice of one

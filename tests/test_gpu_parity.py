@@ -239,6 +239,35 @@ def test_graph_replay_eager_and_repeat_are_identical():
     assert plan.kernel_launches >= 3 * 5
 
 
+@pytest.mark.parametrize("shape", [(3, 32, 48, 1), (24, 64, 96, 1), (2, 24, 40, 3)], ids=["small", "large", "three_layers"])
+def test_programmatic_dependent_launch_chain_is_bit_identical(shape):
+    """das_plan_set_pdl: with programmatic dependent launch every kernel of the chain is scheduled while its predecessor
+    still runs and waits for it on the device (griddepcontrol.wait); the counters the refinement uses are cleared by the
+    top-k kernel instead of memset nodes.  Eager, graph and repeated replays must equal the plain stream-ordered chain bit
+    for bit -- also for the batched phase 1-2 kernel (large) and with dense layers in between (three_layers)."""
+    B, h, w, L = shape
+    tc = dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)
+    cfg = dataclasses.replace(P, num_layers=L)
+    case = util.make_case(cfg, B, h, w, seed=33)
+    blocks = {}
+    for mode in (0, 1):
+        plan = util.make_plan(case, tc)
+        plan.set_pdl(mode)
+        dl = synth.levels_to(case["levels"], "cuda")
+        plan.bind([dict(cls=lv["cls"], ctr=lv["ctr"], pose=lv["pose_raw"], feats=lv["feats"], scales=lv["scales"]) for lv in dl])
+        plan.set_metas(case["metas"])
+        plan.run(use_graph=False)
+        torch.cuda.synchronize()
+        eager = plan.output_block().clone()
+        for _ in range(4):
+            plan.run(use_graph=True)
+        torch.cuda.synchronize()
+        assert torch.equal(eager, plan.output_block()), f"pdl={mode}: graph replay differs from the eager run"
+        blocks[mode] = eager
+    assert torch.equal(blocks[0], blocks[1])
+    assert int(plan.views_of_block(blocks[1])["out_count"].sum()) > 0
+
+
 def test_host_entry_equals_device_entry():
     tc = dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)
     case = util.make_case(P, 3, 24, 40, seed=41, scales=(1.1, 0.9, 1.05, 0.95))
