@@ -42,12 +42,19 @@ __device__ __forceinline__ void copy_chunk_to_peers(const das_peer_blocks& pe, c
     const int head = min(words, static_cast<int>(((16u - (reinterpret_cast<uintptr_t>(src) & 15u)) & 15u) >> 2));
     const int nvec = (words - head) >> 2;
     const int tail0 = head + (nvec << 2);
-    for (int q = 0; q < pe.n; ++q) {
-        uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(const_cast<uint32_t*>(src)) + pe.delta[q]);
-        for (int i = threadIdx.x; i < nvec; i += NT)
-            reinterpret_cast<uint4*>(dst + head)[i] = __ldcg(reinterpret_cast<const uint4*>(src + head) + i);
-        for (int i = threadIdx.x; i < head; i += NT) dst[i] = __ldcg(src + i);
-        for (int i = tail0 + threadIdx.x; i < words; i += NT) dst[i] = __ldcg(src + i);
+    // every value is loaded once and stored to all peers back to back (independent posted writes over NVLink)
+    auto peer = [&](int q) { return reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(const_cast<uint32_t*>(src)) + pe.delta[q]); };
+    for (int i = threadIdx.x; i < nvec; i += NT) {
+        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(src + head) + i);
+        for (int q = 0; q < pe.n; ++q) reinterpret_cast<uint4*>(peer(q) + head)[i] = v;
+    }
+    for (int i = threadIdx.x; i < head; i += NT) {
+        const uint32_t v = __ldcg(src + i);
+        for (int q = 0; q < pe.n; ++q) peer(q)[i] = v;
+    }
+    for (int i = tail0 + threadIdx.x; i < words; i += NT) {
+        const uint32_t v = __ldcg(src + i);
+        for (int q = 0; q < pe.n; ++q) peer(q)[i] = v;
     }
 }
 
@@ -388,10 +395,13 @@ nms_backproject_kernel(const NmsParams p) {
         copy_chunk_to_peers<NT>(pe, o.out_world + bP * J * 3, 6 * P * J);
         if (pe.seq) {
             // publish: the last CTA to finish bumps the block's sequence number on every peer, after every CTA's stores
-            // have been made visible system-wide -- a consumer on the peer that sees seq == s may read step s's results
-            __threadfence_system();
+            // have been made visible system-wide -- a consumer on the peer that sees seq == s may read step s's results.
+            // ONE system-scope fence per CTA, by the thread that takes the ticket, after the block barrier: the fence is
+            // cumulative over the stores it observed through the barrier (the pattern of cooperative groups' grid sync).
+            // A fence in every thread made this kernel 2x (1 peer) to 3x (7 peers) slower: 13 -> 28 -> 43 us per launch.
             __syncthreads();
             if (tid == 0) {
+                __threadfence_system();
                 const int ticket = atomicAdd(pe.ticket, 1);
                 if (ticket == static_cast<int>(gridDim.x) - 1) {
                     *pe.ticket = 0;
@@ -402,6 +412,38 @@ nms_backproject_kernel(const NmsParams p) {
                         *reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(pe.seq) + pe.delta[q]) = sq;
                 }
             }
+        }
+    }
+}
+
+// Result all-gather as its own small kernel right behind nms_backproject_kernel (the default of das_plan): a few CTAs copy
+// the rank's whole packed block to the same offsets of every peer's gathered buffer -- NVLink P2P stores to IPC-mapped
+// memory, 16 bytes wide, every value loaded once and stored to all peers back to back -- then publish the step's sequence
+// number on every peer behind ONE system-scope fence per CTA (cumulative over the stores observed through the block
+// barrier; the last CTA to take a ticket writes the sequence words).  Measured against the stores fused into the NMS
+// kernel's 64 CTAs: the system-scope fence and the posted stores stretched that kernel from 13 us to 28 us (1 peer) and
+// 43 us (7 peers) ON 64 SMs; here they occupy PUB_CTAS SMs, next to the other streams' kernels.
+constexpr int PUB_CTAS = 16;
+__global__ void __launch_bounds__(256)
+peer_publish_kernel(const das_peer_blocks pe, const uint4* __restrict__ block, int n16) {
+    pdl_wait();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) {
+        const uint4 v = __ldcg(block + i);
+        for (int q = 0; q < pe.n; ++q)
+            reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(const_cast<uint4*>(block)) + pe.delta[q])[i] = v;
+    }
+    if (!pe.seq) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const int ticket = atomicAdd(pe.ticket, 1);
+        if (ticket == static_cast<int>(gridDim.x) - 1) {
+            *pe.ticket = 0;
+            const int sq = *pe.seq + 1;
+            *pe.seq = sq;
+            __threadfence_system();
+            for (int q = 0; q < pe.n; ++q)
+                *reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(pe.seq) + pe.delta[q]) = sq;
         }
     }
 }
@@ -449,5 +491,19 @@ extern "C" int das_nms_backproject_peers(const das_decode_cfg* cfg, int32_t batc
     if (cand_slots <= 32) DAS_CUDA_CHECK(launch_chain(nms_backproject_kernel<256>, dim3(batch), dim3(256), smem, static_cast<cudaStream_t>(stream), chain_ctx().pdl, p));
     else DAS_CUDA_CHECK(launch_chain(nms_backproject_kernel<NM_THREADS>, dim3(batch), dim3(NM_THREADS), smem, static_cast<cudaStream_t>(stream), chain_ctx().pdl, p));
     DAS_CUDA_CHECK(cudaGetLastError());
+    return DAS_OK;
+}
+
+// Copies `bytes` (a multiple of 16, 16-byte aligned) of the rank's packed output block to every peer's copy of it and
+// publishes the sequence word (das_peer_blocks); enqueue right behind das_nms_backproject on the same stream.
+extern "C" int das_peer_publish(const das_peer_blocks* peers, const void* local_block, int64_t bytes, void* stream) {
+    using namespace das;
+    DAS_REQUIRE(peers && local_block, DAS_ERR_ARG, "das_peer_publish: null pointer");
+    DAS_REQUIRE(peers->n >= 0 && peers->n <= DAS_MAX_PEERS, DAS_ERR_ARG, "das_peer_publish: %d peers", peers->n);
+    DAS_REQUIRE(bytes > 0 && (bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(local_block) & 15) == 0, DAS_ERR_ARG,
+                "das_peer_publish: block must be 16-byte aligned and sized");
+    if (peers->n == 0) return DAS_OK;
+    DAS_CUDA_CHECK(launch_chain(peer_publish_kernel, dim3(PUB_CTAS), dim3(256), 0, static_cast<cudaStream_t>(stream), chain_ctx().pdl,
+                                *peers, static_cast<const uint4*>(local_block), static_cast<int>(bytes >> 4)));
     return DAS_OK;
 }

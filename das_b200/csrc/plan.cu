@@ -403,9 +403,16 @@ static int enqueue(das_plan* p, cudaStream_t st, int* n_launch, bool events) {
         DAS_TRY(mark(3));
     }
     DAS_TRY(mark(4));
+    // result all-gather: a small publish kernel behind the NMS kernel (default), or the stores fused into the NMS kernel's
+    // own CTAs (DAS_PEER_FUSED=1; measured slower, see das_peer_publish)
+    static const bool fused_peers = std::getenv("DAS_PEER_FUSED") && std::getenv("DAS_PEER_FUSED")[0] == '1';
     DAS_TRY(das_nms_backproject_peers(&c, p->B, p->CT, p->buf.cand_score, p->buf.cand_pose, p->buf.cand_center, p->d_cam,
-                                      p->buf, p->peers.n > 0 ? &p->peers : nullptr, st));
+                                      p->buf, (p->peers.n > 0 && fused_peers) ? &p->peers : nullptr, st));
     ++n;
+    if (p->peers.n > 0 && !fused_peers) {
+        DAS_TRY(das_peer_publish(&p->peers, p->out_block, static_cast<int64_t>((p->out_block_bytes + 15) & ~static_cast<size_t>(15)), st));
+        ++n;
+    }
     DAS_TRY(mark(5));
     *n_launch = n;
     return DAS_OK;

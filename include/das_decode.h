@@ -248,6 +248,10 @@ int das_nms_backproject_peers(const das_decode_cfg* cfg, int32_t batch, int32_t 
                               const float* cand_score, const float* cand_pose, const float* cand_center,
                               const double* cam, das_buffers out, const das_peer_blocks* peers, void* stream);
 
+/* The same collective as its own small kernel behind das_nms_backproject (what das_plan enqueues): a few CTAs copy
+ * `bytes` (multiple of 16, 16-byte aligned) of the rank's packed block to every peer and publish the sequence word. */
+int das_peer_publish(const das_peer_blocks* peers, const void* local_block, int64_t bytes, void* stream);
+
 /* Repack the four 1x1 convolutions of one RecursiveUpdateLayer (nn.Conv2d weight [O,C] + bias [O],
  * recursive_update.py:171-180) into the joint-major layout the kernels read:
  * dst[j][17][C] rows = {sampling_offset 2*nh, update_weight 3, update_offset_value 3, sampling_conf 3}
