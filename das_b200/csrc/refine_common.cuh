@@ -22,6 +22,15 @@ __device__ __forceinline__ Row<CPL> load_row(const float* __restrict__ base, int
     return r;
 }
 
+// the same lane slice of a row staged in shared memory (conflict-free: consecutive lanes read consecutive 16-byte chunks)
+template <int CPL>
+__device__ __forceinline__ Row<CPL> load_row_smem(const float* base, int lane) {
+    Row<CPL> r;
+#pragma unroll
+    for (int q = 0; q < CPL / 4; ++q) r.v[q] = *reinterpret_cast<const float4*>(base + q * 128 + 4 * lane);
+    return r;
+}
+
 // Packed fp32x2 FMA (sm_100a: one FFMA2 issue slot does two fp32 FMAs). d = a * b + c, lane-wise.
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     unsigned long long ra, rb, rc, rd;
@@ -76,6 +85,16 @@ __device__ __forceinline__ float reduce4_permuted(const float (&a)[4]) {
     c += __shfl_xor_sync(FULL, c, 2);
     c += __shfl_xor_sync(FULL, c, 1);
     return c;
+}
+
+// 2-row variant: lane L accumulated row (k ^ h(L)) into a[k], h(L) = (L >> 4) & 1; returns the total of row h(L).
+__device__ __forceinline__ float reduce2_permuted(const float (&a)[2]) {
+    float b = a[0] + __shfl_xor_sync(FULL, a[1], 16);
+    b += __shfl_xor_sync(FULL, b, 8);
+    b += __shfl_xor_sync(FULL, b, 4);
+    b += __shfl_xor_sync(FULL, b, 2);
+    b += __shfl_xor_sync(FULL, b, 1);
+    return b;
 }
 
 // Projection scratch of a dense layer: four joint-major planes [B][J][HW] inside one allocation of 16 floats per

@@ -355,30 +355,45 @@ constexpr int H8_WARPS = 4;
 template <int NB>
 __device__ __forceinline__ float reduce_nb(const float (&a)[NB]) {
     if constexpr (NB == 8) return reduce8_permuted(a);
-    else return reduce4_permuted(a);
+    else if constexpr (NB == 4) return reduce4_permuted(a);
+    else return reduce2_permuted(a);
 }
 
 template <int CPL, int NH, int NB>
-__global__ void __launch_bounds__(H8_WARPS * 32, NB == 4 ? 5 : 4)     // NB = 4: 96 registers, 20 warps per SM (2 960 task slots: BASELINE config #2 has 2 400 tasks -> one wave)
+__global__ void __launch_bounds__(H8_WARPS * 32, NB == 4 ? 5 : (NB == 2 ? 8 : 4))     // NB = 4: 96 registers, 20 warps per SM (2 960 task slots: BASELINE config #2 has 2 400 tasks -> one wave)
 refine_heads8_kernel(const RefineParams p) {
     static_assert(NH == 4, "32 rows per item = 8 heads x 4 corners");
-    static_assert(NB == 4 || NB == 8, "candidates per task");
+    static_assert(NB == 2 || NB == 4 || NB == 8, "candidates per task");
     constexpr int C = CPL * 32;
     constexpr int NOUT = 2 * NH + 9;
     constexpr int O_GATE = 2 * NH, O_VAL = 2 * NH + 3;
     constexpr int GL = 32 / NB;                        // lanes per candidate
-    constexpr int SH = NB == 8 ? 2 : 3;                // log2(GL)
+    constexpr int SH = NB == 8 ? 2 : (NB == 4 ? 3 : 4); // log2(GL)
+    constexpr int NW = 2 * NH + 6;                     // weight rows phases 1-2 use: S (2*NH), gate 3, value 3
     __shared__ float s_head[H8_WARPS][NB][4 * NH];     // per candidate of the block: hx[2*NH], hy[2*NH]
+    __shared__ __align__(16) float s_w[NW * C];        // this CTA's joint: its weight rows, staged once (the global copies sat
+                                                       // on every task's critical path: ~22 dependent L1 / L2 round trips)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int J = p.J;
+    // A CTA serves ONE joint: blockIdx = j * cpj + g; its warps walk the candidate blocks g*H8_WARPS + warp, + cpj*H8_WARPS, ..
+    const int cpj = gridDim.x / J;
+    const int j = blockIdx.x / cpj, g = blockIdx.x - j * cpj;
+    if (j >= J) return;
+    {
+        // weights are static: staged BEFORE the dependency wait, so the copy overlaps the predecessor kernel's tail
+        const float* __restrict__ Wsrc = p.wpack + static_cast<size_t>(j) * NOUT * C;
+        for (int c = threadIdx.x; c < NW * C / 4; c += H8_WARPS * 32)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(s_w + 4 * c))), "l"(Wsrc + 4 * c) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     pdl_wait();          // candidates (and, for L > 1, the dense layers' maps) come from the kernels in front of this one
     pdl_trigger();
     const int r = (lane >> SH) & (NB - 1);             // candidate of the block this lane's group owns
     const das_levels* __restrict__ lvp = p.lv;
     const int nl = lvp->n_levels;
-    const int J = p.J;
     const int n_cand = p.n_items / J;
     const int n_blocks = (n_cand + NB - 1) / NB;
-    const int n_tasks = n_blocks * J;
+    bool weights_ready = false;
 
     auto level_of = [&](int slot) {
         int l = 0, s0 = 0;
@@ -390,15 +405,15 @@ refine_heads8_kernel(const RefineParams p) {
         return l;
     };
 
-    // static round-robin hand-out (a ticket counter would put one more global round trip in front of every task)
-    for (int task = blockIdx.x * H8_WARPS + warp; task < n_tasks; task += gridDim.x * H8_WARPS) {
-        const int j = task / n_blocks, cb = task - j * n_blocks;
+    // static hand-out (a ticket counter would put one more global round trip in front of every task).  The trip count is
+    // CTA-uniform, so the one block barrier behind the weight copy is reached by every warp.
+    const int trips = (n_blocks - g * H8_WARPS + cpj * H8_WARPS - 1) / (cpj * H8_WARPS);
+    for (int t = 0; t < trips; ++t) {
+        const int cb = g * H8_WARPS + warp + t * cpj * H8_WARPS;
         const int cs = cb * NB + r;
-        bool valid = cs < n_cand;
+        bool valid = cb < n_blocks && cs < n_cand;
         if (valid && p.score_thr > 0.f && !(__ldg(p.cand_score + cs) > p.score_thr)) valid = false;   // dropped by das_head.py:763-769 later
         const unsigned vmask = __ballot_sync(FULL, valid);
-        if (vmask == 0u) continue;
-        const float* __restrict__ Wj = p.wpack + static_cast<size_t>(j) * NOUT * C;
         const float* __restrict__ Bj = p.wpack + static_cast<size_t>(J) * NOUT * C + j * NOUT;
 
         // ---- this group's candidate ------------------------------------------------------------------------------
@@ -432,10 +447,15 @@ refine_heads8_kernel(const RefineParams p) {
                 const float* src = reinterpret_cast<const float*>(__shfl_xor_sync(FULL, reinterpret_cast<unsigned long long>(own), k << SH));
                 f[k] = load_row<CPL>(src ? src : p.wpack, lane, src != nullptr);
             }
+            if (!weights_ready) {                         // first trip: the joint's weight rows have landed for the whole CTA
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncthreads();
+                weights_ready = true;
+            }
             float res[2 * NH + 6];
 #pragma unroll
             for (int o = 0; o < 2 * NH + 6; ++o) {
-                const Row<CPL> w = load_row<CPL>(Wj + o * C, lane, true);
+                const Row<CPL> w = load_row_smem<CPL>(s_w + o * C, lane);
                 float acc[NB];
 #pragma unroll
                 for (int k = 0; k < NB; ++k) acc[k] = dot_row<CPL>(f[k], w);
@@ -449,6 +469,8 @@ refine_heads8_kernel(const RefineParams p) {
                 O[k] = __fadd_rn(__fmul_rn(1.0f - g, prev[k]), __fmul_rn(g, res[O_VAL + k]));
             }
         }
+
+        if (vmask == 0u) continue;         // nothing above score_thr in this block (after the CTA-wide barrier of the first trip)
 
         // ---- phase 2: sampling offsets read bilinearly at t = p + O.xy -------------------------------------------
         {
@@ -469,7 +491,7 @@ refine_heads8_kernel(const RefineParams p) {
                 const float* mine = cptr[lane & 3];
                 if (mine) {
 #pragma unroll
-                    for (int q = (lane >> 2) & (GL / 4 > 1 ? 1 : 0); q < C * 4 / 128; q += (GL / 4 > 1 ? 2 : 1))
+                    for (int q = (lane >> 2) & (GL / 4 - 1); q < C * 4 / 128; q += GL / 4)
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(mine + q * 32));
                 }
             }
@@ -496,7 +518,7 @@ refine_heads8_kernel(const RefineParams p) {
             float st[2 * NH];
 #pragma unroll
             for (int o = 0; o < 2 * NH; ++o) {
-                const Row<CPL> w = load_row<CPL>(Wj + o * C, lane, true);
+                const Row<CPL> w = load_row_smem<CPL>(s_w + o * C, lane);
                 float acc[NB];
 #pragma unroll
                 for (int k = 0; k < NB; ++k) acc[k] = dot_row<CPL>(fi[k], w);
@@ -521,6 +543,7 @@ refine_heads8_kernel(const RefineParams p) {
         float r_w[NB], r_hx[NB], r_hy[NB];
         unsigned r_lead[NB];                          // leader lanes of the item's distinct cells
         int m_idx[NB], m_b[NB], m_l[NB];
+        float r_pv[NB][3];                            // leaders: previous offset (u, v, d) at their cell
         int total_u = 0;
 #pragma unroll
         for (int rr = 0; rr < NB; ++rr) {
@@ -548,6 +571,18 @@ refine_heads8_kernel(const RefineParams p) {
             r_lead[rr] = lead_mask;
             r_g[rr] = ok ? total_u + u_of_leader : -1;
             total_u += __popc(lead_mask);
+            // the leaders' previous offsets: requested now, so the loads fly while the reservation below makes its round trip
+            r_pv[rr][0] = r_pv[rr][1] = r_pv[rr][2] = 0.f;
+            if ((lead_mask >> lane) & 1u) {
+                const int HW2 = H2 * W2;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (p.prev_uvd) r_pv[rr][k] = __ldg(p.prev_uvd[m_l[rr]] + ((static_cast<size_t>(m_b[rr]) * J + j) * HW2 + pix) * 4 + k);
+                    else if (!(k == 2 && j == p.root))
+                        r_pv[rr][k] = InMap(d2.pose, lvp->in_dtype)((static_cast<size_t>(m_b[rr]) * (3 + 6 * J) + 3 + 3 * j + k) * HW2 + pix) *
+                                      (k < 2 ? d2.scale_uv : d2.scale_d);
+                }
+            }
         }
         int base = 0;
         if (lane == 0 && total_u) base = atomicAdd(p.work_counter + 4 + j, total_u);
@@ -566,18 +601,10 @@ refine_heads8_kernel(const RefineParams p) {
             const size_t pb2 = static_cast<size_t>(b2) * (3 + 6 * J) * HW2;
             const int pix = r_pix[rr];
             if ((r_lead[rr] >> lane) & 1u) {
-                const float* __restrict__ prev2 = p.prev_uvd ? p.prev_uvd[m_l[rr]] + (static_cast<size_t>(b2) * J + j) * HW2 * 4 : nullptr;
-                float pv[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    if (prev2) pv[k] = __ldg(prev2 + static_cast<size_t>(pix) * 4 + k);
-                    else if (k == 2 && j == p.root) pv[k] = 0.f;
-                    else pv[k] = pose2(pb2 + static_cast<size_t>(3 + 3 * j + k) * HW2 + pix) * (k < 2 ? d2.scale_uv : d2.scale_d);
-                }
                 const unsigned long long pb = reinterpret_cast<unsigned long long>(d2.feats[p.layer] + (static_cast<size_t>(b2) * HW2 + pix) * C);
                 float4* dst = reinterpret_cast<float4*>(p.urow + (static_cast<size_t>(j) * p.row_cap + base + r_g[rr]) * 8);
-                dst[0] = make_float4(__uint_as_float(static_cast<unsigned>(pb)), __uint_as_float(static_cast<unsigned>(pb >> 32)), pv[0], pv[1]);
-                dst[1] = make_float4(pv[2], 0.f, 0.f, 0.f);
+                dst[0] = make_float4(__uint_as_float(static_cast<unsigned>(pb)), __uint_as_float(static_cast<unsigned>(pb >> 32)), r_pv[rr][0], r_pv[rr][1]);
+                dst[1] = make_float4(r_pv[rr][2], 0.f, 0.f, 0.f);
             }
             reinterpret_cast<float4*>(p.lrow)[static_cast<size_t>(item) * 32 + lane] =
                 make_float4(__int_as_float(pix >= 0 ? base + r_g[rr] : -1), r_w[rr], r_hx[rr], r_hy[rr]);
@@ -804,9 +831,13 @@ extern "C" int das_refine_heads(const das_levels* d_levels, const das_levels* h_
         DAS_CUDA_CHECK(launch_chain(refine_sparse_kernel<8, 4, 3, true, false>, dim3(kSMs * 3), dim3(RS_WARPS * 32), 0, st, cx.pdl, p));
     } else {
         static const int nb = std::getenv("DAS_HEADS_NB") ? std::atoi(std::getenv("DAS_HEADS_NB")) : 4;
-        const long long tasks = ((items / cfg->num_joints + nb - 1) / nb) * cfg->num_joints;
-        const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((tasks + H8_WARPS - 1) / H8_WARPS, (nb == 8 ? 4LL : 5LL) * kSMs)));
+        // grid = J x cpj CTAs: CTA (j, g) serves joint j, its H8_WARPS warps walk candidate blocks g*H8_WARPS + warp, + cpj*H8_WARPS, ...
+        const long long n_blocks = (items / cfg->num_joints + nb - 1) / nb;
+        const long long cap = std::max<long long>(1, ((nb == 8 ? 4LL : (nb == 2 ? 8LL : 5LL)) * kSMs) / cfg->num_joints);
+        const int cpj = static_cast<int>(std::max<long long>(1, std::min<long long>((n_blocks + H8_WARPS - 1) / H8_WARPS, cap)));
+        const int grid = cpj * cfg->num_joints;
         if (nb == 8) DAS_CUDA_CHECK(launch_chain(refine_heads8_kernel<8, 4, 8>, dim3(grid), dim3(H8_WARPS * 32), 0, st, cx.pdl, p));
+        else if (nb == 2) DAS_CUDA_CHECK(launch_chain(refine_heads8_kernel<8, 4, 2>, dim3(grid), dim3(H8_WARPS * 32), 0, st, cx.pdl, p));
         else DAS_CUDA_CHECK(launch_chain(refine_heads8_kernel<8, 4, 4>, dim3(grid), dim3(H8_WARPS * 32), 0, st, cx.pdl, p));
     }
     DAS_CUDA_CHECK(cudaGetLastError());
