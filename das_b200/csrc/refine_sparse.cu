@@ -538,28 +538,33 @@ refine_heads8_kernel(const RefineParams p) {
         __syncwarp();
 
         // ---- row records: lane = (head = lane >> 2, corner = lane & 3) of one candidate at a time -----------------
+        // Straight-line over the NB candidates (validity is a predicate, not a branch) so that their dependent chains --
+        // coordinate chain, match, loads -- interleave; everything the owner group already knows about its candidate
+        // (cell, map size, reciprocals) arrives by shuffle instead of being recomputed (an integer division and two
+        // reciprocals per candidate sat on the critical path: 37 % of the kernel's stall samples were in this pass).
         // pass 1: every candidate's sampled cells and their de-duplication inside the item (registers)
         int r_pix[NB], r_g[NB];                       // cell index (-1 = outside the map), position among the item's distinct cells
         float r_w[NB], r_hx[NB], r_hy[NB];
         unsigned r_lead[NB];                          // leader lanes of the item's distinct cells
-        int m_idx[NB], m_b[NB], m_l[NB];
+        int m_idx[NB], m_b[NB], m_l[NB], m_W[NB], m_HW[NB];
         float r_pv[NB][3];                            // leaders: previous offset (u, v, d) at their cell
         int total_u = 0;
 #pragma unroll
         for (int rr = 0; rr < NB; ++rr) {
-            m_idx[rr] = __shfl_sync(FULL, idx, rr * GL);
-            m_b[rr] = __shfl_sync(FULL, b, rr * GL);
-            m_l[rr] = __shfl_sync(FULL, l, rr * GL);
-            r_pix[rr] = -1; r_g[rr] = -1; r_w[rr] = 0.f; r_hx[rr] = 0.f; r_hy[rr] = 0.f; r_lead[rr] = 0u;
-            if (!((vmask >> (rr * GL)) & 1u)) continue;
+            const int src = rr * GL;
+            const bool v = (vmask >> src) & 1u;
+            m_idx[rr] = __shfl_sync(FULL, idx, src);
+            m_b[rr] = __shfl_sync(FULL, b, src);
+            m_l[rr] = __shfl_sync(FULL, l, src);
+            const int x2 = __shfl_sync(FULL, x, src), y2 = __shfl_sync(FULL, y, src);
+            const int W2 = __shfl_sync(FULL, W, src), H2 = __shfl_sync(FULL, H, src);
+            const float rW2 = __shfl_sync(FULL, rW, src), rH2 = __shfl_sync(FULL, rH, src);
+            m_W[rr] = W2; m_HW[rr] = H2 * W2;
             const das_level_desc& d2 = lvp->lv[m_l[rr]];
-            const int H2 = d2.H, W2 = d2.W;
-            const int y2 = m_idx[rr] / W2, x2 = m_idx[rr] - y2 * W2;
-            const float fW2 = static_cast<float>(W2), fH2 = static_cast<float>(H2);
             const int h = lane >> 2, ck2 = lane & 3;
             const float hxv = s_head[warp][rr][h], hyv = s_head[warp][rr][2 * NH + h];
-            const Corner c = make_corner(sample_coord(x2, hxv, fW2, __frcp_rn(fW2)), sample_coord(y2, hyv, fH2, __frcp_rn(fH2)), W2, H2);
-            const bool ok = corner_ok(c, ck2, W2, H2);
+            const Corner c = make_corner(sample_coord(x2, hxv, static_cast<float>(W2), rW2), sample_coord(y2, hyv, static_cast<float>(H2), rH2), W2, H2);
+            const bool ok = v && corner_ok(c, ck2, W2, H2);
             const int pix = ok ? corner_pix(c, ck2, W2) : -1;
             // one entry per DISTINCT sampled cell in the joint's row list (see the warp-per-item kernel above)
             const unsigned same = __match_any_sync(FULL, pix);
@@ -572,16 +577,18 @@ refine_heads8_kernel(const RefineParams p) {
             r_g[rr] = ok ? total_u + u_of_leader : -1;
             total_u += __popc(lead_mask);
             // the leaders' previous offsets: requested now, so the loads fly while the reservation below makes its round trip
-            r_pv[rr][0] = r_pv[rr][1] = r_pv[rr][2] = 0.f;
-            if ((lead_mask >> lane) & 1u) {
-                const int HW2 = H2 * W2;
+            const bool lead = (lead_mask >> lane) & 1u;
+            const int pixs = lead ? pix : 0;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    if (p.prev_uvd) r_pv[rr][k] = __ldg(p.prev_uvd[m_l[rr]] + ((static_cast<size_t>(m_b[rr]) * J + j) * HW2 + pix) * 4 + k);
-                    else if (!(k == 2 && j == p.root))
-                        r_pv[rr][k] = InMap(d2.pose, lvp->in_dtype)((static_cast<size_t>(m_b[rr]) * (3 + 6 * J) + 3 + 3 * j + k) * HW2 + pix) *
-                                      (k < 2 ? d2.scale_uv : d2.scale_d);
+            for (int k = 0; k < 3; ++k) {
+                float pv = 0.f;
+                if (p.prev_uvd) {
+                    if (lead) pv = __ldg(p.prev_uvd[m_l[rr]] + ((static_cast<size_t>(m_b[rr]) * J + j) * m_HW[rr] + pixs) * 4 + k);
+                } else if (!(k == 2 && j == p.root)) {
+                    if (lead) pv = InMap(d2.pose, lvp->in_dtype)((static_cast<size_t>(m_b[rr]) * (3 + 6 * J) + 3 + 3 * j + k) * m_HW[rr] + pixs) *
+                                   (k < 2 ? d2.scale_uv : d2.scale_d);
                 }
+                r_pv[rr][k] = pv;
             }
         }
         int base = 0;
@@ -590,26 +597,28 @@ refine_heads8_kernel(const RefineParams p) {
         // pass 2: the records
 #pragma unroll
         for (int rr = 0; rr < NB; ++rr) {
-            if (!((vmask >> (rr * GL)) & 1u)) continue;
+            const bool v = (vmask >> (rr * GL)) & 1u;
             const int cs2 = cb * NB + rr;
             const int item = cs2 * J + j;
             const int b2 = m_b[rr];
             const das_level_desc& d2 = lvp->lv[m_l[rr]];
-            const int W2 = d2.W, HW2 = d2.H * W2;
+            const int W2 = m_W[rr], HW2 = m_HW[rr];
             const int idx2 = m_idx[rr];
-            const InMap pose2(d2.pose, lvp->in_dtype);
-            const size_t pb2 = static_cast<size_t>(b2) * (3 + 6 * J) * HW2;
             const int pix = r_pix[rr];
-            if ((r_lead[rr] >> lane) & 1u) {
+            if (v && ((r_lead[rr] >> lane) & 1u)) {
                 const unsigned long long pb = reinterpret_cast<unsigned long long>(d2.feats[p.layer] + (static_cast<size_t>(b2) * HW2 + pix) * C);
                 float4* dst = reinterpret_cast<float4*>(p.urow + (static_cast<size_t>(j) * p.row_cap + base + r_g[rr]) * 8);
                 dst[0] = make_float4(__uint_as_float(static_cast<unsigned>(pb)), __uint_as_float(static_cast<unsigned>(pb >> 32)), r_pv[rr][0], r_pv[rr][1]);
                 dst[1] = make_float4(r_pv[rr][2], 0.f, 0.f, 0.f);
             }
-            reinterpret_cast<float4*>(p.lrow)[static_cast<size_t>(item) * 32 + lane] =
-                make_float4(__int_as_float(pix >= 0 ? base + r_g[rr] : -1), r_w[rr], r_hx[rr], r_hy[rr]);
-            if (lane == 0) {
-                // eval-tail / assembly inputs of this item (das_head.py:254-262, 725-743), and the centre for joint 0
+            if (v)
+                reinterpret_cast<float4*>(p.lrow)[static_cast<size_t>(item) * 32 + lane] =
+                    make_float4(__int_as_float(pix >= 0 ? base + r_g[rr] : -1), r_w[rr], r_hx[rr], r_hy[rr]);
+            if (v && lane == rr) {
+                // eval-tail / assembly inputs of this item (das_head.py:254-262, 725-743), and the centre for joint 0;
+                // lane rr takes candidate rr, so the NB assembly records are written side by side, not one after the other
+                const InMap pose2(d2.pose, lvp->in_dtype);
+                const size_t pb2 = static_cast<size_t>(b2) * (3 + 6 * J) * HW2;
                 const int y2 = idx2 / W2, x2 = idx2 - y2 * W2;
                 const float sx = __ldg(p.scale_xy + 2 * b2), sy = __ldg(p.scale_xy + 2 * b2 + 1);
                 const float qf = sqrtf(sx * sy);
