@@ -137,6 +137,7 @@ SIGNATURES = {
     "das_plan_refine_stats": (C.c_int, [_VP, C.POINTER(C.c_int64)]),
     "das_plan_set_pdl": (C.c_int, [_VP, C.c_int32]),
     "das_peer_publish": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
+    "das_plan_publish_wait": (C.c_int, [_VP, _VP]),
 }
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libdas_decode.so")

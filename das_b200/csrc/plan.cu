@@ -66,6 +66,11 @@ struct das_plan {
     cudaGraphExec_t exec_prof = nullptr;   // same graph with event-record nodes between the stages
     cudaEvent_t ev[DAS_NUM_STAGES + 1] = {};
     cudaStream_t cap_stream = nullptr;   // capture happens here (the caller's stream may be the legacy default stream)
+    // result all-gather (peers.n > 0): the publish kernel runs on the plan's own side stream behind the decode, so the
+    // caller's stream can start its next decode while the NVLink stores and the system-scope fences are in flight
+    cudaStream_t pub_stream = nullptr;
+    cudaEvent_t ev_decoded = nullptr, ev_published = nullptr;
+    bool pub_pending = false;
     int64_t launches = 0;
     int launches_per_run = 0;
 };
@@ -238,6 +243,9 @@ extern "C" void das_plan_destroy(das_plan* p) {
     if (!p) return;
     if (p->exec) cudaGraphExecDestroy(p->exec);
     if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
+    if (p->pub_stream) cudaStreamDestroy(p->pub_stream);
+    if (p->ev_decoded) cudaEventDestroy(p->ev_decoded);
+    if (p->ev_published) cudaEventDestroy(p->ev_published);
     if (p->exec_prof) cudaGraphExecDestroy(p->exec_prof);
     for (cudaEvent_t e : p->ev) if (e) cudaEventDestroy(e);
     void* ptrs[] = {p->d_levels, p->buf.cand_score, p->buf.cand_index, p->buf.cand_pose, p->buf.cand_center,
@@ -334,6 +342,15 @@ struct ChainScope {
     ~ChainScope() { das::chain_ctx() = saved; }
 };
 
+static bool peer_inline() {
+    static const bool v = std::getenv("DAS_PEER_INLINE") && std::getenv("DAS_PEER_INLINE")[0] == '1';
+    return v;
+}
+static bool peer_fused() {
+    static const bool v = std::getenv("DAS_PEER_FUSED") && std::getenv("DAS_PEER_FUSED")[0] == '1';
+    return v;
+}
+
 static int enqueue(das_plan* p, cudaStream_t st, int* n_launch, bool events) {
     const das_decode_cfg& c = p->cfg;
     int n = 0;
@@ -405,11 +422,13 @@ static int enqueue(das_plan* p, cudaStream_t st, int* n_launch, bool events) {
     DAS_TRY(mark(4));
     // result all-gather: a small publish kernel behind the NMS kernel (default), or the stores fused into the NMS kernel's
     // own CTAs (DAS_PEER_FUSED=1; measured slower, see das_peer_publish)
-    static const bool fused_peers = std::getenv("DAS_PEER_FUSED") && std::getenv("DAS_PEER_FUSED")[0] == '1';
+    const bool fused_peers = peer_fused();
     DAS_TRY(das_nms_backproject_peers(&c, p->B, p->CT, p->buf.cand_score, p->buf.cand_pose, p->buf.cand_center, p->d_cam,
                                       p->buf, (p->peers.n > 0 && fused_peers) ? &p->peers : nullptr, st));
     ++n;
-    if (p->peers.n > 0 && !fused_peers) {
+    // DAS_PEER_INLINE=1: the publish kernel as the last node of the chain (the next decode on this stream waits for its NVLink
+    // round trips: +3.9 us per step at N = 2); default: on the plan's side stream, see das_plan_run
+    if (p->peers.n > 0 && !fused_peers && peer_inline()) {
         DAS_TRY(das_peer_publish(&p->peers, p->out_block, static_cast<int64_t>((p->out_block_bytes + 15) & ~static_cast<size_t>(15)), st));
         ++n;
     }
@@ -450,6 +469,29 @@ extern "C" int das_plan_run(das_plan* p, void* stream, int32_t mode) {
         }
         for (cudaEvent_t& e : p->ev) DAS_CUDA_CHECK(cudaEventCreate(&e));
     }
+    const bool side_publish = p->peers.n > 0 && !peer_fused() && !peer_inline();
+    if (side_publish && p->pub_pending) {
+        // the previous publish of THIS plan has read the output block this decode is about to overwrite (long done in practice)
+        DAS_CUDA_CHECK(cudaStreamWaitEvent(st, p->ev_published, 0));
+    }
+    struct Publish {          // enqueued behind whatever decode this call launches, on every return path
+        das_plan* p; cudaStream_t st; bool on;
+        int go() {
+            if (!on) return DAS_OK;
+            if (!p->pub_stream) {
+                DAS_CUDA_CHECK(cudaStreamCreateWithFlags(&p->pub_stream, cudaStreamNonBlocking));
+                DAS_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_decoded, cudaEventDisableTiming));
+                DAS_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_published, cudaEventDisableTiming));
+            }
+            DAS_CUDA_CHECK(cudaEventRecord(p->ev_decoded, st));
+            DAS_CUDA_CHECK(cudaStreamWaitEvent(p->pub_stream, p->ev_decoded, 0));
+            DAS_TRY(das_peer_publish(&p->peers, p->out_block, static_cast<int64_t>((p->out_block_bytes + 15) & ~static_cast<size_t>(15)), p->pub_stream));
+            DAS_CUDA_CHECK(cudaEventRecord(p->ev_published, p->pub_stream));
+            p->pub_pending = true;
+            p->launches += 1;
+            return DAS_OK;
+        }
+    } publish{p, st, side_publish};
     if (mode == 0 || p->launches == 0) {
         // the very first run is always eager (module loading and cudaFuncSetAttribute must not land inside a capture);
         // the graph is captured by the next call, so no call runs the decode twice
@@ -457,13 +499,22 @@ extern "C" int das_plan_run(das_plan* p, void* stream, int32_t mode) {
         DAS_TRY(enqueue(p, st, &n, false));
         p->launches_per_run = n;
         p->launches += n;
-        if (mode != 2) return DAS_OK;
+        if (mode != 2) return publish.go();
         DAS_CUDA_CHECK(cudaStreamSynchronize(st));      // profiling replay requested on a fresh plan: capture right away
     }
     cudaGraphExec_t* ex = (mode == 2) ? &p->exec_prof : &p->exec;
     if (!*ex) DAS_TRY(capture(p, ex, mode == 2));
     DAS_CUDA_CHECK(cudaGraphLaunch(*ex, st));
     p->launches += p->launches_per_run;
+    return publish.go();
+}
+
+// Makes `stream` wait until the plan's last result publication to its peers (das_plan_set_peer_blocks) has been issued and
+// completed on the plan's side stream; a no-op without peers.  Call it where the caller needs "every peer has my results".
+extern "C" int das_plan_publish_wait(das_plan* p, void* stream) {
+    using namespace das;
+    DAS_REQUIRE(p, DAS_ERR_ARG, "null plan");
+    if (p->pub_pending) DAS_CUDA_CHECK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), p->ev_published, 0));
     return DAS_OK;
 }
 

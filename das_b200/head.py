@@ -394,6 +394,13 @@ class DecodePlan:
             _lib.check(self.lib.das_plan_row_cache_stats(self._plan, arr), "das_plan_row_cache_stats")
         return int(arr[0]), int(arr[1])
 
+    def publish_wait(self, stream=None):
+        """Make `stream` (a raw cudaStream_t value; default: the current stream) wait until the plan's last result
+        publication to its peers has completed (no-op without peer blocks)."""
+        sp = _stream_ptr(self.device) if stream is None else C.c_void_p(stream)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.das_plan_publish_wait(self._plan, sp), "das_plan_publish_wait")
+
     def set_pdl(self, mode: int):
         """Programmatic dependent launch along the kernel chain: 1 on (latency mode, one decode at a time), 0 off (throughput
         mode, several decodes in flight on different streams), -1 auto (default: on for decodes too small to fill the GPU)."""

@@ -300,6 +300,11 @@ int das_plan_set_output_block(das_plan* plan, void* block, int64_t bytes);
  * peer q's gathered buffer, same layout as the local block.  n_peers == 0 switches it off.  With it on, the local
  * block carries a sequence word right behind the packed outputs (offset das_plan_output_block() bytes, int32). */
 int das_plan_set_peer_blocks(das_plan* plan, int32_t n_peers, void* const* peer_blocks);
+/* With peer blocks set, das_plan_run enqueues the publication (das_peer_publish) on a side stream of the plan behind the
+ * decode, so `stream` is free for the next decode while the NVLink stores are in flight; the plan's own next run waits for
+ * it before overwriting the block.  das_plan_publish_wait makes `stream` wait for the last publication (no-op without
+ * peers). */
+int das_plan_publish_wait(das_plan* plan, void* stream);
 /* Device memory that other processes on the box can map (cudaIpc*): das_ipc_alloc on the owner, the 64-byte handle is
  * sent to the peers through any host channel, das_ipc_open on each peer (enables peer access), das_ipc_close there,
  * das_ipc_free on the owner. */
