@@ -151,3 +151,45 @@ def test_pack_metas_fast_and_general_paths_agree():
     assert c2[2].tolist() == [1, 0, 0, 0, 1, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0]
     two_by_three = [dict(m, cam=dict(K=m["cam"]["K"][:2], R=m["cam"]["R"], t=m["cam"]["t"])) for m in metas]   # MuPoTS K is 2x3
     assert np.array_equal(DecodePlan.pack_metas(two_by_three)[1], c1)
+
+
+def test_head_maps_keep_half_precision_and_upcast_mixed_inputs():
+    """fp16 / bf16 head outputs go to the kernels as they are (das_levels.in_dtype, read natively); anything mixed or
+    exotic is up-cast to fp32 like mmcv's force_fp32 would (das_head.py:180,218 is the reference's fp16 mode)."""
+    mk = lambda dt: [torch.zeros(2, 1, 4, 6, dtype=dt)]
+    for dt in (torch.float32, torch.float16, torch.bfloat16):
+        c, r, p = H._head_maps(mk(dt), mk(dt), [torch.zeros(2, 93, 4, 6, dtype=dt)])
+        assert c[0].dtype == r[0].dtype == p[0].dtype == dt
+    c, r, p = H._head_maps(mk(torch.float16), mk(torch.float32), [torch.zeros(2, 93, 4, 6, dtype=torch.float16)])
+    assert c[0].dtype == r[0].dtype == p[0].dtype == torch.float32
+    c, r, p = H._head_maps(mk(torch.float64), mk(torch.float64), [torch.zeros(2, 93, 4, 6, dtype=torch.float64)])
+    assert c[0].dtype == torch.float32
+    from das_b200 import _lib
+    assert (_lib.DTYPE_F32, _lib.DTYPE_F16, _lib.DTYPE_BF16) == (0, 1, 2)          # include/das_decode.h: DAS_DTYPE_*
+    import re, os
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "das_decode.h")).read()
+    for name, val in (("DAS_DTYPE_F32", 0), ("DAS_DTYPE_F16", 1), ("DAS_DTYPE_BF16", 2)):
+        assert re.search(r"#define\s+%s\s+%d\b" % (name, val), hdr)
+
+
+def test_bench_rank_pinning_gives_disjoint_core_slices():
+    """bench.pin_rank_to_cores: every rank of a node gets its own slice of the allowed cores (and the call never raises)."""
+    import importlib.util, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    before = os.sched_getaffinity(0)
+    try:
+        world = min(4, max(1, len(before)))
+        slices = []
+        for r in range(world):
+            os.sched_setaffinity(0, before)
+            info = bench.pin_rank_to_cores(r, world)
+            assert "error" not in info, info
+            slices.append(frozenset(os.sched_getaffinity(0)))
+        assert all(s and s <= before for s in slices)
+        if len(before) >= world:
+            assert all(a.isdisjoint(b) for i, a in enumerate(slices) for b in slices[i + 1:])
+    finally:
+        os.sched_setaffinity(0, before)
