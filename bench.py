@@ -956,8 +956,9 @@ def main():
                          "region repeats them until --min-seconds have passed")
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--input-sets", type=int, default=4)
-    ap.add_argument("--streams", type=int, default=4, help="independent batches in flight (<= input sets); 3/3: 750 k, 4/4: 778 k, 6/6: 769 k images/s")
+    ap.add_argument("--input-sets", type=int, default=6)
+    ap.add_argument("--streams", type=int, default=6,
+                    help="independent batches in flight (<= input sets); round 2: 3/6: 1.10 M, 4/4: 1.15 M, 6/6: 1.19 M, 8/8: 1.18 M images/s")
     ap.add_argument("--profile-region", action="store_true", help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
