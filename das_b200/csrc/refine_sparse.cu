@@ -797,6 +797,14 @@ extern "C" int das_gather_refine_assemble(const das_levels* d_levels, const das_
 // that point into it (scratch->row_records), the item's assembly record (scratch->item_records) and, for joint 0, the
 // centre and the candidate's entry in valid_list.  counters: [0] work-queue head, [1] number of valid candidates,
 // [4 + j] distinct rows of joint j.
+static int g_heads_force = 0;
+// diagnostics: 0 = automatic choice, 1 = warp-per-item kernel, 2 = batched kernel (process-wide; for tests and A/B timing)
+extern "C" int das_debug_force_heads_kernel(int32_t mode) {
+    if (mode < 0 || mode > 2) return DAS_ERR_ARG;
+    g_heads_force = mode;
+    return DAS_OK;
+}
+
 extern "C" int das_refine_heads(const das_levels* d_levels, const das_levels* h_levels, const das_decode_cfg* cfg,
                                 const float* weights, const float* const* prev_uvd, const float* scale_xy,
                                 const float* cand_score, const int32_t* cand_index, int32_t cand_slots,
@@ -830,10 +838,11 @@ extern "C" int das_refine_heads(const das_levels* d_levels, const das_levels* h_
         DAS_CUDA_CHECK(cudaMemsetAsync(scratch->counters, 0, 2 * sizeof(int32_t), st));
         DAS_CUDA_CHECK(cudaMemsetAsync(scratch->counters + 4, 0, DAS_MAX_JOINTS * sizeof(int32_t), st));
     }
-    // DAS_HEADS_KERNEL=item / =batch forces one of the two kernels (A/B timing, parity tests)
-    static const char* force = std::getenv("DAS_HEADS_KERNEL");
+    // DAS_HEADS_KERNEL=item / =batch, or das_debug_force_heads_kernel(), forces one of the two kernels (A/B timing, parity tests)
+    static const char* force_env = std::getenv("DAS_HEADS_KERNEL");
+    const int force = g_heads_force ? g_heads_force : (force_env ? (force_env[0] == 'i' ? 1 : 2) : 0);
     // fewer items than warp slots (one image, a few centres): one warp per item finishes sooner than 4 items per warp
-    const bool per_item = force ? force[0] == 'i' : items <= 24LL * kSMs;
+    const bool per_item = force ? force == 1 : items <= 24LL * kSMs;
     if (p.rc.keys) {
         DAS_CUDA_CHECK(launch_chain(refine_sparse_kernel<8, 4, 3, true, true>, dim3(kSMs * 3), dim3(RS_WARPS * 32), 0, st, cx.pdl, p));
     } else if (per_item) {

@@ -341,6 +341,10 @@ int das_plan_refine_stats(das_plan* plan, int64_t stats[3]);
 /* Self-test of the tcgen05/TMEM building blocks: D[128,N] = A[128,K] * B[N,K]^T (row-major fp32 device
  * buffers; N in {16,32}, K a multiple of 32). split=0: one TF32 pass; split=1: 3xTF32 (fp32-level accuracy). */
 int das_tc_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t split, void* stream);
+/* Which phase 1-2 kernel das_refine_heads launches on device-resident maps: 0 = automatic (warp-per-item below 24*148 items,
+ * batched above), 1 = warp-per-item, 2 = batched.  Process-wide; for parity tests and A/B timing.  Plans capture the choice
+ * into their graph: set it before the plan's first run. */
+int das_debug_force_heads_kernel(int32_t mode);
 /* tcgen05.mma issue/throughput micro-benchmark: out_cycles[0] = issue only, [1] = issue + completion (device int64[2]) */
 int das_tc_mma_bench(int32_t N, int32_t iters, long long* out_cycles, void* stream);
 

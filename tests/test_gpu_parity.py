@@ -433,10 +433,46 @@ def test_tensor_core_refinement_modes(mode, tol):
             assert util.rel_err(g["poses_cam"].cpu().numpy(), o["poses_cam"]) < tol
 
 
-def test_tensor_core_refinement_with_threshold_and_pyramid():
+@pytest.fixture
+def heads_kernel(request):
+    """Forces the phase 1-2 kernel das_refine_heads launches (1 = warp per item, 2 = 4 candidates per warp); small test
+    decodes would otherwise only ever see the warp-per-item kernel."""
+    from das_b200 import _lib
+    lib = _lib.load()
+    assert lib.das_debug_force_heads_kernel(request.param) == 0
+    yield request.param
+    lib.das_debug_force_heads_kernel(0)
+
+
+@pytest.mark.parametrize("heads_kernel", [1, 2], indirect=True, ids=["per_item", "batched"])
+def test_tensor_core_refinement_with_threshold_and_pyramid(heads_kernel):
     cfg = dataclasses.replace(P, strides=(8, 16, 32))
     tc = dict(nms_pre=60, nms_post=30, nms_thr=0.9, score_thr=0.05)
     case = util.make_case(cfg, 2, 48, 64, seed=73, peaks=20, tc=tc)
+    ref, _ = util.run_oracle(case, tc)
+    util.assert_margins(case, tc, ref)
+    plan, got = util.run_gpu(case, tc, refine=True, refine_mode=1)
+    compare(plan, got, ref)
+
+
+@pytest.mark.parametrize("heads_kernel", [1, 2], indirect=True, ids=["per_item", "batched"])
+@pytest.mark.parametrize("name", ["odd_sizes_3_images", "border_targets", "three_layers_j17"])
+def test_both_phase12_kernels_match_the_oracle(heads_kernel, name):
+    """The batched phase 1-2 kernel (4 candidates per warp, a CTA per joint, weights in shared memory, one row-list
+    reservation per task) against the oracle on the shapes that stress its bookkeeping: a candidate count that is not a
+    multiple of 4 on an odd-sized map, sampling targets outside the map, and dense layers in front (previous offsets from
+    the joint-major maps, J = 17)."""
+    if name == "odd_sizes_3_images":
+        cfg, B, h, w, tc, kw = P, 3, 23, 37, dict(nms_pre=7, nms_post=7, nms_thr=0.9, score_thr=0.0), {}
+    elif name == "border_targets":
+        cfg, B, h, w, tc, kw = P, 2, 16, 24, dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0), dict(peaks=12)
+    else:
+        cfg = dataclasses.replace(synth.MUPOTS17, num_layers=3)
+        B, h, w, tc, kw = 2, 24, 32, dict(nms_pre=9, nms_post=9, nms_thr=0.9, score_thr=0.0), {}
+    case = util.make_case(cfg, B, h, w, seed=77, tc=tc, **kw)
+    if name == "border_targets":
+        for lv in case["levels"]:          # push the joint offsets so that targets and heads leave the map
+            lv["pose_raw"][:, 3:3 + 3 * cfg.num_joints] *= 6.0
     ref, _ = util.run_oracle(case, tc)
     util.assert_margins(case, tc, ref)
     plan, got = util.run_gpu(case, tc, refine=True, refine_mode=1)
