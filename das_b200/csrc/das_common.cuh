@@ -43,6 +43,7 @@ struct ChainCtx {
     bool pdl = false;                 // launch with the PDL attribute (the previous node on the stream is a kernel of this chain)
     int32_t* zero_counters = nullptr; // das_score_topk: refine counters to clear ([0], [1], [4 .. 4+DAS_MAX_JOINTS)) for the chain
     bool counters_cleared = false;    // das_refine_heads: the counters were cleared by das_score_topk of this chain -> no memset nodes
+    int extra_launches = 0;           // kernels a stage launcher enqueued beyond its usual one (das_plan's launch count)
 };
 ChainCtx& chain_ctx();
 

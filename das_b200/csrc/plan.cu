@@ -433,6 +433,7 @@ static int enqueue(das_plan* p, cudaStream_t st, int* n_launch, bool events) {
         ++n;
     }
     DAS_TRY(mark(5));
+    n += das::chain_ctx().extra_launches;
     *n_launch = n;
     return DAS_OK;
 }

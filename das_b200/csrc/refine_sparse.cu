@@ -359,7 +359,9 @@ __device__ __forceinline__ float reduce_nb(const float (&a)[NB]) {
     else return reduce2_permuted(a);
 }
 
-template <int CPL, int NH, int NB>
+// SPLIT: the kernel stops after phase 2 and leaves each item's 16 head offsets in the first 64 bytes of the item's row-record
+// slot; refine_records_kernel (one warp per item, 4x the parallelism, no batch-serial passes) writes the records.
+template <int CPL, int NH, int NB, bool SPLIT>
 __global__ void __launch_bounds__(H8_WARPS * 32, NB == 4 ? 5 : (NB == 2 ? 8 : 4))     // NB = 4: 96 registers, 20 warps per SM (2 960 task slots: BASELINE config #2 has 2 400 tasks -> one wave)
 refine_heads8_kernel(const RefineParams p) {
     static_assert(NH == 4, "32 rows per item = 8 heads x 4 corners");
@@ -525,16 +527,28 @@ refine_heads8_kernel(const RefineParams p) {
                 st[o] = reduce_nb<NB>(acc) + wsum * __ldg(Bj + o);
             }
             if ((lane & (GL - 1)) == 0) {
-                float* sh = s_head[warp][r];
+                if constexpr (SPLIT) {
+                    if (valid) {
+                        // {hx[0..7], hy[0..7]} of item (cs, j): heads 0..3 "from target" (recursive_update.py:59), 4..7 "from source" (:62)
+                        float4* dst = reinterpret_cast<float4*>(p.lrow) + (static_cast<size_t>(cs) * J + j) * 32;
+                        dst[0] = make_float4(st[0] + O[0], st[2] + O[0], st[4] + O[0], st[6] + O[0]);
+                        dst[1] = make_float4(S[0], S[2], S[4], S[6]);
+                        dst[2] = make_float4(st[1] + O[1], st[3] + O[1], st[5] + O[1], st[7] + O[1]);
+                        dst[3] = make_float4(S[1], S[3], S[5], S[7]);
+                    }
+                } else {
+                    float* sh = s_head[warp][r];
 #pragma unroll
-                for (int h = 0; h < NH; ++h) {
-                    sh[h] = st[2 * h] + O[0];                 // "from target" heads, recursive_update.py:59
-                    sh[2 * NH + h] = st[2 * h + 1] + O[1];
-                    sh[NH + h] = S[2 * h];                    // "from source" heads, recursive_update.py:62
-                    sh[2 * NH + NH + h] = S[2 * h + 1];
+                    for (int h = 0; h < NH; ++h) {
+                        sh[h] = st[2 * h] + O[0];                 // "from target" heads, recursive_update.py:59
+                        sh[2 * NH + h] = st[2 * h + 1] + O[1];
+                        sh[NH + h] = S[2 * h];                    // "from source" heads, recursive_update.py:62
+                        sh[2 * NH + NH + h] = S[2 * h + 1];
+                    }
                 }
             }
         }
+        if constexpr (SPLIT) continue;
         __syncwarp();
 
         // ---- row records: lane = (head = lane >> 2, corner = lane & 3) of one candidate at a time -----------------
@@ -641,6 +655,96 @@ refine_heads8_kernel(const RefineParams p) {
             }
         }
         __syncwarp();
+    }
+}
+
+// Row records of the split phase 1-2 path: one warp per (candidate, joint) item, lane = (head = lane >> 2, corner = lane & 3).
+// Reads the item's 16 head offsets left by refine_heads8_kernel<.., SPLIT> in the first 64 bytes of its row-record slot, then
+// overwrites the slot with the 32 records; distinct sampled cells -> the joint's row list; assembly record; centre; valid_list.
+template <int NH>
+__global__ void __launch_bounds__(256)
+refine_records_kernel(const RefineParams p) {
+    static_assert(NH == 4, "32 rows per item = 8 heads x 4 corners");
+    constexpr int C = 256;
+    const int lane = threadIdx.x & 31;
+    pdl_wait();
+    pdl_trigger();
+    const das_levels* __restrict__ lvp = p.lv;
+    const int nl = lvp->n_levels, J = p.J;
+    for (int item = blockIdx.x * 8 + (threadIdx.x >> 5); item < p.n_items; item += gridDim.x * 8) {
+        const int cs = item / J, j = item - cs * J;
+        if (p.score_thr > 0.f && !(__ldg(p.cand_score + cs) > p.score_thr)) continue;
+        const int b = cs / p.CT, slot = cs - b * p.CT;
+        int l = 0, s0 = 0;
+        for (; l < nl - 1; ++l) {
+            const int ns = level_slots(lvp->lv[l].H * lvp->lv[l].W, p.nms_pre);
+            if (slot < s0 + ns) break;
+            s0 += ns;
+        }
+        const das_level_desc& d = lvp->lv[l];
+        const int H = d.H, W = d.W, HW = H * W;
+        const int idx = __ldg(p.cand_index + cs);
+        const int y = idx / W, x = idx - y * W;
+        const float fW = static_cast<float>(W), fH = static_cast<float>(H);
+        float4* slotp = reinterpret_cast<float4*>(p.lrow) + static_cast<size_t>(item) * 32;
+        const int h = lane >> 2, ck2 = lane & 3;
+        // written by the previous kernel: plain (coherent) loads, not the read-only path
+        const float hxv = reinterpret_cast<const volatile float*>(slotp)[h], hyv = reinterpret_cast<const volatile float*>(slotp)[8 + h];
+        __syncwarp();                                  // every lane has its offsets before the slot is overwritten
+        const Corner c = make_corner(sample_coord(x, hxv, fW, __frcp_rn(fW)), sample_coord(y, hyv, fH, __frcp_rn(fH)), W, H);
+        const bool ok = corner_ok(c, ck2, W, H);
+        const int pix = ok ? corner_pix(c, ck2, W) : -1;
+        const float wk = ok ? corner_wgt(c, ck2) : 0.f;
+        const unsigned same = __match_any_sync(FULL, pix);
+        const int leader = __ffs(same) - 1;
+        const bool is_leader = ok && lane == leader;
+        const unsigned lead_mask = __ballot_sync(FULL, is_leader);
+        const int n_u = __popc(lead_mask);
+        // the leaders' previous offsets fly while the reservation makes its round trip
+        float pv[3] = {0.f, 0.f, 0.f};
+        if (is_leader) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (p.prev_uvd) pv[k] = __ldg(p.prev_uvd[l] + ((static_cast<size_t>(b) * J + j) * HW + pix) * 4 + k);
+                else if (!(k == 2 && j == p.root))
+                    pv[k] = InMap(d.pose, lvp->in_dtype)((static_cast<size_t>(b) * (3 + 6 * J) + 3 + 3 * j + k) * HW + pix) * (k < 2 ? d.scale_uv : d.scale_d);
+            }
+        }
+        int base = 0;
+        if (lane == 0 && n_u) base = atomicAdd(p.work_counter + 4 + j, n_u);
+        base = __shfl_sync(FULL, base, 0);
+        const int my_u = __popc(lead_mask & ((1u << lane) - 1u));
+        const int u_of_leader = __shfl_sync(FULL, my_u, leader);
+        if (is_leader) {
+            const unsigned long long pb = reinterpret_cast<unsigned long long>(d.feats[p.layer] + (static_cast<size_t>(b) * HW + pix) * C);
+            float4* dst = reinterpret_cast<float4*>(p.urow + (static_cast<size_t>(j) * p.row_cap + base + my_u) * 8);
+            dst[0] = make_float4(__uint_as_float(static_cast<unsigned>(pb)), __uint_as_float(static_cast<unsigned>(pb >> 32)), pv[0], pv[1]);
+            dst[1] = make_float4(pv[2], 0.f, 0.f, 0.f);
+        }
+        slotp[lane] = make_float4(__int_as_float(ok ? base + u_of_leader : -1), wk, hxv, hyv);
+        if (lane == 0) {
+            // eval-tail / assembly inputs of this item (das_head.py:254-262, 725-743), and the centre for joint 0
+            const InMap pose(d.pose, lvp->in_dtype);
+            const size_t pb = static_cast<size_t>(b) * (3 + 6 * J) * HW;
+            const float sx = __ldg(p.scale_xy + 2 * b), sy = __ldg(p.scale_xy + 2 * b + 1);
+            const float qf = sqrtf(sx * sy);
+            const float stv = static_cast<float>(d.stride), half = static_cast<float>(d.stride / 2);
+            float z = pose(pb + 2 * static_cast<size_t>(HW) + idx) * d.scale_depth;
+            z = __fdiv_rn(z, p.depth_factor);
+            const float zq = __fmul_rn(z, qf);
+            const float Px = static_cast<float>(x) * stv + half, Py = static_cast<float>(y) * stv + half;
+            float4* a = reinterpret_cast<float4*>(p.item_asm + static_cast<size_t>(item) * 8);
+            a[0] = make_float4(Px, Py, zq, sx);
+            a[1] = make_float4(sy, stv, 0.f, 0.f);
+            if (j == 0) {
+                const float offx = pose(pb + idx) * d.scale_offset;
+                const float offy = pose(pb + static_cast<size_t>(HW) + idx) * d.scale_offset;
+                p.cand_center[static_cast<size_t>(cs) * 3 + 0] = __fdiv_rn(__fsub_rn(Px, offx), sx);
+                p.cand_center[static_cast<size_t>(cs) * 3 + 1] = __fdiv_rn(__fsub_rn(Py, offy), sy);
+                p.cand_center[static_cast<size_t>(cs) * 3 + 2] = zq;
+                p.valid_list[atomicAdd(p.work_counter + 1, 1)] = cs;
+            }
+        }
     }
 }
 
@@ -854,9 +958,16 @@ extern "C" int das_refine_heads(const das_levels* d_levels, const das_levels* h_
         const long long cap = std::max<long long>(1, ((nb == 8 ? 4LL : (nb == 2 ? 8LL : 5LL)) * kSMs) / cfg->num_joints);
         const int cpj = static_cast<int>(std::max<long long>(1, std::min<long long>((n_blocks + H8_WARPS - 1) / H8_WARPS, cap)));
         const int grid = cpj * cfg->num_joints;
-        if (nb == 8) DAS_CUDA_CHECK(launch_chain(refine_heads8_kernel<8, 4, 8>, dim3(grid), dim3(H8_WARPS * 32), 0, st, cx.pdl, p));
-        else if (nb == 2) DAS_CUDA_CHECK(launch_chain(refine_heads8_kernel<8, 4, 2>, dim3(grid), dim3(H8_WARPS * 32), 0, st, cx.pdl, p));
-        else DAS_CUDA_CHECK(launch_chain(refine_heads8_kernel<8, 4, 4>, dim3(grid), dim3(H8_WARPS * 32), 0, st, cx.pdl, p));
+        // DAS_HEADS_SPLIT=0: records inside the batched kernel (one launch); default: phases 1-2 batched, records by a warp per item
+        static const bool split = !(std::getenv("DAS_HEADS_SPLIT") && std::getenv("DAS_HEADS_SPLIT")[0] == '0');
+        if (split && nb == 4) {
+            DAS_CUDA_CHECK(launch_chain(refine_heads8_kernel<8, 4, 4, true>, dim3(grid), dim3(H8_WARPS * 32), 0, st, cx.pdl, p));
+            const int grid_r = static_cast<int>(std::max<long long>(1, std::min<long long>((items + 7) / 8, 8LL * kSMs)));
+            DAS_CUDA_CHECK(launch_chain(refine_records_kernel<4>, dim3(grid_r), dim3(256), 0, st, cx.pdl, p));
+            chain_ctx().extra_launches += 1;
+        } else if (nb == 8) DAS_CUDA_CHECK(launch_chain(refine_heads8_kernel<8, 4, 8, false>, dim3(grid), dim3(H8_WARPS * 32), 0, st, cx.pdl, p));
+        else if (nb == 2) DAS_CUDA_CHECK(launch_chain(refine_heads8_kernel<8, 4, 2, false>, dim3(grid), dim3(H8_WARPS * 32), 0, st, cx.pdl, p));
+        else DAS_CUDA_CHECK(launch_chain(refine_heads8_kernel<8, 4, 4, false>, dim3(grid), dim3(H8_WARPS * 32), 0, st, cx.pdl, p));
     }
     DAS_CUDA_CHECK(cudaGetLastError());
     return DAS_OK;
