@@ -520,6 +520,37 @@ def test_fp16_head_outputs_are_read_natively(dtype, refine):
         assert torch.equal(x["poses_cam"], y["poses_cam"])
 
 
+def test_fp16_maps_through_the_host_entry():
+    """das_plan_run_host with fp16 head-output maps in pinned host memory (element size 2 in the staging copies, in-place
+    reads of the fp16 pose map, the centerness plane left on the host) == the device entry on the same fp16 maps, in all
+    three transfer policies."""
+    tc = dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)
+    case = util.make_case(P, 3, 24, 40, seed=43, scales=(1.05, 0.95, 1.1, 0.9))
+    plan = util.make_plan(case, tc)
+    dl = synth.levels_to(case["levels"], "cuda")
+    plan.bind([dict(cls=lv["cls"].half(), ctr=lv["ctr"].half(), pose=lv["pose_raw"].half(), feats=lv["feats"], scales=lv["scales"]) for lv in dl])
+    plan.set_metas(case["metas"])
+    plan.run()
+    torch.cuda.synchronize()
+    want = plan.output_block().clone()
+    assert int(plan.views_of_block(want)["out_count"].sum()) > 0
+    host_levels = [dict(cls=lv["cls"].half().pin_memory(), ctr=lv["ctr"].half().pin_memory(), pose=lv["pose_raw"].half().pin_memory(),
+                        feats=[f.permute(0, 2, 3, 1).contiguous().pin_memory().permute(0, 3, 1, 2) for f in lv["feats"]],
+                        scales=lv["scales"]) for lv in case["levels"]]
+    for zero_copy, row_cache in ((False, False), (True, False), (True, True)):
+        p2 = util.make_plan(case, tc)
+        p2.set_host_mode(zero_copy, row_cache=row_cache)
+        out = p2.alloc_host_out()
+        for _ in range(2):
+            p2.run_host(host_levels, case["metas"], out)
+        torch.cuda.synchronize()
+        a, b = plan.views_of_block(want), p2.views_of_block(p2.output_block().clone())
+        for k in a:                                  # section by section: the 256-byte alignment gaps of a block are never written
+            assert torch.equal(a[k], b[k]), (k, zero_copy, row_cache)
+        res = p2.results(case["metas"], src=out)     # ... and what came back to the host arrays
+        assert [len(r["scores"]) for r in res] == a["out_count"].tolist()
+
+
 @pytest.mark.parametrize("variant", ["pyramid_pass_through", "k200_radix", "peak_mask", "odd_unaligned"])
 def test_fp16_native_scan_paths(variant):
     """Every selection path of score_topk (bounded fast path, scratch keys + radix for K > 128, pass-through levels,
