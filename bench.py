@@ -735,14 +735,19 @@ def run_b200(args):
         el_zc, bytes_zc = time_host(True)
         rows, n_valid = plan0.row_cache_stats()
         row_bytes = (rows + n_valid) * C * 4
-        pose_bytes = n_valid * (3 + J * 33 * 3) * 32 if head.num_layers == 1 else 0     # one 32-B sector per scattered pose value
+        # one 32-byte sector per scattered pose value: root depth / offsets per candidate, and (u, v, d) at the candidate's own
+        # cell and at every DISTINCT sampled cell of every (candidate, joint) item (device counter of the same call);
+        # cross-checked with ncu pcie__read_bytes per kernel: profiles/r02_e2e_probe_mode2.csv (30.7 MB in place + 6.8 MB copied)
+        distinct_rows = plan0.refine_stats()[0]
+        pose_bytes = (n_valid * 3 + (distinct_rows + n_valid * J) * 3) * 32 if head.num_layers == 1 else 0
         sparse_ub = B * K * J * 37 * C * 4 + (B * K * (3 + J * 33 * 3) * 32 if head.num_layers == 1 else 0)
         e2e = dict(value=world * B * n_e2e / el_zc, unit=UNIT, h2d_bytes_per_step=int(bytes_zc + row_bytes + pose_bytes),
                    d2h_bytes_per_step=plan0.d2h_bytes, steps=n_e2e, ms_per_step=el_zc / n_e2e * 1e3,
                    h2d_explicit_bytes=int(bytes_zc), h2d_in_place_row_bytes=int(row_bytes),
                    h2d_in_place_pose_bytes_estimate=int(pose_bytes), h2d_in_place_bytes_upper_bound=int(sparse_ub),
                    h2d_how="explicit cudaMemcpyAsync bytes + distinct feature rows the device row cache fetched over PCIe (counted on "
-                           "the device: %d rows + %d candidate rows of %d B) + one 32-B sector per pose value read in place" % (rows, n_valid, C * 4),
+                           "the device: %d rows + %d candidate rows of %d B) + one 32-B sector per pose value read in place (candidate cells and the "
+                           "distinct sampled cells, counted on the device)" % (rows, n_valid, C * 4),
                    host_input_sets=len(host_sets),
                    api="das_plan_run_host, host_mode 2: pinned host inputs; logit planes H2D-copied, pose / feature maps read "
                        "in place over PCIe by the gather kernels (the decode touches ~5 % of them), every distinct row of the "
