@@ -139,6 +139,7 @@ SIGNATURES = {
     "das_peer_publish": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
     "das_plan_publish_wait": (C.c_int, [_VP, _VP]),
     "das_debug_force_heads_kernel": (C.c_int, [C.c_int32]),
+    "das_dense_set_debug_buffer": (C.c_int, [_VP]),
 }
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libdas_decode.so")

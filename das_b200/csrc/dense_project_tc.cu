@@ -48,6 +48,7 @@ struct DenseTcParams {
     float* proj;                   // four joint-major planes, see DensePlanes (refine_common.cuh)
     int* progress;                 // [G] tiles issued by the Q CTAs that share tile sequence m (zeroed before the launch)
     int level, layer, J, root, B, Q;
+    long long* dbg;                // optional [gridDim.x][8] cycle counters (tools/dense_role_cycles.py); nullptr in production
 };
 
 constexpr int DT_LOCKSTEP_TILES = 2;             // the Q CTAs that read the same feature tiles stay within this many tiles
@@ -66,6 +67,7 @@ dense_project_tc_kernel(const DenseTcParams p, const __grid_constant__ CUtensorM
     __shared__ float s_bias[DT_JG * DT_NOUT];                      // biases of this CTA's joint group
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long kernel_t0 = p.dbg ? clock64() : 0ll;
     const das_level_desc& d = p.lv->lv[p.level];
     const int HW = d.H * d.W, J = p.J;
     const long long cells = static_cast<long long>(p.B) * HW;
@@ -140,27 +142,39 @@ dense_project_tc_kernel(const DenseTcParams p, const __grid_constant__ CUtensorM
         constexpr uint32_t idesc_hi = tc::instr_desc_tf32(128, 2 * DT_N);   // A_hi x [B_hi ; B_lo] -> D[:, 0:128]
         constexpr uint32_t idesc_lo = tc::instr_desc_tf32(128, DT_N);       // A_lo x  B_hi         -> D[:, 0:64]
         int g = 0;
+        long long m_free = 0, m_full = 0, m_issue = 0;
+        const bool prof = p.dbg != nullptr;
         for (int i = 0; i < my_tiles; ++i) {
             const uint32_t dcol = tmem0 + DT_D_COL + (i % DT_EG) * (2 * DT_N);
+            const long long c0 = prof ? clock64() : 0ll;
             if (i >= DT_EG) tc::mbar_wait(&acc_free[i % DT_EG], ((i / DT_EG) - 1) & 1);
+            if (prof) m_free += clock64() - c0;
             for (int kb = 0; kb < DT_KB; ++kb, ++g) {
                 const int slot = g % DT_SLOTS;
+                const long long c1 = prof ? clock64() : 0ll;
                 tc::mbar_wait(&a_full[slot], (g / DT_SLOTS) & 1);
                 tc::tc_fence_after();
+                const long long c2 = prof ? clock64() : 0ll;
                 const uint32_t a_hi = tmem0 + DT_A_COL + slot * 64;
                 tc::umma_kblock_3xtf32_ts(dcol, a_hi, a_hi + 32, tc::smem_desc_sw128(sB_u + kb * DT_PANEL_KB), idesc_hi, idesc_lo, kb != 0);
                 tc::umma_commit_elect(&a_empty[slot]);
                 if (kb == DT_KB - 1) tc::umma_commit_elect(&acc_full[i % DT_EG]);
+                if (prof) { m_full += c2 - c1; m_issue += clock64() - c2; }
             }
         }
+        if (prof && lane == 0) { long long* o = p.dbg + blockIdx.x * 8; o[0] += m_free; o[1] += m_full; o[2] += m_issue; }
     } else if (warp >= DT_FIRST_PRODUCER) {
         // ===== producer groups: own row of the TMA-staged k-block -> hi/lo split in registers -> TMEM ===============
         const int pg = (warp - DT_FIRST_PRODUCER) >> 2;
         const int qw = warp & 3;
         const int gt = (qw << 5) | lane;
+        long long d_tma = 0, d_slot = 0, d_work = 0;
+        const bool prof = p.dbg != nullptr && pg == 0 && gt == 0;
         for (int g = pg; g < total_kb; g += DT_PG) {
             const int slot = g % DT_SLOTS, s = g % DT_STAGES;
+            const long long c0 = prof ? clock64() : 0ll;
             tc::mbar_wait(&st_full[s], (g / DT_STAGES) & 1);
+            const long long c1 = prof ? clock64() : 0ll;
             float hi[32];
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) {
@@ -169,8 +183,10 @@ dense_project_tc_kernel(const DenseTcParams p, const __grid_constant__ CUtensorM
             }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&st_empty[s]);          // this warp's 32 rows are in registers
+            const long long c2 = prof ? clock64() : 0ll;
             if (g >= DT_SLOTS) tc::mbar_wait(&a_empty[slot], ((g / DT_SLOTS) - 1) & 1);
             tc::tc_fence_after();
+            const long long c3 = prof ? clock64() : 0ll;
             const uint32_t taddr = tmem0 + (static_cast<uint32_t>(qw * 32) << 16) + DT_A_COL + slot * 64;
             tc::tmem_st32(taddr, hi);
 #pragma unroll
@@ -180,7 +196,9 @@ dense_project_tc_kernel(const DenseTcParams p, const __grid_constant__ CUtensorM
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&a_full[slot]);
+            if (prof) { d_tma += c1 - c0; d_slot += c3 - c2; d_work += (c2 - c1) + (clock64() - c3); }
         }
+        if (prof) { long long* o = p.dbg + blockIdx.x * 8; o[3] += d_tma; o[4] += d_slot; o[5] += d_work; }
     } else {
         // ===== epilogue groups: thread = cell; bias, gate, blend with the previous offset -> the four planes =============
         const int e = warp >> 2;
@@ -222,8 +240,10 @@ dense_project_tc_kernel(const DenseTcParams p, const __grid_constant__ CUtensorM
             const int b = live ? static_cast<int>(cell / HW) : 0;
             const int pix = live ? static_cast<int>(cell - static_cast<long long>(b) * HW) : 0;
             load_prev(i + DT_EG, nxt);
+            const long long e0 = (p.dbg && e == 0 && row == 0) ? clock64() : 0ll;
             tc::mbar_wait(&acc_full[e], (i / DT_EG) & 1);
             tc::tc_fence_after();
+            if (p.dbg && e == 0 && row == 0) p.dbg[blockIdx.x * 8 + 6] += clock64() - e0;
             const uint32_t tbase = tmem0 + (static_cast<uint32_t>(qw * 32) << 16) + DT_D_COL + e * (2 * DT_N);
 #pragma unroll
             for (int jj = 0; jj < DT_JG; ++jj) {
@@ -267,6 +287,7 @@ dense_project_tc_kernel(const DenseTcParams p, const __grid_constant__ CUtensorM
             for (int jj = 0; jj < DT_JG; ++jj) { prev[jj][0] = nxt[jj][0]; prev[jj][1] = nxt[jj][1]; prev[jj][2] = nxt[jj][2]; }
         }
     }
+    if (p.dbg && tid == 0) p.dbg[blockIdx.x * 8 + 7] += clock64() - kernel_t0;
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
@@ -293,6 +314,12 @@ __global__ void pack_dense_panels_kernel(const float* __restrict__ wpack, unsign
 }
 
 }  // namespace das
+
+static long long* g_dense_dbg = nullptr;
+// profiling aid: per-CTA cycle counters of the dense projection's warp roles ([148][8] int64 device buffer, zeroed by the
+// caller, accumulated over the launches; NULL = off): {mma: wait acc_free, wait a_full, issue | producer group 0: wait TMA,
+// wait TMEM slot, work | epilogue group 0: wait acc_full | CTA total}
+extern "C" int das_dense_set_debug_buffer(long long* dev_buf) { g_dense_dbg = dev_buf; return DAS_OK; }
 
 extern "C" int64_t das_dense_panel_bytes(const das_decode_cfg* cfg) {
     if (!cfg) return 0;
@@ -325,6 +352,7 @@ extern "C" int das_dense_project_tc(const das_levels* d_levels, const das_levels
     p.lv = d_levels; p.wpack = weights; p.panels = static_cast<const unsigned char*>(panels); p.uvd_in = uvd_in; p.proj = proj;
     p.level = level; p.layer = layer; p.J = cfg->num_joints; p.root = cfg->root_idx; p.B = h_levels->batch;
     p.Q = (cfg->num_joints + DT_JG - 1) / DT_JG;
+    p.dbg = g_dense_dbg;
     DAS_REQUIRE(p.Q <= kSMs, DAS_ERR_CAPACITY, "too many joint groups");
     static DeviceOnce attr_done;
     if (attr_done.need()) {

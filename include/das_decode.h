@@ -221,6 +221,9 @@ int das_refine_row_cache(const das_decode_cfg* cfg, const das_refine_scratch* sc
 int64_t das_tc_panel_bytes(const das_decode_cfg* cfg);
 /* profiling aid: per-CTA cycle counters of das_refine_tc's warp roles ([148][16] int64 device buffer; NULL = off) */
 int das_tc_set_debug_buffer(long long* dev_buf);
+/* same for das_dense_project_tc: [148][8] int64 {mma: wait acc_free, wait a_full, issue | producer group 0: wait TMA, wait TMEM
+ * slot, work | epilogue group 0: wait acc_full | CTA total}; the caller zeroes the buffer; NULL = off */
+int das_dense_set_debug_buffer(long long* dev_buf);
 
 /* One dense refinement layer over a whole level (layers 1..L-1 when num_layers > 1): 1x1 projection + gated
  * blend into proj (scratch [B][J][HW][16] fp32), then the progressive sampling into uvd_out (joint-major
