@@ -58,7 +58,7 @@ struct TcParams {
     const int32_t* n_valid;
     const int32_t* joint_count;      // [J] distinct rows of every joint
     float* cand_pose;
-    int CT, J, root, split, row_cap, gather_cg;
+    int CT, J, root, split, row_cap, gather_cg, prefetch_lines;
     float depth_factor, z_norm;
     long long* dbg;                  // optional [gridDim.x][16] cycle counters (profiling builds of the host code)
 };
@@ -91,10 +91,13 @@ __device__ __forceinline__ RowState setup_row(const TcParams& p, const int* pref
                                            (static_cast<unsigned long long>(__float_as_uint(a.y)) << 32));
     r.prev0 = a.z; r.prev1 = a.w; r.prev2 = c.x;
     if (r.ptr) {
-        // the producers gather this row a few tiles from now: pull its 8 lines into L2 already, so that a k-block's
-        // arrival is bounded by L2 latency instead of by its slowest DRAM miss
+        // Optional (DAS_TC_PREFETCH_LINES = 1..8; default 0): pull the row's lines into L2 six tiles ahead of the gather.  It paid
+        // in round 1 (32 rows per item, 2 400 tiles); with the distinct-row lists it costs more than it hides -- the L2 read
+        // path is the kernel's limit, and 6 tiles x 128 KB of prefetch per SM are 113 MB in flight against a 126-MB L2:
+        // config #2 38.9 -> 36.9 us for the stage (1.19 M -> 1.23 M images/s), spread workload 75.8 -> 68.9 us without it
 #pragma unroll
-        for (int q = 0; q < TC_C * 4 / 128; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(r.ptr + q * 32));
+        for (int q = 0; q < TC_C * 4 / 128; ++q)
+            if (q < p.prefetch_lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(r.ptr + q * 32));
     }
     return r;
 }
@@ -592,6 +595,8 @@ extern "C" int das_refine_tc(const das_levels* d_levels, const das_levels* h_lev
     p.dbg = g_tc_dbg;
     static const int gather_cg = std::getenv("DAS_TC_GATHER_CG") ? std::atoi(std::getenv("DAS_TC_GATHER_CG")) : 1;   // .cg: no L1 allocation (the rows are distinct)
     p.gather_cg = gather_cg;
+    static const int pf_lines = std::getenv("DAS_TC_PREFETCH_LINES") ? std::atoi(std::getenv("DAS_TC_PREFETCH_LINES")) : 0;
+    p.prefetch_lines = pf_lines;
     static DeviceOnce attr2_done;
     if (attr2_done.need()) {
         DAS_CUDA_CHECK(cudaFuncSetAttribute(refine_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
