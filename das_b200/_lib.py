@@ -66,7 +66,7 @@ class PeerBlocks(C.Structure):
 class RefineScratch(C.Structure):
     _fields_ = [("unique_rows", C.c_void_p), ("unique_out", C.c_void_p), ("row_records", C.c_void_p),
                 ("item_records", C.c_void_p), ("valid_list", C.c_void_p), ("counters", C.c_void_p),
-                ("row_cap", C.c_int32), ("reserved_", C.c_int32)]
+                ("row_cap", C.c_int32), ("reserved_", C.c_int32), ("prev_planes", C.c_void_p)]
 
 
 class RowCache(C.Structure):
@@ -100,6 +100,7 @@ SIGNATURES = {
     "das_tc_set_debug_buffer": (C.c_int, [_VP]),
     "das_tc_panel_bytes": (C.c_int64, [C.POINTER(DecodeCfg)]),
     "das_plan_set_refine_mode": (C.c_int, [_VP, C.c_int32]),
+    "das_plan_set_on_demand_sampling": (C.c_int, [_VP, C.c_int32]),
     "das_refine_dense_layer": (C.c_int, [_VP, C.POINTER(Levels), C.c_int32, C.c_int32, C.POINTER(DecodeCfg), _VP, _VP, _VP,
                                          _VP, _VP, _VP]),
     "das_dense_project_tc": (C.c_int, [_VP, C.POINTER(Levels), C.c_int32, C.c_int32, C.POINTER(DecodeCfg), _VP, _VP, _VP, _VP, _VP]),

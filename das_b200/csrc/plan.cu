@@ -46,6 +46,11 @@ struct das_plan {
     float* uvd_map[2][DAS_MAX_LEVELS] = {};
     float* proj = nullptr;
     const float** d_prev_ptrs = nullptr;
+    // on-demand sampling of layer L-2 (tensor-core path): that layer's projection planes must outlive the other levels'
+    // dense layers, so every level has its own (one level: the shared scratch itself)
+    float* proj_last[DAS_MAX_LEVELS] = {};
+    const float** d_plane_ptrs = nullptr;
+    int on_demand = 1;                // das_plan_set_on_demand_sampling
     // host-entry staging
     das_levels staging{};
     bool staging_ready = false;
@@ -205,6 +210,11 @@ extern "C" int das_plan_create(const das_decode_cfg* cfg, const das_levels* shap
             if (cfg->feat_channels == 256 && cfg->num_heads == 4)
                 for (int k = 0; k < cfg->num_layers - 1; ++k) A(dev_alloc(&p->dense_panels[k], static_cast<size_t>(das_dense_panel_bytes(cfg))));
             A(dev_alloc(&p->d_prev_ptrs, DAS_MAX_LEVELS));
+            if (cfg->feat_channels == 256 && cfg->num_heads == 4) {
+                A(dev_alloc(&p->d_plane_ptrs, DAS_MAX_LEVELS));
+                for (int l = 0; l < shape->n_levels && shape->n_levels > 1; ++l)
+                    A(dev_alloc(&p->proj_last[l], B * static_cast<size_t>(shape->lv[l].H) * shape->lv[l].W * (2 * cfg->num_heads + 8) * J));
+            }
         }
     }
     if (s != DAS_OK) { das_plan_destroy(p); return s; }
@@ -250,7 +260,7 @@ extern "C" void das_plan_destroy(das_plan* p) {
     for (cudaEvent_t e : p->ev) if (e) cudaEventDestroy(e);
     void* ptrs[] = {p->d_levels, p->buf.cand_score, p->buf.cand_index, p->buf.cand_pose, p->buf.cand_center,
                     p->own_block, p->scratch, p->work_counter, p->d_scale_xy, p->d_cam,
-                    p->proj, p->d_prev_ptrs, p->tc_panels, p->rs.unique_rows, p->rs.unique_out, p->rs.row_records,
+                    p->proj, p->d_prev_ptrs, p->d_plane_ptrs, p->tc_panels, p->rs.unique_rows, p->rs.unique_out, p->rs.row_records,
                     p->rs.item_records, p->rs.valid_list};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->rc.table) cudaFree(p->rc.table);
@@ -258,6 +268,7 @@ extern "C" void das_plan_destroy(das_plan* p) {
     if (p->rc.cand_rows) cudaFree(p->rc.cand_rows);
     for (int k = 0; k < DAS_MAX_LAYERS; ++k) if (p->wpack[k]) cudaFree(p->wpack[k]);
     for (int k = 0; k < DAS_MAX_LAYERS; ++k) if (p->dense_panels[k]) cudaFree(p->dense_panels[k]);
+    for (int l = 0; l < DAS_MAX_LEVELS; ++l) if (p->proj_last[l]) cudaFree(p->proj_last[l]);
     for (int i = 0; i < 2; ++i)
         for (int l = 0; l < DAS_MAX_LEVELS; ++l) if (p->uvd_map[i][l]) cudaFree(p->uvd_map[i][l]);
     if (p->staging_ready) {
@@ -351,6 +362,16 @@ static bool peer_fused() {
     return v;
 }
 
+// Layer L-2's progressive sampling evaluated on demand by the sparse last layer (tensor-core path, default kernels)?
+static bool on_demand_sampling(const das_plan* p) {
+    static const bool env_off = (std::getenv("DAS_ON_DEMAND") && std::getenv("DAS_ON_DEMAND")[0] == '0') ||
+                                (std::getenv("DAS_HEADS_SPLIT") && std::getenv("DAS_HEADS_SPLIT")[0] == '0') ||
+                                (std::getenv("DAS_HEADS_NB") && std::atoi(std::getenv("DAS_HEADS_NB")) != 4);
+    const das_decode_cfg& c = p->cfg;
+    return !env_off && p->on_demand && c.refine && c.num_layers > 1 && p->refine_mode != 0 && p->d_plane_ptrs &&
+           p->dense_panels[c.num_layers - 2];
+}
+
 static int enqueue(das_plan* p, cudaStream_t st, int* n_launch, bool events) {
     const das_decode_cfg& c = p->cfg;
     int n = 0;
@@ -380,10 +401,18 @@ static int enqueue(das_plan* p, cudaStream_t st, int* n_launch, bool events) {
     das::chain_ctx().pdl = pdl_on;
     DAS_TRY(mark(1));
     const float* const* prev = nullptr;
+    const bool lazy = on_demand_sampling(p);
     if (c.refine && c.num_layers > 1) {
         for (int l = 0; l < p->bound.n_levels; ++l) {
             const float* in = nullptr;
             for (int k = 0; k < c.num_layers - 1; ++k) {
+                if (lazy && k == c.num_layers - 2) {
+                    // projection only: the last layer samples these planes at the few cells it looks at (das_refine_heads)
+                    DAS_TRY(das_dense_project_tc(p->d_levels, &p->bound, l, k, &c, p->wpack[k], p->dense_panels[k], in,
+                                                 p->bound.n_levels > 1 ? p->proj_last[l] : p->proj, st));
+                    n += 1;
+                    break;
+                }
                 float* outm = p->uvd_map[k & 1][l];
                 DAS_TRY(das_refine_dense_layer(p->d_levels, &p->bound, l, k, &c, p->wpack[k],
                                                p->refine_mode != 0 ? p->dense_panels[k] : nullptr, in, outm, p->proj, st));
@@ -401,8 +430,10 @@ static int enqueue(das_plan* p, cudaStream_t st, int* n_launch, bool events) {
             DAS_TRY(das_refine_cand_rows(p->d_levels, &p->bound, &c, p->buf.cand_score, p->buf.cand_index, p->CT, &p->rc, st));
             ++n;
         }
+        das_refine_scratch rs_heads = p->rs;
+        rs_heads.prev_planes = lazy ? p->d_plane_ptrs : nullptr;
         DAS_TRY(das_refine_heads(p->d_levels, &p->bound, &c, w, prev, p->d_scale_xy, p->buf.cand_score, p->buf.cand_index, p->CT,
-                                 &p->rs, p->buf.cand_center, p->rc_active ? &p->rc : nullptr, st));
+                                 &rs_heads, p->buf.cand_center, p->rc_active ? &p->rc : nullptr, st));
         DAS_TRY(mark(3));
         if (p->rc_active) {
             DAS_TRY(das_refine_row_cache(&c, &p->rs, &p->rc, st));
@@ -467,6 +498,11 @@ extern "C" int das_plan_run(das_plan* p, void* stream, int32_t mode) {
             const float* host_prev[DAS_MAX_LEVELS] = {};
             for (int l = 0; l < p->bound.n_levels; ++l) host_prev[l] = p->uvd_map[(p->cfg.num_layers - 2) & 1][l];
             DAS_CUDA_CHECK(cudaMemcpy(p->d_prev_ptrs, host_prev, sizeof(host_prev), cudaMemcpyHostToDevice));
+            if (p->d_plane_ptrs) {
+                const float* host_planes[DAS_MAX_LEVELS] = {};
+                for (int l = 0; l < p->bound.n_levels; ++l) host_planes[l] = p->bound.n_levels > 1 ? p->proj_last[l] : p->proj;
+                DAS_CUDA_CHECK(cudaMemcpy(p->d_plane_ptrs, host_planes, sizeof(host_planes), cudaMemcpyHostToDevice));
+            }
         }
         for (cudaEvent_t& e : p->ev) DAS_CUDA_CHECK(cudaEventCreate(&e));
     }
@@ -621,6 +657,15 @@ extern "C" int das_plan_set_pdl(das_plan* p, int32_t mode) {
     DAS_REQUIRE(mode >= -1 && mode <= 1, DAS_ERR_ARG, "das_plan_set_pdl: mode=%d (-1 auto, 0 off, 1 on)", mode);
     if (mode != p->pdl_mode) drop_graphs(p);
     p->pdl_mode = mode;
+    return DAS_OK;
+}
+
+extern "C" int das_plan_set_on_demand_sampling(das_plan* p, int32_t on) {
+    using namespace das;
+    DAS_REQUIRE(p, DAS_ERR_ARG, "null plan");
+    DAS_REQUIRE(on == 0 || on == 1, DAS_ERR_ARG, "das_plan_set_on_demand_sampling: on=%d", on);
+    if (on != p->on_demand) drop_graphs(p);
+    p->on_demand = on;
     return DAS_OK;
 }
 

@@ -169,4 +169,118 @@ __device__ __forceinline__ float corner_wgt(const Corner& c, int k) {
     return wy * wx;
 }
 
+// One (joint, cell) of a dense layer's progressive sampling (recursive_update.py:34-82, 9-31) from the layer's projection
+// planes: 4 bilinear taps of the sampling offsets at t = p + O.xy, 8 heads x 4 taps of {O, conf}, softmax over the heads.
+// Shared by dense_sample2_kernel (every cell of the map) and the sparse last layer's on-demand evaluation (refine_sparse.cu:
+// only the cells the selected candidates sample), so both produce the same bits.  pS0 / pS1 / pOA / pCB point at the
+// (image, joint) slice of the four planes.  The 18 divisions of the coordinate chains use the precomputed reciprocal
+// (div_by); a head whose 4 corners are all inside the map takes a branch-free path (one cell index, +1, +W, +W+1); the 6
+// interpolation FMAs per corner are 3 packed fma.rn.f32x2.
+template <int NH, bool FASTEXP>
+__device__ __forceinline__ float3 dense_sample_cell(const float4* __restrict__ pS0, const float4* __restrict__ pS1,
+                                                    const float4* __restrict__ pOA, const float2* __restrict__ pCB,
+                                                    int pix, int W, int H) {
+    static_assert(NH == 4, "plane layout is for 2*NH = 8 sampling offsets");
+    const float fW = static_cast<float>(W), fH = static_cast<float>(H);
+    const float rW = __frcp_rn(fW), rH = __frcp_rn(fH);
+    const int y = pix / W, x = pix - y * W;
+    const float4 s0 = __ldg(pS0 + pix), s1 = __ldg(pS1 + pix), om = __ldg(pOA + pix);
+    const float ox = om.x, oy = om.y;
+    float hx[2 * NH], hy[2 * NH];
+    {
+        const float ix = sample_coord(x, ox, fW, rW), iy = sample_coord(y, oy, fH, rH);
+        const float fx = floorf(ix), fy = floorf(iy);
+        const float ww = ix - fx, wn = iy - fy;
+        float2 a01 = make_float2(0.f, 0.f), a23 = a01, a45 = a01, a67 = a01;
+        if (fx >= 0.f && fx <= fW - 2.f && fy >= 0.f && fy <= fH - 2.f) {
+            const int cp = static_cast<int>(fy) * W + static_cast<int>(fx);
+            const float we = 1.0f - ww, ws = 1.0f - wn;
+            const float wk4[4] = {ws * we, ws * ww, wn * we, wn * ww};
+            const int off4[4] = {0, 1, W, W + 1};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float4 b0 = __ldg(pS0 + cp + off4[k]), b1 = __ldg(pS1 + cp + off4[k]);
+                const float2 wk2 = make_float2(wk4[k], wk4[k]);
+                a01 = ffma2(make_float2(b0.x, b0.y), wk2, a01); a23 = ffma2(make_float2(b0.z, b0.w), wk2, a23);
+                a45 = ffma2(make_float2(b1.x, b1.y), wk2, a45); a67 = ffma2(make_float2(b1.z, b1.w), wk2, a67);
+            }
+        } else {
+            const Corner ct = make_corner(ix, iy, W, H);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!corner_ok(ct, k, W, H)) continue;
+                const float wk = corner_wgt(ct, k);
+                const int cp = corner_pix(ct, k, W);
+                const float4 b0 = __ldg(pS0 + cp), b1 = __ldg(pS1 + cp);
+                const float2 wk2 = make_float2(wk, wk);
+                a01 = ffma2(make_float2(b0.x, b0.y), wk2, a01); a23 = ffma2(make_float2(b0.z, b0.w), wk2, a23);
+                a45 = ffma2(make_float2(b1.x, b1.y), wk2, a45); a67 = ffma2(make_float2(b1.z, b1.w), wk2, a67);
+            }
+        }
+        hx[0] = a01.x + ox; hy[0] = a01.y + oy;
+        hx[1] = a23.x + ox; hy[1] = a23.y + oy;
+        hx[2] = a45.x + ox; hy[2] = a45.y + oy;
+        hx[3] = a67.x + ox; hy[3] = a67.y + oy;
+        hx[4] = s0.x; hy[4] = s0.y; hx[5] = s0.z; hy[5] = s0.w;
+        hx[6] = s1.x; hy[6] = s1.y; hx[7] = s1.z; hy[7] = s1.w;
+    }
+    float hv[2 * NH][3], hc[2 * NH][3];
+#pragma unroll
+    for (int h = 0; h < 2 * NH; ++h) {
+        const float ix = sample_coord(x, hx[h], fW, rW), iy = sample_coord(y, hy[h], fH, rH);
+        const float fx = floorf(ix), fy = floorf(iy);
+        const float ww = ix - fx, wn = iy - fy;
+        float2 v01 = make_float2(0.f, 0.f), v2c = v01, c12 = v01;      // {O.x, O.y}, {O.z, cf.x}, {cf.y, cf.z}
+        if (fx >= 0.f && fx <= fW - 2.f && fy >= 0.f && fy <= fH - 2.f) {
+            const int cp = static_cast<int>(fy) * W + static_cast<int>(fx);
+            const float we = 1.0f - ww, ws = 1.0f - wn;
+            const float wk4[4] = {ws * we, ws * ww, wn * we, wn * ww};
+            const int off4[4] = {0, 1, W, W + 1};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float4 oo = __ldg(pOA + cp + off4[k]);
+                const float2 cc = __ldg(pCB + cp + off4[k]);
+                const float2 wk2 = make_float2(wk4[k], wk4[k]);
+                v01 = ffma2(make_float2(oo.x, oo.y), wk2, v01);
+                v2c = ffma2(make_float2(oo.z, oo.w), wk2, v2c);
+                c12 = ffma2(cc, wk2, c12);
+            }
+        } else {
+            const Corner ch = make_corner(ix, iy, W, H);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!corner_ok(ch, k, W, H)) continue;
+                const float wk = corner_wgt(ch, k);
+                const int cp = corner_pix(ch, k, W);
+                const float4 oo = __ldg(pOA + cp);
+                const float2 cc = __ldg(pCB + cp);
+                const float2 wk2 = make_float2(wk, wk);
+                v01 = ffma2(make_float2(oo.x, oo.y), wk2, v01);
+                v2c = ffma2(make_float2(oo.z, oo.w), wk2, v2c);
+                c12 = ffma2(cc, wk2, c12);
+            }
+        }
+        hv[h][0] = v01.x + hx[h];
+        hv[h][1] = v01.y + hy[h];
+        hv[h][2] = v2c.x;
+        hc[h][0] = v2c.y; hc[h][1] = c12.x; hc[h][2] = c12.y;
+    }
+    float res[3];
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        float m = hc[0][e];
+#pragma unroll
+        for (int h = 1; h < 2 * NH; ++h) m = fmaxf(m, hc[h][e]);
+        float ex[2 * NH], se = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2 * NH; ++h) { ex[h] = FASTEXP ? __expf(hc[h][e] - m) : expf(hc[h][e] - m); se += ex[h]; }
+        const float inv = __frcp_rn(se);
+        float o = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2 * NH; ++h) o = fmaf(hv[h][e], ex[h] * inv, o);
+        res[e] = o;
+    }
+    return make_float3(res[0], res[1], res[2]);
+}
+
 }  // namespace das

@@ -191,119 +191,16 @@ dense_sample_kernel(const DenseParams p) {
 template <int NH, bool FASTEXP>
 __global__ void __launch_bounds__(256, 3)
 dense_sample2_kernel(const DenseParams p) {
-    static_assert(NH == 4, "plane layout below is for 2*NH = 8 sampling offsets");
     const das_level_desc& d = p.lv->lv[p.level];
     const int H = d.H, W = d.W, HW = H * W, J = p.J;
-    const float fW = static_cast<float>(W), fH = static_cast<float>(H);
-    const float rW = __frcp_rn(fW), rH = __frcp_rn(fH);
     const long long total = static_cast<long long>(p.B) * HW * J;
     const DensePlanes pl = dense_planes(p.proj, p.B, J, HW);
     for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
          t += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int pix = static_cast<int>(t % HW);
-        const long long bj = t / HW;                 // b * J + j
-        const int y = pix / W, x = pix - y * W;
-        const float4* __restrict__ pS0 = pl.s0 + static_cast<size_t>(bj) * HW;
-        const float4* __restrict__ pS1 = pl.s1 + static_cast<size_t>(bj) * HW;
-        const float4* __restrict__ pOA = pl.oa + static_cast<size_t>(bj) * HW;
-        const float2* __restrict__ pCB = pl.cb + static_cast<size_t>(bj) * HW;
-        const float4 s0 = __ldg(pS0 + pix), s1 = __ldg(pS1 + pix), om = __ldg(pOA + pix);
-        const float ox = om.x, oy = om.y;
-        float hx[2 * NH], hy[2 * NH];
-        {
-            const float ix = sample_coord(x, ox, fW, rW), iy = sample_coord(y, oy, fH, rH);
-            const float fx = floorf(ix), fy = floorf(iy);
-            const float ww = ix - fx, wn = iy - fy;
-            float2 a01 = make_float2(0.f, 0.f), a23 = a01, a45 = a01, a67 = a01;
-            if (fx >= 0.f && fx <= fW - 2.f && fy >= 0.f && fy <= fH - 2.f) {
-                const int cp = static_cast<int>(fy) * W + static_cast<int>(fx);
-                const float we = 1.0f - ww, ws = 1.0f - wn;
-                const float wk4[4] = {ws * we, ws * ww, wn * we, wn * ww};
-                const int off4[4] = {0, 1, W, W + 1};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float4 b0 = __ldg(pS0 + cp + off4[k]), b1 = __ldg(pS1 + cp + off4[k]);
-                    const float2 wk2 = make_float2(wk4[k], wk4[k]);
-                    a01 = ffma2(make_float2(b0.x, b0.y), wk2, a01); a23 = ffma2(make_float2(b0.z, b0.w), wk2, a23);
-                    a45 = ffma2(make_float2(b1.x, b1.y), wk2, a45); a67 = ffma2(make_float2(b1.z, b1.w), wk2, a67);
-                }
-            } else {
-                const Corner ct = make_corner(ix, iy, W, H);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (!corner_ok(ct, k, W, H)) continue;
-                    const float wk = corner_wgt(ct, k);
-                    const int cp = corner_pix(ct, k, W);
-                    const float4 b0 = __ldg(pS0 + cp), b1 = __ldg(pS1 + cp);
-                    const float2 wk2 = make_float2(wk, wk);
-                    a01 = ffma2(make_float2(b0.x, b0.y), wk2, a01); a23 = ffma2(make_float2(b0.z, b0.w), wk2, a23);
-                    a45 = ffma2(make_float2(b1.x, b1.y), wk2, a45); a67 = ffma2(make_float2(b1.z, b1.w), wk2, a67);
-                }
-            }
-            hx[0] = a01.x + ox; hy[0] = a01.y + oy;
-            hx[1] = a23.x + ox; hy[1] = a23.y + oy;
-            hx[2] = a45.x + ox; hy[2] = a45.y + oy;
-            hx[3] = a67.x + ox; hy[3] = a67.y + oy;
-            hx[4] = s0.x; hy[4] = s0.y; hx[5] = s0.z; hy[5] = s0.w;
-            hx[6] = s1.x; hy[6] = s1.y; hx[7] = s1.z; hy[7] = s1.w;
-        }
-        float hv[2 * NH][3], hc[2 * NH][3];
-#pragma unroll
-        for (int h = 0; h < 2 * NH; ++h) {
-            const float ix = sample_coord(x, hx[h], fW, rW), iy = sample_coord(y, hy[h], fH, rH);
-            const float fx = floorf(ix), fy = floorf(iy);
-            const float ww = ix - fx, wn = iy - fy;
-            float2 v01 = make_float2(0.f, 0.f), v2c = v01, c12 = v01;      // {O.x, O.y}, {O.z, cf.x}, {cf.y, cf.z}
-            if (fx >= 0.f && fx <= fW - 2.f && fy >= 0.f && fy <= fH - 2.f) {
-                const int cp = static_cast<int>(fy) * W + static_cast<int>(fx);
-                const float we = 1.0f - ww, ws = 1.0f - wn;
-                const float wk4[4] = {ws * we, ws * ww, wn * we, wn * ww};
-                const int off4[4] = {0, 1, W, W + 1};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float4 oo = __ldg(pOA + cp + off4[k]);
-                    const float2 cc = __ldg(pCB + cp + off4[k]);
-                    const float2 wk2 = make_float2(wk4[k], wk4[k]);
-                    v01 = ffma2(make_float2(oo.x, oo.y), wk2, v01);
-                    v2c = ffma2(make_float2(oo.z, oo.w), wk2, v2c);
-                    c12 = ffma2(cc, wk2, c12);
-                }
-            } else {
-                const Corner ch = make_corner(ix, iy, W, H);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (!corner_ok(ch, k, W, H)) continue;
-                    const float wk = corner_wgt(ch, k);
-                    const int cp = corner_pix(ch, k, W);
-                    const float4 oo = __ldg(pOA + cp);
-                    const float2 cc = __ldg(pCB + cp);
-                    const float2 wk2 = make_float2(wk, wk);
-                    v01 = ffma2(make_float2(oo.x, oo.y), wk2, v01);
-                    v2c = ffma2(make_float2(oo.z, oo.w), wk2, v2c);
-                    c12 = ffma2(cc, wk2, c12);
-                }
-            }
-            hv[h][0] = v01.x + hx[h];
-            hv[h][1] = v01.y + hy[h];
-            hv[h][2] = v2c.x;
-            hc[h][0] = v2c.y; hc[h][1] = c12.x; hc[h][2] = c12.y;
-        }
-        float res[3];
-#pragma unroll
-        for (int e = 0; e < 3; ++e) {
-            float m = hc[0][e];
-#pragma unroll
-            for (int h = 1; h < 2 * NH; ++h) m = fmaxf(m, hc[h][e]);
-            float ex[2 * NH], se = 0.f;
-#pragma unroll
-            for (int h = 0; h < 2 * NH; ++h) { ex[h] = FASTEXP ? __expf(hc[h][e] - m) : expf(hc[h][e] - m); se += ex[h]; }
-            const float inv = __frcp_rn(se);
-            float o = 0.f;
-#pragma unroll
-            for (int h = 0; h < 2 * NH; ++h) o = fmaf(hv[h][e], ex[h] * inv, o);
-            res[e] = o;
-        }
-        reinterpret_cast<float4*>(p.uvd_out)[static_cast<size_t>(bj) * HW + pix] = make_float4(res[0], res[1], res[2], 0.f);
+        const size_t bj = static_cast<size_t>(t / HW);   // b * J + j
+        const float3 r = dense_sample_cell<NH, FASTEXP>(pl.s0 + bj * HW, pl.s1 + bj * HW, pl.oa + bj * HW, pl.cb + bj * HW, pix, W, H);
+        reinterpret_cast<float4*>(p.uvd_out)[bj * HW + pix] = make_float4(r.x, r.y, r.z, 0.f);
     }
 }
 

@@ -32,6 +32,9 @@ struct RefineParams {
     const das_levels* lv;
     const float* wpack;            // [J][NOUT][C] then [J][NOUT] biases
     const float* const* prev_uvd;  // nullptr or device array [n_levels] of joint-major maps [B][J][HW][4] (u, v, d, -)
+    const float* const* prev_planes;  // LAZY kernels: device array [n_levels] of layer L-2's projection planes (DensePlanes); the
+                                   // previous offsets are evaluated on demand at the sampled cells (dense_sample_cell)
+    int batch;
     const float* scale_xy;         // [B,2]
     const float* cand_score;
     const int32_t* cand_index;
@@ -49,7 +52,32 @@ struct RefineParams {
     RowCacheView rc;               // heads-only mode, host zero-copy: device row cache (keys == nullptr: off)
 };
 
-template <int CPL, int NH, int MINB, bool HEADS_ONLY, bool ROW_CACHE = false>
+// Previous-layer offsets (u, v, d) of joint j at cell `pix` of image b, level l.  LAZY: layer L-2's progressive sampling is
+// evaluated here, from its projection planes, instead of being read from a map that dense_sample2_kernel filled for every
+// cell -- the last layer looks at <= 33 cells per (candidate, joint), a few per cent of the map (recursive_update.py:220-235
+// evaluates every layer densely; the values are the same ones, produced by the same device function).
+template <bool LAZY>
+__device__ __forceinline__ void prev_offsets(const RefineParams& p, const das_levels* __restrict__ lvp, int l, int b, int j, int pix,
+                                             float (&pv)[3]) {
+    const das_level_desc& d = lvp->lv[l];
+    const int HW = d.H * d.W, J = p.J;
+    if constexpr (LAZY) {
+        const DensePlanes pl = dense_planes(const_cast<float*>(p.prev_planes[l]), p.batch, J, HW);
+        const size_t bj = (static_cast<size_t>(b) * J + j) * HW;
+        const float3 r = dense_sample_cell<4, false>(pl.s0 + bj, pl.s1 + bj, pl.oa + bj, pl.cb + bj, pix, d.W, d.H);
+        pv[0] = r.x; pv[1] = r.y; pv[2] = r.z;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            pv[k] = 0.f;
+            if (p.prev_uvd) pv[k] = __ldg(p.prev_uvd[l] + ((static_cast<size_t>(b) * J + j) * HW + pix) * 4 + k);
+            else if (!(k == 2 && j == p.root))
+                pv[k] = InMap(d.pose, lvp->in_dtype)((static_cast<size_t>(b) * (3 + 6 * J) + 3 + 3 * j + k) * HW + pix) * (k < 2 ? d.scale_uv : d.scale_d);
+        }
+    }
+}
+
+template <int CPL, int NH, int MINB, bool HEADS_ONLY, bool ROW_CACHE = false, bool LAZY = false>
 __global__ void __launch_bounds__(RS_WARPS * 32, MINB)
 refine_sparse_kernel(const RefineParams p) {
     constexpr int C = CPL * 32;
@@ -104,6 +132,9 @@ refine_sparse_kernel(const RefineParams p) {
         float S[2 * NH];
         float O[3];
         {
+            float pvc[3];
+            if constexpr (LAZY) prev_offsets<true>(p, lvp, l, b, j, idx, pvc);
+            else { pvc[0] = prev_at(idx, 0); pvc[1] = prev_at(idx, 1); pvc[2] = prev_at(idx, 2); }
             const float* prow = (ROW_CACHE && p.rc.cand_rows) ? p.rc.cand_rows + static_cast<size_t>(cs) * C : F + static_cast<size_t>(idx) * C;
             const Row<CPL> f = load_row<CPL>(prow, lane, true);
             float acc[2 * NH + 6];
@@ -118,7 +149,7 @@ refine_sparse_kernel(const RefineParams p) {
             for (int k = 0; k < 3; ++k) {
                 const float g = sigmoid_acc(acc[O_GATE + k] + __ldg(Bj + O_GATE + k));
                 const float n = acc[O_VAL + k] + __ldg(Bj + O_VAL + k);
-                O[k] = __fadd_rn(__fmul_rn(1.0f - g, prev_at(idx, k)), __fmul_rn(g, n));
+                O[k] = __fadd_rn(__fmul_rn(1.0f - g, pvc[k]), __fmul_rn(g, n));
             }
         }
 
@@ -224,7 +255,10 @@ refine_sparse_kernel(const RefineParams p) {
                 const int gidx = ok ? base + u_of_leader : -1;
                 if (is_leader) {
                     const float* ptr = F + static_cast<size_t>(pix) * C;
-                    const float pv0 = prev_at(pix, 0), pv1 = prev_at(pix, 1), pv2 = prev_at(pix, 2);
+                    float pvl[3];
+                    if constexpr (LAZY) prev_offsets<true>(p, lvp, l, b, j, pix, pvl);
+                    else { pvl[0] = prev_at(pix, 0); pvl[1] = prev_at(pix, 1); pvl[2] = prev_at(pix, 2); }
+                    const float pv0 = pvl[0], pv1 = pvl[1], pv2 = pvl[2];
                     const unsigned long long pb = reinterpret_cast<unsigned long long>(ptr);
                     float4* dst = reinterpret_cast<float4*>(p.urow + (static_cast<size_t>(j) * p.row_cap + base + my_u) * 8);
                     dst[0] = make_float4(__uint_as_float(static_cast<unsigned>(pb)), __uint_as_float(static_cast<unsigned>(pb >> 32)), pv0, pv1);
@@ -361,11 +395,12 @@ __device__ __forceinline__ float reduce_nb(const float (&a)[NB]) {
 
 // SPLIT: the kernel stops after phase 2 and leaves each item's 16 head offsets in the first 64 bytes of the item's row-record
 // slot; refine_records_kernel (one warp per item, 4x the parallelism, no batch-serial passes) writes the records.
-template <int CPL, int NH, int NB, bool SPLIT>
+template <int CPL, int NH, int NB, bool SPLIT, bool LAZY = false>
 __global__ void __launch_bounds__(H8_WARPS * 32, NB == 4 ? 5 : (NB == 2 ? 8 : 4))     // NB = 4: 96 registers, 20 warps per SM (2 960 task slots: BASELINE config #2 has 2 400 tasks -> one wave)
 refine_heads8_kernel(const RefineParams p) {
     static_assert(NH == 4, "32 rows per item = 8 heads x 4 corners");
     static_assert(NB == 2 || NB == 4 || NB == 8, "candidates per task");
+    static_assert(!LAZY || SPLIT, "on-demand previous offsets: the split path only (refine_records_kernel evaluates the leaders')");
     constexpr int C = CPL * 32;
     constexpr int NOUT = 2 * NH + 9;
     constexpr int O_GATE = 2 * NH, O_VAL = 2 * NH + 3;
@@ -434,14 +469,7 @@ refine_heads8_kernel(const RefineParams p) {
         float S[2 * NH], O[3];
         {
             float prev[3] = {0.f, 0.f, 0.f};
-            if (valid) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    if (p.prev_uvd) prev[k] = __ldg(p.prev_uvd[l] + ((static_cast<size_t>(b) * J + j) * HW + idx) * 4 + k);
-                    else if (!(k == 2 && j == p.root))
-                        prev[k] = InMap(d.pose, lvp->in_dtype)((static_cast<size_t>(b) * (3 + 6 * J) + 3 + 3 * j + k) * HW + idx) * (k < 2 ? d.scale_uv : d.scale_d);
-                }
-            }
+            if (valid) prev_offsets<LAZY>(p, lvp, l, b, j, idx, prev);
             const float* own = valid ? F + static_cast<size_t>(idx) * C : nullptr;
             Row<CPL> f[NB];
 #pragma unroll
@@ -661,7 +689,7 @@ refine_heads8_kernel(const RefineParams p) {
 // Row records of the split phase 1-2 path: one warp per (candidate, joint) item, lane = (head = lane >> 2, corner = lane & 3).
 // Reads the item's 16 head offsets left by refine_heads8_kernel<.., SPLIT> in the first 64 bytes of its row-record slot, then
 // overwrites the slot with the 32 records; distinct sampled cells -> the joint's row list; assembly record; centre; valid_list.
-template <int NH>
+template <int NH, bool LAZY = false>
 __global__ void __launch_bounds__(256)
 refine_records_kernel(const RefineParams p) {
     static_assert(NH == 4, "32 rows per item = 8 heads x 4 corners");
@@ -702,14 +730,7 @@ refine_records_kernel(const RefineParams p) {
         const int n_u = __popc(lead_mask);
         // the leaders' previous offsets fly while the reservation makes its round trip
         float pv[3] = {0.f, 0.f, 0.f};
-        if (is_leader) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (p.prev_uvd) pv[k] = __ldg(p.prev_uvd[l] + ((static_cast<size_t>(b) * J + j) * HW + pix) * 4 + k);
-                else if (!(k == 2 && j == p.root))
-                    pv[k] = InMap(d.pose, lvp->in_dtype)((static_cast<size_t>(b) * (3 + 6 * J) + 3 + 3 * j + k) * HW + pix) * (k < 2 ? d.scale_uv : d.scale_d);
-            }
-        }
+        if (is_leader) prev_offsets<LAZY>(p, lvp, l, b, j, pix, pv);
         int base = 0;
         if (lane == 0 && n_u) base = atomicAdd(p.work_counter + 4 + j, n_u);
         base = __shfl_sync(FULL, base, 0);
@@ -935,6 +956,11 @@ extern "C" int das_refine_heads(const das_levels* d_levels, const das_levels* h_
     DAS_REQUIRE(items < (1ll << 31), DAS_ERR_CAPACITY, "too many work items");
     p.n_items = static_cast<int>(items);
     p.rc = row_cache_view(rc);
+    // scratch->prev_planes: layer L-2's sampling is evaluated on demand from its projection planes (prev_uvd is ignored)
+    const bool lazy = scratch->prev_planes != nullptr;
+    p.prev_planes = scratch->prev_planes;
+    p.batch = h_levels->batch;
+    DAS_REQUIRE(!lazy || cfg->num_layers > 1, DAS_ERR_ARG, "das_refine_heads: prev_planes given but num_layers=%d", cfg->num_layers);
     // [0] queue head, [1] n_valid, [4..4+J) per-joint distinct-row counts; [2] (the peer-store ticket) is left alone.
     // Inside das_plan's chain das_score_topk has already cleared them (no memset nodes between the kernels).
     const ChainCtx& cx = chain_ctx();
@@ -948,9 +974,11 @@ extern "C" int das_refine_heads(const das_levels* d_levels, const das_levels* h_
     // fewer items than warp slots (one image, a few centres): one warp per item finishes sooner than 4 items per warp
     const bool per_item = force ? force == 1 : items <= 24LL * kSMs;
     if (p.rc.keys) {
-        DAS_CUDA_CHECK(launch_chain(refine_sparse_kernel<8, 4, 3, true, true>, dim3(kSMs * 3), dim3(RS_WARPS * 32), 0, st, cx.pdl, p));
+        if (lazy) DAS_CUDA_CHECK(launch_chain(refine_sparse_kernel<8, 4, 3, true, true, true>, dim3(kSMs * 3), dim3(RS_WARPS * 32), 0, st, cx.pdl, p));
+        else DAS_CUDA_CHECK(launch_chain(refine_sparse_kernel<8, 4, 3, true, true>, dim3(kSMs * 3), dim3(RS_WARPS * 32), 0, st, cx.pdl, p));
     } else if (per_item) {
-        DAS_CUDA_CHECK(launch_chain(refine_sparse_kernel<8, 4, 3, true, false>, dim3(kSMs * 3), dim3(RS_WARPS * 32), 0, st, cx.pdl, p));
+        if (lazy) DAS_CUDA_CHECK(launch_chain(refine_sparse_kernel<8, 4, 3, true, false, true>, dim3(kSMs * 3), dim3(RS_WARPS * 32), 0, st, cx.pdl, p));
+        else DAS_CUDA_CHECK(launch_chain(refine_sparse_kernel<8, 4, 3, true, false>, dim3(kSMs * 3), dim3(RS_WARPS * 32), 0, st, cx.pdl, p));
     } else {
         static const int nb = std::getenv("DAS_HEADS_NB") ? std::atoi(std::getenv("DAS_HEADS_NB")) : 4;
         // grid = J x cpj CTAs: CTA (j, g) serves joint j, its H8_WARPS warps walk candidate blocks g*H8_WARPS + warp, + cpj*H8_WARPS, ...
@@ -960,10 +988,17 @@ extern "C" int das_refine_heads(const das_levels* d_levels, const das_levels* h_
         const int grid = cpj * cfg->num_joints;
         // DAS_HEADS_SPLIT=0: records inside the batched kernel (one launch); default: phases 1-2 batched, records by a warp per item
         static const bool split = !(std::getenv("DAS_HEADS_SPLIT") && std::getenv("DAS_HEADS_SPLIT")[0] == '0');
+        DAS_REQUIRE(!lazy || (split && nb == 4), DAS_ERR_UNSUPPORTED,
+                    "das_refine_heads: prev_planes needs the default split kernels (unset DAS_HEADS_SPLIT / DAS_HEADS_NB)");
         if (split && nb == 4) {
-            DAS_CUDA_CHECK(launch_chain(refine_heads8_kernel<8, 4, 4, true>, dim3(grid), dim3(H8_WARPS * 32), 0, st, cx.pdl, p));
             const int grid_r = static_cast<int>(std::max<long long>(1, std::min<long long>((items + 7) / 8, 8LL * kSMs)));
-            DAS_CUDA_CHECK(launch_chain(refine_records_kernel<4>, dim3(grid_r), dim3(256), 0, st, cx.pdl, p));
+            if (lazy) {
+                DAS_CUDA_CHECK(launch_chain(refine_heads8_kernel<8, 4, 4, true, true>, dim3(grid), dim3(H8_WARPS * 32), 0, st, cx.pdl, p));
+                DAS_CUDA_CHECK(launch_chain(refine_records_kernel<4, true>, dim3(grid_r), dim3(256), 0, st, cx.pdl, p));
+            } else {
+                DAS_CUDA_CHECK(launch_chain(refine_heads8_kernel<8, 4, 4, true>, dim3(grid), dim3(H8_WARPS * 32), 0, st, cx.pdl, p));
+                DAS_CUDA_CHECK(launch_chain(refine_records_kernel<4>, dim3(grid_r), dim3(256), 0, st, cx.pdl, p));
+            }
             chain_ctx().extra_launches += 1;
         } else if (nb == 8) DAS_CUDA_CHECK(launch_chain(refine_heads8_kernel<8, 4, 8, false>, dim3(grid), dim3(H8_WARPS * 32), 0, st, cx.pdl, p));
         else if (nb == 2) DAS_CUDA_CHECK(launch_chain(refine_heads8_kernel<8, 4, 2, false>, dim3(grid), dim3(H8_WARPS * 32), 0, st, cx.pdl, p));

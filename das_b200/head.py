@@ -406,6 +406,11 @@ class DecodePlan:
         mode, several decodes in flight on different streams), -1 auto (default: on for decodes too small to fill the GPU)."""
         _lib.check(self.lib.das_plan_set_pdl(self._plan, int(mode)), "das_plan_set_pdl")
 
+    def set_on_demand_sampling(self, on: bool):
+        """num_layers > 1, tensor-core path: True (default) = layer L-2 only projects and the sparse last layer evaluates its
+        progressive sampling at the cells it looks at; False = every dense layer samples its whole map.  Same results."""
+        _lib.check(self.lib.das_plan_set_on_demand_sampling(self._plan, int(bool(on))), "das_plan_set_on_demand_sampling")
+
     def refine_stats(self):
         """(distinct (cell, joint) feature rows the gathered GEMM multiplied, candidates above score_thr, rows without the
         de-duplication) of the last tensor-core-mode run; synchronises with the device."""

@@ -180,6 +180,10 @@ typedef struct das_refine_scratch {
                                                 ticket of the plan), [4+j] distinct rows of joint j                            */
     int32_t row_cap;
     int32_t reserved_;
+    const float* const* prev_planes; /* NULL, or device array [n_levels] of the projection planes das_dense_project_tc wrote for
+                                        layer L-2 (num_layers > 1): das_refine_heads then evaluates that layer's progressive
+                                        sampling on demand, only at the cells the last layer looks at (<= 33 per item), and
+                                        ignores prev_uvd -- layer L-2 needs no das_refine_dense_layer sampling pass            */
 } das_refine_scratch;
 
 /* Tensor-core variant of stage 3+4 (feat_channels = 256, num_heads = 4), three launches:
@@ -293,6 +297,12 @@ int das_plan_set_refine_mode(das_plan* plan, int32_t mode);
  * 0 = plain stream order (the throughput mode, for several independent decodes in flight on different streams: waiting
  * CTAs would take SM resources from them), -1 = auto (default): on when batch * candidate slots * joints <= 24 * 148. */
 int das_plan_set_pdl(das_plan* plan, int32_t mode);
+/* num_layers > 1 on the tensor-core path: 1 (default) = layer L-2 runs its projection only and the sparse last layer
+ * evaluates that layer's progressive sampling on demand, at the <= 33 cells per (candidate, joint) it looks at
+ * (das_refine_scratch.prev_planes); 0 = every dense layer samples its whole map like recursive_update.py:220-235.  Same
+ * values either way (one device function); layers 0..L-3 are always dense because the next projection blends with their
+ * output at every cell. */
+int das_plan_set_on_demand_sampling(das_plan* plan, int32_t on);
 int das_plan_buffers(const das_plan* plan, das_buffers* out, int32_t* cand_slots, int32_t* out_slots);
 /* Caller-owned output block: the plan writes its out_* buffers into `block` (device memory, 256-B aligned, at least
  * das_plan_output_block() bytes + 256 for the sequence word) instead of its own allocation -- e.g. a slice of one

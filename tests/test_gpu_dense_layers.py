@@ -13,26 +13,55 @@ from test_gpu_parity import compare, TOL, GOLDEN
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("mode", [None, 0], ids=["tensor_core", "simt"])
+# mode: refine_mode (None = tensor cores, 0 = fp32 SIMT); on_demand: layer L-2's sampling evaluated by the sparse last layer at
+# the cells it looks at (the default on the tensor-core path) or over the whole map like the reference
+@pytest.mark.parametrize("mode,on_demand", [(None, True), (None, False), (0, None)], ids=["tensor_core", "tensor_core_all_dense", "simt"])
 @pytest.mark.parametrize("layers,J,root", [(2, 15, 2), (3, 17, 14), (2, 21, 14)])
-def test_multi_layer_refinement_matches_oracle(layers, J, root, mode):
+def test_multi_layer_refinement_matches_oracle(layers, J, root, mode, on_demand):
     cfg = synth.HeadConfig(num_joints=J, root_idx=root, depth_factor=1.0, z_norm=50.0, num_layers=layers)
     tc = dict(nms_pre=20, nms_post=20, nms_thr=0.9, score_thr=0.0)
     case = util.make_case(cfg, 2, 28, 36, seed=600 + layers, scales=(1.05, 0.95, 1.1, 0.9), tc=tc)
     ref, _ = util.run_oracle(case, tc)
     util.assert_margins(case, tc, ref)
-    plan, got = util.run_gpu(case, tc, refine=True, refine_mode=mode)
+    plan, got = util.run_gpu(case, tc, refine=True, refine_mode=mode, on_demand=on_demand)
     compare(plan, got, ref)
 
 
-def test_multi_layer_pyramid():
+@pytest.mark.parametrize("on_demand", [True, False], ids=["on_demand", "all_dense"])
+def test_multi_layer_pyramid(on_demand):
     cfg = synth.HeadConfig(num_joints=15, root_idx=2, depth_factor=20.0, z_norm=50.0, num_layers=2, strides=(8, 16, 32))
     tc = dict(nms_pre=50, nms_post=30, nms_thr=0.9, score_thr=0.03)
     case = util.make_case(cfg, 2, 32, 48, seed=700, peaks=20, tc=tc)
     ref, _ = util.run_oracle(case, tc)
     util.assert_margins(case, tc, ref)
-    plan, got = util.run_gpu(case, tc, refine=True)
+    plan, got = util.run_gpu(case, tc, refine=True, on_demand=on_demand)
     compare(plan, got, ref)
+
+
+@pytest.mark.parametrize("layers,force", [(2, 0), (3, 0), (3, 1), (3, 2)], ids=["L2", "L3", "L3_warp_per_item", "L3_batched"])
+def test_on_demand_sampling_equals_the_dense_map(layers, force):
+    """The sparse last layer evaluating layer L-2's sampling at its own cells (one device function shared with the dense
+    kernel) returns the bits the whole-map pass returns -- both phase 1-2 kernels, eager and graph replay."""
+    import torch
+    from das_b200 import _lib
+    cfg = synth.HeadConfig(num_joints=17, root_idx=14, depth_factor=1.0, z_norm=50.0, num_layers=layers)
+    tc = dict(nms_pre=20, nms_post=20, nms_thr=0.9, score_thr=0.0)
+    case = util.make_case(cfg, 3, 40, 52, seed=640 + layers, peaks=12, tc=tc)
+    lib = _lib.load()
+    try:
+        _lib.check(lib.das_debug_force_heads_kernel(force))
+        outs = []
+        for on in (True, False):
+            plan, got = util.run_gpu(case, tc, refine=True, on_demand=on)
+            plan.run(use_graph=True)         # second call: the captured graph
+            torch.cuda.synchronize()
+            outs.append(plan.results(case["metas"]))
+    finally:
+        lib.das_debug_force_heads_kernel(0)
+    for a, b in zip(*outs):
+        assert a.keys() == b.keys() and len(a["scores"]) > 0
+        for k in a:
+            assert torch.equal(a[k], b[k]) if torch.is_tensor(a[k]) else a[k] == b[k], k
 
 
 def test_golden_mupots17_three_layers():

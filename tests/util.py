@@ -76,9 +76,12 @@ def make_plan(case, test_cfg, refine=True, peak_kernel=0, device="cuda", refine_
 
 
 def run_gpu(case, test_cfg, refine=True, peak_kernel=0, pose_override=None, use_graph=True, device="cuda",
-            refine_mode=None):
-    """Decode on the GPU through the C-ABI plan. pose_override: per-level final pose maps for refine=False."""
+            refine_mode=None, on_demand=None):
+    """Decode on the GPU through the C-ABI plan. pose_override: per-level final pose maps for refine=False.
+    on_demand: None = the plan's default, else das_plan_set_on_demand_sampling (num_layers > 1)."""
     plan = make_plan(case, test_cfg, refine, peak_kernel, device, refine_mode)
+    if on_demand is not None:
+        plan.set_on_demand_sampling(on_demand)
     dl = synth.levels_to(case["levels"], device)
     levels = []
     for l, lv in enumerate(dl):
