@@ -128,6 +128,7 @@ SIGNATURES = {
     "das_plan_buffers": (C.c_int, [_VP, C.POINTER(Buffers), _i32p, _i32p]),
     "das_plan_kernel_launches": (C.c_int64, [_VP]),
     "das_plan_run_host": (C.c_int, [_VP, C.POINTER(Levels), _VP, _VP, Buffers, _VP]),
+    "das_plan_run_host_async": (C.c_int, [_VP, C.POINTER(Levels), _VP, _VP, Buffers, _VP]),
     "das_tc_selftest": (C.c_int, [_VP, _VP, _VP, C.c_int32, C.c_int32, C.c_int32, _VP]),
     "das_tc_mma_bench": (C.c_int, [C.c_int32, C.c_int32, _VP, _VP]),
     "das_plan_h2d_bytes": (C.c_int64, [_VP]),

@@ -770,6 +770,14 @@ extern "C" int das_plan_refine_stats(das_plan* p, int64_t stats[3]) {
 extern "C" int das_plan_run_host(das_plan* p, const das_levels* levels, const float* scale_xy, const double* cam,
                                  das_buffers host_out, void* stream) {
     using namespace das;
+    DAS_TRY(das_plan_run_host_async(p, levels, scale_xy, cam, host_out, stream));
+    DAS_CUDA_CHECK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return DAS_OK;
+}
+
+extern "C" int das_plan_run_host_async(das_plan* p, const das_levels* levels, const float* scale_xy, const double* cam,
+                                       das_buffers host_out, void* stream) {
+    using namespace das;
     DAS_REQUIRE(p && levels, DAS_ERR_ARG, "das_plan_run_host: null pointer");
     DAS_REQUIRE(levels->n_levels == p->shape.n_levels && levels->batch == p->shape.batch, DAS_ERR_ARG,
                 "run_host: n_levels/batch differ from the plan");
@@ -885,6 +893,5 @@ extern "C" int das_plan_run_host(das_plan* p, const das_levels* levels, const fl
     DAS_CUDA_CHECK(D2H(host_out.out_world, p->buf.out_world, B * P * J * 3 * 8));
     DAS_CUDA_CHECK(D2H(host_out.cand_score, p->buf.cand_score, B * p->CT * 4));
     DAS_CUDA_CHECK(D2H(host_out.cand_index, p->buf.cand_index, B * p->CT * 4));
-    DAS_CUDA_CHECK(cudaStreamSynchronize(st));
     return DAS_OK;
 }

@@ -357,9 +357,11 @@ class DecodePlan:
         _lib.check(self.lib.das_plan_output_block(self._plan, C.byref(ptr), C.byref(n)), "das_plan_output_block")
         return torch.as_tensor(_DevArray(ptr.value, (n.value,), "|u1"), device=self.device)
 
-    def run_host(self, levels: Sequence[dict], img_metas: Sequence[dict], host_out: Dict[str, torch.Tensor]):
+    def run_host(self, levels: Sequence[dict], img_metas: Sequence[dict], host_out: Dict[str, torch.Tensor], sync: bool = True):
         """End-to-end entry with HOST tensors (pinned for full PCIe speed): H2D of every input,
-        decode, D2H of the packed outputs into ``host_out`` (see alloc_host_out), stream sync."""
+        decode, D2H of the packed outputs into ``host_out`` (see alloc_host_out), stream sync.
+        sync=False (das_plan_run_host_async): everything is enqueued on the current stream and the call returns; the
+        caller synchronises that stream before it reads ``host_out`` or reuses the inputs / this plan."""
         lv = self._levels_struct(levels, host=True)
         sxy, cam = self.pack_metas(img_metas)
         ob = Buffers()
@@ -367,9 +369,9 @@ class DecodePlan:
             if k in host_out:
                 setattr(ob, k, host_out[k].data_ptr())
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.das_plan_run_host(self._plan, C.byref(lv), C.c_void_p(sxy.ctypes.data),
-                                                  C.c_void_p(cam.ctypes.data), ob, _stream_ptr(self.device)),
-                       "das_plan_run_host")
+            fn = self.lib.das_plan_run_host if sync else self.lib.das_plan_run_host_async
+            _lib.check(fn(self._plan, C.byref(lv), C.c_void_p(sxy.ctypes.data), C.c_void_p(cam.ctypes.data), ob,
+                          _stream_ptr(self.device)), "das_plan_run_host")
 
     def alloc_host_out(self, pinned: bool = True) -> Dict[str, torch.Tensor]:
         return {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=pinned)

@@ -333,6 +333,13 @@ int64_t das_plan_kernel_launches(const das_plan* plan);   /* kernels enqueued by
  * synchronises `stream`. `levels` holds HOST pointers here. */
 int das_plan_run_host(das_plan* plan, const das_levels* levels, const float* scale_xy,
                       const double* cam, das_buffers host_out, void* stream);
+/* The same call without the final synchronisation: everything (H2D copies, decode, D2H copies) is enqueued on `stream` and
+ * the call returns; the caller synchronises the stream (or an event recorded behind the call) before it reads `host_out`,
+ * and does not touch the input maps, `host_out` or this plan again before that.  Two plans on two streams driven in turn
+ * this way keep PCIe busy across calls: batch n+1 is copied while the kernels of batch n read their rows in place and
+ * while its results travel back (bench.py `e2e`).  scale_xy / cam are consumed before the call returns. */
+int das_plan_run_host_async(das_plan* plan, const das_levels* levels, const float* scale_xy,
+                            const double* cam, das_buffers host_out, void* stream);
 int64_t das_plan_h2d_bytes(const das_plan* plan);
 /* das_plan_run_host transfer policy: 0 = bulk H2D copy of every input map (default); 1 = only the logit planes are
  * copied, the pose and feature maps (of which the decode touches ~5 %) are read in place from PINNED host memory

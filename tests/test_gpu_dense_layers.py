@@ -78,3 +78,27 @@ def test_golden_mupots17_three_layers():
         assert idx == gold[f"index_{i}"].tolist()
         assert util.rel_err(g["poses"].cpu().numpy(), gold[f"poses_{i}"]) < TOL
         assert util.rel_err(g["poses_cam"].cpu().numpy(), gold[f"cam_{i}"]) < TOL
+
+
+@pytest.mark.parametrize("layers", [2, 3])
+def test_multi_layer_host_entry_equals_device_entry(layers):
+    """das_plan_run_host with num_layers > 1: the dense layers' maps are bulk-copied in every transfer policy, the last layer
+    reads its rows in place / through the row cache, and layer L-2's sampling is evaluated on demand there as well."""
+    import torch
+    cfg = synth.HeadConfig(num_joints=15, root_idx=2, depth_factor=20.0, z_norm=50.0, num_layers=layers)
+    tc = dict(nms_pre=12, nms_post=12, nms_thr=0.9, score_thr=0.0)
+    case = util.make_case(cfg, 2, 32, 40, seed=660 + layers, peaks=8, tc=tc)
+    plan, _ = util.run_gpu(case, tc, refine=True)
+    want = plan.views_of_block(plan.output_block().clone().cpu())
+    assert int(want["out_count"].sum()) > 0
+    host_levels = [dict(cls=lv["cls"].pin_memory(), ctr=lv["ctr"].pin_memory(), pose=lv["pose_raw"].pin_memory(),
+                        feats=[f.permute(0, 2, 3, 1).contiguous().pin_memory().permute(0, 3, 1, 2) for f in lv["feats"]],
+                        scales=lv["scales"]) for lv in case["levels"]]
+    for zero_copy, row_cache in ((False, False), (True, False), (True, True)):
+        p2 = util.make_plan(case, tc, refine=True)
+        p2.set_host_mode(zero_copy, row_cache=row_cache)
+        out = p2.alloc_host_out()
+        for _ in range(3):                     # eager first run, then graph capture + replay
+            p2.run_host(host_levels, case["metas"], out)
+            for k, v in want.items():
+                assert torch.equal(out[k], v), (zero_copy, row_cache, k)

@@ -315,6 +315,43 @@ def test_host_entry_equals_device_entry():
         assert torch.equal(out[k], out3[k]), k
 
 
+def test_async_host_entry_two_plans_in_flight():
+    """das_plan_run_host_async: two plans on two streams driven in turn (the bench's e2e loop) deliver the bits of the
+    synchronous call, in every transfer policy."""
+    tc = dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)
+    cases = [util.make_case(P, 4, 48, 64, seed=43 + i, scales=(1.1, 0.9, 1.05, 0.95)) for i in range(2)]
+    host = [[dict(cls=lv["cls"].pin_memory(), ctr=lv["ctr"].pin_memory(), pose=lv["pose_raw"].pin_memory(),
+                  feats=[f.permute(0, 2, 3, 1).contiguous().pin_memory().permute(0, 3, 1, 2) for f in lv["feats"]],
+                  scales=lv["scales"]) for lv in c["levels"]] for c in cases]
+    want = []
+    for c, h in zip(cases, host):
+        plan = util.make_plan(c, tc, refine=True)
+        o = plan.alloc_host_out()
+        plan.run_host(h, c["metas"], o)
+        assert int(o["out_count"].sum()) > 0
+        want.append({k: v.clone() for k, v in o.items()})
+    for zero_copy, row_cache in ((False, False), (True, False), (True, True)):
+        plans = [util.make_plan(c, tc, refine=True) for c in cases]
+        outs = [p.alloc_host_out() for p in plans]
+        streams = [torch.cuda.Stream() for _ in plans]
+        for p in plans:
+            p.set_host_mode(zero_copy, row_cache=row_cache)
+        for i in range(8):
+            k = i % 2
+            streams[k].synchronize()
+            if i >= 2:
+                for key, v in want[k].items():
+                    assert torch.equal(outs[k][key], v), (zero_copy, row_cache, i, key)
+                for t in outs[k].values():
+                    t.zero_()
+            with torch.cuda.stream(streams[k]):
+                plans[k].run_host(host[k], cases[k]["metas"], outs[k], sync=False)
+        torch.cuda.synchronize()
+        for k in range(2):
+            for key, v in want[k].items():
+                assert torch.equal(outs[k][key], v), (zero_copy, row_cache, "last", key)
+
+
 @pytest.mark.parametrize("cfg,tc,kw", [
     (P, dict(nms_pre=30, nms_post=30, nms_thr=0.9, score_thr=0.0), dict(coherent=8, peaks=6)),
     (dataclasses.replace(P, strides=(8, 16, 32, 64)), dict(nms_pre=40, nms_post=30, nms_thr=0.9, score_thr=0.05), dict(peaks=24)),
