@@ -22,4 +22,11 @@ lib.das_dense_set_debug_buffer(None)
 d = dbg.cpu().numpy().astype(np.float64) / 2.0          # two dense layers per decode accumulate into the same counters: per layer
 names = ['mma: wait acc_free', 'mma: wait a_full', 'mma: issue+execute', 'producer0: wait TMA', 'producer0: wait TMEM slot', 'producer0: work', 'epilogue0: wait acc_full', 'cta total']
 act = d[d[:, 2] > 0]
-for i, n in enumerate(names): print(f'{n:30s} mean {act[:, i].mean():12.0f}  max {act[:, i].max():12.0f}')
+for i, n in enumerate(names): print(f'{n:30s} min {act[:, i].min():12.0f}  mean {act[:, i].mean():12.0f}  max {act[:, i].max():12.0f}')
+# the Q CTAs of a tile sequence m = blockIdx // Q move in lock-step; sequences are independent: spread of their totals
+Q = (cfg.num_joints + 2) // 3
+tot = act[: (len(act) // Q) * Q, 7].reshape(-1, Q).mean(axis=1)
+print('cta total per tile sequence (kcycles):', ' '.join(f'{t / 1e3:.0f}' for t in tot))
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+ev[0].record(); plan.run(use_graph=False); ev[1].record(); torch.cuda.synchronize()
+print('whole decode, eager: %.3f ms' % ev[0].elapsed_time(ev[1]))
