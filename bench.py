@@ -573,20 +573,23 @@ class Runner:
 
     def roofline(self, stage, n_prof):
         """Roofline of the dominant kernel.  Two byte counts are reported for the sparse refinement stages:
-        * `frac`: bytes the kernel REALLY has to move.  The sampling-phase GEMM multiplies every DISTINCT (cell, joint)
-          feature row once (the 32 (head, corner) rows of an item that land on the same cell share one row), so its
-          algorithmic bytes are distinct rows x C x 4, counted on the device in this run (das_plan_refine_stats);
-        * `survey_frac`: SURVEY.md 8(d)'s per-item figure (32 rows per (centre, joint)) over the same time -- the number
-          round 1 reported.  It can exceed 1: that is the de-duplication, not bandwidth."""
+        * `frac` (`achieved`, `algorithmic_bytes_per_launch`): the task's definition -- SURVEY.md 8(d)'s per-unit figure (32
+          feature rows of C*4 bytes per (centre, joint) in the sampling phase) x the units of one launch / time / measured HBM
+          peak.  It can EXCEED 1: the sampling-phase GEMM multiplies every DISTINCT (cell, joint) row once (the 32 (head,
+          corner) rows of an item that land on the same cell share one row), so the kernel no longer moves SURVEY's bytes;
+        * `gathered_frac` (`gathered_bytes_per_launch`): the bytes the kernel REALLY gathers = distinct rows x C x 4, counted on
+          the device in this run (das_plan_refine_stats) -- the bandwidth picture of the kernel as built;
+        * `dram_frac`: ncu's DRAM bytes of the same kernels / time / peak (what came from HBM rather than L2).
+        `survey_frac` repeats `frac` under the name the round-2 documents use."""
         w, head = self.w, self.head
         mode = self.plans[0].refine_mode
-        sb_survey = stage_bytes(w, head, mode)
-        sb = dict(sb_survey)
+        sb = stage_bytes(w, head, mode)                 # SURVEY 8(d)
+        sg = dict(sb)                                   # ... with the sampling phase at its distinct gathered rows
         dedup = None
         if mode != 0 and head.num_layers >= 1:
             rows, n_valid, rows_nodedup = self.plans[0].refine_stats()
             if rows > 0:
-                sb["refine_assemble"] = rows * head.feat_channels * 4
+                sg["refine_assemble"] = rows * head.feat_channels * 4
                 dedup = dict(distinct_rows=rows, rows_without_dedup=rows_nodedup, valid_candidates=n_valid,
                              distinct_rows_per_item=rows / max(1, n_valid * head.num_joints))
         ms = dict(zip(STAGES, [float(x) for x in stage]))
@@ -597,25 +600,33 @@ class Runner:
                       "refine_tc2_kernel (tcgen05 %s: gathered GEMM over the distinct sampled rows) + refine_finish_kernel"
                       % ("3xTF32" if mode == 1 else "TF32"))
         peak, peak_src = measured_peak()
-        achieved = sb[dom] / (ms[dom] / 1e3) / 1e9
+
+        def gbs(nbytes, t_ms):
+            return nbytes / (t_ms / 1e3) / 1e9
+
+        achieved = gbs(sb[dom], ms[dom])
         traffic = ncu_traffic(w["key"], dom)
-        path_bytes, path_survey = sum(sb.values()), sum(sb_survey.values())
+        path_bytes, path_gathered = sum(sb.values()), sum(sg.values())
         total_ms = float(stage.sum())
         out = dict(bound="hbm", kernel=kernel, stage=dom, achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                   survey_frac=sb_survey[dom] / (ms[dom] / 1e3) / 1e9 / peak,
-                   traffic=traffic, dram_frac=(traffic / (ms[dom] / 1e3) / 1e9 / peak) if traffic else None,
+                   survey_frac=achieved / peak,
+                   gathered_achieved=gbs(sg[dom], ms[dom]), gathered_frac=gbs(sg[dom], ms[dom]) / peak,
+                   traffic=traffic, dram_frac=(gbs(traffic, ms[dom]) / peak) if traffic else None,
                    traffic_over_algorithmic=(traffic / sb[dom]) if traffic else None,
-                   peak_source=peak_src, algorithmic_bytes_per_launch=sb[dom], survey_bytes_per_launch=sb_survey[dom],
-                   kernel_ms=ms[dom], stage_ms=ms, stage_algorithmic_bytes=sb, stage_survey_bytes=sb_survey, dedup=dedup,
-                   stage_frac={k: (sb[k] / (ms[k] / 1e3) / 1e9 / peak if ms[k] > 0 else None) for k in STAGES},
-                   path=dict(algorithmic_bytes=path_bytes, survey_bytes=path_survey, ms=total_ms,
-                             frac=path_bytes / (total_ms / 1e3) / 1e9 / peak,
-                             survey_frac=path_survey / (total_ms / 1e3) / 1e9 / peak,
+                   traffic_over_gathered=(traffic / sg[dom]) if traffic else None,
+                   peak_source=peak_src, algorithmic_bytes_per_launch=sb[dom], gathered_bytes_per_launch=sg[dom],
+                   kernel_ms=ms[dom], stage_ms=ms, stage_algorithmic_bytes=sb, stage_gathered_bytes=sg, dedup=dedup,
+                   stage_frac={k: (gbs(sb[k], ms[k]) / peak if ms[k] > 0 else None) for k in STAGES},
+                   stage_gathered_frac={k: (gbs(sg[k], ms[k]) / peak if ms[k] > 0 else None) for k in STAGES},
+                   path=dict(algorithmic_bytes=path_bytes, gathered_bytes=path_gathered, ms=total_ms,
+                             frac=gbs(path_bytes, total_ms) / peak, survey_frac=gbs(path_bytes, total_ms) / peak,
+                             gathered_frac=gbs(path_gathered, total_ms) / peak,
                              note="whole decode over the summed single-stream stage times"),
                    how=f"CUDA-event nodes inside the replayed graph (single stream), mean of {n_prof} replays with a sync between them; "
-                       "frac = algorithmic bytes / time / peak with the sampling phase counted at its DISTINCT gathered rows "
-                       "(device counter); survey_frac = SURVEY 8(d)'s 32 rows per (centre, joint) -- above 1 it measures the "
-                       "de-duplication, not bandwidth; dram_frac = ncu dram__bytes of the same kernel / time / peak")
+                       "frac = SURVEY 8(d) algorithmic bytes (32 feature rows per (centre, joint) in the sampling phase) / time / peak "
+                       "-- above 1 where the kernel multiplies each DISTINCT sampled row once instead of moving those bytes; "
+                       "gathered_frac = the distinct rows it really gathers (device counter of the same run) / time / peak; "
+                       "dram_frac = ncu dram__bytes of the same kernels / time / peak")
         return out
 
     def close(self):
@@ -688,12 +699,14 @@ def run_b200(args):
     ser_ms = run.serial_replay(200 if w["key"] != "mupots" else 10)
     roofline["path"]["serial_replay"] = dict(
         ms=ser_ms, frac=roofline["path"]["algorithmic_bytes"] / (ser_ms / 1e3) / 1e9 / roofline["peak"],
-        survey_frac=roofline["path"]["survey_bytes"] / (ser_ms / 1e3) / 1e9 / roofline["peak"],
+        survey_frac=roofline["path"]["algorithmic_bytes"] / (ser_ms / 1e3) / 1e9 / roofline["peak"],
+        gathered_frac=roofline["path"]["gathered_bytes"] / (ser_ms / 1e3) / 1e9 / roofline["peak"],
         note="one decode at a time: graph replays back to back on ONE stream, programmatic dependent launch on "
              "(the stage times above carry event nodes between the kernels, which rules PDL out)")
     roofline["path"]["pipelined"] = dict(
         ms=step_ms, frac=roofline["path"]["algorithmic_bytes"] / (step_ms / 1e3) / 1e9 / roofline["peak"],
-        survey_frac=roofline["path"]["survey_bytes"] / (step_ms / 1e3) / 1e9 / roofline["peak"],
+        survey_frac=roofline["path"]["algorithmic_bytes"] / (step_ms / 1e3) / 1e9 / roofline["peak"],
+        gathered_frac=roofline["path"]["gathered_bytes"] / (step_ms / 1e3) / 1e9 / roofline["peak"],
         note="the same byte counts over the timed step (independent batches pipelined on %d streams)" % run.n_streams)
 
     # ---- end to end through the host-buffer C-ABI entry: pinned host inputs, H2D + decode + D2H ---
@@ -836,10 +849,10 @@ def run_b200(args):
                 extras[name] = dict(workload=sw["name"], value=world * sw["batch"] * steps / (sms / 1e3), unit=UNIT,
                                     ms_per_step=sms / steps, steps=steps, repetitions=len(sreps),
                                     serial_latency_ms=float(sst.sum()), serial_replay_ms=sser,
-                                    roofline={k: sroof[k] for k in ("kernel", "stage", "frac", "survey_frac", "dram_frac", "achieved", "peak",
-                                                                    "traffic", "algorithmic_bytes_per_launch", "survey_bytes_per_launch",
+                                    roofline={k: sroof[k] for k in ("kernel", "stage", "frac", "gathered_frac", "dram_frac", "achieved", "peak",
+                                                                    "traffic", "algorithmic_bytes_per_launch", "gathered_bytes_per_launch",
                                                                     "kernel_ms", "stage_ms", "stage_frac", "dedup")},
-                                    path_frac=sroof["path"]["frac"], path_survey_frac=sroof["path"]["survey_frac"])
+                                    path_frac=sroof["path"]["frac"], path_gathered_frac=sroof["path"]["gathered_frac"])
                 sub.close()
                 del sub
             except Exception as e:       # an extra must never take the headline line down with it

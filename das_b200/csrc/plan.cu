@@ -884,13 +884,26 @@ extern "C" int das_plan_run_host_async(das_plan* p, const das_levels* levels, co
     auto D2H = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
         return dst ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st) : cudaSuccess;
     };
-    DAS_CUDA_CHECK(D2H(host_out.out_count, p->buf.out_count, B * 4));
-    DAS_CUDA_CHECK(D2H(host_out.out_score, p->buf.out_score, B * P * 4));
-    DAS_CUDA_CHECK(D2H(host_out.out_slot, p->buf.out_slot, B * P * 4));
-    DAS_CUDA_CHECK(D2H(host_out.out_pose, p->buf.out_pose, B * P * J * 3 * 4));
-    DAS_CUDA_CHECK(D2H(host_out.out_center, p->buf.out_center, B * P * 3 * 4));
-    DAS_CUDA_CHECK(D2H(host_out.out_cam, p->buf.out_cam, B * P * J * 3 * 8));
-    DAS_CUDA_CHECK(D2H(host_out.out_world, p->buf.out_world, B * P * J * 3 * 8));
+    // host_out laid out like the device block (das_plan_output_block; DecodePlan.alloc_host_out does that): one copy
+    // instead of seven (each small copy costs the stream ~5-8 us)
+    {
+        unsigned char* hb = reinterpret_cast<unsigned char*>(host_out.out_count);
+        const void* hp[7] = {host_out.out_count, host_out.out_score, host_out.out_slot, host_out.out_pose, host_out.out_center,
+                             host_out.out_cam, host_out.out_world};
+        bool block_layout = hb != nullptr && p->out_off[0] == 0;
+        for (int i = 0; i < 7 && block_layout; ++i) block_layout = hp[i] == hb + p->out_off[i];
+        if (block_layout) {
+            DAS_CUDA_CHECK(cudaMemcpyAsync(hb, p->out_block, p->out_block_bytes, cudaMemcpyDeviceToHost, st));
+        } else {
+            DAS_CUDA_CHECK(D2H(host_out.out_count, p->buf.out_count, B * 4));
+            DAS_CUDA_CHECK(D2H(host_out.out_score, p->buf.out_score, B * P * 4));
+            DAS_CUDA_CHECK(D2H(host_out.out_slot, p->buf.out_slot, B * P * 4));
+            DAS_CUDA_CHECK(D2H(host_out.out_pose, p->buf.out_pose, B * P * J * 3 * 4));
+            DAS_CUDA_CHECK(D2H(host_out.out_center, p->buf.out_center, B * P * 3 * 4));
+            DAS_CUDA_CHECK(D2H(host_out.out_cam, p->buf.out_cam, B * P * J * 3 * 8));
+            DAS_CUDA_CHECK(D2H(host_out.out_world, p->buf.out_world, B * P * J * 3 * 8));
+        }
+    }
     DAS_CUDA_CHECK(D2H(host_out.cand_score, p->buf.cand_score, B * p->CT * 4));
     DAS_CUDA_CHECK(D2H(host_out.cand_index, p->buf.cand_index, B * p->CT * 4));
     return DAS_OK;

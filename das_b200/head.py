@@ -373,7 +373,12 @@ class DecodePlan:
             _lib.check(fn(self._plan, C.byref(lv), C.c_void_p(sxy.ctypes.data), C.c_void_p(cam.ctypes.data), ob,
                           _stream_ptr(self.device)), "das_plan_run_host")
 
-    def alloc_host_out(self, pinned: bool = True) -> Dict[str, torch.Tensor]:
+    def alloc_host_out(self, pinned: bool = True, contiguous: bool = True) -> Dict[str, torch.Tensor]:
+        """Host arrays for run_host's results.  contiguous=True: views into ONE host block with the layout of the device
+        output block, which das_plan_run_host recognises and fills with a single D2H copy; False: one array per field."""
+        if contiguous:
+            block = torch.empty(int(self.output_block().numel()), dtype=torch.uint8, pin_memory=pinned)
+            return self.views_of_block(block)
         return {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=pinned)
                 for k, v in self.t.items() if k.startswith("out_")}
 
