@@ -76,13 +76,53 @@ __device__ __forceinline__ double oks_term(const float* __restrict__ pg, const f
     return exp(-e);
 }
 
-// group of G lanes (16 or 32) cooperates on one pair; every lane of the group returns the float32 OKS
+// group of G lanes (16 or 32) cooperates on one pair, one joint per lane; every lane of the group returns the float32 OKS.
+// The J float64 terms are added in the order NumPy's np.sum adds them (pose_nms.py:91; pairwise_sum for fewer than 128
+// elements): eight running sums over the first 8 * (J / 8) terms -- lane k < 8 adds terms k, k + 8, k + 16, .. -- combined as
+// the balanced tree ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7)) (three xor steps inside the first 8 lanes; a + b == b + a
+// exactly), then the remaining terms one by one; fewer than 8 terms: left to right.  Must be called by all 32 lanes.
 template <int G>
 __device__ __forceinline__ float oks_pair(const float* pg, const float* pd, float ag, float ad, int J, int gl) {
-    double t = (gl < J) ? oks_term(pg, pd, ag, ad, gl, J) : 0.0;
+    const double t = (gl < J) ? oks_term(pg, pd, ag, ad, gl, J) : 0.0;
+    double res;
+    if (J < 8) {
+        res = 0.0;
+        for (int k = 0; k < J; ++k) res += __shfl_sync(0xffffffffu, t, k, G);
+    } else {
+        const int m = J - (J % 8);
+        double r = t;
+        for (int i = 8; i < m; i += 8) r += __shfl_down_sync(0xffffffffu, t, i, G);
+        r += __shfl_xor_sync(0xffffffffu, r, 1, G);
+        r += __shfl_xor_sync(0xffffffffu, r, 2, G);
+        r += __shfl_xor_sync(0xffffffffu, r, 4, G);
+        res = r;
+        for (int i = m; i < J; ++i) res += __shfl_sync(0xffffffffu, t, i, G);
+        res = __shfl_sync(0xffffffffu, res, 0, G);
+    }
+    return static_cast<float>(res / static_cast<double>(J));
+}
+
+// The same value computed by ONE lane, the J terms added in the order NumPy's np.sum adds a contiguous float64 array of
+// J < 128 elements (pairwise_sum: eight running sums over the first 8 * (J / 8) terms, combined as a balanced tree, the
+// remaining terms added one by one; fewer than 8 terms: left to right) -- pose_nms.py:91.
+__device__ __forceinline__ float oks_pair_serial(const float* pg, const float* pd, float ag, float ad, int J) {
+    double res;
+    if (J < 8) {
+        res = 0.0;
+        for (int k = 0; k < J; ++k) res += oks_term(pg, pd, ag, ad, k, J);
+    } else {
+        double r[8];
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    return static_cast<float>(t / static_cast<double>(J));
+        for (int k = 0; k < 8; ++k) r[k] = oks_term(pg, pd, ag, ad, k, J);
+        const int m = J - (J % 8);
+        for (int i = 8; i < m; i += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] += oks_term(pg, pd, ag, ad, i + k, J);
+        }
+        res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (int i = m; i < J; ++i) res += oks_term(pg, pd, ag, ad, i, J);
+    }
+    return static_cast<float>(res / static_cast<double>(J));
 }
 
 // Pair index pr in [0, n(n-1)/2) -> (i < j), rows enumerated as (0,1) (0,2) ... (0,n-1) (1,2) ...; closed form with a
@@ -98,10 +138,16 @@ __device__ __forceinline__ void unrank_pair(int pr, int n, int& i, int& j) {
     j = r + 1 + (pr - start(r));
 }
 
-// Hard NMS only needs the DECISION oks > thr.  A float32 estimate of the same expression (error ~1e-6) settles every pair
-// whose estimate is below thr - 0.05 -- in practice all pairs of distinct people -- and only the others pay for the
-// reference's float64 divide / exp chain, so the decision is still the exact one.  Must be called by all 32 lanes; the
-// exact path is taken warp-wide when any of the warp's groups needs it (the float64 butterfly uses full-warp shuffles).
+// Hard NMS only needs the DECISION oks > thr.  A float32 estimate of the same expression settles every pair whose estimate
+// is further than OKS_BAND from thr -- on either side: pairs of distinct people (estimate ~0) and near-duplicates of one person
+// (estimate ~1) -- and only a pair inside the band pays for the reference's float64 divide / exp chain, so the decision is
+// still the exact one.
+// Error of the estimate: e differs from the float64 value by a relative 4e-7 (float32 variance, two float32 divisions), a
+// term exp(-e) therefore by at most max(e exp(-e)) * 4e-7 = 1.5e-7, ex2.approx adds 2e-8: below 1e-6 for the mean -- the band
+// is 1000 times that.  NaN-safe: anything that is not clearly on one side takes the exact path.  Must be called by all 32
+// lanes; the exact path is taken warp-wide when any of the warp's groups needs it (the float64 butterfly uses full-warp
+// shuffles).
+constexpr float OKS_BAND = 1e-3f;
 template <int G>
 __device__ __forceinline__ bool oks_over(const float* pg, const float* pd, float ag, float ad, int J, int gl, float thr) {
     float t = 0.f;
@@ -112,8 +158,9 @@ __device__ __forceinline__ bool oks_over(const float* pg, const float* pd, float
     }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    const bool maybe = !(t / static_cast<float>(J) < thr - 0.05f);      // NaN-safe: anything odd goes to the exact path
-    if (!__any_sync(0xffffffffu, maybe)) return false;
+    const float est = t / static_cast<float>(J);
+    const bool below = est < thr - OKS_BAND, above = est > thr + OKS_BAND;
+    if (!__any_sync(0xffffffffu, !(below || above))) return above;
     return oks_pair<G>(pg, pd, ag, ad, J, gl) > thr;
 }
 
@@ -265,31 +312,46 @@ nms_backproject_kernel(const NmsParams p) {
             __syncthreads();
         } else if (n <= NM_MATRIX_N) {
             // ---- all pairs in parallel, then a 64-bit mask greedy pass by one thread ---------------
-            if (tid < n) s_mask[tid] = 0ull;
-            __syncthreads();
+            // ncu on the K = 64 decode (BASELINE config #4, 47 us per launch) showed the pair loop ISSUE-bound: with 16 lanes
+            // per pair it spent 223 instructions per pair and warp -- a third of them the closed-form pair un-ranking that
+            // every lane of a group repeated, a quarter the two IEEE divisions and the 64-bit pose addressing, then the
+            // shuffle reduction.  Now ONE LANE owns a pair: the candidates' (x, y) are staged joint-major in shared memory (lanes
+            // of a warp hold consecutive j: conflict-free), the lane walks the J joints with the float32 ESTIMATE (reciprocal
+            // multiplies: its error stays ~1e-6, the band that sends a pair to the exact chain is 1e-3) and only a pair inside
+            // the band runs the reference's float64 chain, serially in that lane: ~15 instructions per joint and pair instead
+            // of ~220 per pair and warp-round.
+            __shared__ float2 s_xy[DAS_MAX_JOINTS * NM_MATRIX_N];     // [joint][rank]
+            __shared__ float s_ar[NM_MATRIX_N], s_iv[DAS_MAX_JOINTS];
             const int npairs = n * (n - 1) / 2;
-            if (J <= 16) {
-                const int grp = tid >> 4, gl = tid & 15;
-                for (int pr = grp; pr < ((npairs + 63) / 64) * 64; pr += NT / 16) {
-                    // both half-warps must run the shuffles together -> loop bound is warp-uniform
-                    int i = 0, j = 1;
-                    const bool live = pr < npairs;
-                    if (live) unrank_pair(pr, n, i, j);
-                    const int ci = order[i], cj = order[live ? j : 1 % max(n, 1)];
-                    const bool over = oks_over<16>(pose + static_cast<size_t>(ci) * J * 3, pose + static_cast<size_t>(cj) * J * 3,
-                                                   area[ci], area[cj], J, gl, p.nms_thr);
-                    if (live && gl == 0 && over) atomicOr(&s_mask[i], 1ull << j);
+            if (tid < n) { s_mask[tid] = 0ull; s_ar[tid] = area[order[tid]]; }
+            if (tid < J) s_iv[tid] = 1.0f / static_cast<float>(oks_var(tid, J));
+            for (int e = tid; e < n * J; e += NT) {
+                const int i = e / J, j = e - i * J;
+                const float* pc = pose + (static_cast<size_t>(order[i]) * J + j) * 3;
+                s_xy[j * NM_MATRIX_N + i] = make_float2(pc[0], pc[1]);
+            }
+            __syncthreads();
+            const float inv_J = 1.0f / static_cast<float>(J);
+            for (int pr = tid; pr < npairs; pr += NT) {
+                int i, j;
+                unrank_pair(pr, n, i, j);
+                const float inv_am = __fdividef(0.5f, (s_ar[i] + s_ar[j]) * 0.5f + 2.220446049250313e-16f);
+                float t = 0.f;
+                for (int k = 0; k < J; ++k) {
+                    const float2 a = s_xy[k * NM_MATRIX_N + i], c2 = s_xy[k * NM_MATRIX_N + j];
+                    const float dx = c2.x - a.x, dy = c2.y - a.y;
+                    t += __expf(-((dx * dx + dy * dy) * s_iv[k] * inv_am));
                 }
-            } else {
-                const int grp = tid >> 5, gl = tid & 31;
-                for (int pr = grp; pr < npairs; pr += NT / 32) {
-                    int i, j;
-                    unrank_pair(pr, n, i, j);
+                const float est = t * inv_J;
+                bool over = est > p.nms_thr + OKS_BAND;
+                if (!over && !(est < p.nms_thr - OKS_BAND)) {
+                    // inside the band (or NaN): pose_nms.py:84-91 in the reference's own precision
                     const int ci = order[i], cj = order[j];
-                    const bool over = oks_over<32>(pose + static_cast<size_t>(ci) * J * 3, pose + static_cast<size_t>(cj) * J * 3,
-                                                   area[ci], area[cj], J, gl, p.nms_thr);
-                    if (gl == 0 && over) atomicOr(&s_mask[i], 1ull << j);
+                    const float* pg = pose + static_cast<size_t>(ci) * J * 3;
+                    const float* pd = pose + static_cast<size_t>(cj) * J * 3;
+                    over = oks_pair_serial(pg, pd, area[ci], area[cj], J) > p.nms_thr;
                 }
+                if (over) atomicOr(&s_mask[i], 1ull << j);
             }
             __syncthreads();
             if (tid == 0) {
