@@ -689,8 +689,12 @@ refine_heads8_kernel(const RefineParams p) {
 // Row records of the split phase 1-2 path: one warp per (candidate, joint) item, lane = (head = lane >> 2, corner = lane & 3).
 // Reads the item's 16 head offsets left by refine_heads8_kernel<.., SPLIT> in the first 64 bytes of its row-record slot, then
 // overwrites the slot with the 32 records; distinct sampled cells -> the joint's row list; assembly record; centre; valid_list.
+// 32 registers (8 CTAs per SM; 36 bytes of spills): the kernel is a chain of three dependent global round trips per item, so
+// what pays is warps in flight and room for the other streams' kernels -- single-stream stage time unchanged, pipelined
+// throughput +3 % (config #2: 1.23 -> 1.27 M images/s, config #4: 239 -> 249 k).  The LAZY variant inlines dense_sample_cell
+// and keeps its registers.
 template <int NH, bool LAZY = false>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, LAZY ? 1 : 8)
 refine_records_kernel(const RefineParams p) {
     static_assert(NH == 4, "32 rows per item = 8 heads x 4 corners");
     constexpr int C = 256;
