@@ -181,7 +181,9 @@ dense_sample_kernel(const DenseParams p) {
     }
 }
 
-// Second version of the sampling kernel (same arithmetic, same accumulation order -> bit-identical results; FASTEXP
+// Second version of the sampling kernel; its body is dense_sample_cell (refine_common.cuh), which the sparse last layer also
+// calls for the cells it needs (on-demand sampling of the last dense layer).  Same arithmetic and accumulation order as the
+// first version -> bit-identical results; FASTEXP
 // swaps the softmax's expf for ex2.approx): ncu showed the first one ISSUE-bound next to its L1 load (1 680 instructions per
 // (cell, joint), issue 64 % busy, l1tex 86 %), so this one removes instructions:
 //   * the 18 divisions of the coordinate chains use the precomputed reciprocal (div_by: 3 instead of ~10 instructions);
