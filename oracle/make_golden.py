@@ -27,6 +27,7 @@ from oracle import ref_extract as R  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 P = synth.PANOPTIC
+SHIPPED_TEST_CFG = dict(nms_across_levels=False, nms_pre=1000, nms_post=100, nms_thr=0.9, score_thr=0.07)   # exp_panoptic.py:47-53
 CASES = {
     # name: (head cfg, batch, H, W, seed, peaks, scales, test_cfg)
     "panoptic_small": (P, 2, 24, 40, 1234, 12, (1.0, 1.0, 1.0, 1.0),
@@ -54,6 +55,13 @@ CASES = {
                        dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.9999)),
     "border_targets": (P, 2, 16, 20, 1245, 10, (1.0, 1.0, 6.0, 1.0),
                        dict(nms_pre=10, nms_post=10, nms_thr=0.9, score_thr=0.0)),
+    # the two SHIPPED models with their shipped test_cfg, on the 4-level pyramid of their shipped test pipelines:
+    # Panoptic J=15, L=1, 1152x640 input -> 80x144 stride-8 map (exp_panoptic.py:31-53,138-155); MuPoTS J=21, L=2, root 14,
+    # 2048^2 frames at (1280, 768) -> 96x96 (exp_mupots.py:7,37-56,142-159)
+    "shipped_panoptic_80x144": (dataclasses.replace(P, strides=(8, 16, 32, 64)), 1, 80, 144, 1246, 24, (1.0, 1.0, 1.0, 1.0),
+                                SHIPPED_TEST_CFG),
+    "shipped_mupots21_L2_96x96": (dataclasses.replace(synth.MUPOTS17, num_joints=21, num_layers=2, strides=(8, 16, 32, 64)),
+                                  1, 96, 96, 1247, 24, (1.0, 1.0, 1.0, 1.0), SHIPPED_TEST_CFG),
 }
 
 
@@ -86,10 +94,13 @@ def run_reference(cfg, levels, layers, metas, tc):
     return res, pose_preds
 
 
-def main():
+def main(only=()):
+    """python -m oracle.make_golden [case ...]: regenerate every golden file, or only the named ones."""
     assert R.available(), "the reference tree is required to (re)generate golden vectors"
     os.makedirs(OUT, exist_ok=True)
-    for name in CASES:
+    unknown = set(only) - set(CASES)
+    assert not unknown, f"unknown cases {sorted(unknown)}"
+    for name in (only or CASES):
         cfg, levels, layers, metas, tc = build_case(name)
         ref, ref_pp = run_reference(cfg, levels, layers, metas, tc)
         ours, our_pp = O.decode_full(levels, layers, metas, cfg.as_dict(), tc)
@@ -128,4 +139,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1:])

@@ -64,8 +64,10 @@ def test_on_demand_sampling_equals_the_dense_map(layers, force):
             assert torch.equal(a[k], b[k]) if torch.is_tensor(a[k]) else a[k] == b[k], k
 
 
-def test_golden_mupots17_three_layers():
-    name = "mupots17_L3"
+@pytest.mark.parametrize("name", sorted(n for n in G.CASES if G.CASES[n][0].num_layers > 1))
+def test_golden_vectors_with_dense_layers(name):
+    """The reference's own outputs for the multi-layer cases: the synthetic J=17 / L=3 variant and the shipped MuPoTS model
+    (J=21, L=2, 4-level pyramid, shipped test_cfg)."""
     gold = np.load(os.path.join(GOLDEN, name + ".npz"))
     cfg, levels, layers, metas, tc = G.build_case(name)
     case = dict(cfg=cfg, levels=levels, layers=layers, metas=metas, batch=levels[0]["cls"].shape[0])
@@ -75,7 +77,7 @@ def test_golden_mupots17_three_layers():
     assert len(got) == int(gold["n_images"])
     for i, g in enumerate(got):
         lv, idx = util.slot_to_level_index(plan, g["slots"].cpu(), ci[i])
-        assert idx == gold[f"index_{i}"].tolist()
+        assert idx == gold[f"index_{i}"].tolist() and lv == gold[f"level_{i}"].tolist()
         assert util.rel_err(g["poses"].cpu().numpy(), gold[f"poses_{i}"]) < TOL
         assert util.rel_err(g["poses_cam"].cpu().numpy(), gold[f"cam_{i}"]) < TOL
 
