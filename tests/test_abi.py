@@ -84,3 +84,22 @@ def test_argument_errors_are_reported_not_swallowed():
     with pytest.raises(_lib.DasError):
         _lib.check(-1, "x")
     assert lib.das_score_topk(None, None, 10, 0, None, None, 10, None, None) == -1
+
+
+def test_c_host_links_against_the_library_and_fails_loudly_without_a_device():
+    """examples/decode_host.c: a C99 caller needs nothing but include/das_decode.h and the shared library; where no CUDA
+    device exists the plan constructor reports DAS_ERR_CUDA with the failing runtime call (there is no CPU path)."""
+    lib_dir = os.path.dirname(_lib.LIB_PATH)
+    _lib.load()
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "decode_host")
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                               os.path.join(ROOT, "examples", "decode_host.c"), "-L", lib_dir, "-ldas_decode",
+                               "-Wl,-rpath," + lib_dir, "-Wl,--allow-shlib-undefined", "-o", exe])
+        r = subprocess.run([exe], capture_output=True, text=True)
+    assert "sm_100a" in r.stdout and "candidate slots per image: 10, output slots: 10" in r.stdout
+    import torch
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "plan ready: 10 candidate slots, 10 output slots" in r.stdout, r.stderr
+    else:
+        assert r.returncode == 2 and "das_plan_create failed (-2)" in r.stderr and "cuda" in r.stderr.lower(), r.stderr
