@@ -588,5 +588,5 @@ class DASHeadB200:
         return plan.results(metas)
 
     def simple_test_decode(self, outs, img_metas, rescale=False):
-        """What DAS.simple_test does after the head forward (detectors/das.py:74-79)."""
+        """What DAS.simple_test does after the head forward (detectors/das.py:34-39)."""
         return self.get_poses(*outs, img_metas, rescale=rescale)

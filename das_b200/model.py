@@ -11,7 +11,7 @@ What it mirrors (behaviour, not code):
                          (not in the reference tree; restated from the published algorithm)
   * DASTowers         <- DASHead conv stack (das_head.py:103-230, anchor_free_mono3d_pose_head.py:100-249) and
                          RecursiveUpdateBranch's conv part (recursive_update.py:171-180, 243-255)
-  * DASNet            <- DAS.extract_feat + bbox_head forward (detectors/das.py:74-79)
+  * DASNet            <- DAS.extract_feat + bbox_head forward (detectors/das.py:34-39)
 
 Parity status: MSPNBackbone is pinned against the reference's own MSPN2 source executed under mmcv shims
 (oracle/make_model_golden.py -> tests/golden/mspn_small.npz).  DASTowers is pinned against the reference head's own

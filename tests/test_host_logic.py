@@ -113,7 +113,7 @@ def test_bench_reference_arm_prints_one_json_line():
 
 def test_get_poses_argument_forms():
     """The call forms get_poses accepts, resolved by content: the reference's (img_metas[, cfg[, rescale]]), positional or
-    by keyword (das_head.py:653-659; detectors/das.py:78 splats the head outputs), and the extended
+    by keyword (das_head.py:653-659; detectors/das.py:37-38 splats the head outputs), and the extended
     (refine_feats, img_metas[, cfg[, rescale]]) one."""
     from das_b200.head import DASHeadB200
     metas = [dict(scale_factor=np.ones(4, np.float32), filename="a.jpg")]
