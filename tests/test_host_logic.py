@@ -1,5 +1,7 @@
 """CPU: host-side logic of the drop-in head -- sharding, meta packing, output-block layout, and that
 the product path refuses to run without its CUDA library/device (no silent fallback)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -7,6 +9,8 @@ import torch
 from das_b200 import dist as ddist
 from das_b200 import head as H
 from das_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_shard_bounds_partition_the_batch():
@@ -193,3 +197,16 @@ def test_bench_rank_pinning_gives_disjoint_core_slices():
             assert all(a.isdisjoint(b) for i, a in enumerate(slices) for b in slices[i + 1:])
     finally:
         os.sched_setaffinity(0, before)
+
+
+def test_reference_citations_point_inside_the_cited_files():
+    """Parity is argued through `file.py:line` citations of the reference; none may point past the end of its file."""
+    import importlib.util
+    ref = os.environ.get("DAS_REFERENCE_ROOT", "/root/reference")
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not mounted (GPU box)")
+    spec = importlib.util.spec_from_file_location("check_citations", os.path.join(ROOT, "tools", "check_citations.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    n, bad = mod.check(ref)
+    assert n > 150 and not bad, bad
